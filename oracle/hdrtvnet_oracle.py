@@ -1,0 +1,493 @@
+"""CPU oracle for the HDRTVNet++ per-frame SDR->HDR path (TEST INFRASTRUCTURE ONLY).
+
+This file is a plain-numpy restatement of the reference's algorithm for the hot
+path.  It is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  The shipped package
+(``hdr_realtime_video_pipeline_b200``) never imports anything from ``oracle/``.
+
+Parity pinning: the reference ships NO golden vectors or known-answer tests of
+its own.  The oracle is therefore pinned against outputs of
+the reference itself, run in the build container by
+``scripts/make_golden.py`` (imports ``/root/reference/src`` read-only) and
+committed under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks every
+function below against those fixtures.
+
+Third-party arithmetic: conv / pool / instance-norm / interpolate live in
+PyTorch ATen (reference pins torch==2.9.1; fixtures were generated with the
+image's torch 2.11.0 CPU).  Their published definitions are restated here.
+
+Each function cites the reference file:line it follows (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+# --------------------------------------------------------------------------
+# P1  preprocess  (src/models/hdrtvnet_torch.py:2239-2296)
+# --------------------------------------------------------------------------
+
+_INV255 = F32(1.0 / 255.0)  # python double 1/255 -> fp32 scalar, as torch's mul_(1.0/255.0)
+
+
+def normalize_bgr_u8(frame_bgr: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """uint8 HxWx3 BGR -> (3,H,W) RGB, ``float(u8) * fp32(1/255)`` rounded to dtype.
+
+    hdrtvnet_torch.py:2256-2261: flip(2) -> permute -> .to(dtype).mul_(1/255).
+    For fp16 the reference converts u8->half (exact) and multiplies in half:
+    the product of a half and the scalar is computed in fp32 and rounded once.
+    """
+    rgb = frame_bgr[:, :, ::-1].transpose(2, 0, 1)
+    if np.dtype(dtype) == np.float16:
+        # torch half mul_ with a python scalar: opmath is float, scalar kept in fp32.
+        return (rgb.astype(F32) * _INV255).astype(np.float16)
+    return rgb.astype(F32) * _INV255
+
+
+def _cubic_aa_filter(x: np.ndarray) -> np.ndarray:
+    """Keys cubic, a = -0.5 (ATen UpSampleKernel.cpp `aa_filter` for bicubic)."""
+    a = F32(-0.5)
+    x = np.abs(x).astype(F32)
+    w1 = ((a + F32(2.0)) * x - (a + F32(3.0))) * x * x + F32(1.0)
+    w2 = (((x - F32(5.0)) * x + F32(8.0)) * x - F32(4.0)) * a
+    return np.where(x < 1.0, w1, np.where(x < 2.0, w2, F32(0.0))).astype(F32)
+
+
+def aa_bicubic_weights(n_in: int, scale_factor: float = 0.25):
+    """Per-output-index tap start, count and normalised weights of
+    F.interpolate(mode='bicubic', antialias=True, align_corners=False,
+    recompute_scale_factor=False) along one axis.  hdrtvnet_torch.py:2277-2285;
+    ATen `_compute_indices_weights_aa`: scale = 1/scale_factor, support =
+    2*scale, center = scale*(i+0.5), taps [int(center-support+0.5),
+    int(center+support+0.5)) clipped to [0,n_in), weight k((j-center+0.5)/scale)
+    normalised by the tap sum.
+    """
+    n_out = int(np.floor(n_in * scale_factor))
+    scale = F32(1.0 / scale_factor)
+    support = F32(2.0) * scale
+    starts, counts, weights = [], [], []
+    for i in range(n_out):
+        center = scale * (F32(i) + F32(0.5))
+        xmin = max(int(center - support + F32(0.5)), 0)
+        xmax = min(int(center + support + F32(0.5)), n_in)
+        j = np.arange(xmin, xmax, dtype=np.float32)
+        w = _cubic_aa_filter((j - center + F32(0.5)) / scale)
+        w = (w / w.sum(dtype=F32)).astype(F32)
+        starts.append(xmin)
+        counts.append(xmax - xmin)
+        weights.append(w)
+    return n_out, starts, counts, weights
+
+
+def _aa_matrix(n_in: int, scale_factor: float = 0.25) -> np.ndarray:
+    n_out, starts, counts, weights = aa_bicubic_weights(n_in, scale_factor)
+    m = np.zeros((n_out, n_in), dtype=F32)
+    for i in range(n_out):
+        m[i, starts[i]:starts[i] + counts[i]] = weights[i]
+    return m
+
+
+def cond_downsample(x_chw: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """(3,H,W) -> (3,H//4,W//4) antialiased bicubic, fp32 accumulate, rounded to dtype."""
+    c, h, w = x_chw.shape
+    my = _aa_matrix(h)
+    mx = _aa_matrix(w)
+    xf = x_chw.astype(F32)
+    # ATen CPU runs the horizontal pass first, then the vertical one; the CUDA kernel
+    # (the fp16 path) accumulates the 2-D tap sum in fp32 and rounds once at the end.
+    tmp = np.einsum("chw,ow->cho", xf, mx, optimize=True).astype(F32)
+    out = np.einsum("chw,oh->cow", tmp, my, optimize=True).astype(F32)
+    return out.astype(dtype)
+
+
+def preprocess(frame_bgr: np.ndarray, dtype=np.float32):
+    """Returns (x (1,3,H,W), cond (1,3,H//4,W//4)) like HDRTVNetTorch.preprocess."""
+    x = normalize_bgr_u8(frame_bgr, dtype)
+    cond = cond_downsample(x, dtype)
+    return x[None], cond[None]
+
+
+# --------------------------------------------------------------------------
+# Primitive ops (ATen definitions restated)
+# --------------------------------------------------------------------------
+
+def conv2d(x: np.ndarray, w: np.ndarray, b: np.ndarray | None, stride: int = 1, pad: int | None = None) -> np.ndarray:
+    """x (C,H,W), w (O,C,kh,kw) -> (O,Ho,Wo).  Zero padding, cross-correlation
+    (torch.nn.Conv2d).  Tap-by-tap matmul accumulation in fp32."""
+    o, c, kh, kw = w.shape
+    if pad is None:
+        pad = kh // 2
+    _, h, wd = x.shape
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (wd + 2 * pad - kw) // stride + 1
+    xp = np.pad(x.astype(F32), ((0, 0), (pad, pad), (pad, pad))) if pad else x.astype(F32)
+    out = np.zeros((o, ho * wo), dtype=F32)
+    for ky in range(kh):
+        for kx in range(kw):
+            patch = xp[:, ky:ky + (ho - 1) * stride + 1:stride, kx:kx + (wo - 1) * stride + 1:stride]
+            out += w[:, :, ky, kx].astype(F32) @ np.ascontiguousarray(patch).reshape(c, ho * wo)
+    if b is not None:
+        out += b.astype(F32)[:, None]
+    return out.reshape(o, ho, wo)
+
+
+def leaky_relu(x: np.ndarray, slope: float) -> np.ndarray:
+    return np.where(x >= 0, x, x * F32(slope)).astype(F32)
+
+
+def relu(x: np.ndarray) -> np.ndarray:
+    return np.maximum(x, F32(0.0))
+
+
+def avg_pool_3s2p1(x: np.ndarray) -> np.ndarray:
+    """nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=True): always /9.
+    Condition_arch.py:10."""
+    c, h, w = x.shape
+    ho = (h - 1) // 2 + 1
+    wo = (w - 1) // 2 + 1
+    xp = np.pad(x.astype(F32), ((0, 0), (1, 1), (1, 1)))
+    acc = np.zeros((c, ho, wo), dtype=F32)
+    for ky in range(3):
+        for kx in range(3):
+            acc += xp[:, ky:ky + (ho - 1) * 2 + 1:2, kx:kx + (wo - 1) * 2 + 1:2]
+    return (acc / F32(9.0)).astype(F32)
+
+
+def instance_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """nn.InstanceNorm2d(affine=True, track_running_stats=False): per-frame,
+    per-channel biased variance.  Condition_arch.py:14."""
+    xm = x.astype(np.float64)
+    mean = xm.mean(axis=(1, 2), keepdims=True)
+    var = xm.var(axis=(1, 2), keepdims=True)
+    y = (xm - mean) / np.sqrt(var + eps)
+    return (y * gamma.astype(np.float64)[:, None, None] + beta.astype(np.float64)[:, None, None]).astype(F32)
+
+
+def pixel_shuffle2(x: np.ndarray) -> np.ndarray:
+    """nn.PixelShuffle(2): (4C,H,W) -> (C,2H,2W); out[c,2y+i,2x+j] = in[4c+2i+j,y,x]."""
+    c4, h, w = x.shape
+    c = c4 // 4
+    return x.reshape(c, 2, 2, h, w).transpose(0, 3, 1, 4, 2).reshape(c, 2 * h, 2 * w)
+
+
+def align_to(x: np.ndarray, rh: int, rw: int) -> np.ndarray:
+    """HDRUNet3T1._align_to (HDRUNet3T1_arch.py:78-104): centre-crop when larger,
+    replicate-pad when smaller."""
+    xh, xw = x.shape[-2:]
+    if xh > rh:
+        top = (xh - rh) // 2
+        x = x[..., top:top + rh, :]
+    if xw > rw:
+        left = (xw - rw) // 2
+        x = x[..., :, left:left + rw]
+    xh, xw = x.shape[-2:]
+    ph, pw = rh - xh, rw - xw
+    if ph > 0 or pw > 0:
+        pt, pl = ph // 2, pw // 2
+        x = np.pad(x, ((0, 0), (pt, ph - pt), (pl, pw - pl)), mode="edge")
+    return x
+
+
+# --------------------------------------------------------------------------
+# P2  AGCM  (Condition_arch.py:8-35, 483-494, 559-585)
+# --------------------------------------------------------------------------
+
+_CLS_CONV = (0, 4, 8, 12, 16)      # nn.Sequential indices of the five 1x1 convs
+_CLS_NORM = (3, 7, 11, 15, None)   # InstanceNorm after blocks 1-4, none after block 5
+
+
+def classifier(sd: dict, cond_chw: np.ndarray, prefix: str = "AGCM.classifier.model.") -> np.ndarray:
+    """Color_Condition: 5x [conv1x1 -> AvgPool(3,2,1) -> LeakyReLU(0.2) -> IN] ->
+    Dropout(eval: identity) -> conv1x1 128->6 -> global mean.  Returns fea[6]."""
+    x = cond_chw.astype(F32)
+    for ci, ni in zip(_CLS_CONV, _CLS_NORM):
+        x = conv2d(x, sd[f"{prefix}{ci}.weight"], sd[f"{prefix}{ci}.bias"], 1, 0)
+        x = avg_pool_3s2p1(x)
+        x = leaky_relu(x, 0.2)
+        if ni is not None:
+            x = instance_norm(x, sd[f"{prefix}{ni}.weight"], sd[f"{prefix}{ni}.bias"])
+    x = conv2d(x, sd[f"{prefix}20.weight"], sd[f"{prefix}20.bias"], 1, 0)
+    return x.astype(np.float64).mean(axis=(1, 2)).astype(F32)
+
+
+def gfm_params(sd: dict, fea: np.ndarray) -> dict:
+    """Six nn.Linear(6 -> 64/64/3) heads.  Condition_arch.py:562-569."""
+    out = {}
+    for name in ("first", "HR", "last"):
+        for kind in ("scale", "shift"):
+            w = sd[f"AGCM.cond_{kind}_{name}.weight"].astype(F32)
+            b = sd[f"AGCM.cond_{kind}_{name}.bias"].astype(F32)
+            out[f"{kind}_{name}"] = (w @ fea.astype(F32) + b).astype(F32)
+    return out
+
+
+def agcm(sd: dict, x_chw: np.ndarray, cond_chw: np.ndarray) -> np.ndarray:
+    """ConditionNet.forward dynamic mode.  `out*scale + shift + out` per layer."""
+    fea = classifier(sd, cond_chw)
+    g = gfm_params(sd, fea)
+
+    def mod(o, s, t):
+        return o * s[:, None, None] + t[:, None, None] + o
+
+    o = conv2d(x_chw, sd["AGCM.conv_first.weight"], sd["AGCM.conv_first.bias"], 1, 0)
+    o = relu(mod(o, g["scale_first"], g["shift_first"]))
+    o = conv2d(o, sd["AGCM.HRconv.weight"], sd["AGCM.HRconv.bias"], 1, 0)
+    o = relu(mod(o, g["scale_HR"], g["shift_HR"]))
+    o = conv2d(o, sd["AGCM.conv_last.weight"], sd["AGCM.conv_last.bias"], 1, 0)
+    return mod(o, g["scale_last"], g["shift_last"]).astype(F32)
+
+
+# --------------------------------------------------------------------------
+# P3  LE  (HDRUNet3T1_arch.py:10-76, 152-206; arch_util.py:60-95)
+# --------------------------------------------------------------------------
+
+def _conv(sd, name, x, stride=1):
+    return conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride)
+
+
+def sft_layer(sd: dict, prefix: str, fea: np.ndarray, cond: np.ndarray) -> np.ndarray:
+    """SFTLayer.forward arch_util.py:68-72."""
+    scale = _conv(sd, prefix + ".SFT_scale_conv1", leaky_relu(_conv(sd, prefix + ".SFT_scale_conv0", cond), 0.1))
+    shift = _conv(sd, prefix + ".SFT_shift_conv1", leaky_relu(_conv(sd, prefix + ".SFT_shift_conv0", cond), 0.1))
+    return (fea * (scale + F32(1.0)) + shift).astype(F32)
+
+
+def resblock_sft(sd: dict, prefix: str, x: np.ndarray, cond: np.ndarray) -> np.ndarray:
+    """ResBlock_with_SFT.forward arch_util.py:89-95."""
+    fea = sft_layer(sd, prefix + ".sft1", x, cond)
+    fea = relu(_conv(sd, prefix + ".conv1", fea))
+    fea = sft_layer(sd, prefix + ".sft2", fea, cond)
+    fea = _conv(sd, prefix + ".conv2", fea)
+    return (x + fea).astype(F32)
+
+
+def _seq(sd, prefix, x, spec):
+    """spec: list of (index, stride, act_after)"""
+    for idx, stride, act in spec:
+        x = _conv(sd, f"{prefix}.{idx}", x, stride)
+        if act:
+            x = leaky_relu(x, 0.1)
+    return x
+
+
+def le(sd: dict, img: np.ndarray, cond_img: np.ndarray, return_intermediates: bool = False):
+    """HDRUNet3T1._forward_safe_aligned with weighting_network=False, act=relu."""
+    p = "LE."
+    cond = _seq(sd, p + "cond_first", cond_img, [(0, 1, True), (2, 1, True), (4, 1, True)])
+    cond1 = _seq(sd, p + "CondNet1", cond, [(0, 1, True), (2, 1, True), (4, 1, False)])
+    cond2 = _seq(sd, p + "CondNet2", cond, [(0, 2, True), (2, 1, True), (4, 1, False)])
+    cond3 = _seq(sd, p + "CondNet3", cond, [(0, 2, True), (2, 2, True), (4, 1, False)])
+    cond4 = _seq(sd, p + "CondNet4", cond, [(0, 2, True), (2, 2, True), (4, 2, False)])
+
+    fea0 = relu(_conv(sd, p + "conv_first", img))
+    fea0 = sft_layer(sd, p + "SFT_layer1", fea0, cond1)
+    fea0 = relu(_conv(sd, p + "HR_conv1", fea0))
+
+    fea1 = relu(_conv(sd, p + "down_conv1", fea0, 2))
+    fea1 = resblock_sft(sd, p + "recon_trunk1.0", fea1, cond2)
+
+    fea2 = relu(_conv(sd, p + "down_conv2", fea1, 2))
+    fea2 = resblock_sft(sd, p + "recon_trunk2.0", fea2, cond3)
+
+    fea3 = relu(_conv(sd, p + "down_conv3", fea2, 2))
+    out = fea3
+    for i in range(4):
+        out = resblock_sft(sd, f"{p}recon_trunk3.{i}", out, cond4)
+    out = out + fea3
+
+    up = relu(pixel_shuffle2(_conv(sd, p + "up_conv1.0", out)))
+    up = align_to(up, *fea2.shape[-2:])
+    out = resblock_sft(sd, p + "recon_trunk4.0", up + fea2, cond3)
+
+    up = relu(pixel_shuffle2(_conv(sd, p + "up_conv2.0", out)))
+    up = align_to(up, *fea1.shape[-2:])
+    out = resblock_sft(sd, p + "recon_trunk5.0", up + fea1, cond2)
+
+    up = relu(pixel_shuffle2(_conv(sd, p + "up_conv3.0", out)))
+    up = align_to(up, *fea0.shape[-2:])
+    out = sft_layer(sd, p + "SFT_layer2", up + fea0, cond1)
+
+    out = relu(_conv(sd, p + "HR_conv2", out))
+    out = _conv(sd, p + "conv_last", out)
+    out = align_to(out, *img.shape[-2:])
+    res = (img + out).astype(F32)
+    if return_intermediates:
+        return res, dict(cond=cond, cond1=cond1, cond2=cond2, cond3=cond3, cond4=cond4,
+                         fea0=fea0, fea1=fea1, fea2=fea2, fea3=fea3)
+    return res
+
+
+# --------------------------------------------------------------------------
+# P3'  Ensemble  (Ensemble_AGCM_LE_arch.py:889-897)
+# --------------------------------------------------------------------------
+
+def strip_module_prefix(sd: dict) -> dict:
+    """hdrtvnet_torch.py:2154-2157."""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
+def infer(sd: dict, x: np.ndarray, cond: np.ndarray):
+    """(1,3,H,W), (1,3,h,w) -> (out (1,3,H,W), agcm_out (1,3,H,W)), fp32."""
+    sd = {k: np.asarray(v, dtype=F32) for k, v in sd.items()}
+    agcm_out = agcm(sd, x[0].astype(F32), cond[0].astype(F32))
+    out = le(sd, agcm_out, agcm_out)
+    return out[None], agcm_out[None]
+
+
+# --------------------------------------------------------------------------
+# P4  RGB48 pack  (gui_pipeline_worker_feeders.py:193-249)
+# --------------------------------------------------------------------------
+
+def pack_rgb48(out_1chw: np.ndarray) -> np.ndarray:
+    """(1,3,H,W) any float dtype -> uint16 (H,W,3) RGB (rgb48le), FP32 math:
+    clamp(0,1) -> *65535.0f (rounded) -> +0.5f (rounded) -> truncate."""
+    f = out_1chw[0].astype(F32).transpose(1, 2, 0)
+    f = np.clip(f, F32(0.0), F32(1.0))
+    f = f * F32(65535.0)
+    f = f + F32(0.5)
+    return f.astype(np.uint16)
+
+
+_PQ_M1 = 2610.0 / 16384.0
+_PQ_M2 = 2523.0 / 32.0
+_PQ_C1 = 3424.0 / 4096.0
+_PQ_C2 = 2413.0 / 128.0
+_PQ_C3 = 2392.0 / 128.0
+
+
+def pq_oetf_absolute(luminance: np.ndarray) -> np.ndarray:
+    """gui_objective_metrics.py:486-491 (_pq_oetf_absolute)."""
+    y = np.clip(luminance.astype(F32, copy=False) / 10000.0, 0.0, 1.0)
+    y_m1 = np.power(y, _PQ_M1).astype(F32, copy=False)
+    num = _PQ_C1 + (_PQ_C2 * y_m1)
+    den = 1.0 + (_PQ_C3 * y_m1)
+    return np.power(num / np.maximum(den, 1e-12), _PQ_M2).astype(F32, copy=False)
+
+
+def pack_rgb48_pq(linear_1chw: np.ndarray, peak_nits: float = 1000.0) -> np.ndarray:
+    """Optional transfer: treat the tensor as linear light in [0,1] of `peak_nits`
+    and PQ-encode it.  Follows _linear_bgr_to_bt2100_pq_bgr_u16
+    (gui_objective_metrics.py:531-539) but keeps RGB channel order."""
+    rgb = np.clip(linear_1chw[0].astype(F32).transpose(1, 2, 0), 0.0, 1.0) * float(peak_nits)
+    pq = pq_oetf_absolute(rgb.astype(F32))
+    return np.clip((pq * 65535.0) + 0.5, 0.0, 65535.0).astype(np.uint16)
+
+
+# --------------------------------------------------------------------------
+# P5  BGR24 postprocess  (hdrtvnet_torch.py:2352-2368)
+# --------------------------------------------------------------------------
+
+def postprocess_bgr24(out_1chw: np.ndarray) -> np.ndarray:
+    """clamp_(0,1).mul_(255).add_(0.5) IN THE TENSOR'S OWN DTYPE (each op rounds
+    to that dtype), truncate to u8, RGB->BGR, HWC."""
+    dt = out_1chw.dtype if out_1chw.dtype in (np.float16, np.float32) else F32
+    t = out_1chw[0].astype(dt)
+    t = np.clip(t, dt.type(0.0), dt.type(1.0))
+    t = (t * dt.type(255.0)).astype(dt)
+    t = (t + dt.type(0.5)).astype(dt)
+    u = t.astype(F32).astype(np.uint8)
+    return np.ascontiguousarray(u[::-1].transpose(1, 2, 0))
+
+
+def process(sd: dict, frame_bgr: np.ndarray):
+    """HDRTVNetTorch.process in fp32: BGR u8 -> BGR u8."""
+    x, cond = preprocess(frame_bgr, np.float32)
+    out, _ = infer(sd, x, cond)
+    return postprocess_bgr24(out)
+
+
+# --------------------------------------------------------------------------
+# Weights helper: seeded random state-dict with the reference's key set/shapes
+# (values are the oracle's own; the reference-initialised set lives in
+# tests/golden/).
+# --------------------------------------------------------------------------
+
+def state_dict_spec():
+    spec = {}
+    cls = "AGCM.classifier.model."
+    chans = [3, 16, 32, 64, 128, 128]
+    for i, ci in enumerate(_CLS_CONV):
+        spec[f"{cls}{ci}.weight"] = (chans[i + 1], chans[i], 1, 1)
+        spec[f"{cls}{ci}.bias"] = (chans[i + 1],)
+        if _CLS_NORM[i] is not None:
+            spec[f"{cls}{_CLS_NORM[i]}.weight"] = (chans[i + 1],)
+            spec[f"{cls}{_CLS_NORM[i]}.bias"] = (chans[i + 1],)
+    spec[f"{cls}20.weight"] = (6, 128, 1, 1)
+    spec[f"{cls}20.bias"] = (6,)
+    for name, n in (("first", 64), ("HR", 64), ("last", 3)):
+        for kind in ("scale", "shift"):
+            spec[f"AGCM.cond_{kind}_{name}.weight"] = (n, 6)
+            spec[f"AGCM.cond_{kind}_{name}.bias"] = (n,)
+    spec["AGCM.conv_first.weight"] = (64, 3, 1, 1)
+    spec["AGCM.HRconv.weight"] = (64, 64, 1, 1)
+    spec["AGCM.conv_last.weight"] = (3, 64, 1, 1)
+
+    def conv(name, o, c, k):
+        spec[name + ".weight"] = (o, c, k, k)
+        spec[name + ".bias"] = (o,)
+
+    for n, o in (("AGCM.conv_first", 64), ("AGCM.HRconv", 64), ("AGCM.conv_last", 3)):
+        spec[n + ".bias"] = (o,)
+
+    def sft(prefix):
+        conv(prefix + ".SFT_scale_conv0", 16, 16, 1)
+        conv(prefix + ".SFT_scale_conv1", 32, 16, 1)
+        conv(prefix + ".SFT_shift_conv0", 16, 16, 1)
+        conv(prefix + ".SFT_shift_conv1", 32, 16, 1)
+
+    conv("LE.conv_first", 32, 3, 3)
+    sft("LE.SFT_layer1")
+    conv("LE.HR_conv1", 32, 32, 3)
+    for i in (1, 2, 3):
+        conv(f"LE.down_conv{i}", 32, 32, 3)
+        conv(f"LE.up_conv{i}.0", 128, 32, 3)
+    for t, n in ((1, 1), (2, 1), (3, 4), (4, 1), (5, 1)):
+        for j in range(n):
+            pre = f"LE.recon_trunk{t}.{j}"
+            conv(pre + ".conv1", 32, 32, 3)
+            conv(pre + ".conv2", 32, 32, 3)
+            sft(pre + ".sft1")
+            sft(pre + ".sft2")
+    sft("LE.SFT_layer2")
+    conv("LE.HR_conv2", 32, 32, 3)
+    conv("LE.conv_last", 3, 32, 3)
+    conv("LE.cond_first.0", 64, 3, 3)
+    conv("LE.cond_first.2", 64, 64, 1)
+    conv("LE.cond_first.4", 64, 64, 1)
+    conv("LE.CondNet1.0", 64, 64, 1)
+    conv("LE.CondNet1.2", 64, 64, 1)
+    conv("LE.CondNet1.4", 16, 64, 1)
+    conv("LE.CondNet2.0", 64, 64, 3)
+    conv("LE.CondNet2.2", 64, 64, 1)
+    conv("LE.CondNet2.4", 16, 64, 1)
+    conv("LE.CondNet3.0", 64, 64, 3)
+    conv("LE.CondNet3.2", 64, 64, 3)
+    conv("LE.CondNet3.4", 16, 64, 1)
+    conv("LE.CondNet4.0", 64, 64, 3)
+    conv("LE.CondNet4.2", 64, 64, 3)
+    conv("LE.CondNet4.4", 16, 64, 3)
+    return spec
+
+
+def random_state_dict(seed: int = 0) -> dict:
+    """Seeded weights with the reference key set.  Kaiming-uniform-like fan-in
+    scaling so activations stay O(1); resblock convs scaled by 0.1 as
+    arch_util.py:87 does; InstanceNorm affine = (1 + small, small)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, shp in state_dict_spec().items():
+        if k.endswith(".weight") and len(shp) == 1:      # InstanceNorm gamma
+            sd[k] = (1.0 + 0.1 * rng.standard_normal(shp)).astype(F32)
+        elif k.endswith(".bias"):
+            sd[k] = (0.05 * rng.standard_normal(shp)).astype(F32)
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            bound = np.sqrt(3.0 / fan_in)
+            w = rng.uniform(-bound, bound, size=shp).astype(F32)
+            if "recon_trunk" in k and (".conv1." in k or ".conv2." in k):
+                w *= F32(0.3)
+            sd[k] = w
+    return sd

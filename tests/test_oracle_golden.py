@@ -1,0 +1,113 @@
+"""Pin the CPU oracle against outputs of the REFERENCE ITSELF (tests/golden/, made by
+scripts/make_golden.py).  The reference ships no golden vectors of its own."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+from oracle import hdrtvnet_oracle as O
+
+NET_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "net_*.npz")))
+
+
+@pytest.mark.parametrize("name", ["pre_64x96.npz", "pre_72x100.npz", "pre_135x241.npz"])
+def test_preprocess_matches_reference(name):
+    g = load_golden(name)
+    x, cond = O.preprocess(g["frame"], np.float32)
+    assert np.array_equal(x, g["x"])                      # normalise is bit-exact (one fp32 multiply)
+    assert np.abs(cond - g["cond"]).max() <= 2e-6          # 16-tap FIR, summation order differs
+    x16, cond16 = O.preprocess(g["frame"], np.float16)
+    assert np.array_equal(x16, g["x16"])
+    # fp16 result may flip one half-ulp where the fp32 sums differ in the last bits
+    assert np.abs(cond16.astype(np.float32) - g["cond16"].astype(np.float32)).max() <= 1e-3
+    assert (cond16 != g["cond16"]).mean() < 0.01
+
+
+def test_aa_bicubic_border_taps():
+    g = load_golden("aa.npz")
+    for k in [k for k in g if k.startswith("in_")]:
+        out = O.cond_downsample(g[k][0], np.float32)
+        ref = g["out_" + k[3:]][0]
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() <= 2e-6, k
+
+
+@pytest.mark.parametrize("name", NET_CASES)
+def test_network_matches_reference(name, weights_hr, weights_rand0):
+    g = load_golden(name)
+    sd = weights_hr if name.startswith("net_hr_") else weights_rand0
+    x, cond = O.preprocess(g["frame"], np.float32)
+    sdf = {k: np.asarray(v, np.float32) for k, v in sd.items()}
+    fea = O.classifier(sdf, cond[0])
+    assert np.abs(fea - g["fea"]).max() <= 2e-5
+    out, agcm_out = O.infer(sd, x, cond)
+    assert np.abs(agcm_out - g["agcm_out"]).max() <= 2e-5
+    assert np.abs(out - g["out"]).max() <= 5e-5
+    # packs: bit-exact on identical float input ...
+    assert np.array_equal(O.pack_rgb48(g["out"]), g["rgb48"])
+    assert np.array_equal(O.postprocess_bgr24(g["out"]), g["bgr24"])
+    # ... and within the float tolerance end to end (1e-4 ~ 6.6 codes of 65535)
+    assert np.abs(O.pack_rgb48(out).astype(np.int32) - g["rgb48"].astype(np.int32)).max() <= 7
+
+
+@pytest.mark.parametrize("wname", ["hr", "rand0"])
+def test_network_540p_config1(wname, weights_hr, weights_rand0):
+    from hdr_realtime_video_pipeline_b200.synth import synth_frame
+    g = load_golden(f"net540_{wname}.npz")
+    sd = weights_hr if wname == "hr" else weights_rand0
+    frame = synth_frame(0, 540, 960, "noise")
+    x, cond = O.preprocess(frame, np.float32)
+    out, agcm_out = O.infer(sd, x, cond)
+    assert np.abs(out[:, :, ::8, ::8] - g["out_sub"]).max() <= 5e-5
+    assert np.abs(out[:, :, -3:, :] - g["out_last_rows"]).max() <= 5e-5      # centre-crop path (68 -> 135)
+    assert np.abs(agcm_out[:, :, ::8, ::8] - g["agcm_sub"]).max() <= 2e-5
+    assert abs(out.mean() - g["out_stats"][0]) <= 1e-5
+
+
+def test_known_answers_from_survey(weights_hr):
+    """SURVEY §8c KATs: reference, HR.pt, frame = default_rng(0) 540x960 noise."""
+    frame = np.random.default_rng(0).integers(0, 256, (540, 960, 3), dtype=np.uint8)
+    x, cond = O.preprocess(frame, np.float32)
+    np.testing.assert_allclose(x[0, :, 0, 0], [0.7607844, 0.5098040, 0.3725490], atol=1e-6)
+    np.testing.assert_allclose(cond[0, :, 0, 0], [0.5773944, 0.5742362, 0.5201451], atol=1e-5)
+    sdf = {k: np.asarray(v, np.float32) for k, v in weights_hr.items()}
+    fea = O.classifier(sdf, cond[0])
+    np.testing.assert_allclose(fea, [0.033736, 0.011883, 0.039485, -0.013184, 0.011853, 0.041158], atol=1e-5)
+    out, agcm_out = O.infer(weights_hr, x, cond)
+    np.testing.assert_allclose(out[0, :, 0, 0], [0.567692, 0.496016, 0.398522], atol=1e-5)
+    np.testing.assert_allclose(out[0, :, 539, 959], [0.320767, 0.406483, 0.226297], atol=1e-5)
+    assert abs(float(agcm_out.mean()) - 0.441951) < 1e-5
+    rgb48 = O.pack_rgb48(out)
+    assert np.abs(rgb48[0, 0].astype(int) - np.array([37204, 32506, 26117])).max() <= 1
+    assert abs(rgb48.astype(np.float64).mean() - 30551.15) < 0.5
+    assert abs(O.postprocess_bgr24(out).astype(np.float64).mean() - 118.876) < 0.01
+
+
+def test_pack_edge_values_bit_exact():
+    g = load_golden("pack.npz")
+    assert np.array_equal(O.pack_rgb48(g["in32"]), g["rgb48_32"])
+    assert np.array_equal(O.pack_rgb48(g["in16"]), g["rgb48_16"])
+    assert np.array_equal(O.postprocess_bgr24(g["in32"]), g["bgr24_32"])
+    assert np.array_equal(O.postprocess_bgr24(g["in16"]), g["bgr24_16"])
+
+
+def test_pq_transfer_option():
+    g = load_golden("pq.npz")
+    lin = g["linear_rgb"].transpose(2, 0, 1)[None]
+    got = O.pack_rgb48_pq(lin, 1000.0)
+    assert np.abs(got.astype(np.int32) - g["pq_rgb_u16"].astype(np.int32)).max() <= 1
+
+
+def test_primitives_small_cases():
+    x = np.arange(2 * 5 * 7, dtype=np.float32).reshape(2, 5, 7)
+    p = O.avg_pool_3s2p1(x)
+    assert p.shape == (2, 3, 4)
+    assert np.isclose(p[0, 0, 0], (0 + 1 + 7 + 8) / 9.0)          # count_include_pad: always /9
+    ps = O.pixel_shuffle2(np.arange(8 * 2 * 3, dtype=np.float32).reshape(8, 2, 3))
+    assert ps.shape == (2, 4, 6) and ps[0, 0, 1] == 6.0 and ps[0, 1, 0] == 12.0 and ps[1, 0, 0] == 24.0
+    a = O.align_to(np.arange(3 * 4 * 6, dtype=np.float32).reshape(3, 4, 6), 3, 5)   # crop: top = 0, left = 0
+    assert a.shape == (3, 3, 5) and a[0, 0, 0] == 0.0
+    b = O.align_to(np.ones((1, 2, 2), np.float32), 3, 4)                             # replicate pad
+    assert b.shape == (1, 3, 4) and b.min() == 1.0
