@@ -1,0 +1,75 @@
+"""ctypes binding of the C ABI in include/hdrtv_b200.h (libhdrtv_b200.so, built in-tree by build.py).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhdrtv_b200.so")
+
+FP32, FP16 = 0, 1
+COND_BICUBIC_AA, COND_ZERO = 0, 1
+TRANSFER_IDENTITY, TRANSFER_LUT = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("precision", C.c_int)]
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("ndim", C.c_int), ("shape", C.c_int64 * 4)]
+
+
+_SIGNATURES = {
+    "hdrtv_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "hdrtv_destroy": (None, [C.c_void_p]),
+    "hdrtv_set_weights": (C.c_int, [C.c_void_p, C.POINTER(TensorDesc), C.c_int]),
+    "hdrtv_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hdrtv_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "hdrtv_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hdrtv_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hdrtv_pack_rgb48": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "hdrtv_set_transfer_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hdrtv_pack_bgr24": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hdrtv_last_error": (C.c_char_p, [C.c_void_p]),
+    "hdrtv_launch_count": (C.c_long, [C.c_void_p]),
+    "hdrtv_debug_tensor_count": (C.c_int, [C.c_void_p]),
+    "hdrtv_debug_tensor_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hdrtv_debug_tensor_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hdrtv_conv_selftest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "hdrtv_version": (C.c_char_p, []),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_lib = None
+
+
+def load():
+    """Load libhdrtv_b200.so and attach signatures.  Raises RuntimeError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -m hdr_realtime_video_pipeline_b200.build` or __graft_entry__.build().")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here means the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error(handle) -> str:
+    msg = load().hdrtv_last_error(handle)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, handle, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {last_error(handle)}")

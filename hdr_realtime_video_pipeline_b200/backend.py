@@ -1,0 +1,358 @@
+"""HDRTVNetB200 — drop-in for the reference's model wrapper on the per-frame SDR->HDR path.
+
+Mirrors ``HDRTVNetTorch`` / ``HDRTVNetTensorRT`` (reference src/models/hdrtvnet_torch.py:1513-2472, :8164-9106):
+same constructor keywords, same ``preprocess / infer / postprocess / process / process_timed / warmup_compile /
+end_profiling`` methods, same attributes the callers read (gui_pipeline_worker_model.py, gui_export.py, main.py,
+cli_playback_benchmark.py).  Underneath it calls the sm_100a kernels through the C ABI in
+``include/hdrtv_b200.h``.  PyTorch is used for device memory, streams and events only.
+
+There is no CPU path, no TensorRT, no Triton and no eager fallback: failures raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _native
+
+_VALID_PRECISIONS = {"auto", "fp16", "fp32", "int8-full", "int8-mixed"}
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _env_bool(name: str, default: bool) -> bool:
+    v = os.environ.get(name)
+    if v is None:
+        return default
+    return str(v).strip().lower() in {"1", "true", "yes", "on"}
+
+
+def _assume_aligned_shapes_for_resolution(width: int, height: int) -> bool:
+    # hdrtvnet_torch.py:204-207: only the two GUI presets are declared aligned.
+    return (int(width), int(height)) in {(1920, 1080), (1280, 720)}
+
+
+def load_state_dict_any(model_path):
+    """Accepts a dict, a ``.npz`` of fp32 arrays, or a torch checkpoint: raw state-dict (HR.pt) or a
+    ``{"state_dict": ..., "architecture": ...}`` source checkpoint (hdrtvnet_torch.py:1491-1498)."""
+    arch = {}
+    if isinstance(model_path, dict):
+        payload = model_path
+    else:
+        ext = os.path.splitext(str(model_path))[1].lower()
+        if not os.path.isfile(model_path):
+            raise FileNotFoundError(f"model weights not found: {model_path}")
+        if ext == ".npz":
+            with np.load(model_path) as z:
+                payload = {k: z[k] for k in z.files}
+        else:
+            payload = torch.load(model_path, map_location="cpu", weights_only=True)
+    if isinstance(payload, dict) and "state_dict" in payload:
+        a = payload.get("architecture") or {}
+        arch = a if isinstance(a, dict) else {}
+        payload = payload.get("state_dict") or {}
+    state = {}
+    for k, v in payload.items():
+        k = k[7:] if k.startswith("module.") else k          # hdrtvnet_torch.py:2154-2157
+        if isinstance(v, torch.Tensor):
+            v = v.detach().to(torch.float32).cpu().numpy()
+        state[k] = np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+    return state, arch
+
+
+class HDRTVNetB200:
+    """B200-native backend with the reference wrapper's interface."""
+
+    def __init__(self, model_path, device="auto", precision="auto",
+                 compile_model=True, force_compile=False, compile_mode="auto",
+                 use_cuda_graphs=False, force_channels_last=False,
+                 predequantize="auto", hg_weights=None, use_hg=True,
+                 warmup_passes=3, fast_condition_resize=False,
+                 # HDRTVNetTensorRT extras (hdrtvnet_torch.py:8172-8189): accepted and ignored
+                 engine_width=None, engine_height=None, mode_name=None, qdq_fusion=None, keep_onnx=None,
+                 **ignored_tensorrt_kwargs):
+        self.model_path = model_path
+        self._warmup_passes = warmup_passes
+        self._fast_condition_resize = bool(fast_condition_resize) or _env_bool("HDRTVNET_FAST_COND_RESIZE", False)
+        self._fast_zero_condition = _env_bool("HDRTVNET_ZERO_COND", False)
+        if self._fast_condition_resize:
+            raise RuntimeError("fast_condition_resize (bilinear condition image) is not implemented by this backend")
+        # argument validation first (ValueError), availability second (RuntimeError) — hdrtvnet_torch.py:1678-1702
+        if str(device).lower() not in ("auto", "cuda", "cpu") and not str(device).lower().startswith("cuda:"):
+            raise ValueError("device must be one of: auto, cuda, cpu")
+        if str(precision).lower() not in _VALID_PRECISIONS:
+            raise ValueError("precision must be one of: auto, fp16, fp32, int8-full, int8-mixed")
+        self.device = self._resolve_device(device)
+        self.precision = self._resolve_precision(precision, self.device)
+        self._use_cuda = True
+        self._dtype = torch.float16 if self.precision == "fp16" else torch.float32
+        self._np_dtype = np.float16 if self.precision == "fp16" else np.float32
+        self._hg_weights_explicit = hg_weights is not None
+        self._hg_weights = hg_weights
+        self._use_hg = bool(use_hg)
+        self._is_flat_model = False
+        self._is_w8_model = False
+        self._compiled = False
+        self._compile_mode = None
+        self._memory_format_name = "contiguous"
+        self._use_channels_last = False
+        self._assume_aligned_shapes = None
+        self._trt_engine = None
+        self._trt_context = None
+        self.engine_path = None
+        self.model = None            # like the TensorRT wrapper after build (hdrtvnet_torch.py:8429)
+        self.expected_hw = None
+        self.is_static_input_model = False
+
+        self._lib = _native.load()
+        self._handle = C.c_void_p()
+        cfg = _native.Config(self.device.index, _native.FP16 if self.precision == "fp16" else _native.FP32)
+        rc = self._lib.hdrtv_create(C.byref(cfg), C.byref(self._handle))
+        if rc != 0:
+            raise RuntimeError("hdrtv_create failed: " + _native.last_error(None))
+        self._load_model(model_path)
+
+        self._buf_hw = None
+        self._gpu_input = self._gpu_cond = self._gpu_raw = None
+        self._gpu_out = self._gpu_agcm = self._gpu_u8 = None
+        self._pin_input = self._pin_output = None
+        print(f"GPU: {torch.cuda.get_device_name(self.device)} (CUDA, sm_100a kernels)")
+        print(f"B200 device : {self.device}")
+        print(f"B200 precision: {self.precision}")
+        if self._warmup_passes and self._warmup_passes > 0:
+            self._warmup()
+
+    # ------------------------------------------------------------------ device / precision (hdrtvnet_torch.py:1678-1702)
+    def _resolve_device(self, device):
+        mode = str(device).lower()
+        if mode in ("auto", "cuda") or mode.startswith("cuda:"):
+            if not torch.cuda.is_available():
+                raise RuntimeError("CUDA device not available; the B200 backend has no CPU fallback.")
+            idx = int(mode.split(":", 1)[1]) if mode.startswith("cuda:") else torch.cuda.current_device()
+            return torch.device("cuda", idx)
+        if mode == "cpu":
+            raise RuntimeError("device='cpu' is not supported: the B200 backend has no CPU fallback.")
+        raise ValueError("device must be one of: auto, cuda, cpu")
+
+    def _resolve_precision(self, precision, device):
+        p = str(precision).lower()
+        if p not in _VALID_PRECISIONS:
+            raise ValueError("precision must be one of: auto, fp16, fp32, int8-full, int8-mixed")
+        if p in ("int8-full", "int8-mixed"):
+            raise RuntimeError(f"precision={p!r} (QAT layouts) is not implemented by this backend yet")
+        return "fp16" if p == "auto" else p
+
+    # ------------------------------------------------------------------ weights (hdrtvnet_torch.py:2044-2169)
+    def _load_model(self, model_path):
+        state, arch = load_state_dict_any(model_path)
+        classifier = str(arch.get("classifier", os.environ.get("HDRTVNET_CLASSIFIER", "color_condition"))).strip()
+        le_arch = str(arch.get("le_arch", os.environ.get("HDRTVNET_LE_ARCH", "")) or "").strip()
+        post = str(arch.get("post_correction", os.environ.get("HDRTVNET_POST_CORRECTION", "")) or "").strip()
+        if (classifier or "color_condition") != "color_condition" or le_arch not in ("", "None", "sft") or post not in ("", "None"):
+            raise RuntimeError(
+                f"unsupported architecture (classifier={classifier!r}, le_arch={le_arch!r}, post_correction={post!r}); "
+                "this backend implements classifier='color_condition', le_arch='sft' (HDRUNet3T1) only")
+        if self._use_hg:
+            hg = self._resolve_hg_weights(model_path)
+            if hg is not None:
+                print("WARNING: HG weights found but the HG stage is out of scope for the B200 backend; "
+                      "continuing with the no-HG (AGCM+LE) model.")
+            elif self._hg_weights_explicit:
+                raise FileNotFoundError(f"HG weights not found: {self._hg_weights}\n"
+                                        "  Check --hg-weights or disable HG with --use-hg 0.")
+            else:
+                print("WARNING: HG weights not found; continuing with no-HG model.")
+            self._use_hg = False
+        descs = (_native.TensorDesc * len(state))()
+        keep = []
+        for i, (k, v) in enumerate(state.items()):
+            v = np.ascontiguousarray(v, dtype=np.float32)
+            keep.append(v)
+            descs[i].name = k.encode()
+            descs[i].data = v.ctypes.data_as(C.POINTER(C.c_float))
+            descs[i].ndim = v.ndim
+            for d in range(v.ndim):
+                descs[i].shape[d] = v.shape[d]
+        _native.check(self._lib.hdrtv_set_weights(self._handle, descs, len(state)), self._handle, "hdrtv_set_weights")
+        self._n_params = int(sum(v.size for v in keep))
+
+    def _resolve_hg_weights(self, model_path):
+        cands = [self._hg_weights]
+        if not isinstance(model_path, dict):
+            cands.append(os.path.join(os.path.dirname(os.path.abspath(str(model_path))), "HG.pt"))
+        cands.append(os.path.join(os.getcwd(), "src", "models", "weights", "original", "HG.pt"))
+        for p in cands:
+            if p and os.path.isfile(os.path.abspath(os.path.expanduser(str(p)))):
+                return p
+        return None
+
+    def _configure_assume_aligned_shapes(self, width: int, height: int) -> None:
+        # The kernels handle aligned and centre-cropped skips alike; the flag is kept for callers that set it.
+        self._assume_aligned_shapes = _assume_aligned_shapes_for_resolution(width, height)
+
+    # ------------------------------------------------------------------ buffers (hdrtvnet_torch.py:2198-2233)
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ensure_buffers(self, h, w):
+        self._configure_assume_aligned_shapes(w, h)
+        if self._buf_hw == (h, w):
+            return
+        if h < 16 or w < 16:
+            raise ValueError("frames must be at least 16x16")
+        torch.cuda.synchronize(self.device)
+        _native.check(self._lib.hdrtv_prepare(self._handle, h, w), self._handle, "hdrtv_prepare")
+        self._buf_hw = (h, w)
+        ch, cw = max(1, h // 4), max(1, w // 4)
+        dev, dt = self.device, self._dtype
+        self._gpu_input = torch.empty((1, 3, h, w), dtype=dt, device=dev)
+        self._gpu_cond = torch.empty((1, 3, ch, cw), dtype=dt, device=dev)
+        self._gpu_out = torch.empty((1, 3, h, w), dtype=dt, device=dev)
+        self._gpu_agcm = torch.empty((1, 3, h, w), dtype=dt, device=dev)
+        self._gpu_raw = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+        self._gpu_u8 = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+        self._pin_input = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+        self._pin_output = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+
+    # ------------------------------------------------------------------ preprocess (hdrtvnet_torch.py:2239-2296)
+    @torch.inference_mode()
+    def preprocess(self, frame_bgr):
+        if not isinstance(frame_bgr, np.ndarray) or frame_bgr.dtype != np.uint8 or frame_bgr.ndim != 3 or frame_bgr.shape[2] != 3:
+            raise ValueError("frame_bgr must be a uint8 HxWx3 BGR array")
+        h, w = frame_bgr.shape[:2]
+        with torch.cuda.device(self.device):
+            self._ensure_buffers(h, w)
+            self._pin_input.copy_(torch.from_numpy(np.ascontiguousarray(frame_bgr)))
+            self._gpu_raw.copy_(self._pin_input, non_blocking=True)
+            mode = _native.COND_ZERO if self._fast_zero_condition else _native.COND_BICUBIC_AA
+            _native.check(self._lib.hdrtv_preprocess(self._handle, self._gpu_raw.data_ptr(), h, w,
+                                                     self._gpu_input.data_ptr(), self._gpu_cond.data_ptr(), mode,
+                                                     self._stream()), self._handle, "hdrtv_preprocess")
+        return self._gpu_input, self._gpu_cond
+
+    def preprocess_device(self, frame_u8_dev: torch.Tensor):
+        """Extension: frame already resident on the device as uint8 (H,W,3) BGR (decode-on-GPU callers, benchmarks)."""
+        h, w = int(frame_u8_dev.shape[0]), int(frame_u8_dev.shape[1])
+        with torch.cuda.device(self.device):
+            self._ensure_buffers(h, w)
+            src = frame_u8_dev.contiguous()
+            mode = _native.COND_ZERO if self._fast_zero_condition else _native.COND_BICUBIC_AA
+            _native.check(self._lib.hdrtv_preprocess(self._handle, src.data_ptr(), h, w, self._gpu_input.data_ptr(),
+                                                     self._gpu_cond.data_ptr(), mode, self._stream()),
+                          self._handle, "hdrtv_preprocess")
+        return self._gpu_input, self._gpu_cond
+
+    # ------------------------------------------------------------------ infer (hdrtvnet_torch.py:2302-2346)
+    @torch.inference_mode()
+    def infer(self, input_cond):
+        tensor, cond = input_cond
+        if tensor.dim() != 4 or tensor.shape[0] != 1 or tensor.shape[1] != 3:
+            raise ValueError("infer expects a (1,3,H,W) tensor")
+        h, w = int(tensor.shape[2]), int(tensor.shape[3])
+        with torch.cuda.device(self.device):
+            self._ensure_buffers(h, w)
+            t = tensor.to(device=self.device, dtype=self._dtype).contiguous()
+            c = cond.to(device=self.device, dtype=self._dtype).contiguous()
+            if tuple(c.shape) != (1, 3, max(1, h // 4), max(1, w // 4)):
+                raise ValueError(f"condition tensor must be (1,3,{h // 4},{w // 4}), got {tuple(c.shape)}")
+            rc = self._lib.hdrtv_infer(self._handle, t.data_ptr(), c.data_ptr(), h, w, self._gpu_out.data_ptr(),
+                                       self._gpu_agcm.data_ptr(), self._stream())
+            if rc != 0:
+                raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle))
+        return self._gpu_out, self._gpu_agcm
+
+    # ------------------------------------------------------------------ postprocess (hdrtvnet_torch.py:2352-2368)
+    @torch.inference_mode()
+    def postprocess(self, output):
+        if isinstance(output, (tuple, list)):
+            output = output[0]
+        if output.dtype not in (torch.float16, torch.float32):
+            output = output.float()
+        h, w = int(output.shape[-2]), int(output.shape[-1])
+        with torch.cuda.device(self.device):
+            self._ensure_buffers(h, w) if self._buf_hw != (h, w) else None
+            src = output.contiguous()
+            dt = _native.FP16 if src.dtype == torch.float16 else _native.FP32
+            _native.check(self._lib.hdrtv_pack_bgr24(self._handle, src.data_ptr(), dt, h, w, self._gpu_u8.data_ptr(),
+                                                     self._stream()), self._handle, "hdrtv_pack_bgr24")
+            self._pin_output.copy_(self._gpu_u8, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return self._pin_output.numpy()
+
+    # ------------------------------------------------------------------ public API (hdrtvnet_torch.py:2373-2395)
+    @torch.inference_mode()
+    def process(self, frame_bgr):
+        tensor, cond = self.preprocess(frame_bgr)
+        out = self.infer((tensor, cond))
+        return self.postprocess(out)
+
+    @torch.inference_mode()
+    def process_timed(self, frame_bgr):
+        t0 = time.perf_counter()
+        tensor, cond = self.preprocess(frame_bgr)
+        torch.cuda.synchronize(self.device)
+        t1 = time.perf_counter()
+        out = self.infer((tensor, cond))
+        torch.cuda.synchronize(self.device)
+        t2 = time.perf_counter()
+        output = self.postprocess(out)
+        t3 = time.perf_counter()
+        return output, (t1 - t0) * 1000.0, (t2 - t1) * 1000.0, (t3 - t2) * 1000.0
+
+    def _warmup(self):
+        h, w = self.expected_hw or (1080, 1920)
+        dummy = np.zeros((h, w, 3), dtype=np.uint8)
+        t0 = time.perf_counter()
+        for _ in range(int(self._warmup_passes)):
+            self.infer(self.preprocess(dummy))
+        torch.cuda.synchronize(self.device)
+        dt = time.perf_counter() - t0
+        print(f"  Warmup done: {self._warmup_passes} passes in {dt:.2f}s")
+
+    @torch.inference_mode()
+    def warmup_compile(self, width=1920, height=1080):
+        if not self._compiled:     # hdrtvnet_torch.py:2413-2414 — nothing is JIT-compiled here
+            return
+
+    def end_profiling(self):
+        return None
+
+    # ------------------------------------------------------------------ introspection (tests / bench)
+    def launch_count(self) -> int:
+        return int(self._lib.hdrtv_launch_count(self._handle))
+
+    def workspace_bytes(self) -> int:
+        return int(self._lib.hdrtv_workspace_bytes(self._handle))
+
+    def debug_tensors(self) -> dict:
+        """Named intermediates of the last infer() as (C,H,W) fp32 numpy arrays (synchronises)."""
+        out = {}
+        n = self._lib.hdrtv_debug_tensor_count(self._handle)
+        name = C.create_string_buffer(128)
+        c, h, w = C.c_int(), C.c_int(), C.c_int()
+        for i in range(n):
+            self._lib.hdrtv_debug_tensor_info(self._handle, i, name, 128, C.byref(c), C.byref(h), C.byref(w))
+            arr = np.empty((c.value, h.value, w.value), dtype=np.float32)
+            _native.check(self._lib.hdrtv_debug_tensor_read(self._handle, i, arr.ctypes.data), self._handle, "debug read")
+            out[name.value.decode()] = arr
+        return out
+
+    def conv_selftest(self, kind, cin, cout, h, w, flags=0):
+        mx, ref = C.c_float(), C.c_float()
+        _native.check(self._lib.hdrtv_conv_selftest(self._handle, kind, cin, cout, h, w, flags, C.byref(mx), C.byref(ref)),
+                      self._handle, "hdrtv_conv_selftest")
+        return float(mx.value), float(ref.value)
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.hdrtv_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

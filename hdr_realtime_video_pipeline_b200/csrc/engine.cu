@@ -1,0 +1,1335 @@
+// HDRTVNet++ B200 engine: context, weight repacking, per-resolution workspace, launch plans and the C ABI
+// declared in include/hdrtv_b200.h.  Two product paths share this file:
+//   HDRTV_FP32  planar fp32 activations, CUDA-core kernels (kernels_f32.cuh)      — <= 1e-4 vs reference fp32
+//   HDRTV_FP16  P8 fp16 activations, tcgen05/TMEM implicit-GEMM convs (conv_p8.cuh) — <= 2e-3 vs reference fp16
+// The AGCM condition classifier runs in fp32 on both.  No CPU fallback: every entry point needs a CUDA device.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hdrtv_b200.h"
+#include "common.cuh"
+#include "conv_p8.cuh"
+#include "kernels_f32.cuh"
+#include "kernels_io.cuh"
+
+namespace hdrtv {
+char g_err[512] = {0};
+
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+// ------------------------------------------------------------------------------------------------
+// B-operand (weight) packing for the un-swizzled K-major UMMA layout: step s = one K=16 MMA,
+// element (n,k) at half index  s*N*16 + (k/8)*N*8 + (n/8)*64 + (n%8)*8 + (k%8)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline long bpack_index(int N, int step, int n, int k) {
+  return static_cast<long>(step) * N * 16 + (k >> 3) * N * 8 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+}
+
+struct HalfK {
+  int tap = -1;  // -1: zero weights
+  int chunk = 0;
+};
+using StepK = std::array<HalfK, 2>;
+using WeightFn = std::function<float(int n, int cin, int tap)>;  // 0 outside the layer's real extent
+
+enum InKind { IN_NAT3x3 = 0, IN_NAT1x1 = 1, IN_NAT3x3_C8 = 2, IN_NAT1x1_C8 = 3, IN_PAR3x3S2 = 4, IN_PAR1x1 = 5 };
+
+// Fills the input-side half of a ConvParams (copies, steps, ring geometry) and the matching weight step list.
+static void build_input_side(InKind kind, const P8& in, int j0, int kchunks, ConvParams& p, std::vector<StepK>& wk) {
+  p.in = reinterpret_cast<const uint4*>(in.base);
+  p.in_row_entries = in.row_entries();
+  p.in_z_entries = 0;
+  p.xmul = 1;
+  p.copy_bytes = kPlaneBytes;
+  p.n_copies = 0;
+  p.n_steps = 0;
+  wk.clear();
+  auto add_copy = [&](uint32_t src, uint32_t dst) {
+    p.copies[p.n_copies].src_off = src;
+    p.copies[p.n_copies].dst_off = dst;
+    ++p.n_copies;
+  };
+  auto add_step = [&](int row, uint32_t a_off, uint32_t lbo, bool rel, HalfK h0, HalfK h1) {
+    ConvStep& s = p.steps[p.n_steps++];
+    s.row = static_cast<uint16_t>(row);
+    s.release = rel ? 1 : 0;
+    s.a_off = a_off;
+    s.a_lbo = lbo;
+    wk.push_back({h0, h1});
+  };
+  const uint32_t PB = kPlaneBytes;
+  switch (kind) {
+    case IN_NAT3x3:
+    case IN_NAT1x1: {
+      for (int j = 0; j < kchunks; ++j) add_copy((j0 + j) * in.Wp, j * PB);
+      p.slot_bytes = kchunks * PB;
+      p.stride = 1;
+      if (kind == IN_NAT3x3) {
+        p.ks = 3;
+        p.row_bias = 0;
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx)
+            for (int i = 0; i < kchunks / 2; ++i)
+              add_step(dy, 2 * i * PB + dx * 16, PB, dy == 0 && dx == 2 && i == kchunks / 2 - 1,
+                       HalfK{dy * 3 + dx, 2 * i}, HalfK{dy * 3 + dx, 2 * i + 1});
+      } else {
+        p.ks = 1;
+        p.row_bias = 1;
+        for (int i = 0; i < kchunks / 2; ++i)
+          add_step(0, 2 * i * PB + 16, PB, i == kchunks / 2 - 1, HalfK{0, 2 * i}, HalfK{0, 2 * i + 1});
+      }
+      break;
+    }
+    case IN_NAT3x3_C8: {
+      add_copy(j0 * in.Wp, 0);
+      p.slot_bytes = PB;
+      p.stride = 1;
+      p.ks = 3;
+      p.row_bias = 0;
+      for (int dy = 0; dy < 3; ++dy) {
+        add_step(dy, 0, 16, false, HalfK{dy * 3 + 0, 0}, HalfK{dy * 3 + 1, 0});   // taps dx=0,1 share one K=16 MMA
+        add_step(dy, 32, 16, dy == 0, HalfK{dy * 3 + 2, 0}, HalfK{-1, 0});        // tap dx=2 (+ zero weights)
+      }
+      break;
+    }
+    case IN_NAT1x1_C8: {
+      add_copy(j0 * in.Wp, 0);
+      p.slot_bytes = PB;
+      p.stride = 1;
+      p.ks = 1;
+      p.row_bias = 1;
+      add_step(0, 16, 16, true, HalfK{0, 0}, HalfK{-1, 0});
+      break;
+    }
+    case IN_PAR3x3S2: {
+      for (int j = 0; j < kchunks; ++j)
+        for (int par = 0; par < 2; ++par) add_copy((j0 + j) * in.Wp + par * (in.Wp / 2), (j * 2 + par) * PB);
+      p.slot_bytes = 2 * kchunks * PB;
+      p.stride = 2;
+      p.ks = 3;
+      p.row_bias = 0;
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int i = 0; i < kchunks / 2; ++i) {
+            const int par = (dx == 1) ? 0 : 1;       // input x = 2*ox + dx - 1
+            const uint32_t shift = (dx == 0) ? 0 : 16;
+            add_step(dy, ((2 * i) * 2 + par) * PB + shift, 2 * PB, dy < 2 && dx == 2 && i == kchunks / 2 - 1,
+                     HalfK{dy * 3 + dx, 2 * i}, HalfK{dy * 3 + dx, 2 * i + 1});
+          }
+      break;
+    }
+    case IN_PAR1x1: {
+      for (int j = 0; j < kchunks; ++j) add_copy((j0 + j) * in.Wp, j * PB);
+      p.in_z_entries = in.Wp / 2;
+      p.xmul = 2;
+      p.slot_bytes = kchunks * PB;
+      p.stride = 1;
+      p.ks = 1;
+      p.row_bias = 1;
+      for (int i = 0; i < kchunks / 2; ++i)
+        add_step(0, 2 * i * PB + 16, PB, i == kchunks / 2 - 1, HalfK{0, 2 * i}, HalfK{0, 2 * i + 1});
+      break;
+    }
+  }
+}
+
+static std::vector<__half> pack_weights(int N, const std::vector<StepK>& wk, const WeightFn& w) {
+  std::vector<__half> out(static_cast<size_t>(wk.size()) * N * 16, __float2half(0.f));
+  for (size_t s = 0; s < wk.size(); ++s)
+    for (int h = 0; h < 2; ++h) {
+      const HalfK hk = wk[s][h];
+      if (hk.tap < 0) continue;
+      for (int e = 0; e < 8; ++e)
+        for (int n = 0; n < N; ++n)
+          out[bpack_index(N, static_cast<int>(s), n, h * 8 + e)] = __float2half(w(n, hk.chunk * 8 + e, hk.tap));
+    }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ConvLaunch {
+  ConvParams p;
+  int N;
+  int mode;
+  dim3 grid;
+  size_t smem;
+  std::string name;
+};
+
+struct DebugTensor {
+  std::string name;
+  int C, H, W;
+  int kind;  // 0 planar fp32, 1 P8, 2 planar fp16
+  const void* ptr;
+  P8 p8;
+  int j0;
+};
+
+struct Ctx {
+  int device = 0;
+  int precision = HDRTV_FP16;
+  std::map<std::string, HostTensor> w;
+  std::map<std::string, float*> wd;  // device fp32 copies
+  std::vector<void*> weight_allocs;
+  bool has_weights = false;
+  // workspace
+  int H = 0, W = 0;
+  std::vector<void*> ws_allocs;
+  size_t ws_bytes = 0;
+  int* d_err = nullptr;
+  long launches = 0;
+  std::string err;
+  std::vector<DebugTensor> dbg;
+  // classifier
+  struct Lvl { int Cin, Cout, H, W, Ho, Wo; float* out; double* stats; };
+  std::vector<Lvl> cls;
+  double* cls_stats_all = nullptr;
+  size_t cls_stats_bytes = 0;
+  float* d_fea = nullptr;      // [6]
+  float* d_fold32 = nullptr;   // W1f[192] b1f[64] W2f[4096] b2f[64] W3f[192] b3f[3]
+  __half* d_agpk[3] = {nullptr, nullptr, nullptr};
+  float* d_agbias[3] = {nullptr, nullptr, nullptr};
+  // cond taps
+  int *d_xstart = nullptr, *d_ystart = nullptr;
+  float *d_xw = nullptr, *d_yw = nullptr;
+  // fp16 plan
+  std::vector<ConvLaunch> plan_agcm, plan_le;
+  P8 xP8;
+  __half* plan_agcm_planar_slot = nullptr;
+  // fp32 buffers
+  std::map<std::string, float*> f32;
+  // lut
+  uint16_t* d_lut = nullptr;
+  // packed static weights (device) by layer name
+  std::map<std::string, __half*> wpk;
+  std::map<std::string, float*> bpk;
+};
+
+static int fail(Ctx* c, const std::string& m) {
+  if (c) c->err = m;
+  snprintf(g_err, sizeof(g_err), "%s", m.c_str());
+  return -1;
+}
+#define CK(c, expr)                                                                                          \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess)                                                                                   \
+      return fail(c, std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " #expr " -> " + cudaGetErrorString(_e)); \
+  } while (0)
+
+template <typename T>
+static T* ws_alloc(Ctx* c, size_t n, bool zero = true) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  if (zero) cudaMemset(p, 0, n * sizeof(T));
+  c->ws_allocs.push_back(p);
+  c->ws_bytes += n * sizeof(T);
+  return static_cast<T*>(p);
+}
+template <typename T>
+static T* w_upload(Ctx* c, const T* host, size_t n) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice);
+  c->weight_allocs.push_back(p);
+  return static_cast<T*>(p);
+}
+
+static const HostTensor& W(Ctx* c, const std::string& k) { return c->w.at(k); }
+static WeightFn conv_weight_fn(Ctx* c, const std::string& name) {
+  const HostTensor& t = W(c, name + ".weight");
+  const int O = static_cast<int>(t.shape[0]), I = static_cast<int>(t.shape[1]);
+  const int taps = t.shape.size() == 4 ? static_cast<int>(t.shape[2] * t.shape[3]) : 1;
+  const float* d = t.v.data();
+  return [=](int n, int ci, int tap) -> float {
+    if (n >= O || ci >= I || tap >= taps) return 0.f;
+    return d[(static_cast<long>(n) * I + ci) * taps + tap];
+  };
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geometry helpers
+// ------------------------------------------------------------------------------------------------
+static int rup(int a, int b) { return (a + b - 1) / b * b; }
+static int down2(int n) { return (n - 1) / 2 + 1; }
+
+static P8 make_p8(Ctx* c, int C, int H, int Wd, bool parity) {
+  P8 t;
+  t.chunks = (C + 7) / 8;
+  t.H = H;
+  t.W = Wd;
+  t.parity = parity ? 1 : 0;
+  if (parity) t.Wp = 2 * (rup(down2(Wd), kTileM) + 8);
+  else t.Wp = rup(Wd, kTileM) + 8;
+  t.base = ws_alloc<__half>(c, static_cast<size_t>(t.entries()) * 8);
+  return t;
+}
+
+static void choose_grid(ConvLaunch& L, int strips) {
+  ConvParams& p = L.p;
+  const int want_bands = std::max(1, (148 * 3 + strips - 1) / strips);
+  int band = std::max(4, (p.Ho + want_bands - 1) / want_bands);
+  band = std::min(band, p.Ho);
+  p.band = band;
+  L.grid = dim3(strips, (p.Ho + band - 1) / band, p.xmul == 2 ? 2 : 1);
+}
+
+struct Epi {
+  int act = ACT_NONE;
+  const P8* res = nullptr;
+  const P8* res2 = nullptr;
+  const P8* sft = nullptr;
+  const P8* raw = nullptr;
+  __half* planar = nullptr;
+};
+
+static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int j0,
+                     int kchunks, int N, int mode, const __half* wpk, const float* bias, const P8& out, int Ho, int Wo,
+                     const Epi& e) {
+  ConvLaunch L;
+  memset(&L.p, 0, sizeof(L.p));
+  std::vector<StepK> wk;
+  build_input_side(kind, in, j0, kchunks, L.p, wk);
+  ConvParams& p = L.p;
+  p.wpk = reinterpret_cast<const uint4*>(wpk);
+  p.w_bytes = p.n_steps * N * 32;
+  p.bias = bias;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.act = e.act;
+  p.out = out;
+  if (e.res) { p.has_res = 1; p.res = *e.res; }
+  if (e.res2) { p.has_res2 = 1; p.res2 = *e.res2; }
+  if (e.sft) { p.has_sft = 1; p.sft = *e.sft; }
+  if (e.raw) { p.has_raw = 1; p.raw = *e.raw; }
+  p.planar = e.planar;
+  p.planar_plane = static_cast<long>(Ho) * Wo;
+  p.planar_W = Wo;
+  p.err = c->d_err;
+  const int min_ring = p.ks + 1;
+  const size_t budget = 200 * 1024;
+  const size_t fixed = 256 + ((p.w_bytes + 127) & ~127);
+  int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
+  ring = std::min(ring, p.stride == 2 ? 6 : 6);
+  if (ring < min_ring) ring = min_ring;
+  if (ring > kMaxRing) ring = kMaxRing;
+  p.ring = ring;
+  L.smem = conv_smem_bytes(p);
+  if (L.smem > 227 * 1024) return fail(c, "conv " + name + ": shared memory budget exceeded");
+  L.N = N;
+  L.mode = mode;
+  L.name = name;
+  const int wstrip = (p.xmul == 2) ? down2(Wo) : Wo;
+  choose_grid(L, (wstrip + kTileM - 1) / kTileM);
+  plan.push_back(L);
+  return 0;
+}
+
+template <int N, int MODE>
+static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
+  static size_t configured = 0;
+  if (L.smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = 227 * 1024;
+  }
+  conv_p8_kernel<N, MODE><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
+  return cudaGetLastError();
+}
+static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
+  if (L.mode == STORE_PLANAR) return launch_conv_t<16, STORE_PLANAR>(L, s);
+  if (L.mode == STORE_PS) return launch_conv_t<128, STORE_PS>(L, s);
+  switch (L.N) {
+    case 16: return launch_conv_t<16, STORE_P8>(L, s);
+    case 32: return launch_conv_t<32, STORE_P8>(L, s);
+    case 64: return launch_conv_t<64, STORE_P8>(L, s);
+    case 128: return launch_conv_t<128, STORE_P8>(L, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Static weight packing (fp16 path), done once in hdrtv_set_weights
+// ------------------------------------------------------------------------------------------------
+static int pack_layer(Ctx* c, const std::string& key, InKind kind, int kchunks, int N, const WeightFn& wf,
+                      const std::function<float(int)>& bf) {
+  ConvParams tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  std::vector<StepK> wk;
+  P8 dummy;
+  dummy.Wp = 16;
+  dummy.chunks = kchunks;
+  build_input_side(kind, dummy, 0, kchunks, tmp, wk);
+  std::vector<__half> pk = pack_weights(N, wk, wf);
+  std::vector<float> b(N, 0.f);
+  for (int n = 0; n < N; ++n) b[n] = bf(n);
+  c->wpk[key] = w_upload(c, pk.data(), pk.size());
+  c->bpk[key] = w_upload(c, b.data(), b.size());
+  if (!c->wpk[key] || !c->bpk[key]) return fail(c, "weight upload failed for " + key);
+  return 0;
+}
+static std::function<float(int)> bias_fn(Ctx* c, const std::string& name) {
+  const HostTensor& t = W(c, name + ".bias");
+  const float* d = t.v.data();
+  const int n0 = static_cast<int>(t.v.size());
+  return [=](int n) { return n < n0 ? d[n] : 0.f; };
+}
+static int pack_std(Ctx* c, const std::string& name, InKind kind, int cin, int N) {
+  return pack_layer(c, name, kind, std::max(1, cin / 8), N, conv_weight_fn(c, name), bias_fn(c, name));
+}
+
+static const char* kSftL0[] = {"LE.SFT_layer1", "LE.SFT_layer2"};
+static const char* kSftL1[] = {"LE.recon_trunk1.0.sft1", "LE.recon_trunk1.0.sft2", "LE.recon_trunk5.0.sft1",
+                               "LE.recon_trunk5.0.sft2"};
+static const char* kSftL2[] = {"LE.recon_trunk2.0.sft1", "LE.recon_trunk2.0.sft2", "LE.recon_trunk4.0.sft1",
+                               "LE.recon_trunk4.0.sft2"};
+static const char* kSftL3[] = {"LE.recon_trunk3.0.sft1", "LE.recon_trunk3.0.sft2", "LE.recon_trunk3.1.sft1",
+                               "LE.recon_trunk3.1.sft2", "LE.recon_trunk3.2.sft1", "LE.recon_trunk3.2.sft2",
+                               "LE.recon_trunk3.3.sft1", "LE.recon_trunk3.3.sft2"};
+
+// Stage 0 of a group of SFT layers that share one condition map: [scale_conv0 | shift_conv0] of every layer
+// stacked along N (16 -> 32 per layer), LeakyReLU(0.1) in the epilogue.
+static int pack_sft_stage0(Ctx* c, const std::string& key, const char* const* names, int n) {
+  std::vector<WeightFn> fs;
+  std::vector<std::function<float(int)>> bs;
+  for (int i = 0; i < n; ++i) {
+    fs.push_back(conv_weight_fn(c, std::string(names[i]) + ".SFT_scale_conv0"));
+    fs.push_back(conv_weight_fn(c, std::string(names[i]) + ".SFT_shift_conv0"));
+    bs.push_back(bias_fn(c, std::string(names[i]) + ".SFT_scale_conv0"));
+    bs.push_back(bias_fn(c, std::string(names[i]) + ".SFT_shift_conv0"));
+  }
+  WeightFn wf = [fs](int nn, int ci, int tap) { return fs[nn / 16](nn % 16, ci, tap); };
+  auto bf = [bs](int nn) { return bs[nn / 16](nn % 16); };
+  return pack_layer(c, key, IN_NAT1x1, 2, 32 * n, wf, bf);
+}
+// Stage 1 of one SFT layer: block-diagonal [scale_conv1 0; 0 shift_conv1] : 32 -> 64.
+static int pack_sft_stage1(Ctx* c, const std::string& name) {
+  WeightFn fs = conv_weight_fn(c, name + ".SFT_scale_conv1"), ft = conv_weight_fn(c, name + ".SFT_shift_conv1");
+  auto bs = bias_fn(c, name + ".SFT_scale_conv1"), bt = bias_fn(c, name + ".SFT_shift_conv1");
+  WeightFn wf = [fs, ft](int nn, int ci, int tap) -> float {
+    if (nn < 32) return ci < 16 ? fs(nn, ci, tap) : 0.f;
+    return ci >= 16 ? ft(nn - 32, ci - 16, tap) : 0.f;
+  };
+  auto bf = [bs, bt](int nn) { return nn < 32 ? bs(nn) : bt(nn - 32); };
+  return pack_layer(c, name + ".stage1", IN_NAT1x1, 4, 64, wf, bf);
+}
+
+static int pack_all_fp16(Ctx* c) {
+  int r = 0;
+  r |= pack_std(c, "LE.cond_first.0", IN_NAT3x3_C8, 8, 64);
+  r |= pack_std(c, "LE.cond_first.2", IN_NAT1x1, 64, 64);
+  r |= pack_std(c, "LE.cond_first.4", IN_NAT1x1, 64, 64);
+  r |= pack_std(c, "LE.CondNet1.0", IN_PAR1x1, 64, 64);
+  r |= pack_std(c, "LE.CondNet1.2", IN_NAT1x1, 64, 64);
+  r |= pack_std(c, "LE.CondNet1.4", IN_NAT1x1, 64, 16);
+  r |= pack_std(c, "LE.CondNet2.0", IN_PAR3x3S2, 64, 64);
+  r |= pack_std(c, "LE.CondNet2.2", IN_NAT1x1, 64, 64);
+  r |= pack_std(c, "LE.CondNet2.4", IN_NAT1x1, 64, 16);
+  r |= pack_std(c, "LE.CondNet3.0", IN_PAR3x3S2, 64, 64);
+  r |= pack_std(c, "LE.CondNet3.2", IN_PAR3x3S2, 64, 64);
+  r |= pack_std(c, "LE.CondNet3.4", IN_NAT1x1, 64, 16);
+  r |= pack_std(c, "LE.CondNet4.0", IN_PAR3x3S2, 64, 64);
+  r |= pack_std(c, "LE.CondNet4.2", IN_PAR3x3S2, 64, 64);
+  r |= pack_std(c, "LE.CondNet4.4", IN_PAR3x3S2, 64, 16);
+  r |= pack_std(c, "LE.conv_first", IN_NAT3x3_C8, 8, 32);
+  r |= pack_std(c, "LE.HR_conv1", IN_NAT3x3, 32, 32);
+  r |= pack_std(c, "LE.HR_conv2", IN_NAT3x3, 32, 32);
+  r |= pack_std(c, "LE.conv_last", IN_NAT3x3, 32, 16);
+  for (int i = 1; i <= 3; ++i) {
+    r |= pack_std(c, "LE.down_conv" + std::to_string(i), IN_PAR3x3S2, 32, 32);
+    r |= pack_std(c, "LE.up_conv" + std::to_string(i) + ".0", IN_NAT3x3, 32, 128);
+  }
+  const int nblk[6] = {0, 1, 1, 4, 1, 1};
+  for (int t = 1; t <= 5; ++t)
+    for (int j = 0; j < nblk[t]; ++j) {
+      const std::string pre = "LE.recon_trunk" + std::to_string(t) + "." + std::to_string(j);
+      r |= pack_std(c, pre + ".conv1", IN_NAT3x3, 32, 32);
+      r |= pack_std(c, pre + ".conv2", IN_NAT3x3, 32, 32);
+    }
+  r |= pack_sft_stage0(c, "sft0.L0", kSftL0, 2);
+  r |= pack_sft_stage0(c, "sft0.L1", kSftL1, 4);
+  r |= pack_sft_stage0(c, "sft0.L2", kSftL2, 4);
+  r |= pack_sft_stage0(c, "sft0.L3a", kSftL3, 4);
+  r |= pack_sft_stage0(c, "sft0.L3b", kSftL3 + 4, 4);
+  for (auto n : kSftL0) r |= pack_sft_stage1(c, n);
+  for (auto n : kSftL1) r |= pack_sft_stage1(c, n);
+  for (auto n : kSftL2) r |= pack_sft_stage1(c, n);
+  for (auto n : kSftL3) r |= pack_sft_stage1(c, n);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AGCM head: fea = W6 . mean(level5) + b6 -> six Linear heads -> GFM folded into the three 1x1 layers:
+//   o*scale + shift + o = (1+scale) (.) (W x + b) + shift   =>   W' = diag(1+scale) W,  b' = (1+scale) (.) b + shift
+// (Condition_arch.py:560-583).  Writes fp32 folded weights (FP32 path) and fp16 packed B operands (tcgen05 path).
+// ------------------------------------------------------------------------------------------------
+struct HeadParams {
+  const double* stats5;  // [128][2]
+  double cnt5;
+  const float *w6, *b6;                 // [6][128], [6]
+  const float *ls[3], *lsb[3];          // scale linears: first, HR, last  ([n][6], [n])
+  const float *lt[3], *ltb[3];          // shift linears
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  float* fea;
+  float* fold32;
+  __half* pk[3];
+  float* pkb[3];
+};
+__global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
+  __shared__ float mean5[128];
+  __shared__ float fea[6];
+  __shared__ float sc[3][64], sh[3][64];
+  const int t = threadIdx.x;
+  if (t < 128) mean5[t] = static_cast<float>(p.stats5[2 * t] / p.cnt5);
+  __syncthreads();
+  if (t < 6) {
+    float a = p.b6[t];
+    for (int k = 0; k < 128; ++k) a = fmaf(p.w6[t * 128 + k], mean5[k], a);
+    fea[t] = a;
+    p.fea[t] = a;
+  }
+  __syncthreads();
+  for (int i = t; i < 3 * 64; i += blockDim.x) {
+    const int l = i / 64, n = i % 64;
+    const int nn = (l == 2) ? 3 : 64;
+    if (n < nn) {
+      float s = p.lsb[l][n], h = p.ltb[l][n];
+      for (int k = 0; k < 6; ++k) {
+        s = fmaf(p.ls[l][n * 6 + k], fea[k], s);
+        h = fmaf(p.lt[l][n * 6 + k], fea[k], h);
+      }
+      sc[l][n] = 1.f + s;
+      sh[l][n] = h;
+    }
+  }
+  __syncthreads();
+  float* W1f = p.fold32;
+  float* b1f = W1f + 192;
+  float* W2f = b1f + 64;
+  float* b2f = W2f + 4096;
+  float* W3f = b2f + 64;
+  float* b3f = W3f + 192;
+  // zero the packed buffers' padding first (K padding of layer 1, N padding of layer 3)
+  for (int i = t; i < 64 * 16; i += blockDim.x) p.pk[0][i] = __float2half_rn(0.f);
+  for (int i = t; i < 4 * 16 * 16; i += blockDim.x) p.pk[2][i] = __float2half_rn(0.f);
+  __syncthreads();
+  for (int i = t; i < 192; i += blockDim.x) {  // layer 1: [64][3]
+    const int n = i / 3, k = i % 3;
+    const float v = sc[0][n] * p.w1[i];
+    W1f[i] = v;
+    p.pk[0][bpack_index(64, 0, n, k)] = __float2half_rn(v);
+  }
+  for (int i = t; i < 4096; i += blockDim.x) {  // layer 2: [64][64]
+    const int n = i / 64, k = i % 64;
+    const float v = sc[1][n] * p.w2[i];
+    W2f[i] = v;
+    p.pk[1][bpack_index(64, k / 16, n, k % 16)] = __float2half_rn(v);
+  }
+  for (int i = t; i < 192; i += blockDim.x) {  // layer 3: [3][64]
+    const int n = i / 64, k = i % 64;
+    const float v = sc[2][n] * p.w3[i];
+    W3f[i] = v;
+    p.pk[2][bpack_index(16, k / 16, n, k % 16)] = __float2half_rn(v);
+  }
+  for (int n = t; n < 64; n += blockDim.x) {
+    const float v1 = sc[0][n] * p.b1[n] + sh[0][n], v2 = sc[1][n] * p.b2[n] + sh[1][n];
+    b1f[n] = v1;
+    b2f[n] = v2;
+    p.pkb[0][n] = v1;
+    p.pkb[1][n] = v2;
+    if (n < 16) {
+      const float v3 = n < 3 ? sc[2][n] * p.b3[n] + sh[2][n] : 0.f;
+      if (n < 3) b3f[n] = v3;
+      p.pkb[2][n] = v3;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Condition-image tap tables (host): same arithmetic as ATen's _compute_indices_weights_aa for bicubic.
+// ------------------------------------------------------------------------------------------------
+static float cubic_aa(float x) {
+  const float a = -0.5f;
+  x = std::fabs(x);
+  if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+  if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+  return 0.f;
+}
+static void aa_taps(int n_in, int n_out, std::vector<int>& start, std::vector<float>& w) {
+  start.assign(n_out, 0);
+  w.assign(static_cast<size_t>(n_out) * 16, 0.f);
+  const float scale = 4.0f, support = 8.0f;
+  for (int i = 0; i < n_out; ++i) {
+    const float center = scale * (i + 0.5f);
+    const int xmin = std::max(static_cast<int>(center - support + 0.5f), 0);
+    const int xmax = std::min(static_cast<int>(center + support + 0.5f), n_in);
+    float total = 0.f;
+    float tmp[16] = {0};
+    for (int j = xmin; j < xmax && j - xmin < 16; ++j) {
+      tmp[j - xmin] = cubic_aa((j - center + 0.5f) / scale);
+      total += tmp[j - xmin];
+    }
+    for (int k = 0; k < 16; ++k) w[static_cast<size_t>(i) * 16 + k] = total != 0.f ? tmp[k] / total : 0.f;
+    start[i] = xmin;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workspace + plans
+// ------------------------------------------------------------------------------------------------
+static void release_workspace(Ctx* c) {
+  for (void* p : c->ws_allocs) cudaFree(p);
+  c->ws_allocs.clear();
+  c->ws_bytes = 0;
+  c->dbg.clear();
+  c->cls.clear();
+  c->plan_agcm.clear();
+  c->plan_le.clear();
+  c->f32.clear();
+  c->H = c->W = 0;
+}
+
+static void dbg_p8(Ctx* c, const std::string& n, const P8& t, int C, int j0 = 0) {
+  DebugTensor d;
+  d.name = n; d.C = C; d.H = t.H; d.W = t.W; d.kind = 1; d.ptr = nullptr; d.p8 = t; d.j0 = j0;
+  c->dbg.push_back(d);
+}
+static void dbg_f32(Ctx* c, const std::string& n, const float* p, int C, int H, int Wd) {
+  DebugTensor d;
+  d.name = n; d.C = C; d.H = H; d.W = Wd; d.kind = 0; d.ptr = p; d.j0 = 0;
+  c->dbg.push_back(d);
+}
+
+static int build_classifier(Ctx* c, int Hc, int Wc) {
+  const int ch[6] = {3, 16, 32, 64, 128, 128};
+  c->cls_stats_bytes = sizeof(double) * 2 * (16 + 32 + 64 + 128 + 128);
+  c->cls_stats_all = ws_alloc<double>(c, c->cls_stats_bytes / sizeof(double));
+  if (!c->cls_stats_all) return fail(c, "alloc classifier stats");
+  double* sp = c->cls_stats_all;
+  int h = Hc, w = Wc;
+  for (int l = 0; l < 5; ++l) {
+    Ctx::Lvl L;
+    L.Cin = ch[l]; L.Cout = ch[l + 1]; L.H = h; L.W = w; L.Ho = down2(h); L.Wo = down2(w);
+    L.out = ws_alloc<float>(c, static_cast<size_t>(L.Cout) * L.Ho * L.Wo);
+    if (!L.out) return fail(c, "alloc classifier level");
+    L.stats = sp;
+    sp += 2 * L.Cout;
+    c->cls.push_back(L);
+    dbg_f32(c, "cls" + std::to_string(l), L.out, L.Cout, L.Ho, L.Wo);
+    h = L.Ho; w = L.Wo;
+  }
+  c->d_fea = ws_alloc<float>(c, 8);
+  c->d_fold32 = ws_alloc<float>(c, 192 + 64 + 4096 + 64 + 192 + 3 + 5);
+  c->d_agpk[0] = ws_alloc<__half>(c, 64 * 16);
+  c->d_agpk[1] = ws_alloc<__half>(c, 4 * 64 * 16);
+  c->d_agpk[2] = ws_alloc<__half>(c, 4 * 16 * 16);
+  c->d_agbias[0] = ws_alloc<float>(c, 64);
+  c->d_agbias[1] = ws_alloc<float>(c, 64);
+  c->d_agbias[2] = ws_alloc<float>(c, 16);
+  if (!c->d_fea || !c->d_fold32 || !c->d_agpk[2] || !c->d_agbias[2]) return fail(c, "alloc agcm head");
+  dbg_f32(c, "fea", c->d_fea, 6, 1, 1);
+  return 0;
+}
+
+static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t s) {
+  CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
+  static const int convi[6] = {0, 4, 8, 12, 16, 20};
+  static const int normi[5] = {3, 7, 11, 15, -1};
+  const std::string pre = "AGCM.classifier.model.";
+  for (int l = 0; l < 5; ++l) {
+    const Ctx::Lvl& L = c->cls[l];
+    ClsLevel p;
+    p.in = l == 0 ? cond : static_cast<const void*>(c->cls[l - 1].out);
+    p.in_is_half = (l == 0 && cond_half) ? 1 : 0;
+    p.in_stats = l == 0 ? nullptr : c->cls[l - 1].stats;
+    p.gamma = l == 0 ? nullptr : c->wd.at(pre + std::to_string(normi[l - 1]) + ".weight");
+    p.beta = l == 0 ? nullptr : c->wd.at(pre + std::to_string(normi[l - 1]) + ".bias");
+    p.w = c->wd.at(pre + std::to_string(convi[l]) + ".weight");
+    p.b = c->wd.at(pre + std::to_string(convi[l]) + ".bias");
+    p.out = L.out;
+    p.out_stats = L.stats;
+    p.Cin = L.Cin; p.Cout = L.Cout; p.H = L.H; p.W = L.W; p.Ho = L.Ho; p.Wo = L.Wo;
+    dim3 grid((L.Ho * L.Wo + 127) / 128, (L.Cout + 15) / 16);
+    const size_t sm = sizeof(float) * (L.Cin * 16 + 2 * L.Cin);
+    cls_level_kernel<<<grid, 128, sm, s>>>(p);
+    CK(c, cudaGetLastError());
+    ++c->launches;
+  }
+  HeadParams hp;
+  hp.stats5 = c->cls[4].stats;
+  hp.cnt5 = static_cast<double>(c->cls[4].Ho) * c->cls[4].Wo;
+  hp.w6 = c->wd.at(pre + "20.weight");
+  hp.b6 = c->wd.at(pre + "20.bias");
+  const char* nm[3] = {"first", "HR", "last"};
+  for (int i = 0; i < 3; ++i) {
+    hp.ls[i] = c->wd.at(std::string("AGCM.cond_scale_") + nm[i] + ".weight");
+    hp.lsb[i] = c->wd.at(std::string("AGCM.cond_scale_") + nm[i] + ".bias");
+    hp.lt[i] = c->wd.at(std::string("AGCM.cond_shift_") + nm[i] + ".weight");
+    hp.ltb[i] = c->wd.at(std::string("AGCM.cond_shift_") + nm[i] + ".bias");
+    hp.pk[i] = c->d_agpk[i];
+    hp.pkb[i] = c->d_agbias[i];
+  }
+  hp.w1 = c->wd.at("AGCM.conv_first.weight"); hp.b1 = c->wd.at("AGCM.conv_first.bias");
+  hp.w2 = c->wd.at("AGCM.HRconv.weight");     hp.b2 = c->wd.at("AGCM.HRconv.bias");
+  hp.w3 = c->wd.at("AGCM.conv_last.weight");  hp.b3 = c->wd.at("AGCM.conv_last.bias");
+  hp.fea = c->d_fea;
+  hp.fold32 = c->d_fold32;
+  agcm_head_kernel<<<1, 256, 0, s>>>(hp);
+  CK(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+
+// ---- FP16 plan ---------------------------------------------------------------------------------
+static int build_plan_fp16(Ctx* c, int H, int Wd) {
+  const int H1 = down2(H), W1 = down2(Wd), H2 = down2(H1), W2 = down2(W1), H3 = down2(H2), W3 = down2(W2);
+  auto P = [&](int C, int h, int w, bool par) { return make_p8(c, C, h, w, par); };
+  // AGCM
+  c->xP8 = P(8, H, Wd, false);
+  P8 A1 = P(64, H, Wd, false), A2 = P(64, H, Wd, false), agP8 = P(8, H, Wd, false);
+  // LE condition pyramid
+  P8 B1 = A1, B2 = A2;                       // reuse AGCM temporaries (dead after the AGCM MLP)
+  P8 COND = P(64, H, Wd, true);
+  P8 C1a = A1, C1b = A2;
+  P8 cond1 = P(16, H, Wd, false);
+  P8 D1 = P(64, H1, W1, false), D2 = P(64, H1, W1, false), cond2 = P(16, H1, W1, false);
+  P8 E1 = P(64, H1, W1, true), E2 = P(64, H2, W2, false), cond3 = P(16, H2, W2, false);
+  P8 F2 = P(64, H2, W2, true), cond4 = P(16, H3, W3, false);
+  // SFT maps
+  P8 S0 = P(64, H, Wd, false), S1 = P(128, H1, W1, false), S2 = P(128, H2, W2, false), S3a = P(128, H3, W3, false),
+     S3b = P(128, H3, W3, false);
+  std::map<std::string, P8> maps;
+  for (auto n : kSftL0) maps[n] = P(64, H, Wd, false);
+  for (auto n : kSftL1) maps[n] = P(64, H1, W1, false);
+  for (auto n : kSftL2) maps[n] = P(64, H2, W2, false);
+  for (auto n : kSftL3) maps[n] = P(64, H3, W3, false);
+  // trunk
+  P8 T0a = P(32, H, Wd, false), FEA0 = P(32, H, Wd, true);
+  P8 X1 = P(32, H1, W1, false), X1m = P(32, H1, W1, false), Y1 = P(32, H1, W1, false), FEA1 = P(32, H1, W1, true);
+  P8 X2 = P(32, H2, W2, false), X2m = P(32, H2, W2, false), Y2 = P(32, H2, W2, false), FEA2 = P(32, H2, W2, true);
+  P8 FEA3 = P(32, H3, W3, false), Zm = P(32, H3, W3, false), Y3 = P(32, H3, W3, false);
+  P8 Z[2] = {P(32, H3, W3, false), P(32, H3, W3, false)};
+  P8 U3 = P(32, H3, W3, false);
+  P8 X4 = P(32, H2, W2, false), X4m = P(32, H2, W2, false), Y4 = P(32, H2, W2, false), U2 = P(32, H2, W2, false);
+  P8 X5 = P(32, H1, W1, false), X5m = P(32, H1, W1, false), Y5 = P(32, H1, W1, false), U1 = P(32, H1, W1, false);
+  P8 V0 = P(32, H, Wd, false), V1 = T0a;
+  for (void* p : c->ws_allocs) if (!p) return fail(c, "workspace allocation failed");
+  if (!V0.base || !U1.base) return fail(c, "workspace allocation failed (P8)");
+
+  auto wk = [&](const std::string& k) { return c->wpk.at(k); };
+  auto bk = [&](const std::string& k) { return c->bpk.at(k); };
+  auto std_conv = [&](std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int cin, int N,
+                      int mode, const P8& out, int Ho, int Wo, const Epi& e) {
+    return make_conv(c, plan, name, kind, in, 0, std::max(1, cin / 8), N, mode, wk(name), bk(name), out, Ho, Wo, e);
+  };
+  int r = 0;
+  Epi relu; relu.act = ACT_RELU;
+  Epi lrelu; lrelu.act = ACT_LRELU;
+  Epi none;
+  // ---- AGCM MLP (weights folded per frame by agcm_head_kernel)
+  r |= make_conv(c, c->plan_agcm, "AGCM.conv_first", IN_NAT1x1_C8, c->xP8, 0, 1, 64, STORE_P8, c->d_agpk[0],
+                 c->d_agbias[0], A1, H, Wd, relu);
+  r |= make_conv(c, c->plan_agcm, "AGCM.HRconv", IN_NAT1x1, A1, 0, 8, 64, STORE_P8, c->d_agpk[1], c->d_agbias[1], A2, H,
+                 Wd, relu);
+  {
+    Epi e; e.raw = &agP8; e.planar = reinterpret_cast<__half*>(1);  // planar pointer patched per call (agcm_out)
+    r |= make_conv(c, c->plan_agcm, "AGCM.conv_last", IN_NAT1x1, A2, 0, 8, 16, STORE_PLANAR, c->d_agpk[2],
+                   c->d_agbias[2], agP8, H, Wd, e);
+  }
+  auto& L = c->plan_le;
+  // ---- LE condition pyramid
+  r |= std_conv(L, "LE.cond_first.0", IN_NAT3x3_C8, agP8, 8, 64, STORE_P8, B1, H, Wd, lrelu);
+  r |= std_conv(L, "LE.cond_first.2", IN_NAT1x1, B1, 64, 64, STORE_P8, B2, H, Wd, lrelu);
+  r |= std_conv(L, "LE.cond_first.4", IN_NAT1x1, B2, 64, 64, STORE_P8, COND, H, Wd, lrelu);
+  r |= std_conv(L, "LE.CondNet1.0", IN_PAR1x1, COND, 64, 64, STORE_P8, C1a, H, Wd, lrelu);
+  r |= std_conv(L, "LE.CondNet1.2", IN_NAT1x1, C1a, 64, 64, STORE_P8, C1b, H, Wd, lrelu);
+  r |= std_conv(L, "LE.CondNet1.4", IN_NAT1x1, C1b, 64, 16, STORE_P8, cond1, H, Wd, none);
+  r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
+  r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
+  r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
+  r |= std_conv(L, "LE.CondNet3.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
+  r |= std_conv(L, "LE.CondNet3.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, E2, H2, W2, lrelu);
+  r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
+  r |= std_conv(L, "LE.CondNet4.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
+  r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, F2, H2, W2, lrelu);
+  r |= std_conv(L, "LE.CondNet4.4", IN_PAR3x3S2, F2, 64, 16, STORE_P8, cond4, H3, W3, none);
+  // ---- SFT maps: stage 0 (stacked, LeakyReLU) then one block-diagonal stage 1 per SFT layer
+  auto sft_group = [&](const std::string& key, const P8& cond, const P8& S, const char* const* names, int n, int h, int w) {
+    r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), bk(key), S, h, w, lrelu);
+    for (int i = 0; i < n; ++i) {
+      const std::string k1 = std::string(names[i]) + ".stage1";
+      r |= make_conv(c, L, k1, IN_NAT1x1, S, 4 * i, 4, 64, STORE_P8, wk(k1), bk(k1), maps.at(names[i]), h, w, none);
+    }
+  };
+  sft_group("sft0.L0", cond1, S0, kSftL0, 2, H, Wd);
+  sft_group("sft0.L1", cond2, S1, kSftL1, 4, H1, W1);
+  sft_group("sft0.L2", cond3, S2, kSftL2, 4, H2, W2);
+  sft_group("sft0.L3a", cond4, S3a, kSftL3, 4, H3, W3);
+  sft_group("sft0.L3b", cond4, S3b, kSftL3 + 4, 4, H3, W3);
+  // ---- trunk
+  { Epi e = relu; e.sft = &maps.at("LE.SFT_layer1");
+    r |= std_conv(L, "LE.conv_first", IN_NAT3x3_C8, agP8, 8, 32, STORE_P8, T0a, H, Wd, e); }
+  r |= std_conv(L, "LE.HR_conv1", IN_NAT3x3, T0a, 32, 32, STORE_P8, FEA0, H, Wd, relu);
+  auto resblock = [&](const std::string& pre, const P8& xm, const P8& xraw, const P8& ytmp, const P8& out,
+                      const P8* res2, const P8* next_sft, const P8* next_raw, int h, int w) {
+    { Epi e = relu; e.sft = &maps.at(pre + ".sft2");
+      r |= std_conv(L, pre + ".conv1", IN_NAT3x3, xm, 32, 32, STORE_P8, ytmp, h, w, e); }
+    { Epi e; e.res = &xraw; e.res2 = res2; e.sft = next_sft; e.raw = next_raw;
+      r |= std_conv(L, pre + ".conv2", IN_NAT3x3, ytmp, 32, 32, STORE_P8, out, h, w, e); }
+  };
+  { Epi e = relu; e.raw = &X1; e.sft = &maps.at("LE.recon_trunk1.0.sft1");
+    r |= std_conv(L, "LE.down_conv1", IN_PAR3x3S2, FEA0, 32, 32, STORE_P8, X1m, H1, W1, e); }
+  resblock("LE.recon_trunk1.0", X1m, X1, Y1, FEA1, nullptr, nullptr, nullptr, H1, W1);
+  { Epi e = relu; e.raw = &X2; e.sft = &maps.at("LE.recon_trunk2.0.sft1");
+    r |= std_conv(L, "LE.down_conv2", IN_PAR3x3S2, FEA1, 32, 32, STORE_P8, X2m, H2, W2, e); }
+  resblock("LE.recon_trunk2.0", X2m, X2, Y2, FEA2, nullptr, nullptr, nullptr, H2, W2);
+  { Epi e = relu; e.raw = &FEA3; e.sft = &maps.at("LE.recon_trunk3.0.sft1");
+    r |= std_conv(L, "LE.down_conv3", IN_PAR3x3S2, FEA2, 32, 32, STORE_P8, Zm, H3, W3, e); }
+  {
+    const P8* xraw = &FEA3;
+    for (int i = 0; i < 4; ++i) {
+      const std::string pre = "LE.recon_trunk3." + std::to_string(i);
+      if (i < 3) {
+        // Z_{i+1} = Z_i + conv2(...): raw copy for the next block's residual, SFT-modulated copy for its conv1
+        resblock(pre, Zm, *xraw, Y3, Zm, nullptr, &maps.at("LE.recon_trunk3." + std::to_string(i + 1) + ".sft1"),
+                 &Z[i & 1], H3, W3);
+        xraw = &Z[i & 1];
+      } else {
+        resblock(pre, Zm, *xraw, Y3, U3, &FEA3, nullptr, nullptr, H3, W3);   // out = trunk3(fea3) + fea3
+      }
+    }
+  }
+  auto up = [&](const std::string& name, const P8& in, const P8& skip, const P8* raw, const P8* sft, const P8& out,
+                int hin, int win) {
+    Epi e = relu; e.res = &skip; e.raw = raw; e.sft = sft;
+    r |= std_conv(L, name, IN_NAT3x3, in, 32, 128, STORE_PS, out, hin, win, e);
+  };
+  up("LE.up_conv1.0", U3, FEA2, &X4, &maps.at("LE.recon_trunk4.0.sft1"), X4m, H3, W3);
+  resblock("LE.recon_trunk4.0", X4m, X4, Y4, U2, nullptr, nullptr, nullptr, H2, W2);
+  up("LE.up_conv2.0", U2, FEA1, &X5, &maps.at("LE.recon_trunk5.0.sft1"), X5m, H2, W2);
+  resblock("LE.recon_trunk5.0", X5m, X5, Y5, U1, nullptr, nullptr, nullptr, H1, W1);
+  up("LE.up_conv3.0", U1, FEA0, nullptr, &maps.at("LE.SFT_layer2"), V0, H1, W1);
+  r |= std_conv(L, "LE.HR_conv2", IN_NAT3x3, V0, 32, 32, STORE_P8, V1, H, Wd, relu);
+  { Epi e; e.res = &agP8; e.planar = reinterpret_cast<__half*>(1);
+    r |= std_conv(L, "LE.conv_last", IN_NAT3x3, V1, 32, 16, STORE_PLANAR, agP8, H, Wd, e); }
+  if (r) return -1;
+
+  dbg_p8(c, "agcm", agP8, 3);
+  dbg_p8(c, "cond", COND, 64);
+  dbg_p8(c, "cond1", cond1, 16);
+  dbg_p8(c, "cond2", cond2, 16);
+  dbg_p8(c, "cond3", cond3, 16);
+  dbg_p8(c, "cond4", cond4, 16);
+  dbg_p8(c, "fea0", FEA0, 32);
+  dbg_p8(c, "fea1", FEA1, 32);
+  dbg_p8(c, "fea2", FEA2, 32);
+  dbg_p8(c, "fea3", FEA3, 32);
+  dbg_p8(c, "u3", U3, 32);
+  dbg_p8(c, "u2", U2, 32);
+  dbg_p8(c, "u1", U1, 32);
+  dbg_p8(c, "v0", V0, 32);
+  return 0;
+}
+
+// ---- FP32 workspace ----------------------------------------------------------------------------
+static int build_ws_fp32(Ctx* c, int H, int Wd) {
+  const int H1 = down2(H), W1 = down2(Wd), H2 = down2(H1), W2 = down2(W1), H3 = down2(H2), W3 = down2(W2);
+  const size_t P0 = static_cast<size_t>(H) * Wd, P1 = static_cast<size_t>(H1) * W1, P2 = static_cast<size_t>(H2) * W2,
+               P3 = static_cast<size_t>(H3) * W3;
+  auto A = [&](const std::string& n, size_t elems) {
+    c->f32[n] = ws_alloc<float>(c, elems, false);
+    return c->f32[n] != nullptr;
+  };
+  bool ok = true;
+  ok &= A("a1", 64 * P0) && A("a2", 64 * P0) && A("cond", 64 * P0) && A("cond1", 16 * P0);
+  ok &= A("u1a", 64 * P1) && A("u1b", 64 * P1) && A("cond2", 16 * P1);
+  ok &= A("u2a", 64 * P2) && A("cond3", 16 * P2) && A("cond4", 16 * P3);
+  ok &= A("f0a", 32 * P0) && A("f0b", 32 * P0) && A("fea0", 32 * P0);
+  ok &= A("s16a", 16 * P0) && A("s16b", 16 * P0) && A("s32a", 32 * P0) && A("s32b", 32 * P0);
+  ok &= A("g1a", 32 * P1) && A("g1b", 32 * P1) && A("g1c", 32 * P1) && A("fea1", 32 * P1) && A("up128", 128 * P1);
+  ok &= A("g2a", 32 * P2) && A("g2b", 32 * P2) && A("g2c", 32 * P2) && A("fea2", 32 * P2);
+  ok &= A("g3a", 32 * P3) && A("g3b", 32 * P3) && A("g3c", 32 * P3) && A("g3d", 32 * P3) && A("fea3", 32 * P3);
+  if (!ok) return fail(c, "fp32 workspace allocation failed");
+  dbg_f32(c, "cond", c->f32["cond"], 64, H, Wd);
+  dbg_f32(c, "cond1", c->f32["cond1"], 16, H, Wd);
+  dbg_f32(c, "cond2", c->f32["cond2"], 16, H1, W1);
+  dbg_f32(c, "cond3", c->f32["cond3"], 16, H2, W2);
+  dbg_f32(c, "cond4", c->f32["cond4"], 16, H3, W3);
+  dbg_f32(c, "fea0", c->f32["fea0"], 32, H, Wd);
+  dbg_f32(c, "fea1", c->f32["fea1"], 32, H1, W1);
+  dbg_f32(c, "fea2", c->f32["fea2"], 32, H2, W2);
+  dbg_f32(c, "fea3", c->f32["fea3"], 32, H3, W3);
+  return 0;
+}
+
+static int conv32(Ctx* c, cudaStream_t s, const float* in, const float* w, const float* b, float* out, int Cin, int Cout,
+                  int H, int Wd, int ks, int stride, int act, float slope, const float* res = nullptr, int ps = 0,
+                  int outH = 0, int outW = 0) {
+  ConvF32 p;
+  p.in = in; p.w = w; p.b = b; p.out = out; p.res = res;
+  p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = Wd;
+  p.Ho = (H + 2 * (ks / 2) - ks) / stride + 1;
+  p.Wo = (Wd + 2 * (ks / 2) - ks) / stride + 1;
+  p.ks = ks; p.stride = stride; p.act = act; p.slope = slope; p.ps = ps; p.outH = outH; p.outW = outW;
+  constexpr int COB = 8;
+  dim3 grid((p.Wo + 127) / 128, p.Ho, (Cout + COB - 1) / COB);
+  const size_t sm = sizeof(float) * Cin * ks * ks * COB;
+  conv_f32_kernel<COB><<<grid, 128, sm, s>>>(p);
+  CK(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+static int conv32n(Ctx* c, cudaStream_t s, const std::string& name, const float* in, float* out, int H, int Wd, int stride,
+                   int act, float slope, const float* res = nullptr, int ps = 0, int outH = 0, int outW = 0) {
+  const HostTensor& t = W(c, name + ".weight");
+  return conv32(c, s, in, c->wd.at(name + ".weight"), c->wd.at(name + ".bias"), out, static_cast<int>(t.shape[1]),
+                static_cast<int>(t.shape[0]), H, Wd, static_cast<int>(t.shape[2]), stride, act, slope, res, ps, outH, outW);
+}
+
+static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float* agcm_out, cudaStream_t s) {
+  const int H = c->H, Wd = c->W;
+  const int H1 = down2(H), W1 = down2(Wd), H2 = down2(H1), W2 = down2(W1), H3 = down2(H2), W3 = down2(W2);
+  auto B = [&](const char* n) { return c->f32.at(n); };
+  if (run_classifier(c, cond, false, s)) return -1;
+  float* f = c->d_fold32;
+  int r = 0;
+  r |= conv32(c, s, x, f, f + 192, B("a1"), 3, 64, H, Wd, 1, 1, ACT_RELU, 0.f);
+  r |= conv32(c, s, B("a1"), f + 256, f + 256 + 4096, B("a2"), 64, 64, H, Wd, 1, 1, ACT_RELU, 0.f);
+  r |= conv32(c, s, B("a2"), f + 4416, f + 4416 + 192, agcm_out, 64, 3, H, Wd, 1, 1, ACT_NONE, 0.f);
+  const float* img = agcm_out;
+  // condition pyramid (LeakyReLU 0.1)
+  r |= conv32n(c, s, "LE.cond_first.0", img, B("a1"), H, Wd, 1, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.cond_first.2", B("a1"), B("a2"), H, Wd, 1, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.cond_first.4", B("a2"), B("cond"), H, Wd, 1, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet1.0", B("cond"), B("a1"), H, Wd, 1, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet1.2", B("a1"), B("a2"), H, Wd, 1, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet1.4", B("a2"), B("cond1"), H, Wd, 1, ACT_NONE, 0.f);
+  r |= conv32n(c, s, "LE.CondNet2.0", B("cond"), B("u1a"), H, Wd, 2, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet2.2", B("u1a"), B("u1b"), H1, W1, 1, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet2.4", B("u1b"), B("cond2"), H1, W1, 1, ACT_NONE, 0.f);
+  r |= conv32n(c, s, "LE.CondNet3.0", B("cond"), B("u1a"), H, Wd, 2, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet3.2", B("u1a"), B("u2a"), H1, W1, 2, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet3.4", B("u2a"), B("cond3"), H2, W2, 1, ACT_NONE, 0.f);
+  r |= conv32n(c, s, "LE.CondNet4.0", B("cond"), B("u1a"), H, Wd, 2, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet4.2", B("u1a"), B("u2a"), H1, W1, 2, ACT_LRELU, 0.1f);
+  r |= conv32n(c, s, "LE.CondNet4.4", B("u2a"), B("cond4"), H2, W2, 2, ACT_NONE, 0.f);
+  if (r) return -1;
+  auto sft = [&](const std::string& pre, const float* xin, const float* cnd, float* y, int h, int w) {
+    int q = 0;
+    q |= conv32n(c, s, pre + ".SFT_scale_conv0", cnd, B("s16a"), h, w, 1, ACT_LRELU, 0.1f);
+    q |= conv32n(c, s, pre + ".SFT_scale_conv1", B("s16a"), B("s32a"), h, w, 1, ACT_NONE, 0.f);
+    q |= conv32n(c, s, pre + ".SFT_shift_conv0", cnd, B("s16b"), h, w, 1, ACT_LRELU, 0.1f);
+    q |= conv32n(c, s, pre + ".SFT_shift_conv1", B("s16b"), B("s32b"), h, w, 1, ACT_NONE, 0.f);
+    const long n = 32L * h * w;
+    sft_mod_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(xin, B("s32a"), B("s32b"), y, n);
+    ++c->launches;
+    return q;
+  };
+  auto resblock = [&](const std::string& pre, const float* xin, const float* cnd, float* t1, float* t2, float* y, int h,
+                      int w) {
+    int q = 0;
+    q |= sft(pre + ".sft1", xin, cnd, t1, h, w);
+    q |= conv32n(c, s, pre + ".conv1", t1, t2, h, w, 1, ACT_RELU, 0.f);
+    q |= sft(pre + ".sft2", t2, cnd, t1, h, w);
+    q |= conv32n(c, s, pre + ".conv2", t1, y, h, w, 1, ACT_NONE, 0.f, xin);
+    return q;
+  };
+  r |= conv32n(c, s, "LE.conv_first", img, B("f0a"), H, Wd, 1, ACT_RELU, 0.f);
+  r |= sft("LE.SFT_layer1", B("f0a"), B("cond1"), B("f0b"), H, Wd);
+  r |= conv32n(c, s, "LE.HR_conv1", B("f0b"), B("fea0"), H, Wd, 1, ACT_RELU, 0.f);
+  r |= conv32n(c, s, "LE.down_conv1", B("fea0"), B("g1a"), H, Wd, 2, ACT_RELU, 0.f);
+  r |= resblock("LE.recon_trunk1.0", B("g1a"), B("cond2"), B("g1b"), B("g1c"), B("fea1"), H1, W1);
+  r |= conv32n(c, s, "LE.down_conv2", B("fea1"), B("g2a"), H1, W1, 2, ACT_RELU, 0.f);
+  r |= resblock("LE.recon_trunk2.0", B("g2a"), B("cond3"), B("g2b"), B("g2c"), B("fea2"), H2, W2);
+  r |= conv32n(c, s, "LE.down_conv3", B("fea2"), B("fea3"), H2, W2, 2, ACT_RELU, 0.f);
+  {
+    const float* cur = B("fea3");
+    float* pp[2] = {B("g3a"), B("g3d")};
+    for (int i = 0; i < 4; ++i) {
+      r |= resblock("LE.recon_trunk3." + std::to_string(i), cur, B("cond4"), B("g3b"), B("g3c"), pp[i & 1], H3, W3);
+      cur = pp[i & 1];
+    }
+    const long n = 32L * H3 * W3;
+    add_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(cur, B("fea3"), B("g3b"), n);
+    ++c->launches;
+  }
+  // up1: relu(PixelShuffle(conv)) cropped to fea2, + fea2
+  r |= conv32n(c, s, "LE.up_conv1.0", B("g3b"), B("g2a"), H3, W3, 1, ACT_RELU, 0.f, B("fea2"), 1, H2, W2);
+  r |= resblock("LE.recon_trunk4.0", B("g2a"), B("cond3"), B("g2b"), B("g2c"), B("up128"), H2, W2);
+  r |= conv32n(c, s, "LE.up_conv2.0", B("up128"), B("g1a"), H2, W2, 1, ACT_RELU, 0.f, B("fea1"), 1, H1, W1);
+  r |= resblock("LE.recon_trunk5.0", B("g1a"), B("cond2"), B("g1b"), B("g1c"), B("up128"), H1, W1);
+  r |= conv32n(c, s, "LE.up_conv3.0", B("up128"), B("f0a"), H1, W1, 1, ACT_RELU, 0.f, B("fea0"), 1, H, Wd);
+  r |= sft("LE.SFT_layer2", B("f0a"), B("cond1"), B("f0b"), H, Wd);
+  r |= conv32n(c, s, "LE.HR_conv2", B("f0b"), B("f0a"), H, Wd, 1, ACT_RELU, 0.f);
+  r |= conv32n(c, s, "LE.conv_last", B("f0a"), out, H, Wd, 1, ACT_NONE, 0.f, img);
+  return r;
+}
+
+static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __half* agcm_out, cudaStream_t s) {
+  const int H = c->H, Wd = c->W;
+  planar_to_p8_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(x, c->xP8, H, Wd);
+  CK(c, cudaGetLastError());
+  ++c->launches;
+  if (run_classifier(c, cond, true, s)) return -1;
+  for (ConvLaunch& L : c->plan_agcm) {
+    if (L.mode == STORE_PLANAR) L.p.planar = agcm_out;
+    CK(c, launch_conv(L, s));
+    ++c->launches;
+  }
+  for (ConvLaunch& L : c->plan_le) {
+    if (L.mode == STORE_PLANAR) L.p.planar = out;
+    CK(c, launch_conv(L, s));
+    ++c->launches;
+  }
+  return 0;
+}
+
+}  // namespace hdrtv
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace hdrtv;
+struct hdrtv_ctx : public Ctx {};
+
+extern "C" {
+
+const char* hdrtv_version(void) { return "hdrtv_b200 0.1 (sm_100a)"; }
+
+const char* hdrtv_last_error(const hdrtv_t* h) { return h ? h->err.c_str() : g_err; }
+
+int hdrtv_create(const hdrtv_config* cfg, hdrtv_t** out) {
+  if (!cfg || !out) return fail(nullptr, "hdrtv_create: null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= cfg->device)
+    return fail(nullptr, "hdrtv_create: CUDA device not available (this engine has no CPU fallback)");
+  if (cfg->precision != HDRTV_FP32 && cfg->precision != HDRTV_FP16) return fail(nullptr, "hdrtv_create: bad precision");
+  cudaSetDevice(cfg->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) return fail(nullptr, "hdrtv_create: sm_100a (B200) device required, got sm_" +
+                                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  hdrtv_ctx* c = new hdrtv_ctx();
+  c->device = cfg->device;
+  c->precision = cfg->precision;
+  if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess) { delete c; return fail(nullptr, "hdrtv_create: cudaMalloc"); }
+  cudaMemset(c->d_err, 0, sizeof(int));
+  *out = c;
+  return 0;
+}
+
+void hdrtv_destroy(hdrtv_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  release_workspace(c);
+  for (void* p : c->weight_allocs) cudaFree(p);
+  if (c->d_err) cudaFree(c->d_err);
+  if (c->d_lut) cudaFree(c->d_lut);
+  delete c;
+}
+
+int hdrtv_set_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {
+  if (!c || !t) return fail(c, "hdrtv_set_weights: null argument");
+  cudaSetDevice(c->device);
+  for (int i = 0; i < n; ++i) {
+    HostTensor ht;
+    size_t cnt = 1;
+    for (int d = 0; d < t[i].ndim; ++d) { ht.shape.push_back(t[i].shape[d]); cnt *= static_cast<size_t>(t[i].shape[d]); }
+    ht.v.assign(t[i].data, t[i].data + cnt);
+    std::string key = t[i].name;
+    if (key.rfind("module.", 0) == 0) key = key.substr(7);
+    c->wd[key] = w_upload(c, ht.v.data(), cnt);
+    if (!c->wd[key]) return fail(c, "hdrtv_set_weights: upload failed for " + key);
+    c->w[key] = std::move(ht);
+  }
+  // strict key check (Ensemble_AGCM_LE.load_state_dict strict=True, hdrtvnet_torch.py:2157)
+  static const char* must[] = {"AGCM.classifier.model.0.weight", "AGCM.classifier.model.20.bias", "AGCM.cond_scale_first.weight",
+                               "AGCM.conv_first.weight", "AGCM.HRconv.weight", "AGCM.conv_last.weight", "LE.conv_first.weight",
+                               "LE.HR_conv1.weight", "LE.conv_last.bias", "LE.cond_first.0.weight", "LE.CondNet4.4.weight",
+                               "LE.up_conv3.0.weight", "LE.recon_trunk3.3.sft2.SFT_shift_conv1.bias", "LE.SFT_layer2.SFT_scale_conv0.weight"};
+  for (auto k : must)
+    if (!c->w.count(k)) return fail(c, std::string("hdrtv_set_weights: missing key ") + k);
+  if (c->w.size() != 264) return fail(c, "hdrtv_set_weights: expected 264 tensors, got " + std::to_string(c->w.size()));
+  try {
+    if (c->precision == HDRTV_FP16 && pack_all_fp16(c)) return -1;
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_set_weights: ") + e.what());
+  }
+  c->has_weights = true;
+  release_workspace(c);
+  return 0;
+}
+
+int hdrtv_prepare(hdrtv_t* c, int H, int Wd) {
+  if (!c) return fail(c, "hdrtv_prepare: null context");
+  if (!c->has_weights) return fail(c, "hdrtv_prepare: weights not set");
+  if (H < 16 || Wd < 16) return fail(c, "hdrtv_prepare: frame must be at least 16x16");
+  if (c->H == H && c->W == Wd) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  release_workspace(c);
+  const int Hc = std::max(1, H / 4), Wc = std::max(1, Wd / 4);
+  std::vector<int> xs, ys;
+  std::vector<float> xw, yw;
+  aa_taps(Wd, Wc, xs, xw);
+  aa_taps(H, Hc, ys, yw);
+  c->d_xstart = ws_alloc<int>(c, xs.size());
+  c->d_ystart = ws_alloc<int>(c, ys.size());
+  c->d_xw = ws_alloc<float>(c, xw.size());
+  c->d_yw = ws_alloc<float>(c, yw.size());
+  if (!c->d_xstart || !c->d_ystart || !c->d_xw || !c->d_yw) return fail(c, "hdrtv_prepare: alloc taps");
+  cudaMemcpy(c->d_xstart, xs.data(), xs.size() * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_ystart, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_xw, xw.data(), xw.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_yw, yw.data(), yw.size() * sizeof(float), cudaMemcpyHostToDevice);
+  try {
+    if (build_classifier(c, Hc, Wc)) return -1;
+    if (c->precision == HDRTV_FP16) {
+      if (build_plan_fp16(c, H, Wd)) return -1;
+    } else {
+      if (build_ws_fp32(c, H, Wd)) return -1;
+    }
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_prepare: ") + e.what());
+  }
+  CK(c, cudaDeviceSynchronize());
+  c->H = H;
+  c->W = Wd;
+  return 0;
+}
+
+size_t hdrtv_workspace_bytes(const hdrtv_t* c) { return c ? c->ws_bytes : 0; }
+long hdrtv_launch_count(const hdrtv_t* c) { return c ? c->launches : 0; }
+
+int hdrtv_preprocess(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out, void* cond_out, int cond_mode, void* stream) {
+  if (!c || !bgr || !x_out || !cond_out) return fail(c, "hdrtv_preprocess: null argument");
+  if (hdrtv_prepare(c, H, Wd)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long npix = static_cast<long>(H) * Wd;
+  const bool vec = (Wd % 16 == 0) && (reinterpret_cast<uintptr_t>(bgr) % 16 == 0);
+  const int Hc = std::max(1, H / 4), Wc = std::max(1, Wd / 4);
+  CondTaps tp{c->d_xstart, c->d_xw, c->d_ystart, c->d_yw};
+  dim3 cgrid((Wc + kCondTW - 1) / kCondTW, (Hc + kCondTH - 1) / kCondTH);
+  if (c->precision == HDRTV_FP16) {
+    if (vec) normalize_vec16_kernel<__half><<<static_cast<unsigned>((npix / 16 + 255) / 256), 256, 0, s>>>(bgr, static_cast<__half*>(x_out), H, Wd);
+    else normalize_scalar_kernel<__half><<<static_cast<unsigned>((npix + 255) / 256), 256, 0, s>>>(bgr, static_cast<__half*>(x_out), H, Wd);
+    cond_aa_kernel<__half><<<cgrid, 256, 0, s>>>(bgr, static_cast<__half*>(cond_out), H, Wd, Hc, Wc, tp, cond_mode);
+  } else {
+    if (vec) normalize_vec16_kernel<float><<<static_cast<unsigned>((npix / 16 + 255) / 256), 256, 0, s>>>(bgr, static_cast<float*>(x_out), H, Wd);
+    else normalize_scalar_kernel<float><<<static_cast<unsigned>((npix + 255) / 256), 256, 0, s>>>(bgr, static_cast<float*>(x_out), H, Wd);
+    cond_aa_kernel<float><<<cgrid, 256, 0, s>>>(bgr, static_cast<float*>(cond_out), H, Wd, Hc, Wc, tp, cond_mode);
+  }
+  CK(c, cudaGetLastError());
+  c->launches += 2;
+  return 0;
+}
+
+int hdrtv_infer(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* out, void* agcm_out, void* stream) {
+  if (!c || !x || !cond || !out || !agcm_out) return fail(c, "hdrtv_infer: null argument");
+  if (hdrtv_prepare(c, H, Wd)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  try {
+    if (c->precision == HDRTV_FP16)
+      return run_fp16(c, static_cast<const __half*>(x), static_cast<const __half*>(cond), static_cast<__half*>(out),
+                      static_cast<__half*>(agcm_out), s);
+    return run_fp32(c, static_cast<const float*>(x), static_cast<const float*>(cond), static_cast<float*>(out),
+                    static_cast<float*>(agcm_out), s);
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_infer: ") + e.what());
+  }
+}
+
+int hdrtv_set_transfer_lut(hdrtv_t* c, const uint16_t* lut, int n) {
+  if (!c || !lut || n != 0x3C01) return fail(c, "hdrtv_set_transfer_lut: need 15361 entries (half patterns 0x0000..0x3C00)");
+  if (!c->d_lut && cudaMalloc(&c->d_lut, 0x3C01 * sizeof(uint16_t)) != cudaSuccess) return fail(c, "lut alloc");
+  CK(c, cudaMemcpy(c->d_lut, lut, 0x3C01 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint16_t* dst, int transfer, void* stream) {
+  if (!c || !src || !dst) return fail(c, "hdrtv_pack_rgb48: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long npix = static_cast<long>(H) * Wd;
+  const unsigned blocks = static_cast<unsigned>(((npix + 7) / 8 + 255) / 256);
+  const uint16_t* lut = nullptr;
+  if (transfer == HDRTV_TRANSFER_LUT) {
+    if (!c->d_lut || dtype != HDRTV_FP16) return fail(c, "hdrtv_pack_rgb48: LUT transfer needs fp16 input and a table");
+    lut = c->d_lut;
+  }
+  if (dtype == HDRTV_FP16) pack_rgb48_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix, lut);
+  else pack_rgb48_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix, lut);
+  CK(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+
+int hdrtv_pack_bgr24(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint8_t* dst, void* stream) {
+  if (!c || !src || !dst) return fail(c, "hdrtv_pack_bgr24: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long npix = static_cast<long>(H) * Wd;
+  const unsigned blocks = static_cast<unsigned>(((npix + 3) / 4 + 255) / 256);
+  if (dtype == HDRTV_FP16) pack_bgr24_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix);
+  else pack_bgr24_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix);
+  CK(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
+}
+
+int hdrtv_debug_tensor_count(const hdrtv_t* c) { return c ? static_cast<int>(c->dbg.size()) : 0; }
+int hdrtv_debug_tensor_info(const hdrtv_t* c, int idx, char* name, int cap, int* C, int* H, int* Wd) {
+  if (!c || idx < 0 || idx >= static_cast<int>(c->dbg.size())) return -1;
+  const DebugTensor& d = c->dbg[idx];
+  snprintf(name, cap, "%s", d.name.c_str());
+  *C = d.C; *H = d.H; *Wd = d.W;
+  return 0;
+}
+int hdrtv_debug_tensor_read(hdrtv_t* c, int idx, float* dst) {
+  if (!c || idx < 0 || idx >= static_cast<int>(c->dbg.size())) return fail(c, "debug index");
+  const DebugTensor& d = c->dbg[idx];
+  cudaSetDevice(c->device);
+  CK(c, cudaDeviceSynchronize());
+  const size_t n = static_cast<size_t>(d.C) * d.H * d.W;
+  if (d.kind == 0) {
+    CK(c, cudaMemcpy(dst, d.ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
+  } else {
+    float* tmp = nullptr;
+    CK(c, cudaMalloc(&tmp, n * sizeof(float)));
+    p8_to_planar_f32_kernel<<<dim3((d.W + 127) / 128, d.H), 128>>>(d.p8, d.j0, d.C, tmp);
+    cudaError_t e = cudaMemcpy(dst, tmp, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    CK(c, e);
+  }
+  return 0;
+}
+
+// One convolution through the tcgen05 path and through the fp32 CUDA-core path on the same fp16-rounded data.
+// kind: InKind; flags bit0: PixelShuffle store (cout must be 128), bit1: planar store (cout 3), bit2: relu,
+// bit3: residual, bit4: sft + raw.
+int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, int flags, float* max_abs, float* ref_max) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  Ctx t;  // scratch context for allocations
+  t.device = c->device;
+  t.d_err = c->d_err;
+  const bool s2 = (kind == IN_PAR3x3S2);
+  const bool par_in = s2 || kind == IN_PAR1x1;
+  const int ks = (kind == IN_NAT1x1 || kind == IN_NAT1x1_C8 || kind == IN_PAR1x1) ? 1 : 3;
+  const int Ho = s2 ? down2(H) : H, Wo = s2 ? down2(Wd) : Wd;
+  const bool ps = flags & 1, planar = flags & 2;
+  const int N = planar ? 16 : cout;
+  const int cin_real = (kind == IN_NAT3x3_C8 || kind == IN_NAT1x1_C8) ? 3 : cin;
+  const int outC = ps ? cout / 4 : cout, outH = ps ? 2 * Ho - 1 : Ho, outW = ps ? 2 * Wo - 1 : Wo;  // crop by one: exercises align
+  // host data
+  std::vector<float> hin(static_cast<size_t>(cin_real) * H * Wd), hw(static_cast<size_t>(cout) * cin_real * ks * ks), hb(cout);
+  uint32_t seed = 12345u + kind * 77 + cin * 3 + cout;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : hin) v = __half2float(__float2half(rnd()));
+  const float wscale = 1.0f / std::sqrt(static_cast<float>(cin_real * ks * ks));
+  for (auto& v : hw) v = __half2float(__float2half(2.f * rnd() * wscale));
+  for (auto& v : hb) v = rnd() * 0.1f;
+  std::vector<float> hres(static_cast<size_t>(outC) * outH * outW), hs(hres.size()), ht(hres.size());
+  for (auto& v : hres) v = __half2float(__float2half(rnd()));
+  for (auto& v : hs) v = __half2float(__float2half(rnd()));
+  for (auto& v : ht) v = __half2float(__float2half(rnd()));
+  // device fp32 reference
+  float *din, *dw, *db, *dout, *dres, *ds, *dt;
+  din = ws_alloc<float>(&t, hin.size()); dw = ws_alloc<float>(&t, hw.size()); db = ws_alloc<float>(&t, std::max(16, cout));
+  dout = ws_alloc<float>(&t, hres.size()); dres = ws_alloc<float>(&t, hres.size());
+  ds = ws_alloc<float>(&t, hres.size()); dt = ws_alloc<float>(&t, hres.size());
+  cudaMemcpy(din, hin.data(), hin.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dres, hres.data(), hres.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(ds, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dt, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+  const int act = (flags & 4) ? ACT_RELU : ACT_NONE;
+  int r = conv32(&t, 0, din, dw, db, dout, cin_real, cout, H, Wd, ks, s2 ? 2 : 1, act, 0.f, (flags & 8) ? dres : nullptr,
+                 ps ? 1 : 0, outH, outW);
+  if (flags & 16) {
+    const long n = static_cast<long>(hres.size());
+    sft_mod_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(dout, ds, dt, dout, n);
+  }
+  std::vector<float> ref(hres.size());
+  cudaDeviceSynchronize();
+  cudaMemcpy(ref.data(), dout, ref.size() * 4, cudaMemcpyDeviceToHost);
+  // tcgen05 path
+  P8 in = make_p8(&t, std::max(8, cin), H, Wd, par_in);
+  P8 outp = make_p8(&t, std::max(8, outC), outH, outW, false);
+  P8 resp = make_p8(&t, std::max(8, outC), outH, outW, true);   // parity residual exercises both address modes
+  P8 sftp = make_p8(&t, 2 * std::max(8, outC), outH, outW, false);
+  P8 rawp = make_p8(&t, std::max(8, outC), outH, outW, false);
+  auto fill_p8 = [&](P8& pt, const std::vector<float>& src, int C, int j0) {
+    std::vector<__half> h(static_cast<size_t>(pt.entries()) * 8);
+    cudaMemcpy(h.data(), pt.base, h.size() * 2, cudaMemcpyDeviceToHost);
+    for (int ch = 0; ch < C; ++ch)
+      for (int y = 0; y < pt.H; ++y)
+        for (int x = 0; x < pt.W; ++x)
+          h[pt.entry(y, j0 + ch / 8, x) * 8 + ch % 8] = __float2half(src[(static_cast<size_t>(ch) * pt.H + y) * pt.W + x]);
+    cudaMemcpy(pt.base, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
+  };
+  fill_p8(in, hin, cin_real, 0);
+  if (!planar) { fill_p8(resp, hres, outC, 0); fill_p8(sftp, hs, outC, 0); fill_p8(sftp, ht, outC, std::max(8, outC) / 8); }
+  // weights
+  ConvParams tmp; memset(&tmp, 0, sizeof(tmp));
+  std::vector<StepK> wk;
+  build_input_side(static_cast<InKind>(kind), in, 0, std::max(1, cin / 8), tmp, wk);
+  WeightFn wf = [&](int n, int ci, int tap) -> float {
+    if (n >= cout || ci >= cin_real || tap >= ks * ks) return 0.f;
+    return hw[(static_cast<size_t>(n) * cin_real + ci) * ks * ks + tap];
+  };
+  std::vector<__half> pk = pack_weights(N, wk, wf);
+  __half* dpk = ws_alloc<__half>(&t, pk.size());
+  cudaMemcpy(dpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
+  __half* dplanar = ws_alloc<__half>(&t, static_cast<size_t>(3) * outH * outW);
+  std::vector<ConvLaunch> plan;
+  Epi e; e.act = act;
+  if (!planar) {
+    if (flags & 8) e.res = &resp;
+    if (flags & 16) { e.sft = &sftp; e.raw = &rawp; }
+  } else {
+    e.planar = dplanar;
+  }
+  if (make_conv(&t, plan, "selftest", static_cast<InKind>(kind), in, 0, std::max(1, cin / 8), N,
+                planar ? STORE_PLANAR : (ps ? STORE_PS : STORE_P8), dpk, db, outp, Ho, Wo, e)) { c->err = t.err; r = -1; }
+  if (!r) {
+    cudaError_t ce = launch_conv(plan[0], 0);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { fail(c, std::string("selftest launch: ") + cudaGetErrorString(ce)); r = -1; }
+  }
+  float mx = 0.f, rmx = 0.f;
+  if (!r) {
+    std::vector<float> got(ref.size());
+    if (planar) {
+      std::vector<__half> hp(static_cast<size_t>(3) * outH * outW);
+      cudaMemcpy(hp.data(), dplanar, hp.size() * 2, cudaMemcpyDeviceToHost);
+      for (size_t i = 0; i < hp.size(); ++i) got[i] = __half2float(hp[i]);
+    } else {
+      float* tmpd = ws_alloc<float>(&t, got.size());
+      p8_to_planar_f32_kernel<<<dim3((outW + 127) / 128, outH), 128>>>(outp, 0, outC, tmpd);
+      cudaMemcpy(got.data(), tmpd, got.size() * 4, cudaMemcpyDeviceToHost);
+    }
+    for (size_t i = 0; i < ref.size(); ++i) {
+      mx = std::max(mx, std::fabs(got[i] - ref[i]));
+      rmx = std::max(rmx, std::fabs(ref[i]));
+    }
+    if (std::isnan(mx)) mx = 1e30f;
+  }
+  *max_abs = mx;
+  *ref_max = rmx;
+  t.d_err = nullptr;
+  for (void* p : t.ws_allocs) cudaFree(p);
+  t.ws_allocs.clear();
+  return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+// FP32 CUDA-core kernels: the precision="fp32" product path (BASELINE config 1, <= 1e-4 vs the reference's
+// FP32 output) and the AGCM condition classifier (always FP32, both precisions).
+// Activations are planar NCHW fp32.  Reference: Condition_arch.py:8-35, 559-585; HDRUNet3T1_arch.py:152-206.
+#pragma once
+#include "common.cuh"
+
+namespace hdrtv {
+
+// ------------------------------------------------------------------------------------------------
+// Direct convolution, planar fp32.  One thread = one output pixel x COB output channels.
+// Weights for the block's COB channels are staged in shared memory as [cin][tap][COB].
+// Epilogue: +bias, activation, optional residual add, optional PixelShuffle(2) scatter with crop.
+// ------------------------------------------------------------------------------------------------
+struct ConvF32 {
+  const float* in;   // [Cin][H][W]
+  const float* w;    // [Cout][Cin][ks][ks]
+  const float* b;    // [Cout]
+  float* out;        // [Cout][Ho][Wo]  (PixelShuffle: [Cout/4][outH][outW])
+  const float* res;  // optional, same shape as out
+  int Cin, Cout, H, W, Ho, Wo, ks, stride, act;
+  float slope;
+  int ps;            // 1: PixelShuffle(2) + crop to (outH,outW)
+  int outH, outW;
+};
+
+template <int COB>
+__global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
+  extern __shared__ float wsm[];  // [Cin*ks*ks][COB]
+  const int co0 = blockIdx.z * COB;
+  const int taps = p.ks * p.ks;
+  const int kk = p.Cin * taps;
+  for (int i = threadIdx.x; i < kk * COB; i += blockDim.x) {
+    const int k = i / COB, c = i % COB;
+    wsm[i] = (co0 + c < p.Cout) ? p.w[static_cast<long>(co0 + c) * kk + k] : 0.f;
+  }
+  __syncthreads();
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= p.Wo) return;
+  float acc[COB];
+#pragma unroll
+  for (int c = 0; c < COB; ++c) acc[c] = 0.f;
+  const int pad = p.ks / 2;
+  for (int ci = 0; ci < p.Cin; ++ci) {
+    const float* ip = p.in + static_cast<long>(ci) * p.H * p.W;
+    for (int ky = 0; ky < p.ks; ++ky) {
+      const int iy = oy * p.stride + ky - pad;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kx = 0; kx < p.ks; ++kx) {
+        const int ix = ox * p.stride + kx - pad;
+        if (ix < 0 || ix >= p.W) continue;
+        const float v = __ldg(ip + static_cast<long>(iy) * p.W + ix);
+        const float* wp = wsm + ((ci * p.ks + ky) * p.ks + kx) * COB;
+#pragma unroll
+        for (int c = 0; c < COB; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < COB; ++c) {
+    const int co = co0 + c;
+    if (co >= p.Cout) break;
+    float v = acc[c] + __ldg(p.b + co);
+    if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+    else if (p.act == ACT_LRELU) v = v >= 0.f ? v : v * p.slope;
+    long o;
+    if (p.ps) {
+      const int Y = 2 * oy + ((co & 3) >> 1), X = 2 * ox + (co & 1);
+      if (Y >= p.outH || X >= p.outW) continue;
+      o = (static_cast<long>(co >> 2) * p.outH + Y) * p.outW + X;
+    } else {
+      o = (static_cast<long>(co) * p.Ho + oy) * p.Wo + ox;
+    }
+    if (p.res) v += __ldg(p.res + o);
+    p.out[o] = v;
+  }
+}
+
+// y = x * (scale + 1) + shift   (arch_util.py:72)
+__global__ void sft_mod_f32_kernel(const float* x, const float* scale, const float* shift, float* y, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * (scale[i] + 1.f) + shift[i];
+}
+__global__ void add_f32_kernel(const float* a, const float* b, float* y, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+__global__ void half_to_f32_kernel(const __half* a, float* y, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __half2float(a[i]);
+}
+__global__ void f32_to_half_kernel(const float* a, __half* y, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(a[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// AGCM condition classifier (Color_Condition, Condition_arch.py:19-35).
+// One kernel per block level: y = LeakyReLU_0.2( AvgPool3/2/1( conv1x1( IN_prev(x) ) ) ), and the per-channel
+// sum / sum-of-squares of y are accumulated in FP64 for the InstanceNorm that the NEXT level folds into its
+// input read (IN is affine per channel once mean/var are known).  count_include_pad=True => always /9, and the
+// zero padding applies to the conv OUTPUT (bias included), so border windows simply have fewer terms.
+// ------------------------------------------------------------------------------------------------
+struct ClsLevel {
+  const void* in;        // [Cin][H][W]  fp32, or fp16/fp32 planar cond for level 0
+  int in_is_half;
+  const double* in_stats;  // [Cin][2] sum, sumsq of the previous level's output (nullptr: no IN before this level)
+  const float* gamma;      // IN affine of the previous level
+  const float* beta;
+  const float* w;          // [Cout][Cin]
+  const float* b;          // [Cout]
+  float* out;              // [Cout][Ho][Wo]
+  double* out_stats;       // [Cout][2], pre-zeroed
+  int Cin, Cout, H, W, Ho, Wo;
+};
+
+// grid: (ceil(Ho*Wo/128), ceil(Cout/16)); block 128; each thread: one pooled pixel, 16 output channels.
+__global__ void __launch_bounds__(128) cls_level_kernel(const ClsLevel p) {
+  extern __shared__ float sm[];
+  float* wsm = sm;                       // [Cin][16]
+  float* na = wsm + p.Cin * 16;          // [Cin] IN scale
+  float* nb = na + p.Cin;                // [Cin] IN shift
+  const int co0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < p.Cin * 16; i += blockDim.x) {
+    const int ci = i / 16, c = i % 16;
+    wsm[i] = (co0 + c < p.Cout) ? p.w[(co0 + c) * p.Cin + ci] : 0.f;
+  }
+  const double cnt = static_cast<double>(p.H) * p.W;
+  for (int ci = threadIdx.x; ci < p.Cin; ci += blockDim.x) {
+    if (p.in_stats) {
+      const double mean = p.in_stats[2 * ci] / cnt;
+      double var = p.in_stats[2 * ci + 1] / cnt - mean * mean;
+      var = var < 0 ? 0 : var;
+      const double rstd = 1.0 / sqrt(var + 1e-5);
+      na[ci] = static_cast<float>(rstd * p.gamma[ci]);
+      nb[ci] = static_cast<float>(p.beta[ci] - mean * rstd * p.gamma[ci]);
+    } else {
+      na[ci] = 1.f;
+      nb[ci] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = idx < p.Ho * p.Wo;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  int nwin = 0;
+  if (valid) {
+    const int oy = idx / p.Wo, ox = idx % p.Wo;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox + kx - 1;
+        if (ix < 0 || ix >= p.W) continue;
+        ++nwin;
+        for (int ci = 0; ci < p.Cin; ++ci) {
+          const long o = (static_cast<long>(ci) * p.H + iy) * p.W + ix;
+          float v = p.in_is_half ? __half2float(reinterpret_cast<const __half*>(p.in)[o])
+                                 : reinterpret_cast<const float*>(p.in)[o];
+          v = fmaf(v, na[ci], nb[ci]);
+          const float* wp = wsm + ci * 16;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
+        }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int co = co0 + c;
+    float y = 0.f;
+    if (valid && co < p.Cout) {
+      y = (acc[c] + nwin * __ldg(p.b + co)) / 9.0f;
+      y = y >= 0.f ? y : 0.2f * y;
+      p.out[static_cast<long>(co) * p.Ho * p.Wo + idx] = y;
+    }
+    double s = y, ss = static_cast<double>(y) * y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0 && co < p.Cout) {
+      atomicAdd(p.out_stats + 2 * co, s);
+      atomicAdd(p.out_stats + 2 * co + 1, ss);
+    }
+  }
+}
+
+}  // namespace hdrtv

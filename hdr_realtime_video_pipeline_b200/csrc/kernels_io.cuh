@@ -1,0 +1,255 @@
+// Bandwidth-bound ends of the path: uint8 BGR -> normalised planar RGB (+ antialiased 1/4 condition image),
+// and the clamp / quantise / interleave packs (RGB48 for the mpv/ffmpeg feeders, BGR24 for postprocess()).
+// Reference: hdrtvnet_torch.py:2239-2296 (preprocess), :2352-2368 (postprocess),
+//            gui_pipeline_worker_feeders.py:193-249 (_tensor_to_rgb48_bytes).
+#pragma once
+#include "common.cuh"
+
+namespace hdrtv {
+
+__device__ __forceinline__ float norm_u8(uint32_t b, bool half_round) {
+  // float(u8) * fp32(1/255): a multiply, not a divide (hdrtvnet_torch.py:2259); fp16 rounds the product once.
+  float f = __fmul_rn(static_cast<float>(b), 0.003921568859368563f);
+  return half_round ? __half2float(__float2half_rn(f)) : f;
+}
+
+// ---- normalise: 16 pixels per thread, 3 x 128-bit loads, planar 128/256-bit stores (needs W % 16 == 0) ----
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_vec16_kernel(const uint8_t* __restrict__ bgr, T* __restrict__ x, int H,
+                                                              int W) {
+  const long g = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;  // group of 16 pixels
+  const long ngroups = static_cast<long>(H) * W / 16;
+  if (g >= ngroups) return;
+  const uint4* src = reinterpret_cast<const uint4*>(bgr) + g * 3;
+  alignas(16) uint4 q[3];
+  q[0] = __ldg(src);
+  q[1] = __ldg(src + 1);
+  q[2] = __ldg(src + 2);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(q);
+  const long plane = static_cast<long>(H) * W;
+  constexpr bool kHalf = sizeof(T) == 2;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // output channel c = R,G,B  <- input byte 2-c of each BGR triple
+    alignas(16) T v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float f = __fmul_rn(static_cast<float>(bytes[3 * i + (2 - c)]), 0.003921568859368563f);
+      if constexpr (kHalf) v[i] = __float2half_rn(f);
+      else v[i] = f;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(x + c * plane + g * 16);
+    const uint4* vs = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(T)) * 16 / 16; ++i) dst[i] = vs[i];
+  }
+}
+template <typename T>
+__global__ void normalize_scalar_kernel(const uint8_t* __restrict__ bgr, T* __restrict__ x, int H, int W) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long plane = static_cast<long>(H) * W;
+  if (i >= plane) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float f = __fmul_rn(static_cast<float>(bgr[3 * i + (2 - c)]), 0.003921568859368563f);
+    if constexpr (sizeof(T) == 2) x[c * plane + i] = __float2half_rn(f);
+    else x[c * plane + i] = f;
+  }
+}
+
+// ---- condition image: antialiased bicubic x0.25 (separable 16-tap Keys cubic, a = -0.5, normalised taps) ----
+// Tap tables are built on the host per resolution: start index + 16 fp32 weights (zero beyond `count`).
+// One block = 8x32 output pixels; the block's u8 window is normalised once into shared memory, a horizontal
+// pass writes row sums, a vertical pass finishes.  fp32 accumulation, one rounding to the output dtype.
+struct CondTaps {
+  const int* xstart;
+  const float* xw;  // [Wc][16]
+  const int* ystart;
+  const float* yw;  // [Hc][16]
+};
+constexpr int kCondTW = 32, kCondTH = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) cond_aa_kernel(const uint8_t* __restrict__ bgr, T* __restrict__ cond, int H, int W,
+                                                      int Hc, int Wc, CondTaps tp, int mode /*0 aa, 1 zero*/) {
+  // window: rows [ys0, ys0+RH), cols [xs0, xs0+RW)
+  constexpr int RW = kCondTW * 4 + 16, RH = kCondTH * 4 + 16;
+  __shared__ float hs[3][RH][kCondTW + 1];
+  const int ox0 = blockIdx.x * kCondTW, oy0 = blockIdx.y * kCondTH;
+  const int tx = threadIdx.x % kCondTW, ty = threadIdx.x / kCondTW;
+  const int ox = ox0 + tx, oy = oy0 + ty;
+  const long cplane = static_cast<long>(Hc) * Wc;
+  if (mode == 1) {
+    if (ox < Wc && oy < Hc)
+      for (int c = 0; c < 3; ++c) {
+        if constexpr (sizeof(T) == 2) cond[c * cplane + static_cast<long>(oy) * Wc + ox] = __float2half_rn(0.f);
+        else cond[c * cplane + static_cast<long>(oy) * Wc + ox] = 0.f;
+      }
+    return;
+  }
+  const int ys0 = tp.ystart[min(oy0, Hc - 1)];
+  // horizontal pass: thread (row r, out col tx) for r = ty, ty+8, ...
+  const int oxc = min(ox, Wc - 1);
+  const int xs = tp.xstart[oxc];
+  float wx[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) wx[k] = tp.xw[oxc * 16 + k];
+  for (int r = ty; r < RH; r += kCondTH) {
+    const int iy = ys0 + r;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (iy < H) {
+      const uint8_t* row = bgr + (static_cast<long>(iy) * W) * 3;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int ix = min(xs + k, W - 1);  // weights beyond `count` are zero
+        const uint8_t* px = row + 3 * ix;
+        a0 = fmaf(wx[k], norm_u8(px[2], sizeof(T) == 2), a0);
+        a1 = fmaf(wx[k], norm_u8(px[1], sizeof(T) == 2), a1);
+        a2 = fmaf(wx[k], norm_u8(px[0], sizeof(T) == 2), a2);
+      }
+    }
+    hs[0][r][tx] = a0;
+    hs[1][r][tx] = a1;
+    hs[2][r][tx] = a2;
+  }
+  __syncthreads();
+  if (ox >= Wc || oy >= Hc) return;
+  const int r0 = tp.ystart[oy] - ys0;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float wy = tp.yw[oy * 16 + k];
+    const int r = min(r0 + k, RH - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] = fmaf(wy, hs[c][r][tx], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if constexpr (sizeof(T) == 2) cond[c * cplane + static_cast<long>(oy) * Wc + ox] = __float2half_rn(acc[c]);
+    else cond[c * cplane + static_cast<long>(oy) * Wc + ox] = acc[c];
+  }
+  (void)RW;
+}
+
+// ---- RGB48 pack: FP32 math, clamp(0,1) -> *65535 (rounded) -> +0.5 (rounded) -> truncate; RGB order, HWC ----
+__device__ __forceinline__ uint32_t q16(float f) {
+  f = fminf(fmaxf(f, 0.f), 1.f);
+  f = __fmul_rn(f, 65535.0f);
+  f = __fadd_rn(f, 0.5f);
+  return static_cast<uint32_t>(f);  // truncating convert (value in [0.5, 65535.5])
+}
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p) {
+  if constexpr (sizeof(T) == 2) return __half2float(*p);
+  else return *p;
+}
+// 8 pixels per thread: planar loads, 3 x 128-bit interleaved stores (needs W*H % 8 == 0).  `lut` (optional,
+// fp16 inputs only) maps the half bit pattern of the clamped value to a code (PQ transfer option).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_rgb48_kernel(const T* __restrict__ src, uint16_t* __restrict__ dst, long npix,
+                                                         const uint16_t* __restrict__ lut) {
+  const long g = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long i0 = g * 8;
+  if (i0 >= npix) return;
+  if (i0 + 8 <= npix) {
+    alignas(16) uint16_t o[24];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      alignas(16) T v[8];
+      if constexpr (sizeof(T) == 2) {
+        *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(src + c * npix + i0));
+      } else {
+        reinterpret_cast<uint4*>(v)[0] = __ldg(reinterpret_cast<const uint4*>(src + c * npix + i0));
+        reinterpret_cast<uint4*>(v)[1] = __ldg(reinterpret_cast<const uint4*>(src + c * npix + i0) + 1);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (lut != nullptr && sizeof(T) == 2) {
+          __half h = __float2half_rn(fminf(fmaxf(ldf(&v[k]), 0.f), 1.f));
+          o[3 * k + c] = lut[__half_as_ushort(h)];
+        } else {
+          o[3 * k + c] = static_cast<uint16_t>(q16(ldf(&v[k])));
+        }
+      }
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst + i0 * 3);
+    const uint4* os = reinterpret_cast<const uint4*>(o);
+    d[0] = os[0];
+    d[1] = os[1];
+    d[2] = os[2];
+  } else {
+    for (long i = i0; i < npix; ++i)
+      for (int c = 0; c < 3; ++c) {
+        if (lut != nullptr && sizeof(T) == 2) {
+          __half h = __float2half_rn(fminf(fmaxf(ldf(src + c * npix + i), 0.f), 1.f));
+          dst[i * 3 + c] = lut[__half_as_ushort(h)];
+        } else {
+          dst[i * 3 + c] = static_cast<uint16_t>(q16(ldf(src + c * npix + i)));
+        }
+      }
+  }
+}
+
+// ---- BGR24 pack: arithmetic IN THE TENSOR'S DTYPE (half: each of mul/add rounds to half), truncate, RGB->BGR ----
+template <typename T>
+__device__ __forceinline__ uint32_t q8(T v) {
+  if constexpr (sizeof(T) == 2) {
+    __half h = __hmin(__hmax(v, __float2half_rn(0.f)), __float2half_rn(1.f));
+    h = __hmul(h, __float2half_rn(255.f));
+    h = __hadd(h, __float2half_rn(0.5f));
+    return static_cast<uint32_t>(__half2float(h));
+  } else {
+    float f = fminf(fmaxf(v, 0.f), 1.f);
+    f = __fmul_rn(f, 255.f);
+    f = __fadd_rn(f, 0.5f);
+    return static_cast<uint32_t>(f);
+  }
+}
+// 4 pixels per thread -> 12 bytes = 3 x 32-bit stores (needs npix % 4 == 0 for the vector body).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_bgr24_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, long npix) {
+  const long g = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long i0 = g * 4;
+  if (i0 >= npix) return;
+  if (i0 + 4 <= npix) {
+    alignas(4) uint8_t o[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[3 * k + (2 - c)] = static_cast<uint8_t>(q8<T>(src[c * npix + i0 + k]));
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + i0 * 3);
+    const uint32_t* os = reinterpret_cast<const uint32_t*>(o);
+    d[0] = os[0];
+    d[1] = os[1];
+    d[2] = os[2];
+  } else {
+    for (long i = i0; i < npix; ++i)
+      for (int c = 0; c < 3; ++c) dst[i * 3 + (2 - c)] = static_cast<uint8_t>(q8<T>(src[c * npix + i]));
+  }
+}
+
+// ---- planar fp16 (3,H,W) -> P8 single chunk [R,G,B,0,0,0,0,0] ----
+__global__ void planar_to_p8_kernel(const __half* __restrict__ src, P8 dst, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const long plane = static_cast<long>(H) * W, o = static_cast<long>(y) * W + x;
+  alignas(16) __half v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = __float2half_rn(0.f);
+  v[0] = src[o];
+  v[1] = src[plane + o];
+  v[2] = src[2 * plane + o];
+  reinterpret_cast<uint4*>(dst.base)[dst.entry(y, 0, x)] = *reinterpret_cast<const uint4*>(v);
+}
+
+// debug: P8 -> planar fp32 (C,H,W)
+__global__ void p8_to_planar_f32_kernel(P8 src, int j0, int C, float* dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= src.W) return;
+  for (int c = 0; c < C; ++c) {
+    const __half* e = src.base + src.entry(y, j0 + c / 8, x) * 8;
+    dst[(static_cast<long>(c) * src.H + y) * src.W + x] = __half2float(e[c % 8]);
+  }
+}
+
+}  // namespace hdrtv

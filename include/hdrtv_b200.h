@@ -1,0 +1,84 @@
+/* hdrtv_b200.h — C ABI of the B200-native HDRTVNet++ per-frame SDR->HDR engine.
+ *
+ * The reference (DanHelmy/hdr-realtime-video-pipeline) has NO native/FFI boundary of its own: its boundary is the
+ * Python class HDRTVNetTorch / HDRTVNetTensorRT (src/models/hdrtvnet_torch.py:1513, :8164).  Each entry point below
+ * names the reference method whose device work it replaces; the Python mirror of that class
+ * (hdr_realtime_video_pipeline_b200/backend.py) binds these symbols with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative code, never throws;
+ * no hidden synchronisation — work is enqueued on the caller's stream (a cudaStream_t passed as void*);
+ * all tensor pointers are caller-owned device (or mapped pinned host) memory; the engine owns only its workspace.
+ */
+#ifndef HDRTV_B200_H
+#define HDRTV_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hdrtv_ctx hdrtv_t;
+
+enum { HDRTV_FP32 = 0, HDRTV_FP16 = 1 };               /* arithmetic/storage type of x, cond, out tensors        */
+enum { HDRTV_COND_BICUBIC_AA = 0, HDRTV_COND_ZERO = 1 }; /* hdrtvnet_torch.py:2265-2294                           */
+enum { HDRTV_TRANSFER_IDENTITY = 0, HDRTV_TRANSFER_LUT = 1 };
+
+typedef struct {
+  int device;    /* CUDA ordinal                                                                                   */
+  int precision; /* HDRTV_FP32 (CUDA-core path, <=1e-4 vs reference fp32) | HDRTV_FP16 (tcgen05 path, <=2e-3)      */
+} hdrtv_config;
+
+typedef struct {
+  const char* name;   /* state-dict key after "module." stripping (hdrtvnet_torch.py:2154-2157), e.g. "LE.HR_conv1.weight" */
+  const float* data;  /* host, fp32, contiguous                                                                     */
+  int ndim;
+  int64_t shape[4];
+} hdrtv_tensor_desc;
+
+/* HDRTVNetTorch.__init__ / _load_model (hdrtvnet_torch.py:1532-1673, 2044-2169): create a context on a device,   */
+/* then hand it the Ensemble_AGCM_LE state-dict (264 tensors); weights are repacked once into kernel-native layouts. */
+int hdrtv_create(const hdrtv_config* cfg, hdrtv_t** out);
+void hdrtv_destroy(hdrtv_t* h);
+int hdrtv_set_weights(hdrtv_t* h, const hdrtv_tensor_desc* tensors, int n);
+
+/* HDRTVNetTorch._ensure_buffers (hdrtvnet_torch.py:2198-2233): (re)allocate the per-resolution workspace.          */
+/* Called implicitly by preprocess/infer; returns bytes held via hdrtv_workspace_bytes.                              */
+int hdrtv_prepare(hdrtv_t* h, int height, int width);
+size_t hdrtv_workspace_bytes(const hdrtv_t* h);
+
+/* HDRTVNetTorch.preprocess (hdrtvnet_torch.py:2239-2296): bgr = uint8 HxWx3 BGR on the device; x_out = (1,3,H,W)   */
+/* RGB planar, cond_out = (1,3,H/4,W/4), both of the context's precision.                                           */
+int hdrtv_preprocess(hdrtv_t* h, const uint8_t* bgr, int height, int width, void* x_out, void* cond_out, int cond_mode,
+                     void* stream);
+
+/* HDRTVNetTorch.infer / Ensemble_AGCM_LE.forward (hdrtvnet_torch.py:2302-2346, Ensemble_AGCM_LE_arch.py:889-897;  */
+/* TensorRT variant :8992-9106): x, cond as produced by preprocess; out, agcm_out = (1,3,H,W) planar.               */
+int hdrtv_infer(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
+                void* stream);
+
+/* _tensor_to_rgb48_bytes (gui_pipeline_worker_feeders.py:193-249): (1,3,H,W) planar of `dtype` -> uint16 HxWx3 RGB */
+/* (rgb48le), FP32 clamp*65535+0.5 truncate.  dst may be device memory or a mapped pinned ring slot.                */
+/* transfer = HDRTV_TRANSFER_LUT applies a 15361-entry code table (half bit pattern of the clamped value -> code).  */
+int hdrtv_pack_rgb48(hdrtv_t* h, const void* src, int dtype, int height, int width, uint16_t* dst, int transfer,
+                     void* stream);
+int hdrtv_set_transfer_lut(hdrtv_t* h, const uint16_t* lut_host, int n);
+
+/* HDRTVNetTorch.postprocess (hdrtvnet_torch.py:2352-2368): planar -> uint8 HxWx3 BGR, arithmetic in `dtype`.       */
+int hdrtv_pack_bgr24(hdrtv_t* h, const void* src, int dtype, int height, int width, uint8_t* dst, void* stream);
+
+/* Introspection used by tests, smoke() and bench.py.                                                               */
+const char* hdrtv_last_error(const hdrtv_t* h);
+long hdrtv_launch_count(const hdrtv_t* h);               /* kernels launched by this context so far                 */
+int hdrtv_debug_tensor_count(const hdrtv_t* h);
+int hdrtv_debug_tensor_info(const hdrtv_t* h, int idx, char* name, int name_cap, int* c, int* height, int* width);
+int hdrtv_debug_tensor_read(hdrtv_t* h, int idx, float* dst_host); /* (C,H,W) fp32; synchronises                    */
+/* One convolution through both paths on random data: returns max |tcgen05(fp16) - cuda-core(fp32)| in *max_abs.   */
+int hdrtv_conv_selftest(hdrtv_t* h, int kind, int cin, int cout, int height, int width, int flags, float* max_abs,
+                        float* ref_max);
+const char* hdrtv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDRTV_B200_H */
