@@ -1,0 +1,156 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares, host logic of the
+drop-in class, frame sharding incl. a world_size-2 gloo run, synthetic-frame determinism."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+
+import hdr_realtime_video_pipeline_b200 as hb
+from hdr_realtime_video_pipeline_b200 import _native, sharding
+from hdr_realtime_video_pipeline_b200 import build as hbuild
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    hbuild.build()
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "hdrtv_b200.h")).read()
+    declared = set(re.findall(r"\b(hdrtv_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hdrtv_t"}
+    assert len(declared) >= 15
+    lib = _native.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hdrtv_b200.h but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in lib.hdrtv_version()
+
+
+def test_library_contains_blackwell_sass():
+    """tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, cp.async.bulk -> UBLKCP (B200_PROFILING.md)."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16" not in sass          # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    w = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hb.HDRTVNetB200(w, device="auto", warmup_passes=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hb.HDRTVNetB200(w, device="cpu", warmup_passes=0)
+    with pytest.raises(RuntimeError):
+        hb.RGB48Packer()
+
+
+def test_argument_validation_matches_reference():
+    w = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
+    with pytest.raises(ValueError, match="device must be one of"):          # hdrtvnet_torch.py:1690
+        hb.HDRTVNetB200(w, device="tpu", warmup_passes=0)
+    with pytest.raises(ValueError, match="precision must be one of"):       # hdrtvnet_torch.py:1694-1695
+        hb.HDRTVNetB200(w, precision="bf16", warmup_passes=0)
+
+
+def test_state_dict_loading_variants(tmp_path, weights_hr):
+    state, arch = hb.load_state_dict_any(os.path.join(REPO, "tests", "golden", "weights_hr.npz"))
+    assert len(state) == 264 and arch == {}
+    assert sum(v.size for v in state.values()) == 591158                     # 591 158 parameters
+    # torch checkpoint, module.-prefixed, wrapped as a source checkpoint with architecture metadata
+    wrapped = {"state_dict": {"module." + k: torch.from_numpy(v) for k, v in weights_hr.items()},
+               "architecture": {"classifier": "color_condition", "le_arch": None}}
+    p = tmp_path / "ckpt.pt"
+    torch.save(wrapped, p)
+    state2, arch2 = hb.load_state_dict_any(str(p))
+    assert set(state2) == set(state) and arch2["classifier"] == "color_condition"
+    assert np.array_equal(state2["LE.HR_conv1.weight"], state["LE.HR_conv1.weight"])
+    with pytest.raises(FileNotFoundError):
+        hb.load_state_dict_any(str(tmp_path / "missing.pt"))
+
+
+def test_frame_chunks_tile_the_clip():
+    for n, g in ((2400, 8), (2400, 4), (2400, 2), (17, 4), (3, 8), (0, 2)):
+        chunks = [hb.frame_chunk(n, r, g) for r in range(g)]
+        assert chunks[0][0] == 0 and chunks[-1][1] == n
+        assert all(chunks[i][1] == chunks[i + 1][0] for i in range(g - 1))
+        sizes = [b - a for a, b in chunks]
+        assert max(sizes) - min(sizes) <= 1
+    assert hb.frame_chunk(2400, 3, 8) == (900, 1200)
+    with pytest.raises(ValueError):
+        hb.frame_chunk(10, 2, 2)
+
+
+def test_descriptor_merge_and_checksum():
+    a = np.arange(24, dtype=np.uint16).reshape(2, 4, 3)
+    b = a.copy()
+    b[0, 0, 0], b[0, 0, 1] = b[0, 0, 1], b[0, 0, 0]
+    assert sharding.frame_checksum(a) != sharding.frame_checksum(b)          # order-sensitive
+    recs = [{"first_frame": 2, "n_frames": 2, "descriptors": [(2, 7), (3, 8)]},
+            {"first_frame": 0, "n_frames": 2, "descriptors": [(0, 5), (1, 6)]}]
+    assert sharding.merge_descriptors(recs) == [(0, 5), (1, 6), (2, 7), (3, 8)]
+    with pytest.raises(ValueError):
+        sharding.merge_descriptors([recs[0], {"first_frame": 5, "n_frames": 1, "descriptors": [(5, 1)]}])
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {repo!r})
+import torch.distributed as dist
+from hdr_realtime_video_pipeline_b200 import sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+first, last = sharding.frame_chunk(11, rank, world)
+rec = dict(rank=rank, first_frame=first, n_frames=last - first, elapsed_s=0.1 * (rank + 1),
+           descriptors=[(i, i * i) for i in range(first, last)])
+recs = sharding.gather_run_records(rec)
+merged = sharding.merge_descriptors(recs)
+assert [d[0] for d in merged] == list(range(11)), merged
+assert max(r["elapsed_s"] for r in recs) == 0.1 * world
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world_size_2_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(repo=REPO))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_synth_frames_deterministic_and_typed():
+    for i in range(4):
+        a, b = hb.synth_frame(i, 36, 52), hb.synth_frame(i, 36, 52)
+        assert a.dtype == np.uint8 and a.shape == (36, 52, 3) and a.flags["C_CONTIGUOUS"]
+        assert np.array_equal(a, b)
+    assert hb.synth_frame(2, 8, 8).max() == 0                    # class C: the reference's zero frame
+    assert (hb.synth_frame(3, 64, 64) == 255).mean() > 0.9       # class D: near-white
+    assert [i for i, _ in hb.synth_clip(3, 8, 8, first_frame=5)] == [5, 6, 7]
+
+
+def test_pq_code_table_matches_oracle_formula():
+    from oracle import hdrtvnet_oracle as O
+    lut = hb.pq_code_table(1000.0)
+    assert lut.shape == (0x3C01,) and lut[0] == 0
+    x = np.arange(0x3C01, dtype=np.uint16).view(np.float16).astype(np.float32)
+    ref = O.pack_rgb48_pq(np.stack([x, x, x])[None, :, None, :], 1000.0)[0, :, 0]
+    assert np.array_equal(lut, ref)
+    assert abs(int(lut[-1]) - round(0.7518 * 65535)) < 40        # PQ(1000 nit) ~ 0.752
