@@ -164,6 +164,22 @@ class RGB48Packer:
         src.record_stream(self.stream)
         return PinnedFrame(slot, ready)
 
+    def pack_device(self, tensor, dst_u16: torch.Tensor, stream=None):
+        """Pack into a caller-owned device (or mapped pinned) uint16 (H,W,3) tensor on `stream` (default: the
+        current stream); no host copy, no event.  Used by device-resident pipelines and the benchmark."""
+        prepared = tensor[0] if isinstance(tensor, (tuple, list)) else tensor
+        src = prepared.contiguous()
+        h, w = int(src.shape[-2]), int(src.shape[-1])
+        dt = _native.FP16 if src.dtype == torch.float16 else _native.FP32
+        tr = _native.TRANSFER_LUT if self.transfer == "pq1000" else _native.TRANSFER_IDENTITY
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _native.check(self._lib.hdrtv_pack_rgb48(self._handle, src.data_ptr(), dt, h, w, dst_u16.data_ptr(), tr,
+                                                 C.c_void_p(st.cuda_stream)), self._handle, "hdrtv_pack_rgb48")
+        return dst_u16
+
+    def launch_count(self) -> int:
+        return int(self._lib.hdrtv_launch_count(self._handle))
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
             self._lib.hdrtv_destroy(self._handle)

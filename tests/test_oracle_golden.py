@@ -111,3 +111,21 @@ def test_primitives_small_cases():
     assert a.shape == (3, 3, 5) and a[0, 0, 0] == 0.0
     b = O.align_to(np.ones((1, 2, 2), np.float32), 3, 4)                             # replicate pad
     assert b.shape == (1, 3, 4) and b.min() == 1.0
+
+
+def test_torch_port_matches_reference_and_numpy_oracle(weights_hr):
+    """oracle/torch_port.py is what bench.py times as the CPU baseline; pin it too."""
+    import torch
+    from oracle import torch_port as TP
+    g = load_golden("net_hr_ramps_72x100.npz")
+    sd = TP.to_torch_state(weights_hr)
+    x, cond = TP.preprocess(g["frame"])
+    out, agcm_out = TP.infer(sd, x, cond)
+    assert np.abs(out.numpy() - g["out"]).max() <= 2e-5
+    assert np.abs(agcm_out.numpy() - g["agcm_out"]).max() <= 2e-5
+    assert np.abs(TP.process(sd, g["frame"]).astype(int) - g["bgr24"].astype(int)).max() <= 1
+    assert np.abs(TP.process_rgb48(sd, g["frame"]).astype(int) - g["rgb48"].astype(int)).max() <= 3
+    xo, co = O.preprocess(g["frame"], np.float32)
+    oo, _ = O.infer(weights_hr, xo, co)
+    assert np.abs(out.numpy() - oo).max() <= 5e-5
+    torch.set_num_threads(torch.get_num_threads())
