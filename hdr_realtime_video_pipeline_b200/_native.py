@@ -40,6 +40,8 @@ _SIGNATURES = {
     "hdrtv_debug_tensor_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hdrtv_debug_tensor_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hdrtv_conv_selftest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "hdrtv_time_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_float), C.c_int, C.c_char_p, C.c_int, C.c_void_p]),
     "hdrtv_version": (C.c_char_p, []),
 }
 

@@ -340,6 +340,19 @@ class HDRTVNetB200:
             out[name.value.decode()] = arr
         return out
 
+    def time_plan(self, input_cond):
+        """[(launch name, ms)] of one fp16 infer, CUDA events between launches."""
+        tensor, cond = input_cond
+        h, w = int(tensor.shape[2]), int(tensor.shape[3])
+        self._ensure_buffers(h, w)
+        ms = (C.c_float * 256)()
+        names = C.create_string_buffer(32768)
+        n = self._lib.hdrtv_time_plan(self._handle, tensor.data_ptr(), cond.data_ptr(), h, w, self._gpu_out.data_ptr(),
+                                      self._gpu_agcm.data_ptr(), ms, 256, names, 32768, self._stream())
+        if n < 0:
+            raise RuntimeError("hdrtv_time_plan failed: " + _native.last_error(self._handle))
+        return list(zip(names.value.decode().strip().split("\n"), [float(ms[i]) for i in range(n)]))
+
     def conv_selftest(self, kind, cin, cout, h, w, flags=0):
         mx, ref = C.c_float(), C.c_float()
         _native.check(self._lib.hdrtv_conv_selftest(self._handle, kind, cin, cout, h, w, flags, C.byref(mx), C.byref(ref)),

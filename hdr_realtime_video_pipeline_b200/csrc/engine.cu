@@ -274,13 +274,25 @@ static P8 make_p8(Ctx* c, int C, int H, int Wd, bool parity) {
   return t;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+// One balanced wave: as many row bands as there are resident CTA slots (148 SMs x occupancy), so that no CTA
+// waits for a second wave and every CTA walks (almost) the same number of rows.
 static void choose_grid(ConvLaunch& L, int strips) {
   ConvParams& p = L.p;
-  const int want_bands = std::max(1, (148 * 3 + strips - 1) / strips);
-  int band = std::max(4, (p.Ho + want_bands - 1) / want_bands);
+  const int z = p.xmul == 2 ? 2 : 1;
+  const int tmem_cols = std::max(32, 2 * L.N);
+  int occ = static_cast<int>((227 * 1024) / (L.smem + 1024));
+  occ = std::max(1, std::min(occ, std::min(512 / tmem_cols, 8)));
+  const int slots = 148 * occ * env_int("HDRTV_WAVES", 1);
+  int nb = std::max(1, slots / (strips * z));
+  int band = (p.Ho + nb - 1) / nb;
+  band = std::max(band, env_int("HDRTV_MIN_BAND", 4));
   band = std::min(band, p.Ho);
   p.band = band;
-  L.grid = dim3(strips, (p.Ho + band - 1) / band, p.xmul == 2 ? 2 : 1);
+  L.grid = dim3(strips, (p.Ho + band - 1) / band, z);
 }
 
 struct Epi {
@@ -319,7 +331,7 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   const size_t budget = 200 * 1024;
   const size_t fixed = 256 + ((p.w_bytes + 127) & ~127);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
-  ring = std::min(ring, p.stride == 2 ? 6 : 6);
+  ring = std::min(ring, env_int("HDRTV_RING_MAX", 6));
   if (ring < min_ring) ring = min_ring;
   if (ring > kMaxRing) ring = kMaxRing;
   p.ring = ring;
@@ -975,21 +987,34 @@ static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float
   return r;
 }
 
-static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __half* agcm_out, cudaStream_t s) {
+static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __half* agcm_out, cudaStream_t s,
+                    std::vector<cudaEvent_t>* evs = nullptr) {
   const int H = c->H, Wd = c->W;
+  auto mark = [&]() {
+    if (!evs) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    evs->push_back(e);
+  };
+  mark();
   planar_to_p8_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(x, c->xP8, H, Wd);
   CK(c, cudaGetLastError());
   ++c->launches;
+  mark();
   if (run_classifier(c, cond, true, s)) return -1;
+  mark();
   for (ConvLaunch& L : c->plan_agcm) {
     if (L.mode == STORE_PLANAR) L.p.planar = agcm_out;
     CK(c, launch_conv(L, s));
     ++c->launches;
+    mark();
   }
   for (ConvLaunch& L : c->plan_le) {
     if (L.mode == STORE_PLANAR) L.p.planar = out;
     CK(c, launch_conv(L, s));
     ++c->launches;
+    mark();
   }
   return 0;
 }
@@ -1149,6 +1174,26 @@ int hdrtv_infer(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void
   }
 }
 
+// Per-launch device times of one fp16 infer (CUDA events between launches).  names: '\n'-separated.
+int hdrtv_time_plan(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* out, void* agcm_out, float* ms,
+                    int cap, char* names, int names_cap, void* stream) {
+  if (!c || c->precision != HDRTV_FP16) return fail(c, "hdrtv_time_plan: fp16 context required");
+  if (hdrtv_prepare(c, H, Wd)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> evs;
+  if (run_fp16(c, static_cast<const __half*>(x), static_cast<const __half*>(cond), static_cast<__half*>(out),
+               static_cast<__half*>(agcm_out), s, &evs)) return -1;
+  CK(c, cudaStreamSynchronize(s));
+  std::string nm = "planar_to_p8\nclassifier+head\n";
+  for (auto& L : c->plan_agcm) nm += L.name + " N" + std::to_string(L.N) + " grid" + std::to_string(L.grid.x) + "x" + std::to_string(L.grid.y) + "x" + std::to_string(L.grid.z) + " ring" + std::to_string(L.p.ring) + " smem" + std::to_string(L.smem) + "\n";
+  for (auto& L : c->plan_le) nm += L.name + " N" + std::to_string(L.N) + " grid" + std::to_string(L.grid.x) + "x" + std::to_string(L.grid.y) + "x" + std::to_string(L.grid.z) + " ring" + std::to_string(L.p.ring) + " smem" + std::to_string(L.smem) + "\n";
+  snprintf(names, names_cap, "%s", nm.c_str());
+  int n = 0;
+  for (size_t i = 0; i + 1 < evs.size() && n < cap; ++i, ++n) cudaEventElapsedTime(&ms[n], evs[i], evs[i + 1]);
+  for (auto e : evs) cudaEventDestroy(e);
+  return n;
+}
+
 int hdrtv_set_transfer_lut(hdrtv_t* c, const uint16_t* lut, int n) {
   if (!c || !lut || n != 0x3C01) return fail(c, "hdrtv_set_transfer_lut: need 15361 entries (half patterns 0x0000..0x3C00)");
   if (!c->d_lut && cudaMalloc(&c->d_lut, 0x3C01 * sizeof(uint16_t)) != cudaSuccess) return fail(c, "lut alloc");
@@ -1166,8 +1211,9 @@ int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint
     if (!c->d_lut || dtype != HDRTV_FP16) return fail(c, "hdrtv_pack_rgb48: LUT transfer needs fp16 input and a table");
     lut = c->d_lut;
   }
-  if (dtype == HDRTV_FP16) pack_rgb48_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix, lut);
-  else pack_rgb48_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix, lut);
+  const int vec_ok = (npix % 8 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  if (dtype == HDRTV_FP16) pack_rgb48_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix, lut, vec_ok);
+  else pack_rgb48_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix, lut, vec_ok);
   CK(c, cudaGetLastError());
   ++c->launches;
   return 0;
@@ -1178,8 +1224,9 @@ int hdrtv_pack_bgr24(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long npix = static_cast<long>(H) * Wd;
   const unsigned blocks = static_cast<unsigned>(((npix + 3) / 4 + 255) / 256);
-  if (dtype == HDRTV_FP16) pack_bgr24_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix);
-  else pack_bgr24_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix);
+  const int vec_ok = (reinterpret_cast<uintptr_t>(dst) % 4 == 0);
+  if (dtype == HDRTV_FP16) pack_bgr24_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix, vec_ok);
+  else pack_bgr24_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix, vec_ok);
   CK(c, cudaGetLastError());
   ++c->launches;
   return 0;

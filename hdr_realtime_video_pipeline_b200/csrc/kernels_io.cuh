@@ -145,11 +145,11 @@ __device__ __forceinline__ float ldf(const T* p) {
 // fp16 inputs only) maps the half bit pattern of the clamped value to a code (PQ transfer option).
 template <typename T>
 __global__ void __launch_bounds__(256) pack_rgb48_kernel(const T* __restrict__ src, uint16_t* __restrict__ dst, long npix,
-                                                         const uint16_t* __restrict__ lut) {
+                                                         const uint16_t* __restrict__ lut, int vec_ok) {
   const long g = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long i0 = g * 8;
   if (i0 >= npix) return;
-  if (i0 + 8 <= npix) {
+  if (vec_ok && i0 + 8 <= npix) {
     alignas(16) uint16_t o[24];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(256) pack_rgb48_kernel(const T* __restrict__ s
     d[1] = os[1];
     d[2] = os[2];
   } else {
-    for (long i = i0; i < npix; ++i)
+    const long i1 = i0 + 8 < npix ? i0 + 8 : npix;
+    for (long i = i0; i < i1; ++i)
       for (int c = 0; c < 3; ++c) {
         if (lut != nullptr && sizeof(T) == 2) {
           __half h = __float2half_rn(fminf(fmaxf(ldf(src + c * npix + i), 0.f), 1.f));
@@ -205,11 +206,12 @@ __device__ __forceinline__ uint32_t q8(T v) {
 }
 // 4 pixels per thread -> 12 bytes = 3 x 32-bit stores (needs npix % 4 == 0 for the vector body).
 template <typename T>
-__global__ void __launch_bounds__(256) pack_bgr24_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, long npix) {
+__global__ void __launch_bounds__(256) pack_bgr24_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, long npix,
+                                                         int vec_ok) {
   const long g = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long i0 = g * 4;
   if (i0 >= npix) return;
-  if (i0 + 4 <= npix) {
+  if (vec_ok && i0 + 4 <= npix) {
     alignas(4) uint8_t o[12];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(256) pack_bgr24_kernel(const T* __restrict__ s
     d[1] = os[1];
     d[2] = os[2];
   } else {
-    for (long i = i0; i < npix; ++i)
+    const long i1 = i0 + 4 < npix ? i0 + 4 : npix;
+    for (long i = i0; i < i1; ++i)
       for (int c = 0; c < 3; ++c) dst[i * 3 + (2 - c)] = static_cast<uint8_t>(q8<T>(src[c * npix + i]));
   }
 }

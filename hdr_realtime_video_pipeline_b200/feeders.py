@@ -88,6 +88,10 @@ class RGB48Packer:
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA device not available; the B200 pack has no CPU fallback.")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RGB48Packer needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _native.load()
         self._handle = C.c_void_p()
         cfg = _native.Config(self.device.index, _native.FP16)

@@ -76,6 +76,9 @@ int hdrtv_debug_tensor_read(hdrtv_t* h, int idx, float* dst_host); /* (C,H,W) fp
 /* One convolution through both paths on random data: returns max |tcgen05(fp16) - cuda-core(fp32)| in *max_abs.   */
 int hdrtv_conv_selftest(hdrtv_t* h, int kind, int cin, int cout, int height, int width, int flags, float* max_abs,
                         float* ref_max);
+/* Per-launch device times (ms) of one FP16 hdrtv_infer, CUDA events between launches; returns the count.          */
+int hdrtv_time_plan(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
+                    float* ms, int cap, char* names, int names_cap, void* stream);
 const char* hdrtv_version(void);
 
 #ifdef __cplusplus
