@@ -7,11 +7,15 @@
 // output row (128 pixels x N output channels, fp32) lives in TMEM, double-buffered so that the epilogue warps
 // drain row t while the single MMA-issuing thread already runs row t+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+// The bias is added by the tensor core too: one extra K=16 step multiplies a constant [1,1,0,..] operand with
+// [bias_hi, bias_lo, 0,..] (fp16 hi/lo split, ~22-bit bias), so the epilogue has no per-channel loads.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 = epilogue:
+// two warps per TMEM lane quadrant, each draining one half of the N columns.  Residual / SFT operands of a row
+// are requested BEFORE the wait on the accumulator so their HBM latency hides behind the MMAs.
 //
 // Replaces the cuDNN conv2d calls of the reference's eager path (Condition_arch.py:571-583,
-// HDRUNet3T1_arch.py:160-205, arch_util.py:68-95) with bias / activation / residual / SFT / PixelShuffle fused
-// into the epilogue.
+// HDRUNet3T1_arch.py:160-205, arch_util.py:68-95) with bias / activation / residual / SFT / PixelShuffle fused.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -24,7 +28,8 @@ constexpr int kPlaneBytes = kPlaneEntries * 16;    // 2176
 constexpr int kMaxSteps = 40;
 constexpr int kMaxCopies = 16;
 constexpr int kMaxRing = 8;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;
+constexpr int kSmemHeader = 256 + kPlaneBytes + 128;   // barriers + constant "ones" operand (bias step)
 
 enum StoreMode : int { STORE_P8 = 0, STORE_PS = 1, STORE_PLANAR = 2 };
 
@@ -48,13 +53,12 @@ struct ConvParams {
   int n_copies, copy_bytes;
   ConvCopy copies[kMaxCopies];
   int slot_bytes, ring;
-  int n_steps;
+  int n_steps;         // tap steps; the weight buffer holds n_steps + 1 (the last one is the bias step)
   ConvStep steps[kMaxSteps];
   const uint4* wpk;
   int w_bytes;
-  const float* bias;
   int Ho, Wo, band;
-  int act;
+  float slope;         // activation as max(v, slope*v): 1 = none, 0 = ReLU, 0.1 = LeakyReLU(0.1)
   int has_res, has_res2, has_sft, has_raw;
   P8 res, res2, sft, out, raw;
   __half* planar;
@@ -62,12 +66,6 @@ struct ConvParams {
   int planar_W;
   int* err;
 };
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_LRELU) return v >= 0.f ? v : 0.1f * v;
-  return v;
-}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -86,33 +84,23 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
-// Finish one 8-channel chunk of one output pixel: residual add, raw store, SFT modulation, store.
-__device__ __forceinline__ void finish_chunk(const ConvParams& p, float* val, int y, int j, int x, int sft_chunks) {
-  if (p.has_res) {
-    float r[8];
-    unpack8(reinterpret_cast<const uint4*>(p.res.base)[p.res.entry(y, j, x)], r);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) val[k] += r[k];
+// Per-thread view of a P8 tensor at a fixed pixel column: entry(y, j) = (y+1)*row_entries + j*Wp + xoff.
+struct ColRef {
+  uint4* base;
+  long row_entries;
+  long xoff;
+  int Wp;
+  __device__ __forceinline__ void init(const P8& t, int x) {
+    base = reinterpret_cast<uint4*>(t.base);
+    row_entries = t.row_entries();
+    Wp = t.Wp;
+    xoff = t.parity ? static_cast<long>(x & 1) * (t.Wp >> 1) + ((x >> 1) + 1) : static_cast<long>(x + 1);
   }
-  if (p.has_res2) {
-    float r[8];
-    unpack8(reinterpret_cast<const uint4*>(p.res2.base)[p.res2.entry(y, j, x)], r);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) val[k] += r[k];
-  }
-  if (p.has_raw) reinterpret_cast<uint4*>(p.raw.base)[p.raw.entry(y, j, x)] = pack8(val);
-  if (p.has_sft) {
-    float s[8], t[8];
-    unpack8(reinterpret_cast<const uint4*>(p.sft.base)[p.sft.entry(y, j, x)], s);
-    unpack8(reinterpret_cast<const uint4*>(p.sft.base)[p.sft.entry(y, j + sft_chunks, x)], t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], s[k], val[k]) + t[k];   // x*(scale+1)+shift
-  }
-  reinterpret_cast<uint4*>(p.out.base)[p.out.entry(y, j, x)] = pack8(val);
-}
+  __device__ __forceinline__ uint4* at(int y, int j) const { return base + (static_cast<long>(y + 1) * row_entries + static_cast<long>(j) * Wp + xoff); }
+};
 
-template <int N, int MODE>
-__global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_constant__ ConvParams p) {
+template <int N, int MODE, bool AUX>
+__global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
   constexpr uint32_t kTmemCols = (2 * N < 32) ? 32 : 2 * N;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -123,7 +111,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_cons
   auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 2 + i); };
   const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxRing + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
-  uint8_t* wsm = smem + 256;
+  uint8_t* ones = smem + 256;
+  uint8_t* wsm = smem + kSmemHeader;
   uint8_t* ring = wsm + ((p.w_bytes + 127) & ~127);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,10 +128,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);
+      mbar_init(tempty_bar(i), 8);
     }
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kPlaneEntries) {
+    // constant A operand of the bias step: every row = [1, 1, 0, 0, 0, 0, 0, 0]
+    reinterpret_cast<uint4*>(ones)[threadIdx.x - 64] = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
@@ -156,15 +150,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_cons
       mbar_expect_tx(wfull_bar, p.w_bytes);
       bulk_g2s(smem_u32(wsm), p.wpk, p.w_bytes, wfull_bar);
       const uint32_t row_tx = p.n_copies * p.copy_bytes;
+      int slot = 0, ph = 1;
+      const uint4* src = p.in + (static_cast<long>(oy0) * p.stride + p.row_bias) * p.in_row_entries + x0 +
+                         blockIdx.z * p.in_z_entries;
       for (int q = 0; q < nrows_in; ++q) {
-        const int slot = q % p.ring;
-        mbar_wait(empty_bar(slot), ((q / p.ring) & 1) ^ 1, p.err, 1);
+        mbar_wait(empty_bar(slot), ph, p.err, 1);
         mbar_expect_tx(full_bar(slot), row_tx);
-        const uint4* src = p.in + (static_cast<long>(oy0) * p.stride + q + p.row_bias) * p.in_row_entries + x0 +
-                           blockIdx.z * p.in_z_entries;
         const uint32_t dst = smem_u32(ring) + slot * p.slot_bytes;
         for (int c = 0; c < p.n_copies; ++c)
           bulk_g2s(dst + p.copies[c].dst_off, src + p.copies[c].src_off, p.copy_bytes, full_bar(slot));
+        src += p.in_row_entries;
+        if (++slot == p.ring) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -173,7 +169,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_cons
       mbar_wait(wfull_bar, 0, p.err, 2);
       constexpr uint32_t idesc = make_idesc_f16_m128(N);
       const uint32_t ring_base = smem_u32(ring), w_base = smem_u32(wsm);
+      const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
+      const uint64_t bias_desc = make_smem_desc(w_base + p.n_steps * (N * 32), N * 16, 128);
       int waited = -1;
+      int base_slot = 0;           // ring slot of input row t*stride
       for (int t = 0; t < nrows_out; ++t) {
         const int stage = t & 1;
         mbar_wait(tempty_bar(stage), ((t >> 1) & 1) ^ 1, p.err, 3);
@@ -182,98 +181,178 @@ __global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_cons
         for (int s = 0; s < p.n_steps; ++s) {
           const ConvStep st = p.steps[s];
           const int q = t * p.stride + st.row;
+          int slot = base_slot + st.row;
+          if (slot >= p.ring) slot -= p.ring;
           if (q > waited) {
             for (int r = waited + 1; r <= q; ++r) mbar_wait(full_bar(r % p.ring), (r / p.ring) & 1, p.err, 4);
             waited = q;
             tc_fence_after();
           }
-          const uint32_t a_addr = ring_base + (q % p.ring) * p.slot_bytes + st.a_off;
-          const uint64_t adesc = make_smem_desc(a_addr, st.a_lbo, 128);
+          const uint64_t adesc = make_smem_desc(ring_base + slot * p.slot_bytes + st.a_off, st.a_lbo, 128);
           const uint64_t bdesc = make_smem_desc(w_base + s * (N * 32), N * 16, 128);
           tc_mma_f16(d_tmem, adesc, bdesc, idesc, s > 0 ? 1u : 0u);
-          if (st.release) tc_commit(empty_bar(q % p.ring));
+          if (st.release) tc_commit(empty_bar(slot));
         }
+        tc_mma_f16(d_tmem, ones_desc, bias_desc, idesc, 1u);      // + bias
         tc_commit(tfull_bar(stage));
+        base_slot += p.stride;
+        if (base_slot >= p.ring) base_slot -= p.ring;
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int x = p.xmul * (x0 + lg * 32 + lane) + blockIdx.z;
     const bool xin = x < p.Wo;
-    for (int t = 0; t < nrows_out; ++t) {
-      const int stage = t & 1;
-      const int oy = oy0 + t;
-      mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + stage * N;
+    const float slope = p.slope;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
 
-      if constexpr (MODE == STORE_PLANAR) {
-        float v[16];
-        tmem_ld16(taddr, v);
+    if constexpr (MODE == STORE_PLANAR) {
+      ColRef res, raw;
+      if (p.has_res) res.init(p.res, x);
+      if (p.has_raw) raw.init(p.raw, x);
+      for (int t = 0; t < nrows_out; ++t) {
+        const int stage = t & 1, oy = oy0 + t;
+        uint4 r4 = make_uint4(0, 0, 0, 0);
+        if (half == 0 && xin && p.has_res) r4 = *res.at(oy, 0);
+        mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
+        tc_fence_after();
+        float v[8];
+        if (half == 0) tmem_ld_cols<8>(tlane + stage * N, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(stage));
+        if (half == 0 && xin) {
+          float val[8], r[8];
+          unpack8(r4, r);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) val[k] = (k < 3) ? fmaxf(v[k], slope * v[k]) + r[k] : 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = __float2half_rn(val[k]);
+          if (p.has_raw) *raw.at(oy, 0) = pack8(val);
+        }
+      }
+    } else if constexpr (MODE == STORE_PS) {
+      // N = 128 conv channels -> 32 channels at (2*oy+i, 2*x+j); conv channel n = 4*c + 2*i + j.
+      // This warp: conv channels [64*half, 64*half+64) = output chunks 2*half, 2*half+1 of all four sub-pixels.
+      ColRef res[2], sft[2], raw[2], out[2];     // index = sub-pixel column parity j
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        out[j].init(p.out, 2 * x + j);
+        if (p.has_res) res[j].init(p.res, 2 * x + j);
+        if (p.has_sft) sft[j].init(p.sft, 2 * x + j);
+        if (p.has_raw) raw[j].init(p.raw, 2 * x + j);
+      }
+      for (int t = 0; t < nrows_out; ++t) {
+        const int stage = t & 1, oy = oy0 + t;
+        mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
+        tc_fence_after();
+        float v[64];
+        tmem_ld_cols<64>(tlane + stage * N + half * 64, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(stage));
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = fmaxf(v[k], slope * v[k]);
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const int Y = 2 * oy + (sub >> 1), j = sub & 1;
+          if (xin && Y < p.out.H && 2 * x + j < p.out.W) {
+            uint4 r4[2], s4[2], t4[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int ch = 2 * half + c;
+              if (p.has_res) r4[c] = *res[j].at(Y, ch);
+              if (p.has_sft) { s4[c] = *sft[j].at(Y, ch); t4[c] = *sft[j].at(Y, ch + 4); }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int ch = 2 * half + c;
+              float val[8];
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) val[cc] = v[32 * c + 4 * cc + sub];
+              if (p.has_res) {
+                float r[8];
+                unpack8(r4[c], r);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) val[k] += r[k];
+              }
+              if (p.has_raw) *raw[j].at(Y, ch) = pack8(val);
+              if (p.has_sft) {
+                float s[8], tt[8];
+                unpack8(s4[c], s);
+                unpack8(t4[c], tt);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], s[k], val[k]) + tt[k];
+              }
+              *out[j].at(Y, ch) = pack8(val);
+            }
+          }
+        }
+      }
+    } else {
+      constexpr int COLS = N / 2;          // columns drained by this warp
+      constexpr int CH = COLS / 8;         // 8-channel chunks per thread
+      const int j0 = half * CH;
+      ColRef out, res, res2, sft, raw;
+      out.init(p.out, x);
+      if constexpr (AUX) {
+        if (p.has_res) res.init(p.res, x);
+        if (p.has_res2) res2.init(p.res2, x);
+        if (p.has_sft) sft.init(p.sft, x);
+        if (p.has_raw) raw.init(p.raw, x);
+      }
+      for (int t = 0; t < nrows_out; ++t) {
+        const int stage = t & 1, oy = oy0 + t;
+        uint4 r4[AUX ? CH : 1], q4[AUX ? CH : 1], s4[AUX ? CH : 1], t4[AUX ? CH : 1];
+        if constexpr (AUX) {
+          if (xin) {       // request the row's auxiliary operands before waiting for the accumulator
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              if (p.has_res) r4[c] = *res.at(oy, j0 + c);
+              if (p.has_res2) q4[c] = *res2.at(oy, j0 + c);
+              if (p.has_sft) { s4[c] = *sft.at(oy, j0 + c); t4[c] = *sft.at(oy, j0 + c + N / 8); }
+            }
+          }
+        }
+        mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
+        tc_fence_after();
+        float v[COLS];
+        tmem_ld_cols<COLS>(tlane + stage * N + half * COLS, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(stage));
         if (xin) {
-          float val[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) val[k] = (k < 3) ? apply_act(v[k] + __ldg(p.bias + k), p.act) : 0.f;
-          if (p.has_res) {
-            float r[8];
-            unpack8(reinterpret_cast<const uint4*>(p.res.base)[p.res.entry(oy, 0, x)], r);
+          for (int c = 0; c < CH; ++c) {
+            float val[8];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) val[k] += r[k];
-          }
+            for (int k = 0; k < 8; ++k) val[k] = fmaxf(v[c * 8 + k], slope * v[c * 8 + k]);
+            if constexpr (AUX) {
+              if (p.has_res) {
+                float r[8];
+                unpack8(r4[c], r);
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = __float2half_rn(val[k]);
-          if (p.has_raw) reinterpret_cast<uint4*>(p.raw.base)[p.raw.entry(oy, 0, x)] = pack8(val);
-        }
-      } else if constexpr (MODE == STORE_PS) {
-        // N = 128 conv channels -> 32 channels at (2*oy+i, 2*x+j); conv channel n = 4*c + 2*i + j.
-#pragma unroll 1
-        for (int pass = 0; pass < N / 32; ++pass) {
-          float v[32];
-          tmem_ld32(taddr + pass * 32, v);
-          if (pass == N / 32 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(stage));
-          }
+                for (int k = 0; k < 8; ++k) val[k] += r[k];
+              }
+              if (p.has_res2) {
+                float r[8];
+                unpack8(q4[c], r);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = apply_act(v[k] + __ldg(p.bias + pass * 32 + k), p.act);
+                for (int k = 0; k < 8; ++k) val[k] += r[k];
+              }
+              if (p.has_raw) *raw.at(oy, j0 + c) = pack8(val);
+              if (p.has_sft) {
+                float s[8], tt[8];
+                unpack8(s4[c], s);
+                unpack8(t4[c], tt);
 #pragma unroll
-          for (int sub = 0; sub < 4; ++sub) {
-            const int Y = 2 * oy + (sub >> 1), X = 2 * x + (sub & 1);
-            if (xin && Y < p.out.H && X < p.out.W) {
-              float val[8];
-#pragma unroll
-              for (int cc = 0; cc < 8; ++cc) val[cc] = v[4 * cc + sub];
-              finish_chunk(p, val, Y, pass, X, N / 32);
+                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], s[k], val[k]) + tt[k];   // x*(scale+1)+shift
+              }
             }
-          }
-        }
-      } else {
-        constexpr int kCols = (N < 32) ? N : 32;
-#pragma unroll 1
-        for (int pass = 0; pass < N / kCols; ++pass) {
-          float v[kCols];
-          if constexpr (kCols == 16) tmem_ld16(taddr + pass * kCols, v);
-          else tmem_ld32(taddr + pass * kCols, v);
-          if (pass == N / kCols - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(stage));
-          }
-          if (xin) {
-#pragma unroll
-            for (int ch = 0; ch < kCols / 8; ++ch) {
-              const int j = pass * (kCols / 8) + ch;
-              float val[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) val[k] = apply_act(v[ch * 8 + k] + __ldg(p.bias + j * 8 + k), p.act);
-              finish_chunk(p, val, oy, j, x, N / 8);
-            }
+            *out.at(oy, j0 + c) = pack8(val);
           }
         }
       }
@@ -286,7 +365,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_p8_kernel(const __grid_cons
 }
 
 inline size_t conv_smem_bytes(const ConvParams& p) {
-  return 256 + ((p.w_bytes + 127) & ~127) + static_cast<size_t>(p.ring) * p.slot_bytes;
+  return kSmemHeader + ((p.w_bytes + 127) & ~127) + static_cast<size_t>(p.ring) * p.slot_bytes;
 }
 
 }  // namespace hdrtv

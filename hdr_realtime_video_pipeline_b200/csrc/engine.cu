@@ -142,8 +142,16 @@ static void build_input_side(InKind kind, const P8& in, int j0, int kchunks, Con
   }
 }
 
-static std::vector<__half> pack_weights(int N, const std::vector<StepK>& wk, const WeightFn& w) {
-  std::vector<__half> out(static_cast<size_t>(wk.size()) * N * 16, __float2half(0.f));
+// The extra last step carries the bias: (n, k=0) = fp16(b), (n, k=1) = fp16(b - fp16(b)); its A operand is [1,1,0..].
+static std::vector<__half> pack_weights(int N, const std::vector<StepK>& wk, const WeightFn& w,
+                                        const std::function<float(int)>& bias) {
+  std::vector<__half> out(static_cast<size_t>(wk.size() + 1) * N * 16, __float2half(0.f));
+  for (int n = 0; n < N; ++n) {
+    const float b = bias(n);
+    const __half hi = __float2half(b);
+    out[bpack_index(N, static_cast<int>(wk.size()), n, 0)] = hi;
+    out[bpack_index(N, static_cast<int>(wk.size()), n, 1)] = __float2half(b - __half2float(hi));
+  }
   for (size_t s = 0; s < wk.size(); ++s)
     for (int h = 0; h < 2; ++h) {
       const HalfK hk = wk[s][h];
@@ -197,7 +205,6 @@ struct Ctx {
   float* d_fea = nullptr;      // [6]
   float* d_fold32 = nullptr;   // W1f[192] b1f[64] W2f[4096] b2f[64] W3f[192] b3f[3]
   __half* d_agpk[3] = {nullptr, nullptr, nullptr};
-  float* d_agbias[3] = {nullptr, nullptr, nullptr};
   // cond taps
   int *d_xstart = nullptr, *d_ystart = nullptr;
   float *d_xw = nullptr, *d_yw = nullptr;
@@ -211,7 +218,6 @@ struct Ctx {
   uint16_t* d_lut = nullptr;
   // packed static weights (device) by layer name
   std::map<std::string, __half*> wpk;
-  std::map<std::string, float*> bpk;
 };
 
 static int fail(Ctx* c, const std::string& m) {
@@ -305,19 +311,17 @@ struct Epi {
 };
 
 static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int j0,
-                     int kchunks, int N, int mode, const __half* wpk, const float* bias, const P8& out, int Ho, int Wo,
-                     const Epi& e) {
+                     int kchunks, int N, int mode, const __half* wpk, const P8& out, int Ho, int Wo, const Epi& e) {
   ConvLaunch L;
   memset(&L.p, 0, sizeof(L.p));
   std::vector<StepK> wk;
   build_input_side(kind, in, j0, kchunks, L.p, wk);
   ConvParams& p = L.p;
   p.wpk = reinterpret_cast<const uint4*>(wpk);
-  p.w_bytes = p.n_steps * N * 32;
-  p.bias = bias;
+  p.w_bytes = (p.n_steps + 1) * N * 32;
   p.Ho = Ho;
   p.Wo = Wo;
-  p.act = e.act;
+  p.slope = e.act == ACT_RELU ? 0.f : (e.act == ACT_LRELU ? 0.1f : 1.f);
   p.out = out;
   if (e.res) { p.has_res = 1; p.res = *e.res; }
   if (e.res2) { p.has_res2 = 1; p.res2 = *e.res2; }
@@ -329,7 +333,7 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   p.err = c->d_err;
   const int min_ring = p.ks + 1;
   const size_t budget = 200 * 1024;
-  const size_t fixed = 256 + ((p.w_bytes + 127) & ~127);
+  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
   ring = std::min(ring, env_int("HDRTV_RING_MAX", 6));
   if (ring < min_ring) ring = min_ring;
@@ -346,26 +350,27 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   return 0;
 }
 
-template <int N, int MODE>
+template <int N, int MODE, bool AUX>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
-  static size_t configured = 0;
-  if (L.smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<N, MODE, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = 227 * 1024;
+    configured = true;
   }
-  conv_p8_kernel<N, MODE><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
+  conv_p8_kernel<N, MODE, AUX><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
   return cudaGetLastError();
 }
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
-  if (L.mode == STORE_PLANAR) return launch_conv_t<16, STORE_PLANAR>(L, s);
-  if (L.mode == STORE_PS) return launch_conv_t<128, STORE_PS>(L, s);
+  if (L.mode == STORE_PLANAR) return launch_conv_t<16, STORE_PLANAR, false>(L, s);
+  if (L.mode == STORE_PS) return launch_conv_t<128, STORE_PS, true>(L, s);
+  const bool aux = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
   switch (L.N) {
-    case 16: return launch_conv_t<16, STORE_P8>(L, s);
-    case 32: return launch_conv_t<32, STORE_P8>(L, s);
-    case 64: return launch_conv_t<64, STORE_P8>(L, s);
-    case 128: return launch_conv_t<128, STORE_P8>(L, s);
+    case 16: return aux ? launch_conv_t<16, STORE_P8, true>(L, s) : launch_conv_t<16, STORE_P8, false>(L, s);
+    case 32: return aux ? launch_conv_t<32, STORE_P8, true>(L, s) : launch_conv_t<32, STORE_P8, false>(L, s);
+    case 64: return aux ? launch_conv_t<64, STORE_P8, true>(L, s) : launch_conv_t<64, STORE_P8, false>(L, s);
+    case 128: return aux ? cudaErrorInvalidValue : launch_conv_t<128, STORE_P8, false>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -382,12 +387,9 @@ static int pack_layer(Ctx* c, const std::string& key, InKind kind, int kchunks, 
   dummy.Wp = 16;
   dummy.chunks = kchunks;
   build_input_side(kind, dummy, 0, kchunks, tmp, wk);
-  std::vector<__half> pk = pack_weights(N, wk, wf);
-  std::vector<float> b(N, 0.f);
-  for (int n = 0; n < N; ++n) b[n] = bf(n);
+  std::vector<__half> pk = pack_weights(N, wk, wf, bf);
   c->wpk[key] = w_upload(c, pk.data(), pk.size());
-  c->bpk[key] = w_upload(c, b.data(), b.size());
-  if (!c->wpk[key] || !c->bpk[key]) return fail(c, "weight upload failed for " + key);
+  if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
   return 0;
 }
 static std::function<float(int)> bias_fn(Ctx* c, const std::string& name) {
@@ -494,8 +496,7 @@ struct HeadParams {
   const float *w1, *b1, *w2, *b2, *w3, *b3;
   float* fea;
   float* fold32;
-  __half* pk[3];
-  float* pkb[3];
+  __half* pk[3];   // packed B operands of the three folded layers, each followed by its bias step
 };
 __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
   __shared__ float mean5[128];
@@ -531,9 +532,10 @@ __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
   float* b2f = W2f + 4096;
   float* W3f = b2f + 64;
   float* b3f = W3f + 192;
-  // zero the packed buffers' padding first (K padding of layer 1, N padding of layer 3)
-  for (int i = t; i < 64 * 16; i += blockDim.x) p.pk[0][i] = __float2half_rn(0.f);
-  for (int i = t; i < 4 * 16 * 16; i += blockDim.x) p.pk[2][i] = __float2half_rn(0.f);
+  // zero the packed buffers' padding first (K padding of layer 1, N padding of layer 3, the three bias steps)
+  for (int i = t; i < 2 * 64 * 16; i += blockDim.x) p.pk[0][i] = __float2half_rn(0.f);
+  for (int i = t; i < 64 * 16; i += blockDim.x) p.pk[1][4 * 64 * 16 + i] = __float2half_rn(0.f);
+  for (int i = t; i < 5 * 16 * 16; i += blockDim.x) p.pk[2][i] = __float2half_rn(0.f);
   __syncthreads();
   for (int i = t; i < 192; i += blockDim.x) {  // layer 1: [64][3]
     const int n = i / 3, k = i % 3;
@@ -557,12 +559,17 @@ __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
     const float v1 = sc[0][n] * p.b1[n] + sh[0][n], v2 = sc[1][n] * p.b2[n] + sh[1][n];
     b1f[n] = v1;
     b2f[n] = v2;
-    p.pkb[0][n] = v1;
-    p.pkb[1][n] = v2;
-    if (n < 16) {
-      const float v3 = n < 3 ? sc[2][n] * p.b3[n] + sh[2][n] : 0.f;
-      if (n < 3) b3f[n] = v3;
-      p.pkb[2][n] = v3;
+    const __half h1 = __float2half_rn(v1), h2 = __float2half_rn(v2);
+    p.pk[0][bpack_index(64, 1, n, 0)] = h1;
+    p.pk[0][bpack_index(64, 1, n, 1)] = __float2half_rn(v1 - __half2float(h1));
+    p.pk[1][bpack_index(64, 4, n, 0)] = h2;
+    p.pk[1][bpack_index(64, 4, n, 1)] = __float2half_rn(v2 - __half2float(h2));
+    if (n < 3) {
+      const float v3 = sc[2][n] * p.b3[n] + sh[2][n];
+      b3f[n] = v3;
+      const __half h3 = __float2half_rn(v3);
+      p.pk[2][bpack_index(16, 4, n, 0)] = h3;
+      p.pk[2][bpack_index(16, 4, n, 1)] = __float2half_rn(v3 - __half2float(h3));
     }
   }
 }
@@ -642,13 +649,10 @@ static int build_classifier(Ctx* c, int Hc, int Wc) {
   }
   c->d_fea = ws_alloc<float>(c, 8);
   c->d_fold32 = ws_alloc<float>(c, 192 + 64 + 4096 + 64 + 192 + 3 + 5);
-  c->d_agpk[0] = ws_alloc<__half>(c, 64 * 16);
-  c->d_agpk[1] = ws_alloc<__half>(c, 4 * 64 * 16);
-  c->d_agpk[2] = ws_alloc<__half>(c, 4 * 16 * 16);
-  c->d_agbias[0] = ws_alloc<float>(c, 64);
-  c->d_agbias[1] = ws_alloc<float>(c, 64);
-  c->d_agbias[2] = ws_alloc<float>(c, 16);
-  if (!c->d_fea || !c->d_fold32 || !c->d_agpk[2] || !c->d_agbias[2]) return fail(c, "alloc agcm head");
+  c->d_agpk[0] = ws_alloc<__half>(c, 2 * 64 * 16);
+  c->d_agpk[1] = ws_alloc<__half>(c, 5 * 64 * 16);
+  c->d_agpk[2] = ws_alloc<__half>(c, 5 * 16 * 16);
+  if (!c->d_fea || !c->d_fold32 || !c->d_agpk[0] || !c->d_agpk[1] || !c->d_agpk[2]) return fail(c, "alloc agcm head");
   dbg_f32(c, "fea", c->d_fea, 6, 1, 1);
   return 0;
 }
@@ -689,7 +693,6 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     hp.lt[i] = c->wd.at(std::string("AGCM.cond_shift_") + nm[i] + ".weight");
     hp.ltb[i] = c->wd.at(std::string("AGCM.cond_shift_") + nm[i] + ".bias");
     hp.pk[i] = c->d_agpk[i];
-    hp.pkb[i] = c->d_agbias[i];
   }
   hp.w1 = c->wd.at("AGCM.conv_first.weight"); hp.b1 = c->wd.at("AGCM.conv_first.bias");
   hp.w2 = c->wd.at("AGCM.HRconv.weight");     hp.b2 = c->wd.at("AGCM.HRconv.bias");
@@ -739,24 +742,22 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   if (!V0.base || !U1.base) return fail(c, "workspace allocation failed (P8)");
 
   auto wk = [&](const std::string& k) { return c->wpk.at(k); };
-  auto bk = [&](const std::string& k) { return c->bpk.at(k); };
   auto std_conv = [&](std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int cin, int N,
                       int mode, const P8& out, int Ho, int Wo, const Epi& e) {
-    return make_conv(c, plan, name, kind, in, 0, std::max(1, cin / 8), N, mode, wk(name), bk(name), out, Ho, Wo, e);
+    return make_conv(c, plan, name, kind, in, 0, std::max(1, cin / 8), N, mode, wk(name), out, Ho, Wo, e);
   };
   int r = 0;
   Epi relu; relu.act = ACT_RELU;
   Epi lrelu; lrelu.act = ACT_LRELU;
   Epi none;
   // ---- AGCM MLP (weights folded per frame by agcm_head_kernel)
-  r |= make_conv(c, c->plan_agcm, "AGCM.conv_first", IN_NAT1x1_C8, c->xP8, 0, 1, 64, STORE_P8, c->d_agpk[0],
-                 c->d_agbias[0], A1, H, Wd, relu);
-  r |= make_conv(c, c->plan_agcm, "AGCM.HRconv", IN_NAT1x1, A1, 0, 8, 64, STORE_P8, c->d_agpk[1], c->d_agbias[1], A2, H,
-                 Wd, relu);
+  r |= make_conv(c, c->plan_agcm, "AGCM.conv_first", IN_NAT1x1_C8, c->xP8, 0, 1, 64, STORE_P8, c->d_agpk[0], A1, H, Wd,
+                 relu);
+  r |= make_conv(c, c->plan_agcm, "AGCM.HRconv", IN_NAT1x1, A1, 0, 8, 64, STORE_P8, c->d_agpk[1], A2, H, Wd, relu);
   {
     Epi e; e.raw = &agP8; e.planar = reinterpret_cast<__half*>(1);  // planar pointer patched per call (agcm_out)
-    r |= make_conv(c, c->plan_agcm, "AGCM.conv_last", IN_NAT1x1, A2, 0, 8, 16, STORE_PLANAR, c->d_agpk[2],
-                   c->d_agbias[2], agP8, H, Wd, e);
+    r |= make_conv(c, c->plan_agcm, "AGCM.conv_last", IN_NAT1x1, A2, 0, 8, 16, STORE_PLANAR, c->d_agpk[2], agP8, H, Wd,
+                   e);
   }
   auto& L = c->plan_le;
   // ---- LE condition pyramid
@@ -777,10 +778,10 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   r |= std_conv(L, "LE.CondNet4.4", IN_PAR3x3S2, F2, 64, 16, STORE_P8, cond4, H3, W3, none);
   // ---- SFT maps: stage 0 (stacked, LeakyReLU) then one block-diagonal stage 1 per SFT layer
   auto sft_group = [&](const std::string& key, const P8& cond, const P8& S, const char* const* names, int n, int h, int w) {
-    r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), bk(key), S, h, w, lrelu);
+    r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), S, h, w, lrelu);
     for (int i = 0; i < n; ++i) {
       const std::string k1 = std::string(names[i]) + ".stage1";
-      r |= make_conv(c, L, k1, IN_NAT1x1, S, 4 * i, 4, 64, STORE_P8, wk(k1), bk(k1), maps.at(names[i]), h, w, none);
+      r |= make_conv(c, L, k1, IN_NAT1x1, S, 4 * i, 4, 64, STORE_P8, wk(k1), maps.at(names[i]), h, w, none);
     }
   };
   sft_group("sft0.L0", cond1, S0, kSftL0, 2, H, Wd);
@@ -1334,7 +1335,7 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
     if (n >= cout || ci >= cin_real || tap >= ks * ks) return 0.f;
     return hw[(static_cast<size_t>(n) * cin_real + ci) * ks * ks + tap];
   };
-  std::vector<__half> pk = pack_weights(N, wk, wf);
+  std::vector<__half> pk = pack_weights(N, wk, wf, [&](int n) { return n < cout ? hb[n] : 0.f; });
   __half* dpk = ws_alloc<__half>(&t, pk.size());
   cudaMemcpy(dpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
   __half* dplanar = ws_alloc<__half>(&t, static_cast<size_t>(3) * outH * outW);
@@ -1347,7 +1348,7 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
     e.planar = dplanar;
   }
   if (make_conv(&t, plan, "selftest", static_cast<InKind>(kind), in, 0, std::max(1, cin / 8), N,
-                planar ? STORE_PLANAR : (ps ? STORE_PS : STORE_P8), dpk, db, outp, Ho, Wo, e)) { c->err = t.err; r = -1; }
+                planar ? STORE_PLANAR : (ps ? STORE_PS : STORE_P8), dpk, outp, Ho, Wo, e)) { c->err = t.err; r = -1; }
   if (!r) {
     cudaError_t ce = launch_conv(plan[0], 0);
     if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
