@@ -353,6 +353,12 @@ class HDRTVNetB200:
             raise RuntimeError("hdrtv_time_plan failed: " + _native.last_error(self._handle))
         return list(zip(names.value.decode().strip().split("\n"), [float(ms[i]) for i in range(n)]))
 
+    def mma_probe(self, n, layout=0, vary=1, iters=2000, blocks=1, nacc=1):
+        cyc = C.c_float()
+        _native.check(self._lib.hdrtv_mma_probe(self._handle, n, layout, vary, iters, blocks, nacc, C.byref(cyc)), self._handle,
+                      "hdrtv_mma_probe")
+        return float(cyc.value)
+
     def conv_selftest(self, kind, cin, cout, h, w, flags=0):
         mx, ref = C.c_float(), C.c_float()
         _native.check(self._lib.hdrtv_conv_selftest(self._handle, kind, cin, cout, h, w, flags, C.byref(mx), C.byref(ref)),

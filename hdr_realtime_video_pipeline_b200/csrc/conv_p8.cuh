@@ -29,7 +29,7 @@ constexpr int kMaxSteps = 40;
 constexpr int kMaxCopies = 16;
 constexpr int kMaxRing = 8;
 constexpr int kConvThreads = 320;
-constexpr int kSmemHeader = 256 + kPlaneBytes + 128;   // barriers + constant "ones" operand (bias step)
+constexpr int kSmemHeader = 512 + kPlaneBytes + 128;   // barriers, step-descriptor table, constant "ones" operand (bias step)
 
 enum StoreMode : int { STORE_P8 = 0, STORE_PS = 1, STORE_PLANAR = 2 };
 
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 2 + i); };
   const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxRing + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
-  uint8_t* ones = smem + 256;
+  uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
   uint8_t* ring = wsm + ((p.w_bytes + 127) & ~127);
 
@@ -165,38 +165,57 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // The single issuing thread is on the critical path (an M=128 x N<=64 x K=16 MMA costs the tensor pipe only
+    // ~45 cycles), so the per-step descriptor halves are precomputed into shared memory once and the inner loop
+    // is one 64-bit shared load + one add per MMA.
+    uint2* dsc = reinterpret_cast<uint2*>(smem + 8 * (2 * kMaxRing + 6));   // [kMaxSteps] {a_lo, b_lo}
+    const uint32_t ring_base = smem_u32(ring), w_base = smem_u32(wsm);
+    for (int s = lane; s < p.n_steps; s += 32) {
+      const ConvStep st = p.steps[s];
+      dsc[s] = make_uint2(((st.a_off >> 4) & 0x3FFF) | (((st.a_lbo >> 4) & 0x3FFF) << 16),
+                          (((w_base + s * (N * 32)) >> 4) & 0x3FFF) | ((((N * 16) >> 4) & 0x3FFF) << 16));
+    }
+    __syncwarp();
     if (lane == 0) {
       mbar_wait(wfull_bar, 0, p.err, 2);
       constexpr uint32_t idesc = make_idesc_f16_m128(N);
-      const uint32_t ring_base = smem_u32(ring), w_base = smem_u32(wsm);
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+      auto mkdesc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
       const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
       const uint64_t bias_desc = make_smem_desc(w_base + p.n_steps * (N * 32), N * 16, 128);
+      const int spd = p.n_steps / p.ks;            // steps per input row (dy), identical for every dy
+      const uint32_t slot16 = p.slot_bytes >> 4, ring16 = ring_base >> 4;
       int waited = -1;
-      int base_slot = 0;           // ring slot of input row t*stride
+      int base_slot = 0, base_ph = 0;              // ring slot / phase of input row t*stride
       for (int t = 0; t < nrows_out; ++t) {
         const int stage = t & 1;
         mbar_wait(tempty_bar(stage), ((t >> 1) & 1) ^ 1, p.err, 3);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + stage * N;
-        for (int s = 0; s < p.n_steps; ++s) {
-          const ConvStep st = p.steps[s];
-          const int q = t * p.stride + st.row;
-          int slot = base_slot + st.row;
-          if (slot >= p.ring) slot -= p.ring;
+        int slot = base_slot, ph = base_ph;
+        uint32_t acc = 0;
+        for (int dy = 0; dy < p.ks; ++dy) {
+          const int q = t * p.stride + dy;
           if (q > waited) {
-            for (int r = waited + 1; r <= q; ++r) mbar_wait(full_bar(r % p.ring), (r / p.ring) & 1, p.err, 4);
+            mbar_wait(full_bar(slot), ph, p.err, 4);
             waited = q;
             tc_fence_after();
           }
-          const uint64_t adesc = make_smem_desc(ring_base + slot * p.slot_bytes + st.a_off, st.a_lbo, 128);
-          const uint64_t bdesc = make_smem_desc(w_base + s * (N * 32), N * 16, 128);
-          tc_mma_f16(d_tmem, adesc, bdesc, idesc, s > 0 ? 1u : 0u);
-          if (st.release) tc_commit(empty_bar(slot));
+          const uint32_t a16 = ring16 + slot * slot16;
+          const uint2* d = dsc + dy * spd;
+#pragma unroll 4
+          for (int i = 0; i < spd; ++i) {
+            const uint2 lo = d[i];
+            tc_mma_f16(d_tmem, mkdesc(a16 + lo.x), mkdesc(lo.y), idesc, acc);
+            acc = 1;
+          }
+          if (dy < p.stride) tc_commit(empty_bar(slot));      // this input row is not needed by later output rows
+          if (++slot == p.ring) { slot = 0; ph ^= 1; }
         }
         tc_mma_f16(d_tmem, ones_desc, bias_desc, idesc, 1u);      // + bias
         tc_commit(tfull_bar(stage));
         base_slot += p.stride;
-        if (base_slot >= p.ring) base_slot -= p.ring;
+        if (base_slot >= p.ring) { base_slot -= p.ring; base_ph ^= 1; }
       }
     }
   } else {

@@ -335,7 +335,8 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   const size_t budget = 200 * 1024;
   const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
-  ring = std::min(ring, env_int("HDRTV_RING_MAX", 6));
+  // ring depth: rows in use (ks) + prefetch; shallow rings keep shared memory small so that more CTAs share an SM
+  ring = std::min(ring, env_int(p.ks == 1 ? "HDRTV_RING_1x1" : "HDRTV_RING_3x3", p.ks == 1 ? 4 : 5));
   if (ring < min_ring) ring = min_ring;
   if (ring > kMaxRing) ring = kMaxRing;
   p.ring = ring;
@@ -1020,6 +1021,68 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 issue-rate probe: `iters` back-to-back accumulating M=128 x N x K=16 MMAs from one thread, timed with
+// clock64 around issue..commit-complete.  Operand contents are irrelevant (zeros); only descriptors matter.
+// layout: 0 = SWIZZLE_NONE with the conv kernel's plane pitch, 1 = SWIZZLE_NONE dense (LBO 128*16... contiguous),
+//         2 = SWIZZLE_128B K-major (SBO 1024).
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) mma_probe_kernel(int iters, int layout, int vary, int nacc, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  for (int i = threadIdx.x; i < 72 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tslot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tslot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_f16_m128(N);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 32 * 1024;
+    uint64_t ad, bd;
+    auto mk = [&](uint32_t addr, int rows) -> uint64_t {
+      if (layout == 2) {
+        uint64_t d = make_smem_desc(addr, 16, 1024);
+        return d | (static_cast<uint64_t>(2) << 61);
+      }
+      if (layout == 1) return make_smem_desc(addr, rows * 16, 128);
+      return make_smem_desc(addr, kPlaneBytes, 128);
+    };
+    bd = mk(b0, N);
+    uint64_t adv[4];
+    uint32_t dv[4];
+    for (int k = 0; k < 4; ++k) {
+      adv[k] = mk(a0 + (vary ? k * 16 : 0), 128);
+      dv[k] = tm + (k % nacc) * N;
+    }
+    ad = adv[0];
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {     // lean issue loop: descriptors are loop-invariant registers
+      tc_mma_f16(dv[0], adv[0], bd, idesc, 1u);
+      tc_mma_f16(dv[1], adv[1], bd, idesc, 1u);
+      tc_mma_f16(dv[2], adv[2], bd, idesc, 1u);
+      tc_mma_f16(dv[3], adv[3], bd, idesc, 1u);
+      tc_mma_f16(dv[0], adv[1], bd, idesc, 1u);
+      tc_mma_f16(dv[1], adv[2], bd, idesc, 1u);
+      tc_mma_f16(dv[2], adv[3], bd, idesc, 1u);
+      tc_mma_f16(dv[3], adv[0], bd, idesc, 1u);
+    }
+    (void)ad;
+    tc_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 }  // namespace hdrtv
 
 // ================================================================================================
@@ -1193,6 +1256,35 @@ int hdrtv_time_plan(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, 
   for (size_t i = 0; i + 1 < evs.size() && n < cap; ++i, ++n) cudaEventElapsedTime(&ms[n], evs[i], evs[i + 1]);
   for (auto e : evs) cudaEventDestroy(e);
   return n;
+}
+
+// cycles per MMA (average over `iters`) on `blocks` concurrently resident CTAs; returns max over CTAs.
+int hdrtv_mma_probe(hdrtv_t* c, int n, int layout, int vary, int iters, int blocks, int nacc, float* cycles_per_mma) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  long long* d = nullptr;
+  CK(c, cudaMalloc(&d, sizeof(long long) * blocks));
+  const size_t sm = 72 * 1024;
+  if (nacc < 1 || nacc * n > 512) return fail(c, "mma_probe: nacc*n must be <= 512");
+#define HDRTV_PROBE(NN)                                                                                   \
+  case NN:                                                                                                \
+    cudaFuncSetAttribute(mma_probe_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);    \
+    mma_probe_kernel<NN><<<blocks, 128, sm>>>(iters, layout, vary, nacc, d);                                    \
+    break;
+  switch (n) {
+    HDRTV_PROBE(16) HDRTV_PROBE(32) HDRTV_PROBE(64) HDRTV_PROBE(96) HDRTV_PROBE(128) HDRTV_PROBE(192) HDRTV_PROBE(256)
+    default: cudaFree(d); return fail(c, "mma_probe: unsupported N");
+  }
+#undef HDRTV_PROBE
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> h(blocks);
+  if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(c, e);
+  long long mx = 0;
+  for (auto v : h) mx = std::max(mx, v);
+  *cycles_per_mma = static_cast<float>(mx) / iters;
+  return 0;
 }
 
 int hdrtv_set_transfer_lut(hdrtv_t* c, const uint16_t* lut, int n) {

@@ -79,6 +79,10 @@ int hdrtv_conv_selftest(hdrtv_t* h, int kind, int cin, int cout, int height, int
 /* Per-launch device times (ms) of one FP16 hdrtv_infer, CUDA events between launches; returns the count.          */
 int hdrtv_time_plan(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
                     float* ms, int cap, char* names, int names_cap, void* stream);
+/* tcgen05 issue-rate probe (design evidence): cycles per M=128 x n x K=16 MMA; layout 0/1 = SWIZZLE_NONE (plane     */
+/* pitch / dense), 2 = SWIZZLE_128B; `blocks` concurrent CTAs.                                                      */
+int hdrtv_mma_probe(hdrtv_t* h, int n, int layout, int vary, int iters, int blocks, int n_accumulators,
+                    float* cycles_per_mma);
 const char* hdrtv_version(void);
 
 #ifdef __cplusplus
