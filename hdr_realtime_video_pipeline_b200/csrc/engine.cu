@@ -336,7 +336,11 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
   // ring depth: rows in use (ks) + prefetch; shallow rings keep shared memory small so that more CTAs share an SM
-  ring = std::min(ring, env_int(p.ks == 1 ? "HDRTV_RING_1x1" : "HDRTV_RING_3x3", p.ks == 1 ? 4 : 5));
+  // ring depth: rows in use (ks) + prefetched rows.  Cheap slots (few channel planes) prefetch deeper: their rows
+  // are short on MMA work, so only depth hides the ~1.5 us HBM latency; fat slots stay shallow so that more CTAs
+  // share an SM.
+  const int prefetch = std::max(1, std::min(5, (24 * 1024) / p.slot_bytes));
+  ring = std::min(ring, env_int(p.ks == 1 ? "HDRTV_RING_1x1" : "HDRTV_RING_3x3", std::max(p.ks == 1 ? 3 : 4, p.ks + prefetch)));
   if (ring < min_ring) ring = min_ring;
   if (ring > kMaxRing) ring = kMaxRing;
   p.ring = ring;
@@ -671,14 +675,23 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     p.in_stats = l == 0 ? nullptr : c->cls[l - 1].stats;
     p.gamma = l == 0 ? nullptr : c->wd.at(pre + std::to_string(normi[l - 1]) + ".weight");
     p.beta = l == 0 ? nullptr : c->wd.at(pre + std::to_string(normi[l - 1]) + ".bias");
-    p.w = c->wd.at(pre + std::to_string(convi[l]) + ".weight");
+    p.w = c->wd.at(pre + std::to_string(convi[l]) + ".weightT");
     p.b = c->wd.at(pre + std::to_string(convi[l]) + ".bias");
     p.out = L.out;
     p.out_stats = L.stats;
     p.Cin = L.Cin; p.Cout = L.Cout; p.H = L.H; p.W = L.W; p.Ho = L.Ho; p.Wo = L.Wo;
-    dim3 grid((L.Ho * L.Wo + 127) / 128, (L.Cout + 15) / 16);
-    const size_t sm = sizeof(float) * (L.Cin * 16 + 2 * L.Cin);
-    cls_level_kernel<<<grid, 128, sm, s>>>(p);
+    const int npix = L.Ho * L.Wo;
+    // pixels per block: enough blocks to cover the GPU on the deep (small) levels, enough work per block on the first
+    const int pix = npix >= 64 * 1024 ? 64 : (npix >= 16 * 1024 ? 32 : (npix >= 4096 ? 16 : (npix >= 1024 ? 8 : 4)));
+    const size_t sm = sizeof(float) * (static_cast<size_t>(pix) * L.Cin + 2 * L.Cin);
+    const unsigned blocks = static_cast<unsigned>((npix + pix - 1) / pix);
+    switch (pix) {
+      case 64: cls_level_kernel<64><<<blocks, 128, sm, s>>>(p); break;
+      case 32: cls_level_kernel<32><<<blocks, 128, sm, s>>>(p); break;
+      case 16: cls_level_kernel<16><<<blocks, 128, sm, s>>>(p); break;
+      case 8: cls_level_kernel<8><<<blocks, 128, sm, s>>>(p); break;
+      default: cls_level_kernel<4><<<blocks, 128, sm, s>>>(p); break;
+    }
     CK(c, cudaGetLastError());
     ++c->launches;
   }
@@ -1149,6 +1162,16 @@ int hdrtv_set_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {
   for (auto k : must)
     if (!c->w.count(k)) return fail(c, std::string("hdrtv_set_weights: missing key ") + k);
   if (c->w.size() != 264) return fail(c, "hdrtv_set_weights: expected 264 tensors, got " + std::to_string(c->w.size()));
+  for (int ci : {0, 4, 8, 12, 16}) {   // classifier 1x1 weights, transposed to [Cin][Cout] for coalesced reads
+    const std::string k = "AGCM.classifier.model." + std::to_string(ci) + ".weight";
+    const HostTensor& t0 = c->w.at(k);
+    const int O = static_cast<int>(t0.shape[0]), I = static_cast<int>(t0.shape[1]);
+    std::vector<float> tr(static_cast<size_t>(O) * I);
+    for (int o = 0; o < O; ++o)
+      for (int i2 = 0; i2 < I; ++i2) tr[static_cast<size_t>(i2) * O + o] = t0.v[static_cast<size_t>(o) * I + i2];
+    c->wd[k + "T"] = w_upload(c, tr.data(), tr.size());
+    if (!c->wd[k + "T"]) return fail(c, "hdrtv_set_weights: upload failed for " + k + "T");
+  }
   try {
     if (c->precision == HDRTV_FP16 && pack_all_fp16(c)) return -1;
   } catch (const std::exception& e) {

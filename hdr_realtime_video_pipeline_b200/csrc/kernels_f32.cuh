@@ -107,26 +107,30 @@ struct ClsLevel {
   const double* in_stats;  // [Cin][2] sum, sumsq of the previous level's output (nullptr: no IN before this level)
   const float* gamma;      // IN affine of the previous level
   const float* beta;
-  const float* w;          // [Cout][Cin]
+  const float* w;          // [Cin][Cout]  (transposed copy made at weight-load time)
   const float* b;          // [Cout]
   float* out;              // [Cout][Ho][Wo]
   double* out_stats;       // [Cout][2], pre-zeroed
   int Cin, Cout, H, W, Ho, Wo;
 };
 
-// grid: (ceil(Ho*Wo/128), ceil(Cout/16)); block 128; each thread: one pooled pixel, 16 output channels.
+// Two phases per block of PIX pooled pixels (128 threads):
+//   1. S[px][ci] = sum over the valid 3x3 window of IN(x)[ci]      (pool BEFORE the 1x1 conv: both are linear)
+//   2. y[px][co] = LeakyReLU_0.2( (W[co,:] . S[px,:] + nwin*b[co]) / 9 ), weights read transposed ([Cin][Cout]) so
+//      that consecutive threads (consecutive co) coalesce; per-channel sum / sum^2 go through shared then global
+//      FP64 atomics (one pair per channel per block).
+// Requires Cout to divide 128 or be a multiple of it (16/32/64/128 here).
+template <int PIX>
 __global__ void __launch_bounds__(128) cls_level_kernel(const ClsLevel p) {
   extern __shared__ float sm[];
-  float* wsm = sm;                       // [Cin][16]
-  float* na = wsm + p.Cin * 16;          // [Cin] IN scale
+  float* S = sm;                         // [PIX][Cin]
+  float* na = S + PIX * p.Cin;           // [Cin] IN scale
   float* nb = na + p.Cin;                // [Cin] IN shift
-  const int co0 = blockIdx.y * 16;
-  for (int i = threadIdx.x; i < p.Cin * 16; i += blockDim.x) {
-    const int ci = i / 16, c = i % 16;
-    wsm[i] = (co0 + c < p.Cout) ? p.w[(co0 + c) * p.Cin + ci] : 0.f;
-  }
+  __shared__ int nwin[PIX];
+  __shared__ double ssum[128][2];
+  const int tid = threadIdx.x;
   const double cnt = static_cast<double>(p.H) * p.W;
-  for (int ci = threadIdx.x; ci < p.Cin; ci += blockDim.x) {
+  for (int ci = tid; ci < p.Cin; ci += 128) {
     if (p.in_stats) {
       const double mean = p.in_stats[2 * ci] / cnt;
       double var = p.in_stats[2 * ci + 1] / cnt - mean * mean;
@@ -139,54 +143,59 @@ __global__ void __launch_bounds__(128) cls_level_kernel(const ClsLevel p) {
       nb[ci] = 0.f;
     }
   }
+  if (tid < p.Cout && tid < 128) { ssum[tid][0] = 0.0; ssum[tid][1] = 0.0; }
   __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = idx < p.Ho * p.Wo;
-  float acc[16];
+  const int npix = p.Ho * p.Wo;
+  const int pix0 = blockIdx.x * PIX;
+  for (int item = tid; item < PIX * p.Cin; item += 128) {
+    const int px = item % PIX, ci = item / PIX;
+    const int idx = pix0 + px;
+    float acc = 0.f;
+    int n = 0;
+    if (idx < npix) {
+      const int oy = idx / p.Wo, ox = idx % p.Wo;
+      const float a = na[ci], b = nb[ci];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  int nwin = 0;
-  if (valid) {
-    const int oy = idx / p.Wo, ox = idx % p.Wo;
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * oy + ky - 1;
-      if (iy < 0 || iy >= p.H) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox + kx - 1;
-        if (ix < 0 || ix >= p.W) continue;
-        ++nwin;
-        for (int ci = 0; ci < p.Cin; ++ci) {
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky - 1;
+        if (iy < 0 || iy >= p.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = 2 * ox + kx - 1;
+          if (ix < 0 || ix >= p.W) continue;
           const long o = (static_cast<long>(ci) * p.H + iy) * p.W + ix;
-          float v = p.in_is_half ? __half2float(reinterpret_cast<const __half*>(p.in)[o])
-                                 : reinterpret_cast<const float*>(p.in)[o];
-          v = fmaf(v, na[ci], nb[ci]);
-          const float* wp = wsm + ci * 16;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
+          const float v = p.in_is_half ? __half2float(reinterpret_cast<const __half*>(p.in)[o])
+                                       : reinterpret_cast<const float*>(p.in)[o];
+          acc += fmaf(v, a, b);
+          ++n;
         }
       }
     }
+    S[px * p.Cin + ci] = acc;
+    if (ci == 0) nwin[px] = n;
   }
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int co = co0 + c;
-    float y = 0.f;
-    if (valid && co < p.Cout) {
-      y = (acc[c] + nwin * __ldg(p.b + co)) / 9.0f;
-      y = y >= 0.f ? y : 0.2f * y;
-      p.out[static_cast<long>(co) * p.Ho * p.Wo + idx] = y;
-    }
-    double s = y, ss = static_cast<double>(y) * y;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if (lane == 0 && co < p.Cout) {
-      atomicAdd(p.out_stats + 2 * co, s);
-      atomicAdd(p.out_stats + 2 * co + 1, ss);
-    }
+  __syncthreads();
+  const int co = tid % p.Cout;                      // fixed per thread (Cout divides 128) or tid (Cout == 128)
+  double s1 = 0.0, s2 = 0.0;
+  for (int item = tid; item < PIX * p.Cout; item += 128) {
+    const int px = item / p.Cout;
+    const int idx = pix0 + px;
+    if (idx >= npix) break;
+    const float* sp = S + px * p.Cin;
+    float acc = 0.f;
+    for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(sp[ci], __ldg(p.w + ci * p.Cout + co), acc);
+    float y = (acc + nwin[px] * __ldg(p.b + co)) / 9.0f;
+    y = y >= 0.f ? y : 0.2f * y;
+    p.out[static_cast<long>(co) * npix + idx] = y;
+    s1 += y;
+    s2 += static_cast<double>(y) * y;
+  }
+  atomicAdd(&ssum[co][0], s1);
+  atomicAdd(&ssum[co][1], s2);
+  __syncthreads();
+  if (tid < p.Cout) {
+    atomicAdd(p.out_stats + 2 * tid, ssum[tid][0]);
+    atomicAdd(p.out_stats + 2 * tid + 1, ssum[tid][1]);
   }
 }
 
