@@ -43,6 +43,8 @@ _SIGNATURES = {
     "hdrtv_time_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_float), C.c_int, C.c_char_p, C.c_int, C.c_void_p]),
     "hdrtv_mma_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "hdrtv_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "hdrtv_chain_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "hdrtv_version": (C.c_char_p, []),
 }
 

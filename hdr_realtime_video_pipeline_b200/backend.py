@@ -359,6 +359,21 @@ class HDRTVNetB200:
                       "hdrtv_mma_probe")
         return float(cyc.value)
 
+    def probe(self, kind, n=64, iters=2000, blocks=1, nwarps=4, nmma=4, groups=1, trace=False):
+        cyc = C.c_float()
+        tr = np.zeros(256, dtype=np.int64) if trace else None
+        _native.check(self._lib.hdrtv_probe(self._handle, kind, n, iters, blocks, nwarps, nmma, groups, C.byref(cyc),
+                                            tr.ctypes.data if trace else None), self._handle, "hdrtv_probe")
+        if trace:
+            return float(cyc.value), tr.reshape(16, 4, 4)
+        return float(cyc.value)
+
+    def chain_trace(self, agcm=False, index=0):
+        tr = np.zeros(64 * 8 * 8, dtype=np.int64)
+        _native.check(self._lib.hdrtv_chain_trace(self._handle, 1 if agcm else 0, index, tr.ctypes.data), self._handle,
+                      "hdrtv_chain_trace")
+        return tr.reshape(64, 8, 8)
+
     def conv_selftest(self, kind, cin, cout, h, w, flags=0):
         mx, ref = C.c_float(), C.c_float()
         _native.check(self._lib.hdrtv_conv_selftest(self._handle, kind, cin, cout, h, w, flags, C.byref(mx), C.byref(ref)),

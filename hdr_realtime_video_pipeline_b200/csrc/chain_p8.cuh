@@ -1,78 +1,158 @@
-// Fused per-pixel layer chains on tcgen05: conv (3x3 / 1x1 from the row ring) followed by up to five 1x1 layers whose
+// Fused per-pixel layer chains on tcgen05: a conv (3x3 / 1x1 from the TMA row ring) followed by 1x1 layers whose
 // 64-channel intermediates never leave the SM.
 //
-//   AGCM MLP        : 1x1 3->64 ReLU, 1x1 64->64 ReLU, 1x1 64->3            (Condition_arch.py:571-583, GFM folded)
-//   LE cond pyramid : 3x3 3->64, 1x1, 1x1 [store cond], 1x1, 1x1, 1x1 ->16 [store cond1], LeakyReLU(0.1)
+//   ProgAGCM : 1x1 3->64 ReLU, 1x1 64->64 ReLU, 1x1 64->3                   (Condition_arch.py:571-583, GFM folded)
+//   ProgCond : 3x3 3->64, 1x1, 1x1 [store cond], 1x1, 1x1, 1x1 ->16 [store cond1], LeakyReLU(0.1)
 //                                                                          (HDRUNet3T1_arch.py:41-46, 160-161)
 //
-// Per output row (128 pixels = UMMA M) the layers run strictly in sequence:
-//   MMA(l) -> TMEM accumulator -> epilogue warps (activation, fp16) -> shared-memory operand tile -> MMA(l+1) ...
-// Two rows are in flight per CTA ("ping-pong"): epilogue warps 2..5 own even rows, warps 6..9 odd rows, each with its
-// own TMEM accumulator and operand tile, while the single MMA-issuing thread alternates between them, so the tensor
-// pipe works on one row while the other row's activations are being converted.
+// Measured on B200 (scripts/tensor_probe.py, scripts/chain_trace.py, profiles/): one tcgen05.mma of K = 16 occupies
+// the SM's tensor pipe for >= ~45 cycles whatever N <= 64 is, the issuing thread cannot run ahead of the pipe, an
+// mbarrier hand-off between warps costs 200-1000 cycles, and every dynamically indexed parameter load in the issuing
+// warp is a long-scoreboard stall with the pipe idle.  A chain step (5 MMAs, ~240 pipe cycles) is therefore latency-
+// bound.  The kernel (a) is specialised per chain "program" so that every layer loop is unrolled and nothing is looked
+// up at run time, and (b) hides the issue -> MMA -> commit -> TMEM load -> activation -> fp16 operand tile -> next issue
+// round trip with SIX independent row slots per CTA.  A slot is one warpgroup (4 warps = the 4 TMEM lane quadrants)
+// that owns a TMEM accumulator and an operand tile and runs its rows strictly in sequence; one of its warps also
+// issues the slot's MMAs, so the only cross-warp hand-offs are the tcgen05.commit -> mbarrier wake-up and a 128-thread
+// named barrier.  All slots share one resident copy of the weights and one TMA row ring (warp 0).  One CTA per SM;
+// the (strip, row) space is cut into one contiguous range per CTA so that all 148 SMs carry the same number of rows.
 #pragma once
+#include <type_traits>
+
 #include "conv_p8.cuh"
 
 namespace hdrtv {
 
-constexpr int kMaxChain = 6;
+constexpr int kMaxChain = 9;
+constexpr int kChainGroups = 6;
+constexpr int kChainMaxRing = 16;                // >= kChainGroups + ks - 1 rows are in use at once; the rest is prefetch
+constexpr int kChainThreads = 32 * (1 + kChainGroups * 4);
 constexpr int kTileBytes = 8 * kPlaneBytes;      // one 64-channel operand tile (8 channel-chunk planes)
 
-struct ChainLayer {
-  int n_steps;   // K/16 MMAs (layer 0: the input side's tap steps)
-  int N;         // 64, or 16 for a last layer
-  int w_off;     // byte offset of this layer's packed weights (tap steps + bias step) in the chain weight buffer
-  int store;     // 0 none, 1 P8, 2 planar fp16 (3 channels) + P8 single chunk
-  float slope;
-  P8 out;
+// ---- chain programs (compile-time layer tables) -------------------------------------------------------------------
+// store: 0 none, 1 P8, 2 planar fp16 (3 channels) + single-chunk P8.   act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).
+struct ProgAGCM {
+  static constexpr int L = 3, KS = 1;
+  static constexpr int N[L] = {64, 64, 16};
+  static constexpr int STEPS[L] = {1, 4, 4};          // K/16 MMAs per layer (layer 0: the input side's tap steps)
+  static constexpr int APLANE[L] = {0, 0, 0};
+  static constexpr int WRITE[L] = {1, 1, 0};
+  static constexpr int STORE[L] = {0, 0, 2};
+  static constexpr int ACT[L] = {1, 1, 0};
+  // layer-0 operand (one 8-channel plane per ring slot): byte offset / K-half distance of each tap step
+  static constexpr int A0_OFF[1] = {16};
+  static constexpr int A0_LBO[1] = {16};
 };
-
-struct ChainParams {
-  ConvParams base;           // input side (ring geometry, layer-0 steps), weights pointer / total bytes, Ho/Wo/band
-  int n_layers;
-  ChainLayer layers[kMaxChain];
+struct ProgCond {
+  static constexpr int L = 6, KS = 3;
+  static constexpr int N[L] = {64, 64, 64, 64, 64, 16};
+  static constexpr int STEPS[L] = {6, 4, 4, 4, 4, 4};
+  static constexpr int APLANE[L] = {0, 0, 0, 0, 0, 0};
+  static constexpr int WRITE[L] = {1, 1, 1, 1, 1, 0};
+  static constexpr int STORE[L] = {0, 0, 1, 0, 0, 1};
+  static constexpr int ACT[L] = {2, 2, 2, 2, 2, 0};
+  static constexpr int A0_OFF[2] = {0, 32};           // per input row: taps (dx 0, dx 1) paired, then dx 2 (+ zero half)
+  static constexpr int A0_LBO[2] = {16, 16};
 };
-
-__device__ __forceinline__ uint32_t act_half2(uint32_t h2, float slope) {
-  __half2 v = *reinterpret_cast<__half2*>(&h2);
-  const __half2 s = __float2half2_rn(slope);
-  v = __hmax2(v, __hmul2(v, s));
-  return *reinterpret_cast<uint32_t*>(&v);
+template <class P>
+__host__ __device__ constexpr int prog_w_off(int l) {   // byte offset of layer l's packed weights (steps + bias step)
+  int off = 0;
+  for (int i = 0; i < l; ++i) off += (P::STEPS[i] + 1) * P::N[i] * 32;
+  return off;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 2) chain_p8_kernel(const __grid_constant__ ChainParams cp) {
+struct ChainParams {
+  ConvParams base;           // input side (ring geometry), weights pointer / total bytes, Ho/Wo, planar output
+  int strips;                // 128-pixel strips per row; the grid is 1-D, each CTA takes a contiguous (strip, row) range
+  P8 outs[kMaxChain];        // per layer, where STORE != 0
+  long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [step<64][slot<8][8]
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void group_barrier(int id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+// Parked wait for the epilogue side (long suspend hint: fewer polling instructions competing with working warps).
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, int* err_word, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000)) {
+    if (++spins > (1u << 20)) {
+      if (err_word) atomicExch(err_word, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// Contiguous range of (strip, row) work items of this CTA, walked as segments that stay inside one strip.
+struct ChainWalk {
+  long lo, hi;
+  int Ho;
+  __device__ __forceinline__ ChainWalk(int strips, int Ho_) : Ho(Ho_) {
+    const long total = static_cast<long>(strips) * Ho_;
+    lo = total * blockIdx.x / gridDim.x;
+    hi = total * (blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ __forceinline__ bool next(int& strip, int& r0, int& n) {
+    if (lo >= hi) return false;
+    strip = static_cast<int>(lo / Ho);
+    r0 = static_cast<int>(lo - static_cast<long>(strip) * Ho);
+    n = static_cast<int>(min(static_cast<long>(Ho - r0), hi - lo));
+    lo += n;
+    return true;
+  }
+};
+
+template <int I, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(f);
+  }
+}
+
+#ifdef HDRTV_CHAIN_TRACE
+#define CHAIN_STAMP(k) do { if (tr) cp.trace[(e * 8 + g) * 8 + (k)] = clock64(); } while (0)
+#else
+#define CHAIN_STAMP(k) do { } while (0)
+#endif
+
+template <class Prog>
+__global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid_constant__ ChainParams cp) {
   const ConvParams& p = cp.base;
-  constexpr uint32_t kTmemCols = 128;
+  constexpr int G = kChainGroups;
+  constexpr int L = Prog::L, KS = Prog::KS;
+  constexpr int SPD = Prog::STEPS[0] / KS;            // layer-0 tap steps per input row
+  constexpr uint32_t kTmemCols = 512;                 // G * 64 = 384 rounded up to a power of two
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int i) { return bar0 + 8u * i; };
-  auto empty_bar = [&](int i) { return bar0 + 8u * (kMaxRing + i); };
-  auto tfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + i); };
-  auto afull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 2 + i); };
-  const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxRing + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
+  auto empty_bar = [&](int i) { return bar0 + 8u * (kChainMaxRing + i); };
+  auto tfull_bar = [&](int i) { return bar0 + 8u * (2 * kChainMaxRing + i); };
+  const uint32_t wfull_bar = bar0 + 8u * (2 * kChainMaxRing + G);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kChainMaxRing + G + 1));
   uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
   uint8_t* tiles = wsm + ((p.w_bytes + 127) & ~127);
-  uint8_t* ring = tiles + 2 * kTileBytes;
+  uint8_t* ring = tiles + G * kTileBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * kTileM;
-  const int oy0 = blockIdx.y * p.band;
-  const int nrows_out = min(p.band, p.Ho - oy0);
-  const int nrows_in = (nrows_out - 1) * p.stride + p.ks;
-  const int L = cp.n_layers;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) {
       mbar_init(full_bar(i), 1);
-      mbar_init(empty_bar(i), 1);
+      mbar_init(empty_bar(i), KS);                    // one arrival per (output row, dy) use of the input row
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull_bar(i), 1);
-      mbar_init(afull_bar(i), 4);
-    }
+    for (int i = 0; i < G; ++i) mbar_init(tfull_bar(i), 1);
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
@@ -80,183 +160,202 @@ __global__ void __launch_bounds__(kConvThreads, 2) chain_p8_kernel(const __grid_
     reinterpret_cast<uint4*>(ones)[threadIdx.x - 64] = make_uint4(0x3C003C00u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ChainWalk walk(cp.strips, p.Ho);
+  int strip, r0, n;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (same as conv_p8_kernel)
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(wfull_bar, p.w_bytes);
       bulk_g2s(smem_u32(wsm), p.wpk, p.w_bytes, wfull_bar);
       const uint32_t row_tx = p.n_copies * p.copy_bytes;
       int slot = 0, ph = 1;
-      const uint4* src = p.in + (static_cast<long>(oy0) * p.stride + p.row_bias) * p.in_row_entries + x0;
-      for (int q = 0; q < nrows_in; ++q) {
-        mbar_wait(empty_bar(slot), ph, p.err, 11);
-        mbar_expect_tx(full_bar(slot), row_tx);
-        const uint32_t dst = smem_u32(ring) + slot * p.slot_bytes;
-        for (int c = 0; c < p.n_copies; ++c)
-          bulk_g2s(dst + p.copies[c].dst_off, src + p.copies[c].src_off, p.copy_bytes, full_bar(slot));
-        src += p.in_row_entries;
-        if (++slot == p.ring) { slot = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer, alternating between two rows
-    uint2* dsc = reinterpret_cast<uint2*>(smem + 8 * (2 * kMaxRing + 6));   // layer-0 {a_lo, b_lo}
-    const uint32_t ring_base = smem_u32(ring), w_base = smem_u32(wsm), tile_base = smem_u32(tiles);
-    const int N0 = cp.layers[0].N;
-    for (int s = lane; s < p.n_steps; s += 32) {
-      const ConvStep st = p.steps[s];
-      dsc[s] = make_uint2(((st.a_off >> 4) & 0x3FFF) | (((st.a_lbo >> 4) & 0x3FFF) << 16),
-                          (((w_base + cp.layers[0].w_off + s * (N0 * 32)) >> 4) & 0x3FFF) | ((((N0 * 16) >> 4) & 0x3FFF) << 16));
-    }
-    __syncwarp();
-    if (lane == 0) {
-      mbar_wait(wfull_bar, 0, p.err, 12);
-      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
-      auto mkdesc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
-      const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
-      const int spd = p.n_steps / p.ks;
-      const uint32_t slot16 = p.slot_bytes >> 4, ring16 = ring_base >> 4;
-      int waited = -1;
-      int base_slot = 0, base_ph = 0;
-      for (int tp = 0; tp < nrows_out; tp += 2) {
-        for (int l = 0; l < L; ++l) {
-          const ChainLayer& ly = cp.layers[l];
-          const uint32_t idesc = make_idesc_f16_m128(ly.N);
-          const uint32_t b_lbo = (((ly.N * 16) >> 4) & 0x3FFF) << 16;
-          for (int g = 0; g < 2; ++g) {
-            const int t = tp + g;
-            if (t >= nrows_out) break;
-            const int e = (t >> 1) * L + l;             // event index of this (row, layer) in slot g
-            if (e > 0) {                                // previous event's epilogue done: TMEM free, tile written
-              mbar_wait(afull_bar(g), (e - 1) & 1, p.err, 13);
-              tc_fence_after();
-            }
-            const uint32_t d_tmem = tmem_base + g * 64;
-            uint32_t acc = 0;
-            if (l == 0) {
-              int slot = base_slot, ph = base_ph;
-              for (int dy = 0; dy < p.ks; ++dy) {
-                const int q = t * p.stride + dy;
-                if (q > waited) {
-                  mbar_wait(full_bar(slot), ph, p.err, 14);
-                  waited = q;
-                  tc_fence_after();
-                }
-                const uint32_t a16 = ring16 + slot * slot16;
-                const uint2* d = dsc + dy * spd;
-#pragma unroll 2
-                for (int i = 0; i < spd; ++i) {
-                  const uint2 lo = d[i];
-                  tc_mma_f16(d_tmem, mkdesc(a16 + lo.x), mkdesc(lo.y), idesc, acc);
-                  acc = 1;
-                }
-                if (dy < p.stride) tc_commit(empty_bar(slot));
-                if (++slot == p.ring) { slot = 0; ph ^= 1; }
-              }
-              base_slot += p.stride;
-              if (base_slot >= p.ring) { base_slot -= p.ring; base_ph ^= 1; }
-            } else {
-              const uint32_t a_lo0 = ((tile_base + g * kTileBytes) >> 4) | (((kPlaneBytes >> 4) & 0x3FFF) << 16);
-              const uint32_t b_lo0 = ((w_base + ly.w_off) >> 4) | b_lbo;
-#pragma unroll 4
-              for (int i = 0; i < ly.n_steps; ++i) {
-                tc_mma_f16(d_tmem, mkdesc(a_lo0 + i * ((2 * kPlaneBytes) >> 4)), mkdesc(b_lo0 + i * ((ly.N * 32) >> 4)), idesc, acc);
-                acc = 1;
-              }
-            }
-            const uint32_t bias_lo = ((w_base + ly.w_off + ly.n_steps * (ly.N * 32)) >> 4) | b_lbo;
-            tc_mma_f16(d_tmem, ones_desc, mkdesc(bias_lo), idesc, 1u);
-            tc_commit(tfull_bar(g));
-          }
+      while (walk.next(strip, r0, n)) {
+        const uint4* src = p.in + (static_cast<long>(r0) + p.row_bias) * p.in_row_entries + strip * kTileM;
+        for (int q = 0; q < n - 1 + KS; ++q) {
+          mbar_wait(empty_bar(slot), ph, p.err, 11);
+          mbar_expect_tx(full_bar(slot), row_tx);
+          const uint32_t dst = smem_u32(ring) + slot * p.slot_bytes;
+          for (int c = 0; c < p.n_copies; ++c)
+            bulk_g2s(dst + p.copies[c].dst_off, src + p.copies[c].src_off, p.copy_bytes, full_bar(slot));
+          src += p.in_row_entries;
+          if (++slot == p.ring) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: group g owns rows t = g, g+2, ...
-    const int g = (warp - 2) >> 2;
-    const int lg = warp & 3;
-    const int m = lg * 32 + lane;                    // pixel inside the strip = TMEM lane
-    const int x = x0 + m;
-    const bool xin = x < p.Wo;
-    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + g * 64;
+    // ------------------------------------------------------------------ row slot g: one warpgroup
+    const int g = (warp - 1) >> 2;
+    const bool issuer = ((warp - 1) & 3) == (g & 3);  // this warp also issues the slot's MMAs; spread over the 4 SMSPs
+    const int lg = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int m = lg * 32 + lane;                     // pixel inside the strip = TMEM lane
+    const uint32_t d_tmem = tmem_base + g * 64;
+    const uint32_t tlane = d_tmem + (static_cast<uint32_t>(lg * 32) << 16);
     uint4* tile = reinterpret_cast<uint4*>(tiles + g * kTileBytes) + m;
-    ColRef outs[kMaxChain];
-    for (int l = 0; l < L; ++l)
-      if (cp.layers[l].store) outs[l].init(cp.layers[l].out, x);
-    int e = 0;
-    for (int t = g; t < nrows_out; t += 2) {
-      const int oy = oy0 + t;
-      for (int l = 0; l < L; ++l, ++e) {
-        const ChainLayer& ly = cp.layers[l];
-        mbar_wait(tfull_bar(g), e & 1, p.err, 15);
-        tc_fence_after();
-        if (ly.N == 64) {
-          float v[64];
-          tmem_ld_cols<64>(tlane, v);
-          tc_fence_before();
-          uint4 h[8];
+    // issuer state
+    const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
+    const uint32_t tile16 = (smem_u32(tiles) + g * kTileBytes) >> 4;
+    const uint32_t slot16 = p.slot_bytes >> 4;
+    const int ring_n = p.ring;
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+    auto mkdesc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+    const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
+    if (issuer) mbar_wait(wfull_bar, 0, p.err, 12);
+
+    int e = 0;                 // steps this slot has run (parity of its tfull barrier)
+    int R = 0, Q = 0;          // output rows / input rows of the segments before the current one
+    while (walk.next(strip, r0, n)) {
+      const int x = strip * kTileM + m;
+      const bool xin = x < p.Wo;
+      for (int t = (g - R % G + G) % G; t < n; t += G) {
+        const int oy = r0 + t;
+        static_for<0, L>([&](auto lc) {
+          constexpr int l = decltype(lc)::value;
+          constexpr int N = Prog::N[l];
+          constexpr int NSTEPS = Prog::STEPS[l];
+          constexpr int kStore = Prog::STORE[l], kWrite = Prog::WRITE[l], kAct = Prog::ACT[l], kAPlane = Prog::APLANE[l];
+#ifdef HDRTV_CHAIN_TRACE
+          const bool tr = cp.trace != nullptr && blockIdx.x == 0 && e < 64 && lane == 0 && issuer;
+#endif
+          CHAIN_STAMP(0);
+          if (issuer) {
+            tc_fence_after();                         // the slot's previous epilogue (group barrier) drained TMEM
+            constexpr uint32_t idesc = make_idesc_f16_m128(N);
+            constexpr uint32_t b_lbo = static_cast<uint32_t>(N) << 16;        // (N*16 bytes) >> 4, in the LBO field
+            constexpr uint32_t b_step = static_cast<uint32_t>(N) * 2;         // (N*32 bytes) >> 4
+            const uint32_t b_lo0 = (w16 + (prog_w_off<Prog>(l) >> 4)) | b_lbo;
+            if constexpr (l == 0) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t w[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              __half2 hh = __floats2half2_rn(v[c * 8 + 2 * k], v[c * 8 + 2 * k + 1]);
-              w[k] = act_half2(*reinterpret_cast<uint32_t*>(&hh), ly.slope);
-            }
-            h[c] = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          if (l + 1 < L) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) tile[c * kPlaneEntries] = h[c];
-            fence_proxy_async_smem();
-          }
-          if (ly.store == 1 && xin) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) *outs[l].at(oy, c) = h[c];
-          }
-        } else {   // N == 16
-          float v[16];
-          tmem_ld_cols<16>(tlane, v);
-          tc_fence_before();
-          if (xin) {
-            if (ly.store == 1) {
-#pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                float a[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] = fmaxf(v[c * 8 + k], ly.slope * v[c * 8 + k]);
-                *outs[l].at(oy, c) = pack8(a);
+              for (int dy = 0; dy < KS; ++dy) {
+                const int q = Q + t + dy;
+                const int slot = q % ring_n, ph = (q / ring_n) & 1;
+                mbar_wait(full_bar(slot), ph, p.err, 14);
+                tc_fence_after();
+                const uint32_t a16 = ring16 + slot * slot16;
+                if (elect_one()) {
+                  static_for<0, SPD>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    constexpr uint32_t a_off16 = Prog::A0_OFF[i] >> 4, a_lbo16 = Prog::A0_LBO[i] >> 4;
+                    tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | (a_lbo16 << 16)), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc,
+                               (dy | i) ? 1u : 0u);
+                  });
+                  // release: this (row t, dy) use of the input row is finished once the MMAs above complete.  The
+                  // first and last rows of a segment have fewer users than KS; their issuer supplies the missing arrivals.
+                  const int uses = 1 + (t == 0 ? KS - 1 - dy : 0) + (t == n - 1 ? dy : 0);
+                  for (int u = 0; u < uses; ++u) tc_commit(empty_bar(slot));
+                }
+                __syncwarp();
               }
-            } else if (ly.store == 2) {
+              if (elect_one()) {
+                tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + NSTEPS * b_step), idesc, 1u);      // + bias
+                tc_commit(tfull_bar(g));
+              }
+            } else {
+              const uint32_t a_lo0 = (tile16 + kAPlane * (kPlaneBytes >> 4)) | ((kPlaneBytes >> 4) << 16);
+              if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < NSTEPS; ++i)
+                  tc_mma_f16(d_tmem, mkdesc(a_lo0 + i * ((2 * kPlaneBytes) >> 4)), mkdesc(b_lo0 + i * b_step), idesc, i ? 1u : 0u);
+                tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + NSTEPS * b_step), idesc, 1u);      // + bias
+                tc_commit(tfull_bar(g));
+              }
+            }
+            __syncwarp();
+          }
+          CHAIN_STAMP(1);
+          mbar_wait_parked(tfull_bar(g), e & 1, p.err, 15);
+          tc_fence_after();
+          CHAIN_STAMP(2);
+          auto act = [](float v) {
+            if constexpr (kAct == 1) return fmaxf(v, 0.f);
+            else if constexpr (kAct == 2) return fmaxf(v, 0.1f * v);
+            else return v;
+          };
+          if constexpr (N == 64) {
+            float v[64];
+            tmem_ld_cols<64>(tlane, v);
+            tc_fence_before();
+            CHAIN_STAMP(3);
+            uint4 h[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
               float a[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) a[k] = k < 3 ? fmaxf(v[k], ly.slope * v[k]) : 0.f;
+              for (int k = 0; k < 8; ++k) a[k] = act(v[c * 8 + k]);
+              h[c] = pack8(a);
+            }
+            CHAIN_STAMP(4);
+            if constexpr (kWrite != 0) {
 #pragma unroll
-              for (int k = 0; k < 3; ++k)
-                p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = __float2half_rn(a[k]);
-              *outs[l].at(oy, 0) = pack8(a);
+              for (int c = 0; c < 8; ++c) tile[c * kPlaneEntries] = h[c];
+              CHAIN_STAMP(5);
+              fence_proxy_async_smem();
+            }
+            CHAIN_STAMP(6);
+            if constexpr (kStore == 1) {
+              if (xin) {
+                ColRef o;
+                o.init(cp.outs[l], x);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *o.at(oy, c) = h[c];
+              }
+            }
+          } else {   // N == 16
+            float v[16];
+            tmem_ld_cols<16>(tlane, v);
+            tc_fence_before();
+            uint4 h[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float a[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) a[k] = (kStore == 2 && c * 8 + k >= 3) ? 0.f : act(v[c * 8 + k]);
+              h[c] = pack8(a);
+            }
+            if constexpr (kWrite != 0) {
+              tile[0] = h[0];
+              tile[kPlaneEntries] = h[1];
+              fence_proxy_async_smem();
+            }
+            if constexpr (kStore != 0) {
+              if (xin) {
+                ColRef o;
+                o.init(cp.outs[l], x);
+                if constexpr (kStore == 1) {
+                  *o.at(oy, 0) = h[0];
+                  *o.at(oy, 1) = h[1];
+                } else {
+                  const __half* hv = reinterpret_cast<const __half*>(&h[0]);
+#pragma unroll
+                  for (int k = 0; k < 3; ++k) p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = hv[k];
+                  *o.at(oy, 0) = h[0];
+                }
+              }
             }
           }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(afull_bar(g));
+          CHAIN_STAMP(7);
+          group_barrier(1 + g);                       // tile written + TMEM drained by all four warps of the slot
+          ++e;
+        });
       }
+      R += n;
+      Q += n - 1 + KS;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 inline size_t chain_smem_bytes(const ChainParams& cp) {
-  return kSmemHeader + ((cp.base.w_bytes + 127) & ~127) + 2 * kTileBytes + static_cast<size_t>(cp.base.ring) * cp.base.slot_bytes;
+  return kSmemHeader + ((cp.base.w_bytes + 127) & ~127) + kChainGroups * kTileBytes +
+         static_cast<size_t>(cp.base.ring) * cp.base.slot_bytes;
 }
 
 }  // namespace hdrtv

@@ -15,6 +15,9 @@
 #include "../../include/hdrtv_b200.h"
 #include "common.cuh"
 #include "conv_p8.cuh"
+#include "chain_p8.cuh"
+#include "probes.cuh"
+#include <memory>
 #include "kernels_f32.cuh"
 #include "kernels_io.cuh"
 
@@ -171,6 +174,8 @@ struct ConvLaunch {
   dim3 grid;
   size_t smem;
   std::string name;
+  std::shared_ptr<ChainParams> chain;   // set: this launch is a fused layer chain (chain_p8_kernel), `p` is a geometry copy
+  int chain_prog = 0;
 };
 
 struct DebugTensor {
@@ -286,12 +291,12 @@ static int env_int(const char* name, int dflt) {
 }
 // One balanced wave: as many row bands as there are resident CTA slots (148 SMs x occupancy), so that no CTA
 // waits for a second wave and every CTA walks (almost) the same number of rows.
-static void choose_grid(ConvLaunch& L, int strips) {
+static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   ConvParams& p = L.p;
   const int z = p.xmul == 2 ? 2 : 1;
   const int tmem_cols = std::max(32, 2 * L.N);
   int occ = static_cast<int>((227 * 1024) / (L.smem + 1024));
-  occ = std::max(1, std::min(occ, std::min(512 / tmem_cols, 8)));
+  occ = std::max(1, std::min(occ, std::min(512 / tmem_cols, max_occ)));
   const int slots = 148 * occ * env_int("HDRTV_WAVES", 1);
   int nb = std::max(1, slots / (strips * z));
   int band = (p.Ho + nb - 1) / nb;
@@ -367,7 +372,9 @@ static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   conv_p8_kernel<N, MODE, AUX><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
   return cudaGetLastError();
 }
+static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
+  if (L.chain) return launch_chain(L, s);
   if (L.mode == STORE_PLANAR) return launch_conv_t<16, STORE_PLANAR, false>(L, s);
   if (L.mode == STORE_PS) return launch_conv_t<128, STORE_PS, true>(L, s);
   const bool aux = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
@@ -376,6 +383,78 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
     case 32: return aux ? launch_conv_t<32, STORE_P8, true>(L, s) : launch_conv_t<32, STORE_P8, false>(L, s);
     case 64: return aux ? launch_conv_t<64, STORE_P8, true>(L, s) : launch_conv_t<64, STORE_P8, false>(L, s);
     case 128: return aux ? cudaErrorInvalidValue : launch_conv_t<128, STORE_P8, false>(L, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ---- fused layer chains (chain_p8.cuh) -----------------------------------------------------------
+enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1 };
+
+template <class Prog>
+static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int prog_id, InKind kind, const P8& in,
+                        int kchunks, const std::vector<const P8*>& outs, const __half* wpk, int Ho, int Wo) {
+  ConvLaunch L;
+  memset(&L.p, 0, sizeof(L.p));
+  L.chain = std::make_shared<ChainParams>();
+  ChainParams& cp = *L.chain;
+  memset(&cp, 0, sizeof(cp));
+  std::vector<StepK> wk;
+  build_input_side(kind, in, 0, kchunks, cp.base, wk);
+  ConvParams& p = cp.base;
+  if (p.n_steps != Prog::STEPS[0] || p.ks != Prog::KS || p.stride != 1 || p.slot_bytes != kPlaneBytes)
+    return fail(c, "chain " + name + ": input side does not match the chain program");
+  if (static_cast<int>(outs.size()) != Prog::L) return fail(c, "chain " + name + ": one output slot per layer expected");
+  bool planar = false;
+  for (int l = 0; l < Prog::L; ++l) {
+    if (Prog::STORE[l]) {
+      if (!outs[l]) return fail(c, "chain " + name + ": missing output tensor");
+      cp.outs[l] = *outs[l];
+    }
+    if (Prog::STORE[l] == 2) planar = true;
+  }
+  p.wpk = reinterpret_cast<const uint4*>(wpk);
+  p.w_bytes = prog_w_off<Prog>(Prog::L);
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.planar = planar ? reinterpret_cast<__half*>(1) : nullptr;
+  p.planar_plane = static_cast<long>(Ho) * Wo;
+  p.planar_W = Wo;
+  p.err = c->d_err;
+  // one CTA per SM: resident weights + one operand tile per row slot + the row ring
+  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127) + kChainGroups * kTileBytes;
+  const size_t budget = 224 * 1024;
+  int ring = fixed < budget ? static_cast<int>((budget - fixed) / p.slot_bytes) : 0;
+  ring = std::min(ring, std::min(kChainMaxRing, env_int("HDRTV_RING_CHAIN", kChainMaxRing)));
+  if (ring < kChainGroups + p.ks) return fail(c, "chain " + name + ": shared memory budget exceeded");
+  p.ring = ring;
+  L.smem = chain_smem_bytes(cp);
+  L.N = 64;
+  L.mode = planar ? STORE_PLANAR : STORE_P8;
+  L.name = name;
+  L.chain_prog = prog_id;
+  cp.strips = (Wo + kTileM - 1) / kTileM;
+  const long items = static_cast<long>(cp.strips) * Ho;
+  L.grid = dim3(static_cast<unsigned>(std::min<long>(env_int("HDRTV_CHAIN_CTAS", 148), items)));
+  p.band = Ho;
+  L.p = p;                       // geometry copy for reporting
+  plan.push_back(L);
+  return 0;
+}
+template <class Prog>
+static cudaError_t launch_chain_t(const ConvLaunch& L, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chain_p8_kernel<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  chain_p8_kernel<Prog><<<L.grid, kChainThreads, L.smem, s>>>(*L.chain);
+  return cudaGetLastError();
+}
+static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
+  switch (L.chain_prog) {
+    case PROG_AGCM: return launch_chain_t<ProgAGCM>(L, s);
+    case PROG_COND: return launch_chain_t<ProgCond>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -443,8 +522,31 @@ static int pack_sft_stage1(Ctx* c, const std::string& name) {
   return pack_layer(c, name + ".stage1", IN_NAT1x1, 4, 64, wf, bf);
 }
 
+// Concatenated B operands of a layer chain: layer 0 reads the row ring (`kind0`), layers >= 1 a 64-channel tile.
+struct ChainPackSpec { std::string name; int N; };
+static int pack_chain(Ctx* c, const std::string& key, InKind kind0, int kchunks0, const std::vector<ChainPackSpec>& layers) {
+  std::vector<__half> all;
+  for (size_t l = 0; l < layers.size(); ++l) {
+    ConvParams tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    std::vector<StepK> wk;
+    P8 dummy;
+    dummy.Wp = 16;
+    dummy.chunks = 8;
+    build_input_side(l == 0 ? kind0 : IN_NAT1x1, dummy, 0, l == 0 ? kchunks0 : 8, tmp, wk);
+    std::vector<__half> pk = pack_weights(layers[l].N, wk, conv_weight_fn(c, layers[l].name), bias_fn(c, layers[l].name));
+    all.insert(all.end(), pk.begin(), pk.end());
+  }
+  c->wpk[key] = w_upload(c, all.data(), all.size());
+  if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
+  return 0;
+}
+
 static int pack_all_fp16(Ctx* c) {
   int r = 0;
+  r |= pack_chain(c, "chain.cond", IN_NAT3x3_C8, 1,
+                  {{"LE.cond_first.0", 64}, {"LE.cond_first.2", 64}, {"LE.cond_first.4", 64}, {"LE.CondNet1.0", 64},
+                   {"LE.CondNet1.2", 64}, {"LE.CondNet1.4", 16}});
   r |= pack_std(c, "LE.cond_first.0", IN_NAT3x3_C8, 8, 64);
   r |= pack_std(c, "LE.cond_first.2", IN_NAT1x1, 64, 64);
   r |= pack_std(c, "LE.cond_first.4", IN_NAT1x1, 64, 64);
@@ -654,9 +756,9 @@ static int build_classifier(Ctx* c, int Hc, int Wc) {
   }
   c->d_fea = ws_alloc<float>(c, 8);
   c->d_fold32 = ws_alloc<float>(c, 192 + 64 + 4096 + 64 + 192 + 3 + 5);
-  c->d_agpk[0] = ws_alloc<__half>(c, 2 * 64 * 16);
-  c->d_agpk[1] = ws_alloc<__half>(c, 5 * 64 * 16);
-  c->d_agpk[2] = ws_alloc<__half>(c, 5 * 16 * 16);
+  c->d_agpk[0] = ws_alloc<__half>(c, 2 * 64 * 16 + 5 * 64 * 16 + 5 * 16 * 16);   // one buffer: the fused AGCM chain reads it whole
+  c->d_agpk[1] = c->d_agpk[0] ? c->d_agpk[0] + 2 * 64 * 16 : nullptr;
+  c->d_agpk[2] = c->d_agpk[0] ? c->d_agpk[1] + 5 * 64 * 16 : nullptr;
   if (!c->d_fea || !c->d_fold32 || !c->d_agpk[0] || !c->d_agpk[1] || !c->d_agpk[2]) return fail(c, "alloc agcm head");
   dbg_f32(c, "fea", c->d_fea, 6, 1, 1);
   return 0;
@@ -765,22 +867,33 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   Epi lrelu; lrelu.act = ACT_LRELU;
   Epi none;
   // ---- AGCM MLP (weights folded per frame by agcm_head_kernel)
+  const bool use_chain = env_int("HDRTV_CHAIN", 1) != 0;
+  if (use_chain) {
+    r |= make_chain_t<ProgAGCM>(c, c->plan_agcm, "AGCM.chain", PROG_AGCM, IN_NAT1x1_C8, c->xP8, 1, {nullptr, nullptr, &agP8},
+                                c->d_agpk[0], H, Wd);
+  } else {
   r |= make_conv(c, c->plan_agcm, "AGCM.conv_first", IN_NAT1x1_C8, c->xP8, 0, 1, 64, STORE_P8, c->d_agpk[0], A1, H, Wd,
-                 relu);
-  r |= make_conv(c, c->plan_agcm, "AGCM.HRconv", IN_NAT1x1, A1, 0, 8, 64, STORE_P8, c->d_agpk[1], A2, H, Wd, relu);
-  {
-    Epi e; e.raw = &agP8; e.planar = reinterpret_cast<__half*>(1);  // planar pointer patched per call (agcm_out)
-    r |= make_conv(c, c->plan_agcm, "AGCM.conv_last", IN_NAT1x1, A2, 0, 8, 16, STORE_PLANAR, c->d_agpk[2], agP8, H, Wd,
-                   e);
+                   relu);
+    r |= make_conv(c, c->plan_agcm, "AGCM.HRconv", IN_NAT1x1, A1, 0, 8, 64, STORE_P8, c->d_agpk[1], A2, H, Wd, relu);
+    {
+      Epi e; e.raw = &agP8; e.planar = reinterpret_cast<__half*>(1);  // planar pointer patched per call (agcm_out)
+      r |= make_conv(c, c->plan_agcm, "AGCM.conv_last", IN_NAT1x1, A2, 0, 8, 16, STORE_PLANAR, c->d_agpk[2], agP8, H, Wd,
+                     e);
+    }
   }
   auto& L = c->plan_le;
   // ---- LE condition pyramid
+  if (use_chain) {
+    r |= make_chain_t<ProgCond>(c, L, "LE.cond_chain", PROG_COND, IN_NAT3x3_C8, agP8, 1,
+                                {nullptr, nullptr, &COND, nullptr, nullptr, &cond1}, wk("chain.cond"), H, Wd);
+  } else {
   r |= std_conv(L, "LE.cond_first.0", IN_NAT3x3_C8, agP8, 8, 64, STORE_P8, B1, H, Wd, lrelu);
-  r |= std_conv(L, "LE.cond_first.2", IN_NAT1x1, B1, 64, 64, STORE_P8, B2, H, Wd, lrelu);
-  r |= std_conv(L, "LE.cond_first.4", IN_NAT1x1, B2, 64, 64, STORE_P8, COND, H, Wd, lrelu);
-  r |= std_conv(L, "LE.CondNet1.0", IN_PAR1x1, COND, 64, 64, STORE_P8, C1a, H, Wd, lrelu);
-  r |= std_conv(L, "LE.CondNet1.2", IN_NAT1x1, C1a, 64, 64, STORE_P8, C1b, H, Wd, lrelu);
-  r |= std_conv(L, "LE.CondNet1.4", IN_NAT1x1, C1b, 64, 16, STORE_P8, cond1, H, Wd, none);
+    r |= std_conv(L, "LE.cond_first.2", IN_NAT1x1, B1, 64, 64, STORE_P8, B2, H, Wd, lrelu);
+    r |= std_conv(L, "LE.cond_first.4", IN_NAT1x1, B2, 64, 64, STORE_P8, COND, H, Wd, lrelu);
+    r |= std_conv(L, "LE.CondNet1.0", IN_PAR1x1, COND, 64, 64, STORE_P8, C1a, H, Wd, lrelu);
+    r |= std_conv(L, "LE.CondNet1.2", IN_NAT1x1, C1a, 64, 64, STORE_P8, C1b, H, Wd, lrelu);
+    r |= std_conv(L, "LE.CondNet1.4", IN_NAT1x1, C1b, 64, 16, STORE_P8, cond1, H, Wd, none);
+  }
   r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
   r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
   r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
@@ -1021,6 +1134,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
   mark();
   for (ConvLaunch& L : c->plan_agcm) {
     if (L.mode == STORE_PLANAR) L.p.planar = agcm_out;
+    if (L.chain && L.mode == STORE_PLANAR) L.chain->base.planar = agcm_out;
     CK(c, launch_conv(L, s));
     ++c->launches;
     mark();
@@ -1307,6 +1421,62 @@ int hdrtv_mma_probe(hdrtv_t* c, int n, int layout, int vary, int iters, int bloc
   long long mx = 0;
   for (auto v : h) mx = std::max(mx, v);
   *cycles_per_mma = static_cast<float>(mx) / iters;
+  return 0;
+}
+
+int hdrtv_probe(hdrtv_t* c, int kind, int n, int iters, int blocks, int nwarps, int nmma, int groups, float* cycles_per_iter,
+                long long* trace_host) {
+  if (!c || !cycles_per_iter || blocks < 1 || iters < 4 || kind < 0 || kind > 7) return fail(c, "hdrtv_probe: bad argument");
+  cudaSetDevice(c->device);
+  long long *d = nullptr, *dtrace = nullptr;
+  CK(c, cudaMalloc(&d, sizeof(long long) * blocks));
+  cudaMemset(d, 0, sizeof(long long) * blocks);
+  if (trace_host) {
+    CK(c, cudaMalloc(&dtrace, sizeof(long long) * 256));
+    cudaMemset(dtrace, 0, sizeof(long long) * 256);
+  }
+  ProbeArgs a{kind, n, iters, nwarps, nmma, groups, d, dtrace};
+  int threads = 128;
+  if (kind == 3) threads = 32 * std::max(4, nwarps);
+  if (kind == 4) threads = 32 * (1 + 4 * std::max(1, groups));
+#define HDRTV_PROBE_K(K)                                                                              \
+  case K:                                                                                             \
+    cudaFuncSetAttribute(probe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   \
+    probe_kernel<K><<<blocks, threads, 96 * 1024>>>(a);                                               \
+    break;
+  switch (kind) { HDRTV_PROBE_K(0) HDRTV_PROBE_K(1) HDRTV_PROBE_K(2) HDRTV_PROBE_K(3) HDRTV_PROBE_K(4) HDRTV_PROBE_K(5) HDRTV_PROBE_K(6) HDRTV_PROBE_K(7) }
+#undef HDRTV_PROBE_K
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> h(blocks);
+  if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && trace_host) e = cudaMemcpy(trace_host, dtrace, sizeof(long long) * 256, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (dtrace) cudaFree(dtrace);
+  CK(c, e);
+  long long mx = 0;
+  for (auto v : h) mx = std::max(mx, v);
+  *cycles_per_iter = static_cast<float>(mx) / iters;
+  return 0;
+}
+
+// Debug: run launch `index` of the LE plan (must be a chain) once with tracing on; 64*4*8 clock64 stamps.
+int hdrtv_chain_trace(hdrtv_t* c, int agcm, int index, long long* trace_host) {
+  if (!c || !trace_host) return fail(c, "hdrtv_chain_trace: null argument");
+  std::vector<ConvLaunch>& plan = agcm ? c->plan_agcm : c->plan_le;
+  if (index < 0 || index >= static_cast<int>(plan.size()) || !plan[index].chain) return fail(c, "hdrtv_chain_trace: not a chain launch");
+  cudaSetDevice(c->device);
+  long long* d = nullptr;
+  CK(c, cudaMalloc(&d, sizeof(long long) * 64 * 8 * 8));
+  cudaMemset(d, 0, sizeof(long long) * 64 * 8 * 8);
+  ConvLaunch L = plan[index];
+  ChainParams cp = *L.chain;
+  cp.trace = d;
+  L.chain = std::make_shared<ChainParams>(cp);
+  cudaError_t e = launch_chain(L, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(trace_host, d, sizeof(long long) * 64 * 8 * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(c, e);
   return 0;
 }
 

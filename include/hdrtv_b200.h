@@ -83,6 +83,15 @@ int hdrtv_time_plan(hdrtv_t* h, const void* x, const void* cond, int height, int
 /* pitch / dense), 2 = SWIZZLE_128B; `blocks` concurrent CTAs.                                                      */
 int hdrtv_mma_probe(hdrtv_t* h, int n, int layout, int vary, int iters, int blocks, int n_accumulators,
                     float* cycles_per_mma);
+/* Micro-probes of the tensor path (csrc/probes.cuh): 0 MMA SS M=128, 1 MMA with A in TMEM, 2 MMA SS M=64,             */
+/* 3 tcgen05.ld throughput (nwarps warps x 64 columns), 4 layer-chain round trip (nmma K-steps, `groups` row slots).   */
+/* 5 free-running MMA + commit stream.  trace_host (optional, 256 entries): clock64 stamps of probe 4's first 16      */
+/* iterations, [iter][group<4][event<4] = issue start, after commit, epilogue woke, epilogue arrived.                  */
+int hdrtv_probe(hdrtv_t* h, int kind, int n, int iters, int blocks, int nwarps, int nmma, int groups,
+                float* cycles_per_iter, long long* trace_host);
+/* Debug timeline of one fused layer-chain launch (after an hdrtv_infer at the current size): clock64 stamps of CTA 0, */
+/* [step < 64][row slot < 8][8].                                                                                        */
+int hdrtv_chain_trace(hdrtv_t* h, int agcm_plan, int launch_index, long long* trace_host);
 const char* hdrtv_version(void);
 
 #ifdef __cplusplus
