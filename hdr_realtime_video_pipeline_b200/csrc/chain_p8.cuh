@@ -68,15 +68,6 @@ struct ChainParams {
   long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [step<64][slot<8][8]
 };
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void group_barrier(int id) {
   asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
@@ -110,14 +101,6 @@ struct ChainWalk {
     return true;
   }
 };
-
-template <int I, int E, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < E) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, E>(f);
-  }
-}
 
 #ifdef HDRTV_CHAIN_TRACE
 #define CHAIN_STAMP(k) do { if (tr) cp.trace[(e * 8 + g) * 8 + (k)] = clock64(); } while (0)

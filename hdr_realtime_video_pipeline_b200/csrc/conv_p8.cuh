@@ -17,6 +17,8 @@
 // Replaces the cuDNN conv2d calls of the reference's eager path (Condition_arch.py:571-583,
 // HDRUNet3T1_arch.py:160-205, arch_util.py:68-95) with bias / activation / residual / SFT / PixelShuffle fused.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -32,6 +34,32 @@ constexpr int kConvThreads = 320;
 constexpr int kSmemHeader = 512 + kPlaneBytes + 128;   // barriers, step-descriptor table, constant "ones" operand (bias step)
 
 enum StoreMode : int { STORE_P8 = 0, STORE_PS = 1, STORE_PLANAR = 2 };
+
+// Input side of a convolution = how the ring slot of one input row is laid out and which K = 16 operand windows
+// ("tap steps") one output row reads from it.  Compile-time per kernel instance: the single MMA-issuing warp must not
+// look anything up while the tensor pipe waits (a dynamically indexed parameter load is a long-scoreboard stall).
+enum InKind : int { IN_NAT3x3 = 0, IN_NAT1x1 = 1, IN_NAT3x3_C8 = 2, IN_NAT1x1_C8 = 3, IN_PAR3x3S2 = 4, IN_PAR1x1 = 5 };
+__host__ __device__ constexpr int kind_ks(int k) { return (k == IN_NAT3x3 || k == IN_NAT3x3_C8 || k == IN_PAR3x3S2) ? 3 : 1; }
+__host__ __device__ constexpr int kind_stride(int k) { return k == IN_PAR3x3S2 ? 2 : 1; }
+__host__ __device__ constexpr int kind_copies(int k, int kch) { return k == IN_PAR3x3S2 ? 2 * kch : kch; }
+// tap steps per input row (dy)
+__host__ __device__ constexpr int kind_spd(int k, int kch) {
+  return (k == IN_NAT3x3 || k == IN_PAR3x3S2) ? 3 * kch / 2 : (k == IN_NAT3x3_C8 ? 2 : (k == IN_NAT1x1_C8 ? 1 : kch / 2));
+}
+// byte offset of tap step i's A operand inside the slot, and distance between its two 8-channel K halves
+__host__ __device__ constexpr uint32_t kind_a_off(int k, int kch, int i) {
+  constexpr uint32_t PB = 2176;   // kPlaneBytes
+  if (k == IN_NAT3x3) return static_cast<uint32_t>(2 * (i % (kch / 2))) * PB + static_cast<uint32_t>(i / (kch / 2)) * 16;
+  if (k == IN_NAT1x1 || k == IN_PAR1x1) return static_cast<uint32_t>(2 * i) * PB + 16;
+  if (k == IN_NAT3x3_C8) return i == 0 ? 0 : 32;
+  if (k == IN_NAT1x1_C8) return 16;
+  // IN_PAR3x3S2: dx = i / (kch/2); input x = 2*ox + dx - 1 -> parity plane (dx == 1 ? even : odd), shift (dx == 0 ? 0 : 16)
+  const int dx = i / (kch / 2), c = i % (kch / 2);
+  return static_cast<uint32_t>((2 * c) * 2 + (dx == 1 ? 0 : 1)) * PB + (dx == 0 ? 0u : 16u);
+}
+__host__ __device__ constexpr uint32_t kind_a_lbo(int k) {
+  return (k == IN_NAT3x3_C8 || k == IN_NAT1x1_C8) ? 16u : (k == IN_PAR3x3S2 ? 2u * 2176u : 2176u);
+}
 
 struct ConvStep {
   uint16_t row;      // input row of this output row's window (dy)
@@ -52,6 +80,7 @@ struct ConvParams {
   int row_bias, stride, ks;
   int n_copies, copy_bytes;
   ConvCopy copies[kMaxCopies];
+  uint32_t copy_src0, copy_src_stride, copy_par_off;   // source entry of copy c: src0 + (c / npar) * stride + (c % npar) * par_off
   int slot_bytes, ring;
   int n_steps;         // tap steps; the weight buffer holds n_steps + 1 (the last one is the bias step)
   ConvStep steps[kMaxSteps];
@@ -99,9 +128,28 @@ struct ColRef {
   __device__ __forceinline__ uint4* at(int y, int j) const { return base + (static_cast<long>(y + 1) * row_entries + static_cast<long>(j) * Wp + xoff); }
 };
 
-template <int N, int MODE, bool AUX>
+template <int I, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(f);
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <int KIND, int KCH, int N, int MODE, bool AUX>
 __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
   constexpr uint32_t kTmemCols = (2 * N < 32) ? 32 : 2 * N;
+  constexpr int KS = kind_ks(KIND), STRIDE = kind_stride(KIND), SPD = kind_spd(KIND, KCH), NCOPY = kind_copies(KIND, KCH);
+  constexpr int NPAR = KIND == IN_PAR3x3S2 ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -119,7 +167,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   const int x0 = blockIdx.x * kTileM;
   const int oy0 = blockIdx.y * p.band;
   const int nrows_out = min(p.band, p.Ho - oy0);
-  const int nrows_in = (nrows_out - 1) * p.stride + p.ks;
+  const int nrows_in = (nrows_out - 1) * STRIDE + KS;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) {
@@ -149,74 +197,80 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     if (lane == 0) {
       mbar_expect_tx(wfull_bar, p.w_bytes);
       bulk_g2s(smem_u32(wsm), p.wpk, p.w_bytes, wfull_bar);
-      const uint32_t row_tx = p.n_copies * p.copy_bytes;
-      int slot = 0, ph = 1;
-      const uint4* src = p.in + (static_cast<long>(oy0) * p.stride + p.row_bias) * p.in_row_entries + x0 +
-                         blockIdx.z * p.in_z_entries;
+      constexpr uint32_t row_tx = NCOPY * kPlaneBytes;
+      const uint32_t ring_n = p.ring, slot_bytes = NCOPY * kPlaneBytes;
+      // The per-copy source address is formed with an explicit mad.wide: for `pointer + 32-bit offset` feeding
+      // cp.async.bulk, ptxas 12.9 emitted a 32-bit uniform ULEA with a zeroed high word (illegal global address).
+      const uint32_t sstride = p.copy_src_stride, spar = p.copy_par_off;
+      const long row_entries = p.in_row_entries;
+      uint32_t slot = 0, ph = 1;
+      const uint4* src = p.in + (static_cast<long>(oy0) * STRIDE + p.row_bias) * row_entries + x0 + blockIdx.z * p.in_z_entries +
+                         static_cast<long>(p.copy_src0);
       for (int q = 0; q < nrows_in; ++q) {
         mbar_wait(empty_bar(slot), ph, p.err, 1);
         mbar_expect_tx(full_bar(slot), row_tx);
-        const uint32_t dst = smem_u32(ring) + slot * p.slot_bytes;
-        for (int c = 0; c < p.n_copies; ++c)
-          bulk_g2s(dst + p.copies[c].dst_off, src + p.copies[c].src_off, p.copy_bytes, full_bar(slot));
-        src += p.in_row_entries;
-        if (++slot == p.ring) { slot = 0; ph ^= 1; }
+        const uint32_t dst = smem_u32(ring) + slot * slot_bytes;
+#pragma unroll
+        for (int c = 0; c < NCOPY; ++c) {
+          unsigned long long a;
+          asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(src));
+          bulk_g2s(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot));
+        }
+        src += row_entries;
+        if (++slot == ring_n) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The single issuing thread is on the critical path (an M=128 x N<=64 x K=16 MMA costs the tensor pipe only
-    // ~45 cycles), so the per-step descriptor halves are precomputed into shared memory once and the inner loop
-    // is one 64-bit shared load + one add per MMA.
-    uint2* dsc = reinterpret_cast<uint2*>(smem + 8 * (2 * kMaxRing + 6));   // [kMaxSteps] {a_lo, b_lo}
-    const uint32_t ring_base = smem_u32(ring), w_base = smem_u32(wsm);
-    for (int s = lane; s < p.n_steps; s += 32) {
-      const ConvStep st = p.steps[s];
-      dsc[s] = make_uint2(((st.a_off >> 4) & 0x3FFF) | (((st.a_lbo >> 4) & 0x3FFF) << 16),
-                          (((w_base + s * (N * 32)) >> 4) & 0x3FFF) | ((((N * 16) >> 4) & 0x3FFF) << 16));
-    }
-    __syncwarp();
-    if (lane == 0) {
-      mbar_wait(wfull_bar, 0, p.err, 2);
-      constexpr uint32_t idesc = make_idesc_f16_m128(N);
-      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
-      auto mkdesc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
-      const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
-      const uint64_t bias_desc = make_smem_desc(w_base + p.n_steps * (N * 32), N * 16, 128);
-      const int spd = p.n_steps / p.ks;            // steps per input row (dy), identical for every dy
-      const uint32_t slot16 = p.slot_bytes >> 4, ring16 = ring_base >> 4;
-      int waited = -1;
-      int base_slot = 0, base_ph = 0;              // ring slot / phase of input row t*stride
-      for (int t = 0; t < nrows_out; ++t) {
-        const int stage = t & 1;
-        mbar_wait(tempty_bar(stage), ((t >> 1) & 1) ^ 1, p.err, 3);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + stage * N;
-        int slot = base_slot, ph = base_ph;
-        uint32_t acc = 0;
-        for (int dy = 0; dy < p.ks; ++dy) {
-          const int q = t * p.stride + dy;
-          if (q > waited) {
-            mbar_wait(full_bar(slot), ph, p.err, 4);
-            waited = q;
-            tc_fence_after();
-          }
-          const uint32_t a16 = ring16 + slot * slot16;
-          const uint2* d = dsc + dy * spd;
-#pragma unroll 4
-          for (int i = 0; i < spd; ++i) {
-            const uint2 lo = d[i];
-            tc_mma_f16(d_tmem, mkdesc(a16 + lo.x), mkdesc(lo.y), idesc, acc);
-            acc = 1;
-          }
-          if (dy < p.stride) tc_commit(empty_bar(slot));      // this input row is not needed by later output rows
-          if (++slot == p.ring) { slot = 0; ph ^= 1; }
+    // The whole warp runs this (warp-uniform) loop so that descriptor arithmetic stays in uniform registers; one
+    // elected lane issues.  Tap-step offsets are compile-time constants: the issuing warp looks nothing up while
+    // the tensor pipe waits (an M=128 x N<=64 x K=16 MMA costs the pipe only ~45 cycles).
+    mbar_wait(wfull_bar, 0, p.err, 2);
+    constexpr uint32_t idesc = make_idesc_f16_m128(N);
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+    auto mkdesc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+    const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
+    constexpr uint32_t b_lbo = static_cast<uint32_t>(N) << 16;   // (N*16 bytes) >> 4 in the LBO field
+    constexpr uint32_t b_step = static_cast<uint32_t>(N) * 2;    // (N*32 bytes) >> 4
+    constexpr uint32_t a_lbo = (kind_a_lbo(KIND) >> 4) << 16;
+    const uint32_t b_lo0 = (smem_u32(wsm) >> 4) | b_lbo;
+    constexpr uint32_t slot16 = (NCOPY * kPlaneBytes) >> 4;
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const int ring_n = p.ring;
+    int waited = -1;
+    int base_slot = 0, base_ph = 0;              // ring slot / phase of input row t*stride
+    for (int t = 0; t < nrows_out; ++t) {
+      const int stage = t & 1;
+      mbar_wait(tempty_bar(stage), ((t >> 1) & 1) ^ 1, p.err, 3);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + stage * N;
+      int slot = base_slot, ph = base_ph;
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy) {
+        const int q = t * STRIDE + dy;
+        if (q > waited) {
+          mbar_wait(full_bar(slot), ph, p.err, 4);
+          waited = q;
+          tc_fence_after();
         }
-        tc_mma_f16(d_tmem, ones_desc, bias_desc, idesc, 1u);      // + bias
-        tc_commit(tfull_bar(stage));
-        base_slot += p.stride;
-        if (base_slot >= p.ring) { base_slot -= p.ring; base_ph ^= 1; }
+        const uint32_t a16 = ring16 + slot * slot16;
+        if (elect_one()) {
+          static_for<0, SPD>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr uint32_t a_off16 = kind_a_off(KIND, KCH, i) >> 4;
+            tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
+          });
+          if (dy < STRIDE) tc_commit(empty_bar(slot));      // this input row is not needed by later output rows
+          if (dy == KS - 1) {
+            tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
+            tc_commit(tfull_bar(stage));
+          }
+        }
+        __syncwarp();
+        if (++slot == ring_n) { slot = 0; ph ^= 1; }
       }
+      base_slot += STRIDE;
+      if (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant

@@ -44,7 +44,6 @@ struct HalfK {
 using StepK = std::array<HalfK, 2>;
 using WeightFn = std::function<float(int n, int cin, int tap)>;  // 0 outside the layer's real extent
 
-enum InKind { IN_NAT3x3 = 0, IN_NAT1x1 = 1, IN_NAT3x3_C8 = 2, IN_NAT1x1_C8 = 3, IN_PAR3x3S2 = 4, IN_PAR1x1 = 5 };
 
 // Fills the input-side half of a ConvParams (copies, steps, ring geometry) and the matching weight step list.
 static void build_input_side(InKind kind, const P8& in, int j0, int kchunks, ConvParams& p, std::vector<StepK>& wk) {
@@ -143,6 +142,16 @@ static void build_input_side(InKind kind, const P8& in, int j0, int kchunks, Con
       break;
     }
   }
+  // the same copies in closed form (what the specialised kernels use): copy c reads source entry
+  // src0 + (c / npar) * stride + (c % npar) * par_off into slot plane c
+  p.copy_src0 = static_cast<uint32_t>(j0) * in.Wp;
+  p.copy_src_stride = static_cast<uint32_t>(in.Wp);
+  p.copy_par_off = static_cast<uint32_t>(in.Wp / 2);
+  for (int cidx = 0; cidx < p.n_copies; ++cidx) {   // consistency of the closed form with the table above
+    const int npar = kind == IN_PAR3x3S2 ? 2 : 1;
+    const uint32_t src = p.copy_src0 + (cidx / npar) * p.copy_src_stride + (cidx % npar) * p.copy_par_off;
+    if (src != p.copies[cidx].src_off || p.copies[cidx].dst_off != static_cast<uint32_t>(cidx) * PB) abort();
+  }
 }
 
 // The extra last step carries the bias: (n, k=0) = fp16(b), (n, k=1) = fp16(b - fp16(b)); its A operand is [1,1,0..].
@@ -169,6 +178,7 @@ static std::vector<__half> pack_weights(int N, const std::vector<StepK>& wk, con
 // ------------------------------------------------------------------------------------------------
 struct ConvLaunch {
   ConvParams p;
+  int kind = 0, kch = 0;
   int N;
   int mode;
   dim3 grid;
@@ -352,6 +362,8 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   L.smem = conv_smem_bytes(p);
   if (L.smem > 227 * 1024) return fail(c, "conv " + name + ": shared memory budget exceeded");
   L.N = N;
+  L.kind = kind;
+  L.kch = kchunks;
   L.mode = mode;
   L.name = name;
   const int wstrip = (p.xmul == 2) ? down2(Wo) : Wo;
@@ -360,30 +372,56 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   return 0;
 }
 
-template <int N, int MODE, bool AUX>
+template <int KIND, int KCH, int N, int MODE, bool AUX>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<N, MODE, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_p8_kernel<N, MODE, AUX><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
+  conv_p8_kernel<KIND, KCH, N, MODE, AUX><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
   return cudaGetLastError();
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
+// Every (input kind, channel chunks, N, store mode, auxiliary operands) combination the plans and the self-tests use.
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
-  if (L.mode == STORE_PLANAR) return launch_conv_t<16, STORE_PLANAR, false>(L, s);
-  if (L.mode == STORE_PS) return launch_conv_t<128, STORE_PS, true>(L, s);
   const bool aux = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
-  switch (L.N) {
-    case 16: return aux ? launch_conv_t<16, STORE_P8, true>(L, s) : launch_conv_t<16, STORE_P8, false>(L, s);
-    case 32: return aux ? launch_conv_t<32, STORE_P8, true>(L, s) : launch_conv_t<32, STORE_P8, false>(L, s);
-    case 64: return aux ? launch_conv_t<64, STORE_P8, true>(L, s) : launch_conv_t<64, STORE_P8, false>(L, s);
-    case 128: return aux ? cudaErrorInvalidValue : launch_conv_t<128, STORE_P8, false>(L, s);
+  const int key = ((L.kind * 16 + L.kch) * 256 + L.N) * 8 + L.mode * 2 + (aux ? 1 : 0);
+#define HDRTV_CONV_CASE(KIND, KCH, N, MODE, AUX) \
+  case ((KIND * 16 + KCH) * 256 + N) * 8 + MODE * 2 + (AUX ? 1 : 0): return launch_conv_t<KIND, KCH, N, MODE, AUX>(L, s);
+#define HDRTV_CONV_P8(KIND, KCH, N) HDRTV_CONV_CASE(KIND, KCH, N, STORE_P8, false) HDRTV_CONV_CASE(KIND, KCH, N, STORE_P8, true)
+  switch (key) {
+    // 3x3, 32 input channels: trunk convs, conv_last (planar), up-convs (PixelShuffle store)
+    HDRTV_CONV_P8(IN_NAT3x3, 4, 32)
+    HDRTV_CONV_CASE(IN_NAT3x3, 4, 16, STORE_PLANAR, false)
+    HDRTV_CONV_CASE(IN_NAT3x3, 4, 16, STORE_PLANAR, true)
+    HDRTV_CONV_CASE(IN_NAT3x3, 4, 128, STORE_PS, true)
+    HDRTV_CONV_CASE(IN_NAT3x3, 4, 128, STORE_PS, false)
+    // 3x3 on the 3-channel image (8-channel padded)
+    HDRTV_CONV_P8(IN_NAT3x3_C8, 1, 32)
+    HDRTV_CONV_P8(IN_NAT3x3_C8, 1, 64)
+    HDRTV_CONV_P8(IN_NAT1x1_C8, 1, 64)
+    // 1x1
+    HDRTV_CONV_P8(IN_NAT1x1, 2, 16)
+    HDRTV_CONV_P8(IN_NAT1x1, 2, 32)
+    HDRTV_CONV_P8(IN_NAT1x1, 2, 64)
+    HDRTV_CONV_P8(IN_NAT1x1, 2, 128)
+    HDRTV_CONV_P8(IN_NAT1x1, 4, 64)
+    HDRTV_CONV_P8(IN_NAT1x1, 8, 64)
+    HDRTV_CONV_P8(IN_NAT1x1, 8, 16)
+    HDRTV_CONV_CASE(IN_NAT1x1, 8, 16, STORE_PLANAR, false)
+    HDRTV_CONV_CASE(IN_NAT1x1, 8, 16, STORE_PLANAR, true)
+    HDRTV_CONV_P8(IN_PAR1x1, 8, 64)
+    // stride-2 3x3 on parity-split inputs
+    HDRTV_CONV_P8(IN_PAR3x3S2, 4, 32)
+    HDRTV_CONV_P8(IN_PAR3x3S2, 8, 64)
+    HDRTV_CONV_P8(IN_PAR3x3S2, 8, 16)
   }
+#undef HDRTV_CONV_P8
+#undef HDRTV_CONV_CASE
   return cudaErrorInvalidValue;
 }
 
