@@ -86,6 +86,14 @@ struct ConvParams {
   ConvStep steps[kMaxSteps];
   const uint4* wpk;
   int w_bytes;
+  // in-kernel SFT generator (SFTG instances): per output row, scale/shift = stage-1 1x1 conv (32 -> 64, block diagonal)
+  // of the 32-channel stage-0 map `s0` (arch_util.py:63-72), accumulated in TMEM next to the conv accumulator
+  const uint4* wpk2;        // packed stage-1 weights: 2 tap steps + bias step, N = 64
+  int w2_bytes;
+  const uint4* s0;          // stage-0 map (P8, natural layout, output resolution)
+  long s0_row_entries;      // entries per row of that tensor
+  uint32_t s0_src0;         // first chunk plane of this SFT layer: j0 * Wp
+  uint32_t s0_wp;
   int Ho, Wo, band;
   float slope;         // activation as max(v, slope*v): 1 = none, 0 = ReLU, 0.1 = LeakyReLU(0.1)
   int has_res, has_res2, has_sft, has_raw;
@@ -145,9 +153,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int KIND, int KCH, int N, int MODE, bool AUX>
+constexpr int kSRing = 4;                         // stage-0 rows in flight (SFTG)
+constexpr int kSSlotBytes = 4 * kPlaneBytes;      // one 32-channel stage-0 row
+
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false>
 __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
-  constexpr uint32_t kTmemCols = (2 * N < 32) ? 32 : 2 * N;
+  static_assert(!SFTG || (AUX && MODE == STORE_P8 && N == 32), "in-kernel SFT generator: 32-channel P8 outputs only");
+  constexpr uint32_t kTmemCols = SFTG ? 256 : ((2 * N < 32) ? 32 : 2 * N);       // SFTG: 2 x 32 conv + 2 x 64 scale|shift
   constexpr int KS = kind_ks(KIND), STRIDE = kind_stride(KIND), SPD = kind_spd(KIND, KCH), NCOPY = kind_copies(KIND, KCH);
   constexpr int NPAR = KIND == IN_PAR3x3S2 ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -159,9 +171,13 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 2 + i); };
   const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxRing + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
+  auto sfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };
+  auto sempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + kSRing + i); };
   uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
-  uint8_t* ring = wsm + ((p.w_bytes + 127) & ~127);
+  uint8_t* wsm2 = wsm + ((p.w_bytes + 127) & ~127);
+  uint8_t* ring = wsm2 + (SFTG ? ((p.w2_bytes + 127) & ~127) : 0);
+  uint8_t* sring = ring + p.ring * (kind_copies(KIND, KCH) * kPlaneBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * kTileM;
@@ -179,6 +195,12 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       mbar_init(tempty_bar(i), 8);
     }
     mbar_init(wfull_bar, 1);
+    if constexpr (SFTG) {
+      for (int i = 0; i < kSRing; ++i) {
+        mbar_init(sfull_bar(i), 1);
+        mbar_init(sempty_bar(i), 1);
+      }
+    }
     mbar_fence_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kPlaneEntries) {
@@ -195,8 +217,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(wfull_bar, p.w_bytes);
+      mbar_expect_tx(wfull_bar, p.w_bytes + (SFTG ? p.w2_bytes : 0));
       bulk_g2s(smem_u32(wsm), p.wpk, p.w_bytes, wfull_bar);
+      if constexpr (SFTG) bulk_g2s(smem_u32(wsm2), p.wpk2, p.w2_bytes, wfull_bar);
       constexpr uint32_t row_tx = NCOPY * kPlaneBytes;
       const uint32_t ring_n = p.ring, slot_bytes = NCOPY * kPlaneBytes;
       // The per-copy source address is formed with an explicit mad.wide: for `pointer + 32-bit offset` feeding
@@ -206,6 +229,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       uint32_t slot = 0, ph = 1;
       const uint4* src = p.in + (static_cast<long>(oy0) * STRIDE + p.row_bias) * row_entries + x0 + blockIdx.z * p.in_z_entries +
                          static_cast<long>(p.copy_src0);
+      int ts = 0;
+      uint32_t sslot = 0, sph = 1;
+      const uint4* ssrc = SFTG ? p.s0 + (static_cast<long>(oy0) + 1) * p.s0_row_entries + static_cast<long>(p.s0_src0) + x0 : nullptr;
       for (int q = 0; q < nrows_in; ++q) {
         mbar_wait(empty_bar(slot), ph, p.err, 1);
         mbar_expect_tx(full_bar(slot), row_tx);
@@ -218,6 +244,23 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         }
         src += row_entries;
         if (++slot == ring_n) { slot = 0; ph ^= 1; }
+        if constexpr (SFTG) {
+          // stage-0 row of every output row whose last input row has just been requested
+          while (ts < nrows_out && ts * STRIDE + KS - 1 <= q) {
+            mbar_wait(sempty_bar(sslot), sph, p.err, 6);
+            mbar_expect_tx(sfull_bar(sslot), kSSlotBytes);
+            const uint32_t sdst = smem_u32(sring) + sslot * kSSlotBytes;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              unsigned long long a;
+              asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(c * p.s0_wp), "l"(ssrc));
+              bulk_g2s(sdst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, sfull_bar(sslot));
+            }
+            ssrc += p.s0_row_entries;
+            ++ts;
+            if (++sslot == kSRing) { sslot = 0; sph ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -239,6 +282,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     const int ring_n = p.ring;
     int waited = -1;
     int base_slot = 0, base_ph = 0;              // ring slot / phase of input row t*stride
+    int sslot = 0, sph = 0;                      // stage-0 ring (SFTG)
     for (int t = 0; t < nrows_out; ++t) {
       const int stage = t & 1;
       mbar_wait(tempty_bar(stage), ((t >> 1) & 1) ^ 1, p.err, 3);
@@ -261,13 +305,32 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
             tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
           });
           if (dy < STRIDE) tc_commit(empty_bar(slot));      // this input row is not needed by later output rows
-          if (dy == KS - 1) {
+          if (!SFTG && dy == KS - 1) {
             tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
             tc_commit(tfull_bar(stage));
           }
         }
         __syncwarp();
         if (++slot == ring_n) { slot = 0; ph ^= 1; }
+      }
+      if constexpr (SFTG) {
+        // scale|shift of this output row: [128 px x 32 stage-0 channels] x [32 -> 64 block-diagonal] (+ bias step)
+        mbar_wait(sfull_bar(sslot), sph, p.err, 7);
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t idesc64 = make_idesc_f16_m128(64);
+          const uint32_t sa = ((smem_u32(sring) + sslot * kSSlotBytes + 16) >> 4) | ((kPlaneBytes >> 4) << 16);
+          const uint32_t sb = (smem_u32(wsm2) >> 4) | (64u << 16);
+          const uint32_t s_tmem = tmem_base + 2 * N + stage * 64;
+          tc_mma_f16(s_tmem, mkdesc(sa), mkdesc(sb), idesc64, 0u);
+          tc_mma_f16(s_tmem, mkdesc(sa + ((2 * kPlaneBytes) >> 4)), mkdesc(sb + 128), idesc64, 1u);
+          tc_mma_f16(s_tmem, ones_desc, mkdesc(sb + 256), idesc64, 1u);
+          tc_commit(sempty_bar(sslot));
+          tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // conv bias
+          tc_commit(tfull_bar(stage));
+        }
+        __syncwarp();
+        if (++sslot == kSRing) { sslot = 0; sph ^= 1; }
       }
       base_slot += STRIDE;
       if (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
@@ -393,7 +456,12 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
         tc_fence_after();
         float v[COLS];
+        float sv[SFTG ? COLS : 1], tv[SFTG ? COLS : 1];
         tmem_ld_cols<COLS>(tlane + stage * N + half * COLS, v);
+        if constexpr (SFTG) {
+          tmem_ld_cols<COLS>(tlane + 2 * N + stage * 64 + half * COLS, sv);
+          tmem_ld_cols<COLS>(tlane + 2 * N + stage * 64 + 32 + half * COLS, tv);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(stage));
@@ -417,7 +485,10 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
                 for (int k = 0; k < 8; ++k) val[k] += r[k];
               }
               if (p.has_raw) *raw.at(oy, j0 + c) = pack8(val);
-              if (p.has_sft) {
+              if constexpr (SFTG) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], sv[c * 8 + k], val[k]) + tv[c * 8 + k];
+              } else if (p.has_sft) {
                 float s[8], tt[8];
                 unpack8(s4[c], s);
                 unpack8(t4[c], tt);
@@ -438,7 +509,8 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
 }
 
 inline size_t conv_smem_bytes(const ConvParams& p) {
-  return kSmemHeader + ((p.w_bytes + 127) & ~127) + static_cast<size_t>(p.ring) * p.slot_bytes;
+  const size_t sftg = p.wpk2 ? ((p.w2_bytes + 127) & ~127) + static_cast<size_t>(kSRing) * kSSlotBytes : 0;
+  return kSmemHeader + ((p.w_bytes + 127) & ~127) + static_cast<size_t>(p.ring) * p.slot_bytes + sftg;
 }
 
 }  // namespace hdrtv

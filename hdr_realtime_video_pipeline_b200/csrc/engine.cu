@@ -179,6 +179,7 @@ static std::vector<__half> pack_weights(int N, const std::vector<StepK>& wk, con
 struct ConvLaunch {
   ConvParams p;
   int kind = 0, kch = 0;
+  bool sftg = false;
   int N;
   int mode;
   dim3 grid;
@@ -304,7 +305,7 @@ static int env_int(const char* name, int dflt) {
 static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   ConvParams& p = L.p;
   const int z = p.xmul == 2 ? 2 : 1;
-  const int tmem_cols = std::max(32, 2 * L.N);
+  const int tmem_cols = L.sftg ? 256 : std::max(32, 2 * L.N);
   int occ = static_cast<int>((227 * 1024) / (L.smem + 1024));
   occ = std::max(1, std::min(occ, std::min(512 / tmem_cols, max_occ)));
   const int slots = 148 * occ * env_int("HDRTV_WAVES", 1);
@@ -320,7 +321,10 @@ struct Epi {
   int act = ACT_NONE;
   const P8* res = nullptr;
   const P8* res2 = nullptr;
-  const P8* sft = nullptr;
+  const P8* sft = nullptr;          // precomputed scale|shift map (64 ch), or
+  const P8* sft_s0 = nullptr;       // stage-0 map + stage-1 weights: scale|shift generated inside the kernel (SFTG)
+  int sft_j0 = 0;
+  const __half* sft_w2 = nullptr;
   const P8* raw = nullptr;
   __half* planar = nullptr;
 };
@@ -341,6 +345,16 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   if (e.res) { p.has_res = 1; p.res = *e.res; }
   if (e.res2) { p.has_res2 = 1; p.res2 = *e.res2; }
   if (e.sft) { p.has_sft = 1; p.sft = *e.sft; }
+  if (e.sft_s0) {
+    if (e.sft_s0->parity) return fail(c, "conv " + name + ": stage-0 SFT map must be in natural layout");
+    p.wpk2 = reinterpret_cast<const uint4*>(e.sft_w2);
+    p.w2_bytes = 3 * 64 * 32;
+    p.s0 = reinterpret_cast<const uint4*>(e.sft_s0->base);
+    p.s0_row_entries = e.sft_s0->row_entries();
+    p.s0_src0 = static_cast<uint32_t>(e.sft_j0) * e.sft_s0->Wp;
+    p.s0_wp = static_cast<uint32_t>(e.sft_s0->Wp);
+    L.sftg = true;
+  }
   if (e.raw) { p.has_raw = 1; p.raw = *e.raw; }
   p.planar = e.planar;
   p.planar_plane = static_cast<long>(Ho) * Wo;
@@ -348,7 +362,8 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   p.err = c->d_err;
   const int min_ring = p.ks + 1;
   const size_t budget = 200 * 1024;
-  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127);
+  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127) +
+                       (p.wpk2 ? ((p.w2_bytes + 127) & ~127) + static_cast<size_t>(kSRing) * kSSlotBytes : 0);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
   // ring depth: rows in use (ks) + prefetch; shallow rings keep shared memory small so that more CTAs share an SM
   // ring depth: rows in use (ks) + prefetched rows.  Cheap slots (few channel planes) prefetch deeper: their rows
@@ -372,22 +387,29 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   return 0;
 }
 
-template <int KIND, int KCH, int N, int MODE, bool AUX>
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_p8_kernel<KIND, KCH, N, MODE, AUX><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
+  conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
   return cudaGetLastError();
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 // Every (input kind, channel chunks, N, store mode, auxiliary operands) combination the plans and the self-tests use.
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
+  if (L.sftg) {     // in-kernel SFT generator: 32-channel P8 outputs
+    if (L.N != 32 || L.mode != STORE_P8) return cudaErrorInvalidValue;
+    if (L.kind == IN_NAT3x3 && L.kch == 4) return launch_conv_t<IN_NAT3x3, 4, 32, STORE_P8, true, true>(L, s);
+    if (L.kind == IN_NAT3x3_C8 && L.kch == 1) return launch_conv_t<IN_NAT3x3_C8, 1, 32, STORE_P8, true, true>(L, s);
+    if (L.kind == IN_PAR3x3S2 && L.kch == 4) return launch_conv_t<IN_PAR3x3S2, 4, 32, STORE_P8, true, true>(L, s);
+    return cudaErrorInvalidValue;
+  }
   const bool aux = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
   const int key = ((L.kind * 16 + L.kch) * 256 + L.N) * 8 + L.mode * 2 + (aux ? 1 : 0);
 #define HDRTV_CONV_CASE(KIND, KCH, N, MODE, AUX) \
@@ -941,12 +963,21 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   r |= std_conv(L, "LE.CondNet4.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
   r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, F2, H2, W2, lrelu);
   r |= std_conv(L, "LE.CondNet4.4", IN_PAR3x3S2, F2, 64, 16, STORE_P8, cond4, H3, W3, none);
-  // ---- SFT maps: stage 0 (stacked, LeakyReLU) then one block-diagonal stage 1 per SFT layer
+  // ---- SFT: stage 0 of every SFT layer of a level stacked into one 1x1 conv (LeakyReLU).  Stage 1 (32 -> 64, block
+  // diagonal scale|shift) runs inside the consuming conv kernel (SFTG) from the stage-0 map; only the PixelShuffle
+  // consumers (up-convs) still read a precomputed scale|shift map.
+  const bool use_sftg = env_int("HDRTV_SFTG", 1) != 0;
+  struct S0Ref { const P8* S; int j0; };
+  std::map<std::string, S0Ref> s0of;
   auto sft_group = [&](const std::string& key, const P8& cond, const P8& S, const char* const* names, int n, int h, int w) {
     r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), S, h, w, lrelu);
     for (int i = 0; i < n; ++i) {
-      const std::string k1 = std::string(names[i]) + ".stage1";
-      r |= make_conv(c, L, k1, IN_NAT1x1, S, 4 * i, 4, 64, STORE_P8, wk(k1), maps.at(names[i]), h, w, none);
+      const std::string nm = names[i];
+      s0of[nm] = S0Ref{&S, 4 * i};
+      const bool ps_consumer = nm == "LE.recon_trunk4.0.sft1" || nm == "LE.recon_trunk5.0.sft1" || nm == "LE.SFT_layer2";
+      if (use_sftg && !ps_consumer) continue;
+      const std::string k1 = nm + ".stage1";
+      r |= make_conv(c, L, k1, IN_NAT1x1, S, 4 * i, 4, 64, STORE_P8, wk(k1), maps.at(nm), h, w, none);
     }
   };
   sft_group("sft0.L0", cond1, S0, kSftL0, 2, H, Wd);
@@ -954,24 +985,36 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   sft_group("sft0.L2", cond3, S2, kSftL2, 4, H2, W2);
   sft_group("sft0.L3a", cond4, S3a, kSftL3, 4, H3, W3);
   sft_group("sft0.L3b", cond4, S3b, kSftL3 + 4, 4, H3, W3);
+  // SFT applied in a conv epilogue: in-kernel generator where possible, else the precomputed map
+  auto with_sft = [&](Epi& e, const std::string& nm) {
+    if (use_sftg) {
+      const S0Ref& ref = s0of.at(nm);
+      e.sft_s0 = ref.S;
+      e.sft_j0 = ref.j0;
+      e.sft_w2 = wk(nm + ".stage1");
+    } else {
+      e.sft = &maps.at(nm);
+    }
+  };
   // ---- trunk
-  { Epi e = relu; e.sft = &maps.at("LE.SFT_layer1");
+  { Epi e = relu; with_sft(e, "LE.SFT_layer1");
     r |= std_conv(L, "LE.conv_first", IN_NAT3x3_C8, agP8, 8, 32, STORE_P8, T0a, H, Wd, e); }
   r |= std_conv(L, "LE.HR_conv1", IN_NAT3x3, T0a, 32, 32, STORE_P8, FEA0, H, Wd, relu);
   auto resblock = [&](const std::string& pre, const P8& xm, const P8& xraw, const P8& ytmp, const P8& out,
-                      const P8* res2, const P8* next_sft, const P8* next_raw, int h, int w) {
-    { Epi e = relu; e.sft = &maps.at(pre + ".sft2");
+                      const P8* res2, const char* next_sft, const P8* next_raw, int h, int w) {
+    { Epi e = relu; with_sft(e, pre + ".sft2");
       r |= std_conv(L, pre + ".conv1", IN_NAT3x3, xm, 32, 32, STORE_P8, ytmp, h, w, e); }
-    { Epi e; e.res = &xraw; e.res2 = res2; e.sft = next_sft; e.raw = next_raw;
+    { Epi e; e.res = &xraw; e.res2 = res2; e.raw = next_raw;
+      if (next_sft) with_sft(e, next_sft);
       r |= std_conv(L, pre + ".conv2", IN_NAT3x3, ytmp, 32, 32, STORE_P8, out, h, w, e); }
   };
-  { Epi e = relu; e.raw = &X1; e.sft = &maps.at("LE.recon_trunk1.0.sft1");
+  { Epi e = relu; e.raw = &X1; with_sft(e, "LE.recon_trunk1.0.sft1");
     r |= std_conv(L, "LE.down_conv1", IN_PAR3x3S2, FEA0, 32, 32, STORE_P8, X1m, H1, W1, e); }
   resblock("LE.recon_trunk1.0", X1m, X1, Y1, FEA1, nullptr, nullptr, nullptr, H1, W1);
-  { Epi e = relu; e.raw = &X2; e.sft = &maps.at("LE.recon_trunk2.0.sft1");
+  { Epi e = relu; e.raw = &X2; with_sft(e, "LE.recon_trunk2.0.sft1");
     r |= std_conv(L, "LE.down_conv2", IN_PAR3x3S2, FEA1, 32, 32, STORE_P8, X2m, H2, W2, e); }
   resblock("LE.recon_trunk2.0", X2m, X2, Y2, FEA2, nullptr, nullptr, nullptr, H2, W2);
-  { Epi e = relu; e.raw = &FEA3; e.sft = &maps.at("LE.recon_trunk3.0.sft1");
+  { Epi e = relu; e.raw = &FEA3; with_sft(e, "LE.recon_trunk3.0.sft1");
     r |= std_conv(L, "LE.down_conv3", IN_PAR3x3S2, FEA2, 32, 32, STORE_P8, Zm, H3, W3, e); }
   {
     const P8* xraw = &FEA3;
@@ -979,8 +1022,8 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
       const std::string pre = "LE.recon_trunk3." + std::to_string(i);
       if (i < 3) {
         // Z_{i+1} = Z_i + conv2(...): raw copy for the next block's residual, SFT-modulated copy for its conv1
-        resblock(pre, Zm, *xraw, Y3, Zm, nullptr, &maps.at("LE.recon_trunk3." + std::to_string(i + 1) + ".sft1"),
-                 &Z[i & 1], H3, W3);
+        const std::string nxt = "LE.recon_trunk3." + std::to_string(i + 1) + ".sft1";
+        resblock(pre, Zm, *xraw, Y3, Zm, nullptr, nxt.c_str(), &Z[i & 1], H3, W3);
         xraw = &Z[i & 1];
       } else {
         resblock(pre, Zm, *xraw, Y3, U3, &FEA3, nullptr, nullptr, H3, W3);   // out = trunk3(fea3) + fea3
@@ -1630,6 +1673,28 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
     const long n = static_cast<long>(hres.size());
     sft_mod_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(dout, ds, dt, dout, n);
   }
+  // bit5: SFT generated in-kernel from a 32-channel stage-0 map through a block-diagonal 32 -> 64 stage 1
+  std::vector<float> hs0, hw2, hb2(64);
+  if (flags & 32) {
+    if (outC != 32 || ps || planar) { c->err = "selftest: SFTG needs a 32-channel P8 output"; return -1; }
+    hs0.resize(static_cast<size_t>(32) * outH * outW);
+    hw2.assign(static_cast<size_t>(64) * 32, 0.f);
+    for (auto& v : hs0) v = __half2float(__float2half(rnd()));
+    for (int n2 = 0; n2 < 64; ++n2)
+      for (int k2 = 0; k2 < 32; ++k2)
+        if ((n2 < 32) == (k2 < 16)) hw2[static_cast<size_t>(n2) * 32 + k2] = __half2float(__float2half(rnd() * 0.5f));
+    for (auto& v : hb2) v = rnd() * 0.1f;
+    float* ds0 = ws_alloc<float>(&t, hs0.size());
+    float* dw2 = ws_alloc<float>(&t, hw2.size());
+    float* db2 = ws_alloc<float>(&t, 64);
+    float* dmap = ws_alloc<float>(&t, static_cast<size_t>(64) * outH * outW);
+    cudaMemcpy(ds0, hs0.data(), hs0.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dw2, hw2.data(), hw2.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db2, hb2.data(), 64 * 4, cudaMemcpyHostToDevice);
+    r |= conv32(&t, 0, ds0, dw2, db2, dmap, 32, 64, outH, outW, 1, 1, ACT_NONE, 0.f);
+    const long n = static_cast<long>(hres.size());
+    sft_mod_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(dout, dmap, dmap + n, dout, n);
+  }
   std::vector<float> ref(hres.size());
   cudaDeviceSynchronize();
   cudaMemcpy(ref.data(), dout, ref.size() * 4, cudaMemcpyDeviceToHost);
@@ -1664,6 +1729,20 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
   __half* dplanar = ws_alloc<__half>(&t, static_cast<size_t>(3) * outH * outW);
   std::vector<ConvLaunch> plan;
   Epi e; e.act = act;
+  P8 s0p;
+  if (flags & 32) {
+    s0p = make_p8(&t, 64, outH, outW, false);         // the layer's 32 channels sit at chunk planes 4..7
+    fill_p8(s0p, hs0, 32, 4);
+    ConvParams tmp2; memset(&tmp2, 0, sizeof(tmp2));
+    std::vector<StepK> wk2;
+    P8 dummy; dummy.Wp = 16; dummy.chunks = 4;
+    build_input_side(IN_NAT1x1, dummy, 0, 4, tmp2, wk2);
+    WeightFn wf2 = [&](int n2, int ci, int tap) -> float { return (n2 < 64 && ci < 32 && tap == 0) ? hw2[static_cast<size_t>(n2) * 32 + ci] : 0.f; };
+    std::vector<__half> pk2 = pack_weights(64, wk2, wf2, [&](int n2) { return n2 < 64 ? hb2[n2] : 0.f; });
+    __half* dpk2 = ws_alloc<__half>(&t, pk2.size());
+    cudaMemcpy(dpk2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice);
+    e.sft_s0 = &s0p; e.sft_j0 = 4; e.sft_w2 = dpk2; e.raw = &rawp;
+  }
   if (!planar) {
     if (flags & 8) e.res = &resp;
     if (flags & 16) { e.sft = &sftp; e.raw = &rawp; }
