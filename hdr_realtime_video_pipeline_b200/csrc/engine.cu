@@ -811,7 +811,6 @@ static int build_classifier(Ctx* c, int Hc, int Wc) {
     L.stats = sp;
     sp += 2 * L.Cout;
     c->cls.push_back(L);
-    dbg_f32(c, "cls" + std::to_string(l), L.out, L.Cout, L.Ho, L.Wo);
     h = L.Ho; w = L.Wo;
   }
   c->d_fea = ws_alloc<float>(c, 8);
@@ -824,7 +823,14 @@ static int build_classifier(Ctx* c, int Hc, int Wc) {
   return 0;
 }
 
-static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t s) {
+static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t s, std::vector<cudaEvent_t>* evs = nullptr) {
+  auto mark = [&]() {
+    if (!evs) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    evs->push_back(e);
+  };
   CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
   static const int convi[6] = {0, 4, 8, 12, 16, 20};
   static const int normi[5] = {3, 7, 11, 15, -1};
@@ -843,19 +849,23 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     p.out_stats = L.stats;
     p.Cin = L.Cin; p.Cout = L.Cout; p.H = L.H; p.W = L.W; p.Ho = L.Ho; p.Wo = L.Wo;
     const int npix = L.Ho * L.Wo;
-    // pixels per block: enough blocks to cover the GPU on the deep (small) levels, enough work per block on the first
-    const int pix = npix >= 64 * 1024 ? 64 : (npix >= 16 * 1024 ? 32 : (npix >= 4096 ? 16 : (npix >= 1024 ? 8 : 4)));
-    const size_t sm = sizeof(float) * (static_cast<size_t>(pix) * L.Cin + 2 * L.Cin);
+    // ~256 blocks per level; the first (3-channel) level takes more pixels per block
+    int pix = 1;
+    while (pix < 128 && (npix + pix - 1) / pix > 296) pix *= 2;
+    if (l == 0) pix = std::max(pix, 64);
+    p.pix = pix;
+    p.in_planar = l == 0 ? 1 : 0;
+    const size_t sm = sizeof(float) * (static_cast<size_t>(L.Cin) * L.Cout + static_cast<size_t>(pix) * L.Cin + 2 * L.Cin + pix);
     const unsigned blocks = static_cast<unsigned>((npix + pix - 1) / pix);
-    switch (pix) {
-      case 64: cls_level_kernel<64><<<blocks, 128, sm, s>>>(p); break;
-      case 32: cls_level_kernel<32><<<blocks, 128, sm, s>>>(p); break;
-      case 16: cls_level_kernel<16><<<blocks, 128, sm, s>>>(p); break;
-      case 8: cls_level_kernel<8><<<blocks, 128, sm, s>>>(p); break;
-      default: cls_level_kernel<4><<<blocks, 128, sm, s>>>(p); break;
+    static bool configured = false;
+    if (!configured) {
+      CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      configured = true;
     }
+    cls_level_kernel<<<blocks, 256, sm, s>>>(p);
     CK(c, cudaGetLastError());
     ++c->launches;
+    mark();
   }
   HeadParams hp;
   hp.stats5 = c->cls[4].stats;
@@ -1211,7 +1221,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
   CK(c, cudaGetLastError());
   ++c->launches;
   mark();
-  if (run_classifier(c, cond, true, s)) return -1;
+  if (run_classifier(c, cond, true, s, evs)) return -1;
   mark();
   for (ConvLaunch& L : c->plan_agcm) {
     if (L.mode == STORE_PLANAR) L.p.planar = agcm_out;
@@ -1466,7 +1476,7 @@ int hdrtv_time_plan(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, 
   if (run_fp16(c, static_cast<const __half*>(x), static_cast<const __half*>(cond), static_cast<__half*>(out),
                static_cast<__half*>(agcm_out), s, &evs)) return -1;
   CK(c, cudaStreamSynchronize(s));
-  std::string nm = "planar_to_p8\nclassifier+head\n";
+  std::string nm = "planar_to_p8\ncls.level0 (+memset)\ncls.level1\ncls.level2\ncls.level3\ncls.level4\nagcm_head\n";
   for (auto& L : c->plan_agcm) nm += L.name + " N" + std::to_string(L.N) + " grid" + std::to_string(L.grid.x) + "x" + std::to_string(L.grid.y) + "x" + std::to_string(L.grid.z) + " ring" + std::to_string(L.p.ring) + " smem" + std::to_string(L.smem) + "\n";
   for (auto& L : c->plan_le) nm += L.name + " N" + std::to_string(L.N) + " grid" + std::to_string(L.grid.x) + "x" + std::to_string(L.grid.y) + "x" + std::to_string(L.grid.z) + " ring" + std::to_string(L.p.ring) + " smem" + std::to_string(L.smem) + "\n";
   snprintf(names, names_cap, "%s", nm.c_str());

@@ -102,35 +102,40 @@ __global__ void f32_to_half_kernel(const float* a, __half* y, long n) {
 // zero padding applies to the conv OUTPUT (bias included), so border windows simply have fewer terms.
 // ------------------------------------------------------------------------------------------------
 struct ClsLevel {
-  const void* in;        // [Cin][H][W]  fp32, or fp16/fp32 planar cond for level 0
+  const void* in;          // level 0: planar cond [3][H][W] (fp16 or fp32); deeper levels: pixel-major fp32 [H][W][Cin]
+  int in_planar;
   int in_is_half;
   const double* in_stats;  // [Cin][2] sum, sumsq of the previous level's output (nullptr: no IN before this level)
   const float* gamma;      // IN affine of the previous level
   const float* beta;
   const float* w;          // [Cin][Cout]  (transposed copy made at weight-load time)
   const float* b;          // [Cout]
-  float* out;              // [Cout][Ho][Wo]
+  float* out;              // pixel-major [Ho][Wo][Cout]
   double* out_stats;       // [Cout][2], pre-zeroed
   int Cin, Cout, H, W, Ho, Wo;
+  int pix;                 // pooled pixels per block
 };
 
-// Two phases per block of PIX pooled pixels (128 threads):
-//   1. S[px][ci] = sum over the valid 3x3 window of IN(x)[ci]      (pool BEFORE the 1x1 conv: both are linear)
-//   2. y[px][co] = LeakyReLU_0.2( (W[co,:] . S[px,:] + nwin*b[co]) / 9 ), weights read transposed ([Cin][Cout]) so
-//      that consecutive threads (consecutive co) coalesce; per-channel sum / sum^2 go through shared then global
-//      FP64 atomics (one pair per channel per block).
-// Requires Cout to divide 128 or be a multiple of it (16/32/64/128 here).
-template <int PIX>
-__global__ void __launch_bounds__(128) cls_level_kernel(const ClsLevel p) {
+// One level of the AGCM condition classifier (Condition_arch.py:8-35): IN-affine of the previous level, AvgPool(3,2,1)
+// and the 1x1 conv commute (all linear), so a block of 256 threads computes for `pix` pooled pixels
+//   1. S[px][ci] = sum over the valid 3x3 window of IN(x)[ci]           (coalesced: channels are the fast index)
+//   2. y[px][co] = LeakyReLU_0.2((W[co,:] . S[px,:] + nwin * b[co]) / 9) with the level's weights staged in shared memory
+//   3. per-channel sum / sum^2 in FP64: registers -> shared -> one global atomic pair per channel per block.
+// The work is tiny (<= 17 MMAC per level); the kernel is built for latency: ~256 blocks per level, no long dependent
+// chains of global loads.
+__global__ void __launch_bounds__(256) cls_level_kernel(const ClsLevel p) {
   extern __shared__ float sm[];
-  float* S = sm;                         // [PIX][Cin]
-  float* na = S + PIX * p.Cin;           // [Cin] IN scale
-  float* nb = na + p.Cin;                // [Cin] IN shift
-  __shared__ int nwin[PIX];
+  const int Cin = p.Cin, Cout = p.Cout, PIX = p.pix;
+  float* Wsm = sm;                       // [Cin][Cout]
+  float* S = Wsm + Cin * Cout;           // [PIX][Cin]
+  float* na = S + PIX * Cin;             // [Cin] IN scale
+  float* nb = na + Cin;                  // [Cin] IN shift
+  int* nwin = reinterpret_cast<int*>(nb + Cin);   // [PIX]
   __shared__ double ssum[128][2];
   const int tid = threadIdx.x;
+  for (int i = tid; i < Cin * Cout; i += 256) Wsm[i] = __ldg(p.w + i);
   const double cnt = static_cast<double>(p.H) * p.W;
-  for (int ci = tid; ci < p.Cin; ci += 128) {
+  for (int ci = tid; ci < Cin; ci += 256) {
     if (p.in_stats) {
       const double mean = p.in_stats[2 * ci] / cnt;
       double var = p.in_stats[2 * ci + 1] / cnt - mean * mean;
@@ -143,12 +148,14 @@ __global__ void __launch_bounds__(128) cls_level_kernel(const ClsLevel p) {
       nb[ci] = 0.f;
     }
   }
-  if (tid < p.Cout && tid < 128) { ssum[tid][0] = 0.0; ssum[tid][1] = 0.0; }
+  if (tid < 128) { ssum[tid][0] = 0.0; ssum[tid][1] = 0.0; }
   __syncthreads();
   const int npix = p.Ho * p.Wo;
   const int pix0 = blockIdx.x * PIX;
-  for (int item = tid; item < PIX * p.Cin; item += 128) {
-    const int px = item % PIX, ci = item / PIX;
+  for (int item = tid; item < PIX * Cin; item += 256) {
+    int px, ci;
+    if (p.in_planar) { px = item % PIX; ci = item / PIX; }      // planar input: pixels are the fast index
+    else { ci = item % Cin; px = item / Cin; }
     const int idx = pix0 + px;
     float acc = 0.f;
     int n = 0;
@@ -163,37 +170,47 @@ __global__ void __launch_bounds__(128) cls_level_kernel(const ClsLevel p) {
         for (int kx = 0; kx < 3; ++kx) {
           const int ix = 2 * ox + kx - 1;
           if (ix < 0 || ix >= p.W) continue;
-          const long o = (static_cast<long>(ci) * p.H + iy) * p.W + ix;
-          const float v = p.in_is_half ? __half2float(reinterpret_cast<const __half*>(p.in)[o])
-                                       : reinterpret_cast<const float*>(p.in)[o];
+          float v;
+          if (p.in_planar) {
+            const long o = (static_cast<long>(ci) * p.H + iy) * p.W + ix;
+            v = p.in_is_half ? __half2float(reinterpret_cast<const __half*>(p.in)[o]) : reinterpret_cast<const float*>(p.in)[o];
+          } else {
+            v = reinterpret_cast<const float*>(p.in)[(static_cast<long>(iy) * p.W + ix) * Cin + ci];
+          }
           acc += fmaf(v, a, b);
           ++n;
         }
       }
     }
-    S[px * p.Cin + ci] = acc;
+    S[px * Cin + ci] = acc;
     if (ci == 0) nwin[px] = n;
   }
   __syncthreads();
-  const int co = tid % p.Cout;                      // fixed per thread (Cout divides 128) or tid (Cout == 128)
+  const int co = tid % Cout;                        // fixed per thread: Cout divides 256
+  const float bias = __ldg(p.b + co);
   double s1 = 0.0, s2 = 0.0;
-  for (int item = tid; item < PIX * p.Cout; item += 128) {
-    const int px = item / p.Cout;
+  for (int item = tid; item < PIX * Cout; item += 256) {
+    const int px = item / Cout;
     const int idx = pix0 + px;
     if (idx >= npix) break;
-    const float* sp = S + px * p.Cin;
-    float acc = 0.f;
-    for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(sp[ci], __ldg(p.w + ci * p.Cout + co), acc);
-    float y = (acc + nwin[px] * __ldg(p.b + co)) / 9.0f;
+    const float* sp = S + px * Cin;
+    float acc0 = 0.f, acc1 = 0.f;
+    int ci = 0;
+    for (; ci + 1 < Cin; ci += 2) {
+      acc0 = fmaf(sp[ci], Wsm[ci * Cout + co], acc0);
+      acc1 = fmaf(sp[ci + 1], Wsm[(ci + 1) * Cout + co], acc1);
+    }
+    if (ci < Cin) acc0 = fmaf(sp[ci], Wsm[ci * Cout + co], acc0);
+    float y = (acc0 + acc1 + nwin[px] * bias) / 9.0f;
     y = y >= 0.f ? y : 0.2f * y;
-    p.out[static_cast<long>(co) * npix + idx] = y;
+    p.out[static_cast<long>(idx) * Cout + co] = y;
     s1 += y;
     s2 += static_cast<double>(y) * y;
   }
   atomicAdd(&ssum[co][0], s1);
   atomicAdd(&ssum[co][1], s2);
   __syncthreads();
-  if (tid < p.Cout) {
+  if (tid < Cout) {
     atomicAdd(p.out_stats + 2 * tid, ssum[tid][0]);
     atomicAdd(p.out_stats + 2 * tid + 1, ssum[tid][1]);
   }
