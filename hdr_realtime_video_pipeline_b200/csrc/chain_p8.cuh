@@ -4,6 +4,7 @@
 //   ProgAGCM : 1x1 3->64 ReLU, 1x1 64->64 ReLU, 1x1 64->3                   (Condition_arch.py:571-583, GFM folded)
 //   ProgCond : 3x3 3->64, 1x1, 1x1 [store cond], 1x1, 1x1, 1x1 ->16 [store cond1], LeakyReLU(0.1)
 //                                                                          (HDRUNet3T1_arch.py:41-46, 160-161)
+//   ProgCondSft : ProgCond + the stage-0 convs of the full-resolution SFT layers on cond1 (arch_util.py:63-72)
 //
 // Measured on B200 (scripts/tensor_probe.py, scripts/chain_trace.py, profiles/): one tcgen05.mma of K = 16 occupies
 // the SM's tensor pipe for >= ~45 cycles whatever N <= 64 is, the issuing thread cannot run ahead of the pipe, an
@@ -54,6 +55,21 @@ struct ProgCond {
   static constexpr int A0_OFF[2] = {0, 32};           // per input row: taps (dx 0, dx 1) paired, then dx 2 (+ zero half)
   static constexpr int A0_LBO[2] = {16, 16};
 };
+// ProgCond + the stage-0 convs of the two full-resolution SFT layers (16 -> 2 x 32, LeakyReLU) as a seventh step on
+// cond1: S0STORE = 1 stores all 64 channels to outs[6]; 3 stores chunks 0-3 to outs[6] and chunks 4-7 to outs2 (the
+// parity-split home of the layer an up-conv applies).                                   (arch_util.py:63-72)
+template <int S0STORE>
+struct ProgCondSft {
+  static constexpr int L = 7, KS = 3;
+  static constexpr int N[L] = {64, 64, 64, 64, 64, 16, 64};
+  static constexpr int STEPS[L] = {6, 4, 4, 4, 4, 4, 1};
+  static constexpr int APLANE[L] = {0, 0, 0, 0, 0, 0, 0};
+  static constexpr int WRITE[L] = {1, 1, 1, 1, 1, 1, 0};
+  static constexpr int STORE[L] = {0, 0, 1, 0, 0, 1, S0STORE};
+  static constexpr int ACT[L] = {2, 2, 2, 2, 2, 0, 2};
+  static constexpr int A0_OFF[2] = {0, 32};
+  static constexpr int A0_LBO[2] = {16, 16};
+};
 template <class P>
 __host__ __device__ constexpr int prog_w_off(int l) {   // byte offset of layer l's packed weights (steps + bias step)
   int off = 0;
@@ -65,6 +81,7 @@ struct ChainParams {
   ConvParams base;           // input side (ring geometry), weights pointer / total bytes, Ho/Wo, planar output
   int strips;                // 128-pixel strips per row; the grid is 1-D, each CTA takes a contiguous (strip, row) range
   P8 outs[kMaxChain];        // per layer, where STORE != 0
+  P8 outs2;                  // second home of a split store (STORE == 3)
   long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [step<64][slot<8][8]
 };
 
@@ -286,6 +303,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
                 o.init(cp.outs[l], x);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) *o.at(oy, c) = h[c];
+              }
+            } else if constexpr (kStore == 3) {
+              if (xin) {
+                ColRef o, o2;
+                o.init(cp.outs[l], x);
+                o2.init(cp.outs2, x);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *o.at(oy, c) = h[c];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *o2.at(oy, c) = h[4 + c];
               }
             }
           } else {   // N == 16

@@ -98,6 +98,8 @@ struct ConvParams {
   float slope;         // activation as max(v, slope*v): 1 = none, 0 = ReLU, 0.1 = LeakyReLU(0.1)
   int has_res, has_res2, has_sft, has_raw;
   P8 res, res2, sft, out, raw;
+  int out_split;            // > 0: output chunks >= out_split go to out2 (chunk index - out_split) instead of out
+  P8 out2;
   __half* planar;
   long planar_plane;
   int planar_W;
@@ -155,11 +157,18 @@ __device__ __forceinline__ bool elect_one() {
 
 constexpr int kSRing = 4;                         // stage-0 rows in flight (SFTG)
 constexpr int kSSlotBytes = 4 * kPlaneBytes;      // one 32-channel stage-0 row
+constexpr int kSRingPS = 2;                       // PixelShuffle consumers: 4 sub-pixel rows (2 fine rows x 2 column
+constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels per coarse output row
 
 template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false>
 __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
-  static_assert(!SFTG || (AUX && MODE == STORE_P8 && N == 32), "in-kernel SFT generator: 32-channel P8 outputs only");
-  constexpr uint32_t kTmemCols = SFTG ? 256 : ((2 * N < 32) ? 32 : 2 * N);       // SFTG: 2 x 32 conv + 2 x 64 scale|shift
+  static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
+                "in-kernel SFT generator: 32-channel outputs only");
+  constexpr bool PSG = SFTG && MODE == STORE_PS;
+  // SFTG: 2 x 32 conv + 2 x 64 scale|shift columns; PixelShuffle: 2 x 128 conv + 4 sub-pixels x 64 (single-buffered)
+  constexpr uint32_t kTmemCols = SFTG ? (PSG ? 512 : 256) : ((2 * N < 32) ? 32 : 2 * N);
+  constexpr int SRING = PSG ? kSRingPS : kSRing;
+  constexpr int SSLOT = PSG ? kSSlotBytesPS : kSSlotBytes;
   constexpr int KS = kind_ks(KIND), STRIDE = kind_stride(KIND), SPD = kind_spd(KIND, KCH), NCOPY = kind_copies(KIND, KCH);
   constexpr int NPAR = KIND == IN_PAR3x3S2 ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxRing + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
   auto sfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };
-  auto sempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + kSRing + i); };
+  auto sempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + kSRing + i); };   // kSRing >= kSRingPS
   uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
   uint8_t* wsm2 = wsm + ((p.w_bytes + 127) & ~127);
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     }
     mbar_init(wfull_bar, 1);
     if constexpr (SFTG) {
-      for (int i = 0; i < kSRing; ++i) {
+      for (int i = 0; i < SRING; ++i) {
         mbar_init(sfull_bar(i), 1);
         mbar_init(sempty_bar(i), 1);
       }
@@ -231,7 +240,10 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
                          static_cast<long>(p.copy_src0);
       int ts = 0;
       uint32_t sslot = 0, sph = 1;
-      const uint4* ssrc = SFTG ? p.s0 + (static_cast<long>(oy0) + 1) * p.s0_row_entries + static_cast<long>(p.s0_src0) + x0 : nullptr;
+      // first stage-0 row of the band: output row oy0 (fine row 2*oy0 for PixelShuffle); +1 = the tensor's top pad row
+      const uint4* ssrc = SFTG ? p.s0 + (static_cast<long>(oy0) * (PSG ? 2 : 1) + 1) * p.s0_row_entries +
+                                     static_cast<long>(p.s0_src0) + x0
+                               : nullptr;
       for (int q = 0; q < nrows_in; ++q) {
         mbar_wait(empty_bar(slot), ph, p.err, 1);
         mbar_expect_tx(full_bar(slot), row_tx);
@@ -248,17 +260,30 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
           // stage-0 row of every output row whose last input row has just been requested
           while (ts < nrows_out && ts * STRIDE + KS - 1 <= q) {
             mbar_wait(sempty_bar(sslot), sph, p.err, 6);
-            mbar_expect_tx(sfull_bar(sslot), kSSlotBytes);
-            const uint32_t sdst = smem_u32(sring) + sslot * kSSlotBytes;
+            mbar_expect_tx(sfull_bar(sslot), SSLOT);
+            const uint32_t sdst = smem_u32(sring) + sslot * SSLOT;
+            if constexpr (PSG) {
+              // sub-pixel (i, j) of coarse pixel x: fine row 2*oy + i, column parity plane j, entry x (parity layout)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              unsigned long long a;
-              asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(c * p.s0_wp), "l"(ssrc));
-              bulk_g2s(sdst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, sfull_bar(sslot));
+              for (int c = 0; c < 16; ++c) {
+                const int sub = c >> 2, ch = c & 3;
+                unsigned long long a;
+                asm volatile("mad.wide.u32 %0, %1, 16, %2;"
+                             : "=l"(a)
+                             : "r"(ch * p.s0_wp + (sub & 1) * (p.s0_wp >> 1)), "l"(ssrc + (sub >> 1) * p.s0_row_entries));
+                bulk_g2s(sdst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, sfull_bar(sslot));
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                unsigned long long a;
+                asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(c * p.s0_wp), "l"(ssrc));
+                bulk_g2s(sdst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, sfull_bar(sslot));
+              }
             }
-            ssrc += p.s0_row_entries;
+            ssrc += (PSG ? 2 : 1) * p.s0_row_entries;
             ++ts;
-            if (++sslot == kSRing) { sslot = 0; sph ^= 1; }
+            if (++sslot == SRING) { sslot = 0; sph ^= 1; }
           }
         }
       }
@@ -314,23 +339,29 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         if (++slot == ring_n) { slot = 0; ph ^= 1; }
       }
       if constexpr (SFTG) {
-        // scale|shift of this output row: [128 px x 32 stage-0 channels] x [32 -> 64 block-diagonal] (+ bias step)
+        // scale|shift of this output row: [128 px x 32 stage-0 channels] x [32 -> 64 block-diagonal] (+ bias step);
+        // PixelShuffle: one such GEMM per sub-pixel, into a single-buffered accumulator -> wait for the previous
+        // row's epilogue (it arrives on tempty of the other stage after its last TMEM read)
         mbar_wait(sfull_bar(sslot), sph, p.err, 7);
+        if (PSG && t > 0) mbar_wait(tempty_bar((t - 1) & 1), ((t - 1) >> 1) & 1, p.err, 8);
         tc_fence_after();
         if (elect_one()) {
           constexpr uint32_t idesc64 = make_idesc_f16_m128(64);
-          const uint32_t sa = ((smem_u32(sring) + sslot * kSSlotBytes + 16) >> 4) | ((kPlaneBytes >> 4) << 16);
           const uint32_t sb = (smem_u32(wsm2) >> 4) | (64u << 16);
-          const uint32_t s_tmem = tmem_base + 2 * N + stage * 64;
-          tc_mma_f16(s_tmem, mkdesc(sa), mkdesc(sb), idesc64, 0u);
-          tc_mma_f16(s_tmem, mkdesc(sa + ((2 * kPlaneBytes) >> 4)), mkdesc(sb + 128), idesc64, 1u);
-          tc_mma_f16(s_tmem, ones_desc, mkdesc(sb + 256), idesc64, 1u);
+#pragma unroll
+          for (int sub = 0; sub < (PSG ? 4 : 1); ++sub) {
+            const uint32_t sa = ((smem_u32(sring) + sslot * SSLOT + sub * kSSlotBytes + 16) >> 4) | ((kPlaneBytes >> 4) << 16);
+            const uint32_t s_tmem = PSG ? tmem_base + 2 * N + sub * 64 : tmem_base + 2 * N + stage * 64;
+            tc_mma_f16(s_tmem, mkdesc(sa), mkdesc(sb), idesc64, 0u);
+            tc_mma_f16(s_tmem, mkdesc(sa + ((2 * kPlaneBytes) >> 4)), mkdesc(sb + 128), idesc64, 1u);
+            tc_mma_f16(s_tmem, ones_desc, mkdesc(sb + 256), idesc64, 1u);
+          }
           tc_commit(sempty_bar(sslot));
           tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // conv bias
           tc_commit(tfull_bar(stage));
         }
         __syncwarp();
-        if (++sslot == kSRing) { sslot = 0; sph ^= 1; }
+        if (++sslot == SRING) { sslot = 0; sph ^= 1; }
       }
       base_slot += STRIDE;
       if (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
@@ -383,25 +414,50 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       }
       for (int t = 0; t < nrows_out; ++t) {
         const int stage = t & 1, oy = oy0 + t;
+        // request the row's skip-connection operands (4 sub-pixels x 2 chunks) before waiting for the accumulator:
+        // with one CTA per SM nothing else hides their HBM latency
+        uint4 r4[4][2];
+        bool ok[4];
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const int Y = 2 * oy + (sub >> 1), j = sub & 1;
+          ok[sub] = xin && Y < p.out.H && 2 * x + j < p.out.W;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            r4[sub][c] = make_uint4(0, 0, 0, 0);
+            if (p.has_res && ok[sub]) r4[sub][c] = *res[j].at(Y, 2 * half + c);
+          }
+        }
         mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
         tc_fence_after();
         float v[64];
         tmem_ld_cols<64>(tlane + stage * N + half * 64, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(stage));
+        if constexpr (!SFTG) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(stage));
+        }
 #pragma unroll
         for (int k = 0; k < 64; ++k) v[k] = fmaxf(v[k], slope * v[k]);
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
           const int Y = 2 * oy + (sub >> 1), j = sub & 1;
-          if (xin && Y < p.out.H && 2 * x + j < p.out.W) {
-            uint4 r4[2], s4[2], t4[2];
+          float sv[SFTG ? 16 : 1], tv[SFTG ? 16 : 1];
+          if constexpr (SFTG) {     // scale / shift of this sub-pixel, channels [16*half, 16*half + 16)
+            tmem_ld16_async(tlane + 2 * N + sub * 64 + 16 * half, reinterpret_cast<uint32_t*>(sv));
+            tmem_ld16_async(tlane + 2 * N + sub * 64 + 32 + 16 * half, reinterpret_cast<uint32_t*>(tv));
+            tc_wait_ld();
+            if (sub == 3) {         // last TMEM read of this row: release the conv stage and the scale|shift columns
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(stage));
+            }
+          }
+          if (ok[sub]) {
+            uint4 s4[2], t4[2];
+            if (!SFTG && p.has_sft) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int ch = 2 * half + c;
-              if (p.has_res) r4[c] = *res[j].at(Y, ch);
-              if (p.has_sft) { s4[c] = *sft[j].at(Y, ch); t4[c] = *sft[j].at(Y, ch + 4); }
+              for (int c = 0; c < 2; ++c) { s4[c] = *sft[j].at(Y, 2 * half + c); t4[c] = *sft[j].at(Y, 2 * half + c + 4); }
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -411,12 +467,15 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
               for (int cc = 0; cc < 8; ++cc) val[cc] = v[32 * c + 4 * cc + sub];
               if (p.has_res) {
                 float r[8];
-                unpack8(r4[c], r);
+                unpack8(r4[sub][c], r);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) val[k] += r[k];
               }
               if (p.has_raw) *raw[j].at(Y, ch) = pack8(val);
-              if (p.has_sft) {
+              if constexpr (SFTG) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], sv[c * 8 + k], val[k]) + tv[c * 8 + k];
+              } else if (p.has_sft) {
                 float s[8], tt[8];
                 unpack8(s4[c], s);
                 unpack8(t4[c], tt);
@@ -432,8 +491,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       constexpr int COLS = N / 2;          // columns drained by this warp
       constexpr int CH = COLS / 8;         // 8-channel chunks per thread
       const int j0 = half * CH;
-      ColRef out, res, res2, sft, raw;
+      ColRef out, out2, res, res2, sft, raw;
       out.init(p.out, x);
+      if (p.out_split > 0) out2.init(p.out2, x);
       if constexpr (AUX) {
         if (p.has_res) res.init(p.res, x);
         if (p.has_res2) res2.init(p.res2, x);
@@ -496,7 +556,8 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
                 for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], s[k], val[k]) + tt[k];   // x*(scale+1)+shift
               }
             }
-            *out.at(oy, j0 + c) = pack8(val);
+            if (p.out_split > 0 && j0 + c >= p.out_split) *out2.at(oy, j0 + c - p.out_split) = pack8(val);
+            else *out.at(oy, j0 + c) = pack8(val);
           }
         }
       }
@@ -508,8 +569,12 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-inline size_t conv_smem_bytes(const ConvParams& p) {
-  const size_t sftg = p.wpk2 ? ((p.w2_bytes + 127) & ~127) + static_cast<size_t>(kSRing) * kSSlotBytes : 0;
+inline size_t conv_sftg_bytes(const ConvParams& p, bool ps) {
+  if (!p.wpk2) return 0;
+  return ((p.w2_bytes + 127) & ~127) + (ps ? static_cast<size_t>(kSRingPS) * kSSlotBytesPS : static_cast<size_t>(kSRing) * kSSlotBytes);
+}
+inline size_t conv_smem_bytes(const ConvParams& p, bool ps = false) {
+  const size_t sftg = conv_sftg_bytes(p, ps);
   return kSmemHeader + ((p.w_bytes + 127) & ~127) + static_cast<size_t>(p.ring) * p.slot_bytes + sftg;
 }
 

@@ -234,6 +234,7 @@ struct Ctx {
   uint16_t* d_lut = nullptr;
   // packed static weights (device) by layer name
   std::map<std::string, __half*> wpk;
+  std::map<std::string, std::vector<__half>> host_pk;   // host copies (chains concatenate them)
 };
 
 static int fail(Ctx* c, const std::string& m) {
@@ -305,7 +306,7 @@ static int env_int(const char* name, int dflt) {
 static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   ConvParams& p = L.p;
   const int z = p.xmul == 2 ? 2 : 1;
-  const int tmem_cols = L.sftg ? 256 : std::max(32, 2 * L.N);
+  const int tmem_cols = L.sftg ? (L.mode == STORE_PS ? 512 : 256) : std::max(32, 2 * L.N);
   int occ = static_cast<int>((227 * 1024) / (L.smem + 1024));
   occ = std::max(1, std::min(occ, std::min(512 / tmem_cols, max_occ)));
   const int slots = 148 * occ * env_int("HDRTV_WAVES", 1);
@@ -327,6 +328,8 @@ struct Epi {
   const __half* sft_w2 = nullptr;
   const P8* raw = nullptr;
   __half* planar = nullptr;
+  int out_split = 0;                // output chunks >= out_split are stored to out2 instead
+  const P8* out2 = nullptr;
 };
 
 static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int j0,
@@ -346,7 +349,8 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   if (e.res2) { p.has_res2 = 1; p.res2 = *e.res2; }
   if (e.sft) { p.has_sft = 1; p.sft = *e.sft; }
   if (e.sft_s0) {
-    if (e.sft_s0->parity) return fail(c, "conv " + name + ": stage-0 SFT map must be in natural layout");
+    if ((e.sft_s0->parity != 0) != (mode == STORE_PS))
+      return fail(c, "conv " + name + ": stage-0 SFT map must be natural (parity-split for PixelShuffle consumers)");
     p.wpk2 = reinterpret_cast<const uint4*>(e.sft_w2);
     p.w2_bytes = 3 * 64 * 32;
     p.s0 = reinterpret_cast<const uint4*>(e.sft_s0->base);
@@ -356,14 +360,14 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
     L.sftg = true;
   }
   if (e.raw) { p.has_raw = 1; p.raw = *e.raw; }
+  if (e.out_split > 0 && e.out2) { p.out_split = e.out_split; p.out2 = *e.out2; }
   p.planar = e.planar;
   p.planar_plane = static_cast<long>(Ho) * Wo;
   p.planar_W = Wo;
   p.err = c->d_err;
   const int min_ring = p.ks + 1;
-  const size_t budget = 200 * 1024;
-  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127) +
-                       (p.wpk2 ? ((p.w2_bytes + 127) & ~127) + static_cast<size_t>(kSRing) * kSSlotBytes : 0);
+  const size_t budget = (mode == STORE_PS && p.wpk2) ? 224 * 1024 : 200 * 1024;
+  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127) + conv_sftg_bytes(p, mode == STORE_PS);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
   // ring depth: rows in use (ks) + prefetch; shallow rings keep shared memory small so that more CTAs share an SM
   // ring depth: rows in use (ks) + prefetched rows.  Cheap slots (few channel planes) prefetch deeper: their rows
@@ -374,7 +378,7 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   if (ring < min_ring) ring = min_ring;
   if (ring > kMaxRing) ring = kMaxRing;
   p.ring = ring;
-  L.smem = conv_smem_bytes(p);
+  L.smem = conv_smem_bytes(p, mode == STORE_PS);
   if (L.smem > 227 * 1024) return fail(c, "conv " + name + ": shared memory budget exceeded");
   L.N = N;
   L.kind = kind;
@@ -403,7 +407,9 @@ static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 // Every (input kind, channel chunks, N, store mode, auxiliary operands) combination the plans and the self-tests use.
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
-  if (L.sftg) {     // in-kernel SFT generator: 32-channel P8 outputs
+  if (L.sftg) {     // in-kernel SFT generator: 32-channel outputs
+    if (L.mode == STORE_PS && L.N == 128 && L.kind == IN_NAT3x3 && L.kch == 4)
+      return launch_conv_t<IN_NAT3x3, 4, 128, STORE_PS, true, true>(L, s);
     if (L.N != 32 || L.mode != STORE_P8) return cudaErrorInvalidValue;
     if (L.kind == IN_NAT3x3 && L.kch == 4) return launch_conv_t<IN_NAT3x3, 4, 32, STORE_P8, true, true>(L, s);
     if (L.kind == IN_NAT3x3_C8 && L.kch == 1) return launch_conv_t<IN_NAT3x3_C8, 1, 32, STORE_P8, true, true>(L, s);
@@ -448,11 +454,12 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
 }
 
 // ---- fused layer chains (chain_p8.cuh) -----------------------------------------------------------
-enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1 };
+enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3 };
 
 template <class Prog>
 static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int prog_id, InKind kind, const P8& in,
-                        int kchunks, const std::vector<const P8*>& outs, const __half* wpk, int Ho, int Wo) {
+                        int kchunks, const std::vector<const P8*>& outs, const __half* wpk, int Ho, int Wo,
+                        const P8* outs2 = nullptr) {
   ConvLaunch L;
   memset(&L.p, 0, sizeof(L.p));
   L.chain = std::make_shared<ChainParams>();
@@ -471,6 +478,10 @@ static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string
       cp.outs[l] = *outs[l];
     }
     if (Prog::STORE[l] == 2) planar = true;
+    if (Prog::STORE[l] == 3) {
+      if (!outs2) return fail(c, "chain " + name + ": missing second output tensor");
+      cp.outs2 = *outs2;
+    }
   }
   p.wpk = reinterpret_cast<const uint4*>(wpk);
   p.w_bytes = prog_w_off<Prog>(Prog::L);
@@ -515,6 +526,8 @@ static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
   switch (L.chain_prog) {
     case PROG_AGCM: return launch_chain_t<ProgAGCM>(L, s);
     case PROG_COND: return launch_chain_t<ProgCond>(L, s);
+    case PROG_COND_SFT1: return launch_chain_t<ProgCondSft<1>>(L, s);
+    case PROG_COND_SFT3: return launch_chain_t<ProgCondSft<3>>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -522,8 +535,7 @@ static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Static weight packing (fp16 path), done once in hdrtv_set_weights
 // ------------------------------------------------------------------------------------------------
-static int pack_layer(Ctx* c, const std::string& key, InKind kind, int kchunks, int N, const WeightFn& wf,
-                      const std::function<float(int)>& bf) {
+static std::vector<__half> pack_layer_host(InKind kind, int kchunks, int N, const WeightFn& wf, const std::function<float(int)>& bf) {
   ConvParams tmp;
   memset(&tmp, 0, sizeof(tmp));
   std::vector<StepK> wk;
@@ -531,7 +543,12 @@ static int pack_layer(Ctx* c, const std::string& key, InKind kind, int kchunks, 
   dummy.Wp = 16;
   dummy.chunks = kchunks;
   build_input_side(kind, dummy, 0, kchunks, tmp, wk);
-  std::vector<__half> pk = pack_weights(N, wk, wf, bf);
+  return pack_weights(N, wk, wf, bf);
+}
+static int pack_layer(Ctx* c, const std::string& key, InKind kind, int kchunks, int N, const WeightFn& wf,
+                      const std::function<float(int)>& bf) {
+  std::vector<__half> pk = pack_layer_host(kind, kchunks, N, wf, bf);
+  c->host_pk[key] = pk;
   c->wpk[key] = w_upload(c, pk.data(), pk.size());
   if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
   return 0;
@@ -547,10 +564,11 @@ static int pack_std(Ctx* c, const std::string& name, InKind kind, int cin, int N
 }
 
 static const char* kSftL0[] = {"LE.SFT_layer1", "LE.SFT_layer2"};
-static const char* kSftL1[] = {"LE.recon_trunk1.0.sft1", "LE.recon_trunk1.0.sft2", "LE.recon_trunk5.0.sft1",
-                               "LE.recon_trunk5.0.sft2"};
-static const char* kSftL2[] = {"LE.recon_trunk2.0.sft1", "LE.recon_trunk2.0.sft2", "LE.recon_trunk4.0.sft1",
-                               "LE.recon_trunk4.0.sft2"};
+// the layer applied by an up-conv (PixelShuffle consumer) is LAST in its group: its stage-0 map is stored parity-split
+static const char* kSftL1[] = {"LE.recon_trunk1.0.sft1", "LE.recon_trunk1.0.sft2", "LE.recon_trunk5.0.sft2",
+                               "LE.recon_trunk5.0.sft1"};
+static const char* kSftL2[] = {"LE.recon_trunk2.0.sft1", "LE.recon_trunk2.0.sft2", "LE.recon_trunk4.0.sft2",
+                               "LE.recon_trunk4.0.sft1"};
 static const char* kSftL3[] = {"LE.recon_trunk3.0.sft1", "LE.recon_trunk3.0.sft2", "LE.recon_trunk3.1.sft1",
                                "LE.recon_trunk3.1.sft2", "LE.recon_trunk3.2.sft1", "LE.recon_trunk3.2.sft2",
                                "LE.recon_trunk3.3.sft1", "LE.recon_trunk3.3.sft2"};
@@ -597,6 +615,7 @@ static int pack_chain(Ctx* c, const std::string& key, InKind kind0, int kchunks0
     std::vector<__half> pk = pack_weights(layers[l].N, wk, conv_weight_fn(c, layers[l].name), bias_fn(c, layers[l].name));
     all.insert(all.end(), pk.begin(), pk.end());
   }
+  c->host_pk[key] = all;
   c->wpk[key] = w_upload(c, all.data(), all.size());
   if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
   return 0;
@@ -638,6 +657,13 @@ static int pack_all_fp16(Ctx* c) {
       r |= pack_std(c, pre + ".conv2", IN_NAT3x3, 32, 32);
     }
   r |= pack_sft_stage0(c, "sft0.L0", kSftL0, 2);
+  if (!r) {   // cond chain + the stage-0 convs of the two full-resolution SFT layers as its seventh step
+    std::vector<__half> all = c->host_pk.at("chain.cond");
+    const std::vector<__half>& s0 = c->host_pk.at("sft0.L0");
+    all.insert(all.end(), s0.begin(), s0.end());
+    c->wpk["chain.cond_sft"] = w_upload(c, all.data(), all.size());
+    if (!c->wpk["chain.cond_sft"]) r |= fail(c, "weight upload failed for chain.cond_sft");
+  }
   r |= pack_sft_stage0(c, "sft0.L1", kSftL1, 4);
   r |= pack_sft_stage0(c, "sft0.L2", kSftL2, 4);
   r |= pack_sft_stage0(c, "sft0.L3a", kSftL3, 4);
@@ -909,11 +935,15 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   // SFT maps
   P8 S0 = P(64, H, Wd, false), S1 = P(128, H1, W1, false), S2 = P(128, H2, W2, false), S3a = P(128, H3, W3, false),
      S3b = P(128, H3, W3, false);
-  std::map<std::string, P8> maps;
-  for (auto n : kSftL0) maps[n] = P(64, H, Wd, false);
-  for (auto n : kSftL1) maps[n] = P(64, H1, W1, false);
-  for (auto n : kSftL2) maps[n] = P(64, H2, W2, false);
-  for (auto n : kSftL3) maps[n] = P(64, H3, W3, false);
+  P8 S0ps = P(32, H, Wd, true), S1ps = P(32, H1, W1, true), S2ps = P(32, H2, W2, true);
+  const bool use_sftg = env_int("HDRTV_SFTG", 1) != 0;     // SFT scale|shift generated inside the consuming conv kernels
+  std::map<std::string, P8> maps;                          // precomputed scale|shift maps (HDRTV_SFTG=0 only)
+  if (!use_sftg) {
+    for (auto n : kSftL0) maps[n] = P(64, H, Wd, false);
+    for (auto n : kSftL1) maps[n] = P(64, H1, W1, false);
+    for (auto n : kSftL2) maps[n] = P(64, H2, W2, false);
+    for (auto n : kSftL3) maps[n] = P(64, H3, W3, false);
+  }
   // trunk
   P8 T0a = P(32, H, Wd, false), FEA0 = P(32, H, Wd, true);
   P8 X1 = P(32, H1, W1, false), X1m = P(32, H1, W1, false), Y1 = P(32, H1, W1, false), FEA1 = P(32, H1, W1, true);
@@ -954,8 +984,13 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   auto& L = c->plan_le;
   // ---- LE condition pyramid
   if (use_chain) {
-    r |= make_chain_t<ProgCond>(c, L, "LE.cond_chain", PROG_COND, IN_NAT3x3_C8, agP8, 1,
-                                {nullptr, nullptr, &COND, nullptr, nullptr, &cond1}, wk("chain.cond"), H, Wd);
+    // cond_first + CondNet1 + the stage-0 convs of SFT_layer1 / SFT_layer2 (seventh step, on cond1)
+    if (use_sftg)
+      r |= make_chain_t<ProgCondSft<3>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT3, IN_NAT3x3_C8, agP8, 1,
+                                        {nullptr, nullptr, &COND, nullptr, nullptr, &cond1, &S0}, wk("chain.cond_sft"), H, Wd, &S0ps);
+    else
+      r |= make_chain_t<ProgCondSft<1>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT1, IN_NAT3x3_C8, agP8, 1,
+                                        {nullptr, nullptr, &COND, nullptr, nullptr, &cond1, &S0}, wk("chain.cond_sft"), H, Wd);
   } else {
   r |= std_conv(L, "LE.cond_first.0", IN_NAT3x3_C8, agP8, 8, 64, STORE_P8, B1, H, Wd, lrelu);
     r |= std_conv(L, "LE.cond_first.2", IN_NAT1x1, B1, 64, 64, STORE_P8, B2, H, Wd, lrelu);
@@ -976,25 +1011,29 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   // ---- SFT: stage 0 of every SFT layer of a level stacked into one 1x1 conv (LeakyReLU).  Stage 1 (32 -> 64, block
   // diagonal scale|shift) runs inside the consuming conv kernel (SFTG) from the stage-0 map; only the PixelShuffle
   // consumers (up-convs) still read a precomputed scale|shift map.
-  const bool use_sftg = env_int("HDRTV_SFTG", 1) != 0;
   struct S0Ref { const P8* S; int j0; };
   std::map<std::string, S0Ref> s0of;
-  auto sft_group = [&](const std::string& key, const P8& cond, const P8& S, const char* const* names, int n, int h, int w) {
-    r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), S, h, w, lrelu);
+  auto sft_group = [&](const std::string& key, const P8& cond, const P8& S, const P8* Sps, const char* const* names, int n,
+                       int h, int w) {
+    // Sps: parity-split home of the group's last layer (the one an up-conv applies through its PixelShuffle store)
+    Epi e0 = lrelu;
+    if (use_sftg && Sps) { e0.out_split = 4 * (n - 1); e0.out2 = Sps; }
+    if (!(use_chain && key == "sft0.L0"))     // the full-resolution stage 0 is the last step of the cond chain
+      r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), S, h, w, e0);
     for (int i = 0; i < n; ++i) {
       const std::string nm = names[i];
-      s0of[nm] = S0Ref{&S, 4 * i};
-      const bool ps_consumer = nm == "LE.recon_trunk4.0.sft1" || nm == "LE.recon_trunk5.0.sft1" || nm == "LE.SFT_layer2";
-      if (use_sftg && !ps_consumer) continue;
+      const bool ps_consumer = Sps && i == n - 1;
+      s0of[nm] = (use_sftg && ps_consumer) ? S0Ref{Sps, 0} : S0Ref{&S, 4 * i};
+      if (use_sftg) continue;
       const std::string k1 = nm + ".stage1";
       r |= make_conv(c, L, k1, IN_NAT1x1, S, 4 * i, 4, 64, STORE_P8, wk(k1), maps.at(nm), h, w, none);
     }
   };
-  sft_group("sft0.L0", cond1, S0, kSftL0, 2, H, Wd);
-  sft_group("sft0.L1", cond2, S1, kSftL1, 4, H1, W1);
-  sft_group("sft0.L2", cond3, S2, kSftL2, 4, H2, W2);
-  sft_group("sft0.L3a", cond4, S3a, kSftL3, 4, H3, W3);
-  sft_group("sft0.L3b", cond4, S3b, kSftL3 + 4, 4, H3, W3);
+  sft_group("sft0.L0", cond1, S0, &S0ps, kSftL0, 2, H, Wd);
+  sft_group("sft0.L1", cond2, S1, &S1ps, kSftL1, 4, H1, W1);
+  sft_group("sft0.L2", cond3, S2, &S2ps, kSftL2, 4, H2, W2);
+  sft_group("sft0.L3a", cond4, S3a, nullptr, kSftL3, 4, H3, W3);
+  sft_group("sft0.L3b", cond4, S3b, nullptr, kSftL3 + 4, 4, H3, W3);
   // SFT applied in a conv epilogue: in-kernel generator where possible, else the precomputed map
   auto with_sft = [&](Epi& e, const std::string& nm) {
     if (use_sftg) {
@@ -1040,16 +1079,16 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
       }
     }
   }
-  auto up = [&](const std::string& name, const P8& in, const P8& skip, const P8* raw, const P8* sft, const P8& out,
+  auto up = [&](const std::string& name, const P8& in, const P8& skip, const P8* raw, const char* sft, const P8& out,
                 int hin, int win) {
-    Epi e = relu; e.res = &skip; e.raw = raw; e.sft = sft;
+    Epi e = relu; e.res = &skip; e.raw = raw; with_sft(e, sft);
     r |= std_conv(L, name, IN_NAT3x3, in, 32, 128, STORE_PS, out, hin, win, e);
   };
-  up("LE.up_conv1.0", U3, FEA2, &X4, &maps.at("LE.recon_trunk4.0.sft1"), X4m, H3, W3);
+  up("LE.up_conv1.0", U3, FEA2, &X4, "LE.recon_trunk4.0.sft1", X4m, H3, W3);
   resblock("LE.recon_trunk4.0", X4m, X4, Y4, U2, nullptr, nullptr, nullptr, H2, W2);
-  up("LE.up_conv2.0", U2, FEA1, &X5, &maps.at("LE.recon_trunk5.0.sft1"), X5m, H2, W2);
+  up("LE.up_conv2.0", U2, FEA1, &X5, "LE.recon_trunk5.0.sft1", X5m, H2, W2);
   resblock("LE.recon_trunk5.0", X5m, X5, Y5, U1, nullptr, nullptr, nullptr, H1, W1);
-  up("LE.up_conv3.0", U1, FEA0, nullptr, &maps.at("LE.SFT_layer2"), V0, H1, W1);
+  up("LE.up_conv3.0", U1, FEA0, nullptr, "LE.SFT_layer2", V0, H1, W1);
   r |= std_conv(L, "LE.HR_conv2", IN_NAT3x3, V0, 32, 32, STORE_P8, V1, H, Wd, relu);
   { Epi e; e.res = &agP8; e.planar = reinterpret_cast<__half*>(1);
     r |= std_conv(L, "LE.conv_last", IN_NAT3x3, V1, 32, 16, STORE_PLANAR, agP8, H, Wd, e); }
@@ -1686,7 +1725,7 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
   // bit5: SFT generated in-kernel from a 32-channel stage-0 map through a block-diagonal 32 -> 64 stage 1
   std::vector<float> hs0, hw2, hb2(64);
   if (flags & 32) {
-    if (outC != 32 || ps || planar) { c->err = "selftest: SFTG needs a 32-channel P8 output"; return -1; }
+    if (outC != 32 || planar) { c->err = "selftest: SFTG needs a 32-channel output"; return -1; }
     hs0.resize(static_cast<size_t>(32) * outH * outW);
     hw2.assign(static_cast<size_t>(64) * 32, 0.f);
     for (auto& v : hs0) v = __half2float(__float2half(rnd()));
@@ -1741,8 +1780,9 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
   Epi e; e.act = act;
   P8 s0p;
   if (flags & 32) {
-    s0p = make_p8(&t, 64, outH, outW, false);         // the layer's 32 channels sit at chunk planes 4..7
-    fill_p8(s0p, hs0, 32, 4);
+    const int sj0 = ps ? 0 : 4;                       // P8 consumers: the layer's 32 channels sit at chunk planes 4..7
+    s0p = ps ? make_p8(&t, 32, outH, outW, true) : make_p8(&t, 64, outH, outW, false);
+    fill_p8(s0p, hs0, 32, sj0);
     ConvParams tmp2; memset(&tmp2, 0, sizeof(tmp2));
     std::vector<StepK> wk2;
     P8 dummy; dummy.Wp = 16; dummy.chunks = 4;
@@ -1751,7 +1791,7 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
     std::vector<__half> pk2 = pack_weights(64, wk2, wf2, [&](int n2) { return n2 < 64 ? hb2[n2] : 0.f; });
     __half* dpk2 = ws_alloc<__half>(&t, pk2.size());
     cudaMemcpy(dpk2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice);
-    e.sft_s0 = &s0p; e.sft_j0 = 4; e.sft_w2 = dpk2; e.raw = &rawp;
+    e.sft_s0 = &s0p; e.sft_j0 = sj0; e.sft_w2 = dpk2; e.raw = &rawp;
   }
   if (!planar) {
     if (flags & 8) e.res = &resp;

@@ -47,6 +47,7 @@ SELFTESTS = [
     (4, 64, 16, 21, 301, 0), (5, 64, 64, 12, 200, 4), (5, 64, 64, 13, 201, 4), (0, 32, 32, 300, 700, 4),
     # bit5: SFT scale|shift generated inside the conv kernel (stage-1 1x1 on the tensor core, read back from TMEM)
     (0, 32, 32, 20, 300, 4 | 32), (0, 32, 32, 37, 301, 4 | 8 | 32), (2, 8, 32, 20, 300, 4 | 32), (4, 32, 32, 21, 301, 4 | 32),
+    (0, 32, 128, 10, 140, 4 | 1 | 32), (0, 32, 128, 33, 300, 4 | 1 | 8 | 32),
 ]
 
 
