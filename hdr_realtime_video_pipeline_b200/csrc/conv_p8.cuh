@@ -100,6 +100,12 @@ struct ConvParams {
   P8 res, res2, sft, out, raw;
   int out_split;            // > 0: output chunks >= out_split go to out2 (chunk index - out_split) instead of out
   P8 out2;
+  // zsplit > 1: `zsplit` convolutions that read the SAME input (different weights / outputs of identical geometry) share
+  // one launch; CTA blockIdx.x serves variant blockIdx.x % zsplit of strip blockIdx.x / zsplit, so the variants of a
+  // strip run side by side and the input rows are fetched from HBM once (the other reads hit L2).
+  int zsplit;
+  const uint4* wpk_z[3];
+  P8 out_zp[3];             // per-variant output tensors (layouts may differ)
   __half* planar;
   long planar_plane;
   int planar_W;
@@ -189,7 +195,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   uint8_t* sring = ring + p.ring * (kind_copies(KIND, KCH) * kPlaneBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * kTileM;
+  const int zs = p.zsplit > 1 ? p.zsplit : 1;
+  const int zsel = zs > 1 ? static_cast<int>(blockIdx.x % zs) : 0;
+  const int x0 = static_cast<int>(blockIdx.x / zs) * kTileM;
   const int oy0 = blockIdx.y * p.band;
   const int nrows_out = min(p.band, p.Ho - oy0);
   const int nrows_in = (nrows_out - 1) * STRIDE + KS;
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(wfull_bar, p.w_bytes + (SFTG ? p.w2_bytes : 0));
-      bulk_g2s(smem_u32(wsm), p.wpk, p.w_bytes, wfull_bar);
+      bulk_g2s(smem_u32(wsm), zs > 1 ? p.wpk_z[zsel] : p.wpk, p.w_bytes, wfull_bar);
       if constexpr (SFTG) bulk_g2s(smem_u32(wsm2), p.wpk2, p.w2_bytes, wfull_bar);
       constexpr uint32_t row_tx = NCOPY * kPlaneBytes;
       const uint32_t ring_n = p.ring, slot_bytes = NCOPY * kPlaneBytes;
@@ -492,7 +500,8 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       constexpr int CH = COLS / 8;         // 8-channel chunks per thread
       const int j0 = half * CH;
       ColRef out, out2, res, res2, sft, raw;
-      out.init(p.out, x);
+      if (zs > 1) out.init(p.out_zp[zsel], x);
+      else out.init(p.out, x);
       if (p.out_split > 0) out2.init(p.out2, x);
       if constexpr (AUX) {
         if (p.has_res) res.init(p.res, x);

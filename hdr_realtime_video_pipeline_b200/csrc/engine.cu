@@ -310,12 +310,13 @@ static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   int occ = static_cast<int>((227 * 1024) / (L.smem + 1024));
   occ = std::max(1, std::min(occ, std::min(512 / tmem_cols, max_occ)));
   const int slots = 148 * occ * env_int("HDRTV_WAVES", 1);
-  int nb = std::max(1, slots / (strips * z));
+  const int zs = p.zsplit > 1 ? p.zsplit : 1;
+  int nb = std::max(1, slots / (strips * z * zs));
   int band = (p.Ho + nb - 1) / nb;
   band = std::max(band, env_int("HDRTV_MIN_BAND", 4));
   band = std::min(band, p.Ho);
   p.band = band;
-  L.grid = dim3(strips, (p.Ho + band - 1) / band, z);
+  L.grid = dim3(strips * zs, (p.Ho + band - 1) / band, z);
 }
 
 struct Epi {
@@ -330,6 +331,9 @@ struct Epi {
   __half* planar = nullptr;
   int out_split = 0;                // output chunks >= out_split are stored to out2 instead
   const P8* out2 = nullptr;
+  int zsplit = 0;                   // > 1: this launch runs `zsplit` convs on the same input (weights / outputs below)
+  const __half* wpk_z[3] = {nullptr, nullptr, nullptr};
+  const P8* out_z[3] = {nullptr, nullptr, nullptr};
 };
 
 static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int j0,
@@ -361,6 +365,15 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   }
   if (e.raw) { p.has_raw = 1; p.raw = *e.raw; }
   if (e.out_split > 0 && e.out2) { p.out_split = e.out_split; p.out2 = *e.out2; }
+  if (e.zsplit > 1) {
+    p.zsplit = e.zsplit;
+    for (int z = 0; z < e.zsplit; ++z) {
+      if (!e.wpk_z[z] || !e.out_z[z] || e.out_z[z]->H != out.H || e.out_z[z]->W != out.W)
+        return fail(c, "conv " + name + ": fused variants need outputs of the same size");
+      p.wpk_z[z] = reinterpret_cast<const uint4*>(e.wpk_z[z]);
+      p.out_zp[z] = *e.out_z[z];
+    }
+  }
   p.planar = e.planar;
   p.planar_plane = static_cast<long>(Ho) * Wo;
   p.planar_W = Wo;
@@ -931,6 +944,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   P8 cond1 = P(16, H, Wd, false);
   P8 D1 = P(64, H1, W1, false), D2 = P(64, H1, W1, false), cond2 = P(16, H1, W1, false);
   P8 E1 = P(64, H1, W1, true), E2 = P(64, H2, W2, false), cond3 = P(16, H2, W2, false);
+  P8 E1b = P(64, H1, W1, true);      // fused CondNet{2,3,4}.0 launch: CondNet4's own stride-2 input
   P8 F2 = P(64, H2, W2, true), cond4 = P(16, H3, W3, false);
   // SFT maps
   P8 S0 = P(64, H, Wd, false), S1 = P(128, H1, W1, false), S2 = P(128, H2, W2, false), S3a = P(128, H3, W3, false),
@@ -999,14 +1013,29 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     r |= std_conv(L, "LE.CondNet1.2", IN_NAT1x1, C1a, 64, 64, STORE_P8, C1b, H, Wd, lrelu);
     r |= std_conv(L, "LE.CondNet1.4", IN_NAT1x1, C1b, 64, 16, STORE_P8, cond1, H, Wd, none);
   }
-  r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
-  r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
-  r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
-  r |= std_conv(L, "LE.CondNet3.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
-  r |= std_conv(L, "LE.CondNet3.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, E2, H2, W2, lrelu);
-  r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
-  r |= std_conv(L, "LE.CondNet4.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
-  r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, F2, H2, W2, lrelu);
+  if (env_int("HDRTV_ZFUSE", 1)) {
+    // the three stride-2 3x3 convs that read `cond` share one launch (cond is fetched from HBM once)
+    Epi e = lrelu;
+    e.zsplit = 3;
+    e.wpk_z[0] = wk("LE.CondNet2.0"); e.wpk_z[1] = wk("LE.CondNet3.0"); e.wpk_z[2] = wk("LE.CondNet4.0");
+    e.out_z[0] = &D1; e.out_z[1] = &E1; e.out_z[2] = &E1b;
+    r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, e);
+    L.back().name = "LE.CondNet{2,3,4}.0";
+    r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
+    r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
+    r |= std_conv(L, "LE.CondNet3.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, E2, H2, W2, lrelu);
+    r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
+    r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1b, 64, 64, STORE_P8, F2, H2, W2, lrelu);
+  } else {
+    r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
+    r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
+    r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
+    r |= std_conv(L, "LE.CondNet3.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
+    r |= std_conv(L, "LE.CondNet3.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, E2, H2, W2, lrelu);
+    r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
+    r |= std_conv(L, "LE.CondNet4.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
+    r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, F2, H2, W2, lrelu);
+  }
   r |= std_conv(L, "LE.CondNet4.4", IN_PAR3x3S2, F2, 64, 16, STORE_P8, cond4, H3, W3, none);
   // ---- SFT: stage 0 of every SFT layer of a level stacked into one 1x1 conv (LeakyReLU).  Stage 1 (32 -> 64, block
   // diagonal scale|shift) runs inside the consuming conv kernel (SFTG) from the stage-0 map; only the PixelShuffle
