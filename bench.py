@@ -176,7 +176,7 @@ def run_b200_arm(args):
     out_dev = torch.empty((h, w, 3), dtype=torch.uint16, device=dev)
 
     def step_device(i):
-        x, c = net.preprocess_device(dev_frames[i % n_distinct])
+        x, c = net.preprocess_device(dev_frames[i % n_distinct], assume_ready=True)
         out = net.infer((x, c))
         packer.pack_device(out, out_dev)
 
@@ -195,7 +195,7 @@ def run_b200_arm(args):
     t_wall0 = time.perf_counter()
     ev0.record()
     for i in range(K):
-        x, c = net.preprocess_device(dev_frames[i % n_distinct])
+        x, c = net.preprocess_device(dev_frames[i % n_distinct], assume_ready=True)
         infer_ev[i][0].record()
         out = net.infer((x, c))
         infer_ev[i][1].record()

@@ -115,6 +115,13 @@ class HDRTVNetB200:
             raise RuntimeError("hdrtv_create failed: " + _native.last_error(None))
         self._load_model(model_path)
 
+        # Frame pipelining: preprocess() puts the H2D copy, the normalise / condition kernels and the AGCM condition
+        # classifier (which depends on `cond` alone) on a side stream, so they overlap the previous frame's LE network;
+        # infer() then skips the classifier.  Results are identical; HDRTV_B200_PIPELINE=0 keeps everything in-stream.
+        self._pipeline = _env_bool("HDRTV_B200_PIPELINE", True)
+        self._side = None
+        self._ev_inputs_free = self._ev_pre_done = None
+        self._cls_ready = False
         self._buf_hw = None
         self._gpu_input = self._gpu_cond = self._gpu_raw = None
         self._gpu_out = self._gpu_agcm = self._gpu_u8 = None
@@ -214,10 +221,29 @@ class HDRTVNetB200:
         self._gpu_agcm = torch.empty((1, 3, h, w), dtype=dt, device=dev)
         self._gpu_raw = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
         self._gpu_u8 = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
-        self._pin_input = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+        self._pin_inputs = [torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        self._pin_events = [None, None]          # H2D of the slot's previous frame
+        self._pin_idx = 0
+        self._pin_input = self._pin_inputs[0]
         self._pin_output = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        self._ev_inputs_free = torch.cuda.Event()
+        self._ev_pre_done = torch.cuda.Event()
+        self._ev_inputs_free.record(torch.cuda.current_stream(dev))     # materialise the handles
+        self._ev_pre_done.record(torch.cuda.current_stream(dev))
+        self._cls_ready = False
 
     # ------------------------------------------------------------------ preprocess (hdrtvnet_torch.py:2239-2296)
+    def _launch_preprocess(self, raw_dev, h, w, stream):
+        mode = _native.COND_ZERO if self._fast_zero_condition else _native.COND_BICUBIC_AA
+        sp = C.c_void_p(stream.cuda_stream)
+        _native.check(self._lib.hdrtv_preprocess(self._handle, raw_dev.data_ptr(), h, w, self._gpu_input.data_ptr(),
+                                                 self._gpu_cond.data_ptr(), mode, sp), self._handle, "hdrtv_preprocess")
+        if self._pipeline:
+            _native.check(self._lib.hdrtv_classify(self._handle, self._gpu_cond.data_ptr(), h, w, sp), self._handle,
+                          "hdrtv_classify")
+
     @torch.inference_mode()
     def preprocess(self, frame_bgr):
         if not isinstance(frame_bgr, np.ndarray) or frame_bgr.dtype != np.uint8 or frame_bgr.ndim != 3 or frame_bgr.shape[2] != 3:
@@ -225,24 +251,52 @@ class HDRTVNetB200:
         h, w = frame_bgr.shape[:2]
         with torch.cuda.device(self.device):
             self._ensure_buffers(h, w)
-            self._pin_input.copy_(torch.from_numpy(np.ascontiguousarray(frame_bgr)))
-            self._gpu_raw.copy_(self._pin_input, non_blocking=True)
-            mode = _native.COND_ZERO if self._fast_zero_condition else _native.COND_BICUBIC_AA
-            _native.check(self._lib.hdrtv_preprocess(self._handle, self._gpu_raw.data_ptr(), h, w,
-                                                     self._gpu_input.data_ptr(), self._gpu_cond.data_ptr(), mode,
-                                                     self._stream()), self._handle, "hdrtv_preprocess")
+            slot = self._pin_idx
+            self._pin_idx ^= 1
+            if self._pin_events[slot] is not None:
+                self._pin_events[slot].synchronize()              # the slot's previous H2D copy has left the pinned buffer
+            pin = self._pin_inputs[slot]
+            self._pin_input = pin
+            pin.copy_(torch.from_numpy(np.ascontiguousarray(frame_bgr)))
+            cur = torch.cuda.current_stream(self.device)
+            work = self._side if self._pipeline else cur
+            if self._pipeline:
+                work.wait_event(self._ev_inputs_free)             # previous infer() has read x / cond / folded weights
+            with torch.cuda.stream(work):
+                self._gpu_raw.copy_(pin, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(work)
+                self._pin_events[slot] = ev
+                self._launch_preprocess(self._gpu_raw, h, w, work)
+                if self._pipeline:
+                    self._ev_pre_done.record(work)
+            if self._pipeline:
+                cur.wait_event(self._ev_pre_done)
+                self._cls_ready = True
         return self._gpu_input, self._gpu_cond
 
-    def preprocess_device(self, frame_u8_dev: torch.Tensor):
-        """Extension: frame already resident on the device as uint8 (H,W,3) BGR (decode-on-GPU callers, benchmarks)."""
+    def preprocess_device(self, frame_u8_dev: torch.Tensor, assume_ready: bool = False):
+        """Extension: frame already resident on the device as uint8 (H,W,3) BGR (decode-on-GPU callers, benchmarks).
+        assume_ready=True: the frame's producer finished long ago (static test frames) — the side stream does not
+        wait for the current stream, so the work overlaps the previous frame's network."""
         h, w = int(frame_u8_dev.shape[0]), int(frame_u8_dev.shape[1])
         with torch.cuda.device(self.device):
             self._ensure_buffers(h, w)
             src = frame_u8_dev.contiguous()
-            mode = _native.COND_ZERO if self._fast_zero_condition else _native.COND_BICUBIC_AA
-            _native.check(self._lib.hdrtv_preprocess(self._handle, src.data_ptr(), h, w, self._gpu_input.data_ptr(),
-                                                     self._gpu_cond.data_ptr(), mode, self._stream()),
-                          self._handle, "hdrtv_preprocess")
+            cur = torch.cuda.current_stream(self.device)
+            work = self._side if self._pipeline else cur
+            if self._pipeline:
+                if not assume_ready:
+                    work.wait_stream(cur)
+                work.wait_event(self._ev_inputs_free)
+            with torch.cuda.stream(work):
+                self._launch_preprocess(src, h, w, work)
+                if self._pipeline:
+                    self._ev_pre_done.record(work)
+            if self._pipeline:
+                src.record_stream(work)
+                cur.wait_event(self._ev_pre_done)
+                self._cls_ready = True
         return self._gpu_input, self._gpu_cond
 
     # ------------------------------------------------------------------ infer (hdrtvnet_torch.py:2302-2346)
@@ -258,8 +312,15 @@ class HDRTVNetB200:
             c = cond.to(device=self.device, dtype=self._dtype).contiguous()
             if tuple(c.shape) != (1, 3, max(1, h // 4), max(1, w // 4)):
                 raise ValueError(f"condition tensor must be (1,3,{h // 4},{w // 4}), got {tuple(c.shape)}")
-            rc = self._lib.hdrtv_infer(self._handle, t.data_ptr(), c.data_ptr(), h, w, self._gpu_out.data_ptr(),
-                                       self._gpu_agcm.data_ptr(), self._stream())
+            # classifier already run by preprocess() on the side stream?  Only for exactly the tensors it produced.
+            skip = bool(self._pipeline and self._cls_ready and t.data_ptr() == self._gpu_input.data_ptr()
+                        and c.data_ptr() == self._gpu_cond.data_ptr())
+            self._cls_ready = False
+            if self._pipeline:      # any side-stream work of the last preprocess() is ordered before this infer
+                torch.cuda.current_stream(self.device).wait_event(self._ev_pre_done)
+            rc = self._lib.hdrtv_infer_ex(self._handle, t.data_ptr(), c.data_ptr(), h, w, self._gpu_out.data_ptr(),
+                                          self._gpu_agcm.data_ptr(), 1 if skip else 0,
+                                          C.c_void_p(self._ev_inputs_free.cuda_event), self._stream())
             if rc != 0:
                 raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle))
         return self._gpu_out, self._gpu_agcm

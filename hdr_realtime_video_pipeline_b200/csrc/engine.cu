@@ -1195,16 +1195,18 @@ static int conv32n(Ctx* c, cudaStream_t s, const std::string& name, const float*
                 static_cast<int>(t.shape[0]), H, Wd, static_cast<int>(t.shape[2]), stride, act, slope, res, ps, outH, outW);
 }
 
-static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float* agcm_out, cudaStream_t s) {
+static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float* agcm_out, cudaStream_t s,
+                    bool skip_classifier = false, cudaEvent_t inputs_consumed = nullptr) {
   const int H = c->H, Wd = c->W;
   const int H1 = down2(H), W1 = down2(Wd), H2 = down2(H1), W2 = down2(W1), H3 = down2(H2), W3 = down2(W2);
   auto B = [&](const char* n) { return c->f32.at(n); };
-  if (run_classifier(c, cond, false, s)) return -1;
+  if (!skip_classifier && run_classifier(c, cond, false, s)) return -1;
   float* f = c->d_fold32;
   int r = 0;
   r |= conv32(c, s, x, f, f + 192, B("a1"), 3, 64, H, Wd, 1, 1, ACT_RELU, 0.f);
   r |= conv32(c, s, B("a1"), f + 256, f + 256 + 4096, B("a2"), 64, 64, H, Wd, 1, 1, ACT_RELU, 0.f);
   r |= conv32(c, s, B("a2"), f + 4416, f + 4416 + 192, agcm_out, 64, 3, H, Wd, 1, 1, ACT_NONE, 0.f);
+  if (inputs_consumed) CK(c, cudaEventRecord(inputs_consumed, s));   // x, cond and the folded AGCM weights are free again
   const float* img = agcm_out;
   // condition pyramid (LeakyReLU 0.1)
   r |= conv32n(c, s, "LE.cond_first.0", img, B("a1"), H, Wd, 1, ACT_LRELU, 0.1f);
@@ -1275,7 +1277,7 @@ static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float
 }
 
 static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __half* agcm_out, cudaStream_t s,
-                    std::vector<cudaEvent_t>* evs = nullptr) {
+                    std::vector<cudaEvent_t>* evs = nullptr, bool skip_classifier = false, cudaEvent_t inputs_consumed = nullptr) {
   const int H = c->H, Wd = c->W;
   auto mark = [&]() {
     if (!evs) return;
@@ -1289,7 +1291,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
   CK(c, cudaGetLastError());
   ++c->launches;
   mark();
-  if (run_classifier(c, cond, true, s, evs)) return -1;
+  if (!skip_classifier && run_classifier(c, cond, true, s, evs)) return -1;
   mark();
   for (ConvLaunch& L : c->plan_agcm) {
     if (L.mode == STORE_PLANAR) L.p.planar = agcm_out;
@@ -1298,6 +1300,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
     ++c->launches;
     mark();
   }
+  if (inputs_consumed) CK(c, cudaEventRecord(inputs_consumed, s));   // x, cond and the folded AGCM weights are free again
   for (ConvLaunch& L : c->plan_le) {
     if (L.mode == STORE_PLANAR) L.p.planar = out;
     CK(c, launch_conv(L, s));
@@ -1519,18 +1522,34 @@ int hdrtv_preprocess(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out,
   return 0;
 }
 
-int hdrtv_infer(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* out, void* agcm_out, void* stream) {
+int hdrtv_infer_ex(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* out, void* agcm_out, int skip_classifier,
+                   void* inputs_consumed_event, void* stream) {
   if (!c || !x || !cond || !out || !agcm_out) return fail(c, "hdrtv_infer: null argument");
   if (hdrtv_prepare(c, H, Wd)) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev = static_cast<cudaEvent_t>(inputs_consumed_event);
   try {
     if (c->precision == HDRTV_FP16)
       return run_fp16(c, static_cast<const __half*>(x), static_cast<const __half*>(cond), static_cast<__half*>(out),
-                      static_cast<__half*>(agcm_out), s);
+                      static_cast<__half*>(agcm_out), s, nullptr, skip_classifier != 0, ev);
     return run_fp32(c, static_cast<const float*>(x), static_cast<const float*>(cond), static_cast<float*>(out),
-                    static_cast<float*>(agcm_out), s);
+                    static_cast<float*>(agcm_out), s, skip_classifier != 0, ev);
   } catch (const std::exception& e) {
     return fail(c, std::string("hdrtv_infer: ") + e.what());
+  }
+}
+
+int hdrtv_infer(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* out, void* agcm_out, void* stream) {
+  return hdrtv_infer_ex(c, x, cond, H, Wd, out, agcm_out, 0, nullptr, stream);
+}
+
+int hdrtv_classify(hdrtv_t* c, const void* cond, int H, int Wd, void* stream) {
+  if (!c || !cond) return fail(c, "hdrtv_classify: null argument");
+  if (hdrtv_prepare(c, H, Wd)) return -1;
+  try {
+    return run_classifier(c, cond, c->precision == HDRTV_FP16, static_cast<cudaStream_t>(stream));
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_classify: ") + e.what());
   }
 }
 

@@ -57,6 +57,14 @@ int hdrtv_preprocess(hdrtv_t* h, const uint8_t* bgr, int height, int width, void
 int hdrtv_infer(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
                 void* stream);
 
+/* The same inference split for frame pipelining: hdrtv_classify runs only the AGCM condition classifier + GFM fold   */
+/* (Condition_arch.py:559-569; it depends on `cond` alone, so it can run on a side stream while the previous frame's   */
+/* LE network still occupies the GPU); hdrtv_infer_ex(skip_classifier = 1) then runs everything else.                 */
+/* inputs_consumed_event (cudaEvent_t, optional) is recorded once x, cond and the classifier results have been read. */
+int hdrtv_classify(hdrtv_t* h, const void* cond, int height, int width, void* stream);
+int hdrtv_infer_ex(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
+                   int skip_classifier, void* inputs_consumed_event, void* stream);
+
 /* _tensor_to_rgb48_bytes (gui_pipeline_worker_feeders.py:193-249): (1,3,H,W) planar of `dtype` -> uint16 HxWx3 RGB */
 /* (rgb48le), FP32 clamp*65535+0.5 truncate.  dst may be device memory or a mapped pinned ring slot.                */
 /* transfer = HDRTV_TRANSFER_LUT applies a 15361-entry code table (half bit pattern of the clamped value -> code).  */
