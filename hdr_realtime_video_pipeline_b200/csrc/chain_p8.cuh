@@ -25,10 +25,11 @@
 namespace hdrtv {
 
 constexpr int kMaxChain = 9;
-constexpr int kChainGroups = 6;
+constexpr int kChainGroups = 5;
 constexpr int kChainMaxRing = 16;                // >= kChainGroups + ks - 1 rows are in use at once; the rest is prefetch
 constexpr int kChainThreads = 32 * (1 + kChainGroups * 4);
-constexpr int kTileBytes = 8 * kPlaneBytes;      // one 64-channel operand tile (8 channel-chunk planes)
+constexpr int kTileBytes = 8 * kPlaneBytes;      // one 64-channel operand tile in shared memory (probes only)
+constexpr int kSlotCols = 96;                    // TMEM columns per row slot: 64 accumulator + 32 operand (64 ch fp16)
 
 // ---- chain programs (compile-time layer tables) -------------------------------------------------------------------
 // store: 0 none, 1 P8, 2 planar fp16 (3 channels) + single-chunk P8.   act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
   constexpr int G = kChainGroups;
   constexpr int L = Prog::L, KS = Prog::KS;
   constexpr int SPD = Prog::STEPS[0] / KS;            // layer-0 tap steps per input row
-  constexpr uint32_t kTmemCols = 512;                 // G * 64 = 384 rounded up to a power of two
+  constexpr uint32_t kTmemCols = 512;                 // G * kSlotCols = 480 rounded up to a power of two
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -142,8 +143,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kChainMaxRing + G + 1));
   uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
-  uint8_t* tiles = wsm + ((p.w_bytes + 127) & ~127);
-  uint8_t* ring = tiles + G * kTileBytes;
+  uint8_t* ring = wsm + ((p.w_bytes + 127) & ~127);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
     const bool issuer = ((warp - 1) & 3) == (g & 3);  // this warp also issues the slot's MMAs; spread over the 4 SMSPs
     const int lg = warp & 3;                          // TMEM lane quadrant this warp may read
     const int m = lg * 32 + lane;                     // pixel inside the strip = TMEM lane
-    const uint32_t d_tmem = tmem_base + g * 64;
+    const uint32_t d_tmem = tmem_base + g * kSlotCols;          // accumulator: 64 columns
+    const uint32_t a_tmem = d_tmem + 64;                        // next layer's A operand: 32 columns (2 channels each)
     const uint32_t tlane = d_tmem + (static_cast<uint32_t>(lg * 32) << 16);
-    uint4* tile = reinterpret_cast<uint4*>(tiles + g * kTileBytes) + m;
+    const uint32_t alane = a_tmem + (static_cast<uint32_t>(lg * 32) << 16);
     // issuer state
     const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
-    const uint32_t tile16 = (smem_u32(tiles) + g * kTileBytes) >> 4;
     const uint32_t slot16 = p.slot_bytes >> 4;
     const int ring_n = p.ring;
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
@@ -256,11 +256,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
                 tc_commit(tfull_bar(g));
               }
             } else {
-              const uint32_t a_lo0 = (tile16 + kAPlane * (kPlaneBytes >> 4)) | ((kPlaneBytes >> 4) << 16);
               if (elect_one()) {
+                // A = the previous layer's activations, written to TMEM by the epilogue (8 columns per K = 16 step)
 #pragma unroll
                 for (int i = 0; i < NSTEPS; ++i)
-                  tc_mma_f16(d_tmem, mkdesc(a_lo0 + i * ((2 * kPlaneBytes) >> 4)), mkdesc(b_lo0 + i * b_step), idesc, i ? 1u : 0u);
+                  tc_mma_f16_ts(d_tmem, a_tmem + kAPlane * 4 + i * 8, mkdesc(b_lo0 + i * b_step), idesc, i ? 1u : 0u);
                 tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + NSTEPS * b_step), idesc, 1u);      // + bias
                 tc_commit(tfull_bar(g));
               }
@@ -291,10 +291,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
             }
             CHAIN_STAMP(4);
             if constexpr (kWrite != 0) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) tile[c * kPlaneEntries] = h[c];
+              tmem_st32(alane, reinterpret_cast<const uint32_t*>(h));
               CHAIN_STAMP(5);
-              fence_proxy_async_smem();
+              tc_wait_st();
             }
             CHAIN_STAMP(6);
             if constexpr (kStore == 1) {
@@ -328,9 +327,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
               h[c] = pack8(a);
             }
             if constexpr (kWrite != 0) {
-              tile[0] = h[0];
-              tile[kPlaneEntries] = h[1];
-              fence_proxy_async_smem();
+              tmem_st8(alane, reinterpret_cast<const uint32_t*>(h));
+              tc_wait_st();
             }
             if constexpr (kStore != 0) {
               if (xin) {
@@ -349,7 +347,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
             }
           }
           CHAIN_STAMP(7);
-          group_barrier(1 + g);                       // tile written + TMEM drained by all four warps of the slot
+          tc_fence_before();
+          group_barrier(1 + g);                       // operand written + accumulator drained by all four warps of the slot
           ++e;
         });
       }
@@ -364,8 +363,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
 }
 
 inline size_t chain_smem_bytes(const ChainParams& cp) {
-  return kSmemHeader + ((cp.base.w_bytes + 127) & ~127) + kChainGroups * kTileBytes +
-         static_cast<size_t>(cp.base.ring) * cp.base.slot_bytes;
+  return kSmemHeader + ((cp.base.w_bytes + 127) & ~127) + static_cast<size_t>(cp.base.ring) * cp.base.slot_bytes;
 }
 
 }  // namespace hdrtv

@@ -505,7 +505,7 @@ static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string
   p.planar_W = Wo;
   p.err = c->d_err;
   // one CTA per SM: resident weights + one operand tile per row slot + the row ring
-  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127) + kChainGroups * kTileBytes;
+  const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127);
   const size_t budget = 224 * 1024;
   int ring = fixed < budget ? static_cast<int>((budget - fixed) / p.slot_bytes) : 0;
   ring = std::min(ring, std::min(kChainMaxRing, env_int("HDRTV_RING_CHAIN", kChainMaxRing)));

@@ -11,14 +11,6 @@
 
 namespace hdrtv {
 
-__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
