@@ -34,6 +34,17 @@ CONFIG_NAME = {
     "4k": "HDRTVNet++ FP16 3840x2160 single-B200 inference with fused RGB48 pack into pinned host ring — BASELINE configs[2]",
 }
 FLOP_PER_PX = 221054.0          # SURVEY §8d / BASELINE.md §2: 2 x 110 527 conv+linear MACs per pixel
+# algorithmic MACs per full-resolution pixel of the largest launches
+KERNEL_MAC_PER_PX = {
+    "LE.cond_chain+sft0.L0": 9920 + 9216 + 1024,         # cond_first + CondNet1 + stage 0 of SFT_layer1/2 (16 -> 64)
+    "LE.CondNet{2,3,4}.0": 27648,                         # three 3x3 s2 64->64 convs on cond
+    "AGCM.chain": 4480,
+    "LE.up_conv3.0": 9216 + 1536,                         # 3x3 32->128 at H/2 + SFT_layer2 stage 1
+    "LE.HR_conv1": 9216, "LE.HR_conv2": 9216, "LE.conv_first": 864 + 1536, "LE.conv_last": 864,
+    "LE.down_conv1": 2304 + 96,
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 1920x1080 from profiles/r1_ncu_top_kernels.md (ncu --set full)
+NCU_TRAFFIC_1080P = {"LE.cond_chain+sft0.L0": 54152448 + 556210432, "AGCM.chain": 33399552 + 2764544}
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
 
 
@@ -243,6 +254,26 @@ def run_b200_arm(args):
         lat.append((time.perf_counter() - t0) * 1000.0)
         fr.release()
 
+    # ---- per-launch device times of one frame (CUDA events between launches, median of 5) -> top-kernel rooflines
+    top_kernels = []
+    if rank == 0 and precision == "fp16":
+        x, c = net.preprocess_device(dev_frames[0], assume_ready=True)
+        runs = [net.time_plan((x, c)) for _ in range(5)]
+        names = [n for n, _ in runs[0]]
+        med = np.median(np.array([[t for _, t in r] for r in runs]), axis=0)
+        order = np.argsort(-med)[:4]
+        for i in order:
+            name = names[i].split(" ")[0]
+            mac = KERNEL_MAC_PER_PX.get(name)
+            entry = {"launch": names[i], "ms": float(med[i]), "share_of_infer": float(med[i] / med.sum())}
+            if mac is not None:
+                tf = 2.0 * mac * h * w / (med[i] / 1000.0) / 1e12
+                entry.update({"algorithmic_mac_per_px": mac, "achieved_tflops": tf})
+            traffic = NCU_TRAFFIC_1080P.get(name)
+            if traffic is not None and (h, w) == (1080, 1920):
+                entry["traffic_bytes_per_launch"] = traffic
+            top_kernels.append(entry)
+
     # ---- max over ranks ------------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s * 1000.0, infer_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -257,7 +288,8 @@ def run_b200_arm(args):
         px = h * w
         fps = world * K / (dev_ms / 1000.0)
         e2e_fps = world * K / (e2e_ms / 1000.0)
-        achieved_tf = FLOP_PER_PX * px / (infer_ms / 1000.0) / 1e12
+        step_ms = dev_ms / K                                   # whole step: preprocess + infer + pack, device-timed
+        achieved_tf = FLOP_PER_PX * px / (step_ms / 1000.0) / 1e12
         line = {
             "metric": "HDRTVNet++ frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -274,9 +306,13 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["tflops"], "traffic": None,
-                         "kernel": "conv_p8_kernel family (all tcgen05 conv launches of one infer(), CUDA events around infer)",
+                         "kernel": "whole hot path of one frame (49 launches: chain_p8_kernel x2, conv_p8_kernel family, "
+                                   "classifier, pre/pack); CUDA events around the timed steps on the launching stream",
                          "algorithmic": f"{FLOP_PER_PX:.0f} FLOP/px x {px} px per frame", "peak_source": peaks["source"],
-                         "ms_per_launch_group": infer_ms},
+                         "ms_per_frame": step_ms, "infer_only_ms": infer_ms,
+                         "note": "tcgen05.mma K=16 costs >= 44.6 pipe cycles for any N <= 64 (profiles/r1_tensor_probe.log): "
+                                 "with C_out in {16,32,64} the pipe-bound ceiling of this network is ~0.65 of dense peak",
+                         "top_kernels": top_kernels},
             "clocks": clocks,
             "ranks": [{"rank": r["rank"], "first_frame": r["first_frame"], "n_frames": r["n_frames"]} for r in records],
         }

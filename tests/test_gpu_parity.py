@@ -225,6 +225,40 @@ def test_resolution_change_and_determinism(nets):
     assert np.array_equal(o1, o2)                                                # bitwise repeatable across re-allocation
 
 
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_frame_pipelining_is_transparent(monkeypatch, precision):
+    """preprocess() runs H2D + normalise + the AGCM classifier on a side stream (overlapping the previous frame's LE
+    network); a stream of frames enqueued back to back without host synchronisation must give bit-identical outputs to
+    the fully serial configuration, and infer() on foreign tensors must still run the classifier itself."""
+    frames = [hb.synth_frame(i, 136, 248) for i in range(6)]
+    monkeypatch.setenv("HDRTV_B200_PIPELINE", "0")
+    serial = hb.HDRTVNetB200(W_HR, device="cuda", precision=precision, warmup_passes=0, use_hg=False)
+    monkeypatch.setenv("HDRTV_B200_PIPELINE", "1")
+    piped = hb.HDRTVNetB200(W_HR, device="cuda", precision=precision, warmup_passes=0, use_hg=False)
+    assert serial._pipeline is False and piped._pipeline is True
+    want = []
+    for f in frames:
+        out, _ = serial.infer(serial.preprocess(f))
+        torch.cuda.synchronize()
+        want.append(out.clone())
+    got = []
+    for f in frames:                                   # no synchronisation between frames
+        out, _ = piped.infer(piped.preprocess(f))
+        got.append(out.clone())
+    torch.cuda.synchronize()
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    # tensors that did not come from preprocess(): the classifier must run inside infer()
+    x, c = piped.preprocess(frames[0])
+    x2, c2 = x.clone(), c.clone()
+    piped.preprocess(frames[3])                        # leaves classifier results of ANOTHER frame behind
+    out, _ = piped.infer((x2, c2))
+    torch.cuda.synchronize()
+    assert torch.equal(out, want[0])
+    serial.close()
+    piped.close()
+
+
 @pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840)])
 def test_full_size_properties_fp16(nets, hw):
     """BASELINE configs 2/3 sizes: size-independent properties instead of a CPU oracle run —
