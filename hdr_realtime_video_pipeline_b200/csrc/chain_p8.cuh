@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      if (p.weights_dynamic) grid_dep_wait();
       mbar_expect_tx(wfull_bar, p.w_bytes);
       bulk_g2s(smem_u32(wsm), p.wpk, p.w_bytes, wfull_bar);
+      grid_dep_wait();          // static weights are on their way; activations need the previous kernel finished
       const uint32_t row_tx = p.n_copies * p.copy_bytes;
       int slot = 0, ph = 1;
       while (walk.next(strip, r0, n)) {
@@ -187,9 +189,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
           if (++slot == p.ring) { slot = 0; ph ^= 1; }
         }
       }
+      grid_dep_launch();        // all input requested: the next kernel's CTAs may start their prologue
     }
   } else {
     // ------------------------------------------------------------------ row slot g: one warpgroup
+    grid_dep_wait();            // the epilogue overwrites buffers the previous kernel may still read
     const int g = (warp - 1) >> 2;
     const bool issuer = ((warp - 1) & 3) == (g & 3);  // this warp also issues the slot's MMAs; spread over the 4 SMSPs
     const int lg = warp & 3;                          // TMEM lane quadrant this warp may read

@@ -103,6 +103,7 @@ struct ConvParams {
   // zsplit > 1: `zsplit` convolutions that read the SAME input (different weights / outputs of identical geometry) share
   // one launch; CTA blockIdx.x serves variant blockIdx.x % zsplit of strip blockIdx.x / zsplit, so the variants of a
   // strip run side by side and the input rows are fetched from HBM once (the other reads hit L2).
+  int weights_dynamic;      // the packed weights are written by the previous kernel in the stream (AGCM fold)
   int zsplit;
   const uint4* wpk_z[3];
   P8 out_zp[3];             // per-variant output tensors (layouts may differ)
@@ -234,9 +235,11 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      if (p.weights_dynamic) grid_dep_wait();
       mbar_expect_tx(wfull_bar, p.w_bytes + (SFTG ? p.w2_bytes : 0));
       bulk_g2s(smem_u32(wsm), zs > 1 ? p.wpk_z[zsel] : p.wpk, p.w_bytes, wfull_bar);
       if constexpr (SFTG) bulk_g2s(smem_u32(wsm2), p.wpk2, p.w2_bytes, wfull_bar);
+      grid_dep_wait();          // static weights are on their way; activations need the previous kernel finished
       constexpr uint32_t row_tx = NCOPY * kPlaneBytes;
       const uint32_t ring_n = p.ring, slot_bytes = NCOPY * kPlaneBytes;
       // The per-copy source address is formed with an explicit mad.wide: for `pointer + 32-bit offset` feeding
@@ -295,6 +298,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
           }
         }
       }
+      // all of this CTA's input has been requested: let the next kernel's CTAs start their prologue.  (Triggering
+      // earlier lets them pile onto whichever SMs drain first and unbalances the single-wave grids.)
+      grid_dep_launch();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -376,6 +382,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant
+    grid_dep_wait();            // reads skip/SFT operands and overwrites buffers the previous kernel may still use
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
     const int x = p.xmul * (x0 + lg * 32 + lane) + blockIdx.z;

@@ -404,6 +404,30 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   return 0;
 }
 
+// Programmatic dependent launch: the kernel may start (prologue, static weight loads) while its predecessor drains.
+// Measured on B200: +5.7 % frames/s at 1920x1080 (49 short launches per frame), -1 % at 3840x2160 (long single-wave
+// kernels, nothing to hide) -> on by default below 4 Mpixel; HDRTV_PDL=0/1 overrides.
+static bool g_pdl_small_frame = true;
+static bool use_pdl() {
+  static const int v = env_int("HDRTV_PDL", -1);
+  return v < 0 ? g_pdl_small_frame : v != 0;
+}
+template <typename Kernel, typename Params>
+static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, const Params& params) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
@@ -413,8 +437,7 @@ static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG><<<L.grid, kConvThreads, L.smem, s>>>(L.p);
-  return cudaGetLastError();
+  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>, L.grid, kConvThreads, L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 // Every (input kind, channel chunks, N, store mode, auxiliary operands) combination the plans and the self-tests use.
@@ -532,8 +555,7 @@ static cudaError_t launch_chain_t(const ConvLaunch& L, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  chain_p8_kernel<Prog><<<L.grid, kChainThreads, L.smem, s>>>(*L.chain);
-  return cudaGetLastError();
+  return launch_pdl(chain_p8_kernel<Prog>, L.grid, kChainThreads, L.smem, s, *L.chain);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
   switch (L.chain_prog) {
@@ -995,6 +1017,10 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
                      e);
     }
   }
+  for (ConvLaunch& A : c->plan_agcm) {      // AGCM weights are folded per frame by agcm_head_kernel, earlier in the stream
+    A.p.weights_dynamic = 1;
+    if (A.chain) A.chain->base.weights_dynamic = 1;
+  }
   auto& L = c->plan_le;
   // ---- LE condition pyramid
   if (use_chain) {
@@ -1279,6 +1305,7 @@ static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float
 static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __half* agcm_out, cudaStream_t s,
                     std::vector<cudaEvent_t>* evs = nullptr, bool skip_classifier = false, cudaEvent_t inputs_consumed = nullptr) {
   const int H = c->H, Wd = c->W;
+  g_pdl_small_frame = static_cast<long>(H) * Wd < 4000000L;
   auto mark = [&]() {
     if (!evs) return;
     cudaEvent_t e;

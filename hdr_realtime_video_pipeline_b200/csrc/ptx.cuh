@@ -61,6 +61,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
 }
 
+// ------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining: everything before grid_dep_wait() (barrier init, TMEM allocation, static weight loads)
+// overlaps the predecessor's tail; grid_dep_wait() returns once the predecessor grid has completed and its writes are
+// visible.  grid_dep_launch() lets the successor's CTAs be scheduled as soon as resources free up.  Both are no-ops
+// for ordinary launches.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------- 1-D bulk TMA copy
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
