@@ -104,10 +104,22 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline legs
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every core this process may run on."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_sample(n_frames: int, height: int, width: int, budget_s: float = 25.0):
     """The reference's setup_cpu configuration (torch CPU eager fp32) through oracle/torch_port.py."""
     import torch
     from oracle import torch_port as TP
+    _use_all_host_threads()
     from hdr_realtime_video_pipeline_b200.synth import synth_frame
     sd = TP.to_torch_state(dict(np.load(WEIGHTS)))
     TP.process_rgb48(sd, synth_frame(0, height, width))          # first frame discarded (BASELINE.md §3)
@@ -127,6 +139,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import torch
+    _use_all_host_threads()
     h, w = WORKLOADS[args.workload]
     sh, sw = 540, 960                                           # bounded sample: one config-1-size frame per step
     from oracle import torch_port as TP

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhdrtv_b200.so")
 
 FP32, FP16 = 0, 1
-COND_BICUBIC_AA, COND_ZERO = 0, 1
+COND_BICUBIC_AA, COND_ZERO, COND_BILINEAR = 0, 1, 2
 TRANSFER_IDENTITY, TRANSFER_LUT = 0, 1
 
 
@@ -31,7 +31,7 @@ _SIGNATURES = {
     "hdrtv_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "hdrtv_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "hdrtv_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "hdrtv_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hdrtv_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "hdrtv_infer_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "hdrtv_pack_rgb48": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

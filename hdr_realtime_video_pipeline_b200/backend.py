@@ -78,8 +78,6 @@ class HDRTVNetB200:
         self._warmup_passes = warmup_passes
         self._fast_condition_resize = bool(fast_condition_resize) or _env_bool("HDRTVNET_FAST_COND_RESIZE", False)
         self._fast_zero_condition = _env_bool("HDRTVNET_ZERO_COND", False)
-        if self._fast_condition_resize:
-            raise RuntimeError("fast_condition_resize (bilinear condition image) is not implemented by this backend")
         # argument validation first (ValueError), availability second (RuntimeError) — hdrtvnet_torch.py:1678-1702
         if str(device).lower() not in ("auto", "cuda", "cpu") and not str(device).lower().startswith("cuda:"):
             raise ValueError("device must be one of: auto, cuda, cpu")
@@ -236,13 +234,15 @@ class HDRTVNetB200:
 
     # ------------------------------------------------------------------ preprocess (hdrtvnet_torch.py:2239-2296)
     def _launch_preprocess(self, raw_dev, h, w, stream):
-        mode = _native.COND_ZERO if self._fast_zero_condition else _native.COND_BICUBIC_AA
+        # hdrtvnet_torch.py:2265-2294: zero condition > bilinear (fast_condition_resize) > antialiased bicubic
+        mode = (_native.COND_ZERO if self._fast_zero_condition else
+                (_native.COND_BILINEAR if self._fast_condition_resize else _native.COND_BICUBIC_AA))
         sp = C.c_void_p(stream.cuda_stream)
         _native.check(self._lib.hdrtv_preprocess(self._handle, raw_dev.data_ptr(), h, w, self._gpu_input.data_ptr(),
                                                  self._gpu_cond.data_ptr(), mode, sp), self._handle, "hdrtv_preprocess")
         if self._pipeline:
-            _native.check(self._lib.hdrtv_classify(self._handle, self._gpu_cond.data_ptr(), h, w, sp), self._handle,
-                          "hdrtv_classify")
+            _native.check(self._lib.hdrtv_classify(self._handle, self._gpu_input.data_ptr(), self._gpu_cond.data_ptr(), h, w, sp),
+                          self._handle, "hdrtv_classify")
 
     @torch.inference_mode()
     def preprocess(self, frame_bgr):

@@ -1314,9 +1314,11 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
     evs->push_back(e);
   };
   mark();
-  planar_to_p8_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(x, c->xP8, H, Wd);
-  CK(c, cudaGetLastError());
-  ++c->launches;
+  if (!skip_classifier) {      // otherwise hdrtv_classify already staged x into the P8 layout and ran the classifier
+    planar_to_p8_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(x, c->xP8, H, Wd);
+    CK(c, cudaGetLastError());
+    ++c->launches;
+  }
   mark();
   if (!skip_classifier && run_classifier(c, cond, true, s, evs)) return -1;
   mark();
@@ -1570,11 +1572,17 @@ int hdrtv_infer(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void
   return hdrtv_infer_ex(c, x, cond, H, Wd, out, agcm_out, 0, nullptr, stream);
 }
 
-int hdrtv_classify(hdrtv_t* c, const void* cond, int H, int Wd, void* stream) {
-  if (!c || !cond) return fail(c, "hdrtv_classify: null argument");
+int hdrtv_classify(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* stream) {
+  if (!c || !x || !cond) return fail(c, "hdrtv_classify: null argument");
   if (hdrtv_prepare(c, H, Wd)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   try {
-    return run_classifier(c, cond, c->precision == HDRTV_FP16, static_cast<cudaStream_t>(stream));
+    if (c->precision == HDRTV_FP16) {     // stage the image into the tensor-core layout (first step of the FP16 network)
+      planar_to_p8_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(static_cast<const __half*>(x), c->xP8, H, Wd);
+      CK(c, cudaGetLastError());
+      ++c->launches;
+    }
+    return run_classifier(c, cond, c->precision == HDRTV_FP16, s);
   } catch (const std::exception& e) {
     return fail(c, std::string("hdrtv_classify: ") + e.what());
   }

@@ -69,7 +69,7 @@ struct CondTaps {
 constexpr int kCondTW = 32, kCondTH = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) cond_aa_kernel(const uint8_t* __restrict__ bgr, T* __restrict__ cond, int H, int W,
-                                                      int Hc, int Wc, CondTaps tp, int mode /*0 aa, 1 zero*/) {
+                                                      int Hc, int Wc, CondTaps tp, int mode /*0 aa, 1 zero, 2 bilinear*/) {
   // window: rows [ys0, ys0+RH), cols [xs0, xs0+RW)
   constexpr int RW = kCondTW * 4 + 16, RH = kCondTH * 4 + 16;
   __shared__ float hs[3][RH][kCondTW + 1];
@@ -83,6 +83,29 @@ __global__ void __launch_bounds__(256) cond_aa_kernel(const uint8_t* __restrict_
         if constexpr (sizeof(T) == 2) cond[c * cplane + static_cast<long>(oy) * Wc + ox] = __float2half_rn(0.f);
         else cond[c * cplane + static_cast<long>(oy) * Wc + ox] = 0.f;
       }
+    return;
+  }
+  if (mode == 2) {
+    // fast_condition_resize (hdrtvnet_torch.py:2268-2275): bilinear x0.25, align_corners=False -> source coordinate
+    // 4i + 1.5, i.e. the mean of pixels 4i+1 and 4i+2 in both directions (fp32 accumulate, one rounding)
+    if (ox < Wc && oy < Hc) {
+      for (int c = 0; c < 3; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = 1; dy <= 2; ++dy) {
+          const int iy = min(4 * oy + dy, H - 1);
+          float rowv = 0.f;
+#pragma unroll
+          for (int dx = 1; dx <= 2; ++dx) {
+            const int ix = min(4 * ox + dx, W - 1);
+            rowv += 0.5f * norm_u8(bgr[(static_cast<long>(iy) * W + ix) * 3 + (2 - c)], sizeof(T) == 2);
+          }
+          acc += 0.5f * rowv;
+        }
+        if constexpr (sizeof(T) == 2) cond[c * cplane + static_cast<long>(oy) * Wc + ox] = __float2half_rn(acc);
+        else cond[c * cplane + static_cast<long>(oy) * Wc + ox] = acc;
+      }
+    }
     return;
   }
   const int ys0 = tp.ystart[min(oy0, Hc - 1)];

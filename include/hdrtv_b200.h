@@ -21,7 +21,7 @@ extern "C" {
 typedef struct hdrtv_ctx hdrtv_t;
 
 enum { HDRTV_FP32 = 0, HDRTV_FP16 = 1 };               /* arithmetic/storage type of x, cond, out tensors        */
-enum { HDRTV_COND_BICUBIC_AA = 0, HDRTV_COND_ZERO = 1 }; /* hdrtvnet_torch.py:2265-2294                           */
+enum { HDRTV_COND_BICUBIC_AA = 0, HDRTV_COND_ZERO = 1, HDRTV_COND_BILINEAR = 2 }; /* hdrtvnet_torch.py:2265-2294      */
 enum { HDRTV_TRANSFER_IDENTITY = 0, HDRTV_TRANSFER_LUT = 1 };
 
 typedef struct {
@@ -57,11 +57,12 @@ int hdrtv_preprocess(hdrtv_t* h, const uint8_t* bgr, int height, int width, void
 int hdrtv_infer(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
                 void* stream);
 
-/* The same inference split for frame pipelining: hdrtv_classify runs only the AGCM condition classifier + GFM fold   */
-/* (Condition_arch.py:559-569; it depends on `cond` alone, so it can run on a side stream while the previous frame's   */
-/* LE network still occupies the GPU); hdrtv_infer_ex(skip_classifier = 1) then runs everything else.                 */
+/* The same inference split for frame pipelining: hdrtv_classify runs the input-only part of the network — staging x */
+/* into the tensor-core layout and the AGCM condition classifier + GFM fold (Condition_arch.py:559-569), which depend  */
+/* on x / cond alone — so it can run on a side stream while the previous frame's LE network still occupies the GPU;    */
+/* hdrtv_infer_ex(skip_classifier = 1) then runs everything else for exactly those x / cond.                           */
 /* inputs_consumed_event (cudaEvent_t, optional) is recorded once x, cond and the classifier results have been read. */
-int hdrtv_classify(hdrtv_t* h, const void* cond, int height, int width, void* stream);
+int hdrtv_classify(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* stream);
 int hdrtv_infer_ex(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
                    int skip_classifier, void* inputs_consumed_event, void* stream);
 

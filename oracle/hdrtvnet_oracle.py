@@ -103,10 +103,30 @@ def cond_downsample(x_chw: np.ndarray, dtype=np.float32) -> np.ndarray:
     return out.astype(dtype)
 
 
-def preprocess(frame_bgr: np.ndarray, dtype=np.float32):
-    """Returns (x (1,3,H,W), cond (1,3,H//4,W//4)) like HDRTVNetTorch.preprocess."""
+def cond_bilinear(x: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """fast_condition_resize (hdrtvnet_torch.py:2268-2275): F.interpolate(scale_factor=0.25, mode="bilinear",
+    align_corners=False, recompute_scale_factor=False).  Source coordinate (i+0.5)*4-0.5 = 4i+1.5: the mean of input
+    pixels 4i+1 and 4i+2 in both directions (ATen accumulates half inputs in fp32 and rounds once)."""
+    xf = x.astype(F32)
+    c, h, w = xf.shape
+    ho, wo = h // 4, w // 4
+    iy1, iy2 = 4 * np.arange(ho) + 1, np.minimum(4 * np.arange(ho) + 2, h - 1)
+    ix1, ix2 = 4 * np.arange(wo) + 1, np.minimum(4 * np.arange(wo) + 2, w - 1)
+    top = F32(0.5) * xf[:, iy1][:, :, ix1] + F32(0.5) * xf[:, iy1][:, :, ix2]
+    bot = F32(0.5) * xf[:, iy2][:, :, ix1] + F32(0.5) * xf[:, iy2][:, :, ix2]
+    return (F32(0.5) * top + F32(0.5) * bot).astype(dtype)
+
+
+def preprocess(frame_bgr: np.ndarray, dtype=np.float32, cond_mode: str = "bicubic_aa"):
+    """Returns (x (1,3,H,W), cond (1,3,H//4,W//4)) like HDRTVNetTorch.preprocess; cond_mode "bilinear" is the
+    reference's fast_condition_resize option, "zero" its HDRTVNET_ZERO_COND shortcut."""
     x = normalize_bgr_u8(frame_bgr, dtype)
-    cond = cond_downsample(x, dtype)
+    if cond_mode == "bilinear":
+        cond = cond_bilinear(x, dtype)
+    elif cond_mode == "zero":
+        cond = np.zeros((3, x.shape[1] // 4, x.shape[2] // 4), dtype)
+    else:
+        cond = cond_downsample(x, dtype)
     return x[None], cond[None]
 
 

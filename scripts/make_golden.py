@@ -93,6 +93,22 @@ def main():
         save(f"pre_{h}x{w}.npz", frame=frame, x=x.numpy().copy(), cond=cond.numpy().copy(),
              x16=x16.numpy(), cond16=cond16.numpy())
 
+    # ---- fast_condition_resize (bilinear condition image) through the real wrapper (hdrtvnet_torch.py:2268-2275)
+    proc_fast = HDRTVNetTorch(hr_path, device="cpu", precision="fp32", compile_model=False, use_hg=False,
+                              warmup_passes=0, fast_condition_resize=True)
+    bil = {}
+    for (h, w) in ((64, 96), (73, 101)):
+        frame = synth_frame(0, h, w, "noise")
+        x, cond = proc_fast.preprocess(frame)
+        bil[f"frame_{h}x{w}"] = frame
+        bil[f"cond_{h}x{w}"] = cond.numpy().copy()
+        x16 = torch.from_numpy(frame).flip(2).permute(2, 0, 1).unsqueeze(0).to(torch.float16).mul_(1.0 / 255.0)
+        bil[f"cond16_{h}x{w}"] = F.interpolate(x16.float(), scale_factor=0.25, mode="bilinear", align_corners=False,
+                                               recompute_scale_factor=False).to(torch.float16).numpy()
+    save("pre_bilinear.npz", **bil)
+    if os.environ.get("HDRTV_GOLDEN_ONLY") == "bilinear":
+        return
+
     # ---- AA bicubic on awkward sizes -------------------------------------
     rng = np.random.default_rng(7)
     aa = {}

@@ -75,6 +75,28 @@ def test_preprocess(nets, precision, hw):
     assert np.abs(cond.float().cpu().numpy() - c_o.astype(np.float32)).max() <= tol
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_fast_condition_resize_and_zero_condition(monkeypatch, precision):
+    """The reference's two condition-image shortcuts: fast_condition_resize=True (bilinear, hdrtvnet_torch.py:2268-2275)
+    and HDRTVNET_ZERO_COND (:2265-2267)."""
+    g = load_golden("pre_bilinear.npz")
+    net = hb.HDRTVNetB200(W_HR, device="cuda", precision=precision, warmup_passes=0, use_hg=False, fast_condition_resize=True)
+    for hw in ("64x96", "73x101"):
+        x, cond = net.preprocess(g[f"frame_{hw}"])
+        torch.cuda.synchronize()
+        ref = g[f"cond_{hw}"] if precision == "fp32" else g[f"cond16_{hw}"].astype(np.float32)
+        assert np.abs(cond.float().cpu().numpy() - ref).max() <= (1e-6 if precision == "fp32" else 1e-3)
+        out, _ = net.infer((x, cond))
+        assert torch.isfinite(out).all()
+    net.close()
+    monkeypatch.setenv("HDRTVNET_ZERO_COND", "1")
+    netz = hb.HDRTVNetB200(W_HR, device="cuda", precision=precision, warmup_passes=0, use_hg=False)
+    _, cond = netz.preprocess(g["frame_64x96"])
+    torch.cuda.synchronize()
+    assert not cond.any()
+    netz.close()
+
+
 def test_preprocess_matches_reference_fixture(nets):
     for name in ("pre_64x96.npz", "pre_72x100.npz", "pre_135x241.npz"):
         g = load_golden(name)

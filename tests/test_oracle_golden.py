@@ -129,3 +129,17 @@ def test_torch_port_matches_reference_and_numpy_oracle(weights_hr):
     oo, _ = O.infer(weights_hr, xo, co)
     assert np.abs(out.numpy() - oo).max() <= 5e-5
     torch.set_num_threads(torch.get_num_threads())
+
+
+def test_bilinear_condition_matches_reference_fixture():
+    """fast_condition_resize (hdrtvnet_torch.py:2268-2275) through the reference wrapper itself."""
+    g = load_golden("pre_bilinear.npz")
+    for hw in ("64x96", "73x101"):
+        frame = g[f"frame_{hw}"]
+        x, cond = O.preprocess(frame, np.float32, cond_mode="bilinear")
+        assert cond.shape == g[f"cond_{hw}"].shape
+        assert np.abs(cond - g[f"cond_{hw}"]).max() <= 1e-6
+        _, cond16 = O.preprocess(frame, np.float16, cond_mode="bilinear")
+        assert np.abs(cond16.astype(np.float32) - g[f"cond16_{hw}"].astype(np.float32)).max() <= 1e-3
+    z = O.preprocess(g["frame_64x96"], np.float32, cond_mode="zero")[1]
+    assert z.shape == (1, 3, 16, 24) and not z.any()
