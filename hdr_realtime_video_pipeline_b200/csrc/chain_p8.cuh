@@ -59,14 +59,15 @@ struct ProgCond {
 // ProgCond + the stage-0 convs of the two full-resolution SFT layers (16 -> 2 x 32, LeakyReLU) as a seventh step on
 // cond1: S0STORE = 1 stores all 64 channels to outs[6]; 3 stores chunks 0-3 to outs[6] and chunks 4-7 to outs2 (the
 // parity-split home of the layer an up-conv applies).                                   (arch_util.py:63-72)
-template <int S0STORE>
+// C1STORE = 1 also stores cond1 (only a debugging output once its sole consumer, the SFT stage 0, is the next step).
+template <int S0STORE, int C1STORE = 0>
 struct ProgCondSft {
   static constexpr int L = 7, KS = 3;
   static constexpr int N[L] = {64, 64, 64, 64, 64, 16, 64};
   static constexpr int STEPS[L] = {6, 4, 4, 4, 4, 4, 1};
   static constexpr int APLANE[L] = {0, 0, 0, 0, 0, 0, 0};
   static constexpr int WRITE[L] = {1, 1, 1, 1, 1, 1, 0};
-  static constexpr int STORE[L] = {0, 0, 1, 0, 0, 1, S0STORE};
+  static constexpr int STORE[L] = {0, 0, 1, 0, 0, C1STORE, S0STORE};
   static constexpr int ACT[L] = {2, 2, 2, 2, 2, 0, 2};
   static constexpr int A0_OFF[2] = {0, 32};
   static constexpr int A0_LBO[2] = {16, 16};
@@ -80,6 +81,7 @@ __host__ __device__ constexpr int prog_w_off(int l) {   // byte offset of layer 
 
 struct ChainParams {
   ConvParams base;           // input side (ring geometry), weights pointer / total bytes, Ho/Wo, planar output
+  int active_slots;          // row slots in use (<= kChainGroups; tuning / experiments)
   int strips;                // 128-pixel strips per row; the grid is 1-D, each CTA takes a contiguous (strip, row) range
   P8 outs[kMaxChain];        // per layer, where STORE != 0
   P8 outs2;                  // second home of a split store (STORE == 3)
@@ -216,7 +218,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
     while (walk.next(strip, r0, n)) {
       const int x = strip * kTileM + m;
       const bool xin = x < p.Wo;
-      for (int t = (g - R % G + G) % G; t < n; t += G) {
+      const int GA = cp.active_slots;
+      for (int t = (g - R % GA + GA) % GA; t < n && g < GA; t += GA) {
         const int oy = r0 + t;
         static_for<0, L>([&](auto lc) {
           constexpr int l = decltype(lc)::value;

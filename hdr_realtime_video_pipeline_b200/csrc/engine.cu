@@ -490,7 +490,7 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
 }
 
 // ---- fused layer chains (chain_p8.cuh) -----------------------------------------------------------
-enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3 };
+enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3, PROG_COND_SFT3_DBG = 4 };
 
 template <class Prog>
 static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int prog_id, InKind kind, const P8& in,
@@ -539,6 +539,7 @@ static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string
   L.mode = planar ? STORE_PLANAR : STORE_P8;
   L.name = name;
   L.chain_prog = prog_id;
+  cp.active_slots = std::max(1, std::min(kChainGroups, env_int("HDRTV_CHAIN_ACTIVE", kChainGroups)));
   cp.strips = (Wo + kTileM - 1) / kTileM;
   const long items = static_cast<long>(cp.strips) * Ho;
   L.grid = dim3(static_cast<unsigned>(std::min<long>(env_int("HDRTV_CHAIN_CTAS", 148), items)));
@@ -561,8 +562,9 @@ static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
   switch (L.chain_prog) {
     case PROG_AGCM: return launch_chain_t<ProgAGCM>(L, s);
     case PROG_COND: return launch_chain_t<ProgCond>(L, s);
-    case PROG_COND_SFT1: return launch_chain_t<ProgCondSft<1>>(L, s);
+    case PROG_COND_SFT1: return launch_chain_t<ProgCondSft<1, 1>>(L, s);
     case PROG_COND_SFT3: return launch_chain_t<ProgCondSft<3>>(L, s);
+    case PROG_COND_SFT3_DBG: return launch_chain_t<ProgCondSft<3, 1>>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -1025,11 +1027,15 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   // ---- LE condition pyramid
   if (use_chain) {
     // cond_first + CondNet1 + the stage-0 convs of SFT_layer1 / SFT_layer2 (seventh step, on cond1)
-    if (use_sftg)
+    // cond1 itself has no consumer left (its SFT stage 0 is the next step): stored only when HDRTV_DEBUG_TENSORS=1
+    if (use_sftg && env_int("HDRTV_DEBUG_TENSORS", 0))
+      r |= make_chain_t<ProgCondSft<3, 1>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT3_DBG, IN_NAT3x3_C8, agP8, 1,
+                                           {nullptr, nullptr, &COND, nullptr, nullptr, &cond1, &S0}, wk("chain.cond_sft"), H, Wd, &S0ps);
+    else if (use_sftg)
       r |= make_chain_t<ProgCondSft<3>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT3, IN_NAT3x3_C8, agP8, 1,
-                                        {nullptr, nullptr, &COND, nullptr, nullptr, &cond1, &S0}, wk("chain.cond_sft"), H, Wd, &S0ps);
+                                        {nullptr, nullptr, &COND, nullptr, nullptr, nullptr, &S0}, wk("chain.cond_sft"), H, Wd, &S0ps);
     else
-      r |= make_chain_t<ProgCondSft<1>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT1, IN_NAT3x3_C8, agP8, 1,
+      r |= make_chain_t<ProgCondSft<1, 1>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT1, IN_NAT3x3_C8, agP8, 1,
                                         {nullptr, nullptr, &COND, nullptr, nullptr, &cond1, &S0}, wk("chain.cond_sft"), H, Wd);
   } else {
   r |= std_conv(L, "LE.cond_first.0", IN_NAT3x3_C8, agP8, 8, 64, STORE_P8, B1, H, Wd, lrelu);
