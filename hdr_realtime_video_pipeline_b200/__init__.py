@@ -6,8 +6,9 @@ Drop-in for the reference's model wrapper and feeder pack on this path only:
 """
 from .backend import HDRTVNetB200, load_state_dict_any  # noqa: F401
 from .feeders import PinnedFrame, RGB48Packer, pq_code_table, tensor_to_rgb48_bytes  # noqa: F401
+from .export import Rgb48RawWriter, export_clip, ffmpeg_rawvideo_args  # noqa: F401
 from .sharding import frame_chunk, gather_run_records  # noqa: F401
 from .synth import synth_clip, synth_frame  # noqa: F401
 
 __all__ = ["HDRTVNetB200", "load_state_dict_any", "PinnedFrame", "RGB48Packer", "pq_code_table",
-           "tensor_to_rgb48_bytes", "frame_chunk", "gather_run_records", "synth_clip", "synth_frame"]
+           "tensor_to_rgb48_bytes", "Rgb48RawWriter", "export_clip", "ffmpeg_rawvideo_args", "frame_chunk", "gather_run_records", "synth_clip", "synth_frame"]

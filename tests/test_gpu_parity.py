@@ -304,6 +304,20 @@ def test_full_size_properties_fp16(nets, hw):
     fr.release()
 
 
+def test_export_clip_matches_per_frame_pack(nets, tmp_path):
+    """BASELINE config 4 in miniature: the sharded export writer produces, frame for frame, the bytes of the feeder pack."""
+    net = nets("hr", "fp16")
+    frames = [hb.synth_frame(i, 72, 100) for i in range(5)]
+    out = tmp_path / "clip.rgb48"
+    rec = hb.export_clip(net, lambda i: frames[i], 5, str(out))
+    data = np.fromfile(out, dtype=np.uint16).reshape(5, 72, 100, 3)
+    for i, f in enumerate(frames):
+        o, _ = net.infer(net.preprocess(f))
+        torch.cuda.synchronize()
+        assert np.array_equal(data[i], O.pack_rgb48(o.cpu().numpy()))
+    assert [d[0] for d in rec["descriptors"]] == list(range(5))
+
+
 def test_errors_are_python_exceptions(nets):
     net = nets("hr", "fp16")
     with pytest.raises(ValueError):

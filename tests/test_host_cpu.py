@@ -136,6 +136,96 @@ def test_gloo_world_size_2_gather(tmp_path):
         assert "ok" in out
 
 
+class _FakePayload:
+    def __init__(self, arr):
+        self._a = np.ascontiguousarray(arr)
+        self.released = False
+
+    def wait_ready(self):
+        pass
+
+    def buffer_view(self):
+        return memoryview(self._a).cast("B")
+
+    def release(self):
+        self.released = True
+
+
+class _FakeProcessor:
+    """preprocess/infer stand-in: the 'network output' of frame i is a uint16 ramp offset by the frame's first byte."""
+    def preprocess(self, frame):
+        return frame
+
+    def infer(self, frame):
+        return frame
+
+
+def _fake_pack(frame):
+    h, w = frame.shape[:2]
+    base = (np.arange(h * w * 3, dtype=np.uint32) % 65000).astype(np.uint16).reshape(h, w, 3)
+    return _FakePayload(base + np.uint16(frame[0, 0, 0]))
+
+
+def _fake_frames(i):
+    return np.full((6, 10, 3), i, dtype=np.uint8)
+
+
+def test_export_writer_orders_frames_and_ffmpeg_contract(tmp_path):
+    out = tmp_path / "clip.rgb48"
+    rec = hb.export_clip(_FakeProcessor(), _fake_frames, 7, str(out), pack=_fake_pack)
+    assert rec["n_frames"] == 7 and [d[0] for d in rec["descriptors"]] == list(range(7))
+    data = np.fromfile(out, dtype=np.uint16).reshape(7, 6, 10, 3)
+    for i in range(7):
+        assert np.array_equal(data[i], _fake_pack(_fake_frames(i))._a)
+    assert sharding.merge_descriptors([rec])[3][1] == sharding.frame_checksum(data[3])
+    args = hb.ffmpeg_rawvideo_args(3840, 2160, 23.976, "out.mov")
+    joined = " ".join(args)                                                  # src/gui_export.py:966-1023
+    for token in ("-f rawvideo", "-pix_fmt rgb48le", "-s:v 3840x2160", "-color_range pc", "-colorspace bt2020nc",
+                  "-color_trc smpte2084", "-color_primaries bt2020", "-c:v prores_ks", "-profile:v 3",
+                  "transferin=smpte2084", "format=yuv422p10le"):
+        assert token in joined, token
+    with pytest.raises(ValueError):
+        hb.Rgb48RawWriter(str(out), 7, 6, 10, create=False).write(9, b"")
+
+
+_EXPORT_WORKER = r"""
+import os, sys
+sys.path.insert(0, {repo!r})
+sys.path.insert(0, os.path.join({repo!r}, "tests"))
+import torch.distributed as dist
+import hdr_realtime_video_pipeline_b200 as hb
+from hdr_realtime_video_pipeline_b200 import sharding
+from test_host_cpu import _FakeProcessor, _fake_frames, _fake_pack
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rec = hb.export_clip(_FakeProcessor(), _fake_frames, 9, {out!r}, rank=rank, world_size=world, pack=_fake_pack,
+                     barrier=dist.barrier)
+recs = sharding.gather_run_records(rec)
+merged = sharding.merge_descriptors(recs)
+assert [d[0] for d in merged] == list(range(9)), merged
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world_size_2_sharded_export(tmp_path):
+    out = tmp_path / "clip2.rgb48"
+    script = tmp_path / "export_worker.py"
+    script.write_text(_EXPORT_WORKER.format(repo=REPO, out=str(out)))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29534")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, o
+    data = np.fromfile(out, dtype=np.uint16).reshape(9, 6, 10, 3)
+    for i in range(9):
+        assert np.array_equal(data[i], _fake_pack(_fake_frames(i))._a)      # both ranks' chunks, in clip order
+
+
 def test_synth_frames_deterministic_and_typed():
     for i in range(4):
         a, b = hb.synth_frame(i, 36, 52), hb.synth_frame(i, 36, 52)
