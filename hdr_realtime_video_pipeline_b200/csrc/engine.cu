@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "conv_p8.cuh"
 #include "chain_p8.cuh"
+#include "conv2x_p8.cuh"
 #include "probes.cuh"
 #include <memory>
 #include "kernels_f32.cuh"
@@ -187,6 +188,8 @@ struct ConvLaunch {
   std::string name;
   std::shared_ptr<ChainParams> chain;   // set: this launch is a fused layer chain (chain_p8_kernel), `p` is a geometry copy
   int chain_prog = 0;
+  std::shared_ptr<Conv2xParams> c2x;    // set: two chained 3x3 convs in one kernel (conv2x_p8_kernel)
+  int c2x_variant = 0;
 };
 
 struct DebugTensor {
@@ -440,9 +443,29 @@ static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>, L.grid, kConvThreads, L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
+template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB>
+static cudaError_t launch_conv2x_t(const ConvLaunch& L, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  return launch_pdl(conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB>, L.grid, kC2Threads, L.smem, s, *L.c2x);
+}
+static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
+  switch (L.c2x_variant) {
+    case 0: return launch_conv2x_t<IN_NAT3x3_C8, 1, true, 32, STORE_P8>(L, s);
+    case 1: return launch_conv2x_t<IN_NAT3x3, 4, true, 32, STORE_P8>(L, s);
+    case 2: return launch_conv2x_t<IN_NAT3x3, 4, false, 16, STORE_PLANAR>(L, s);
+  }
+  return cudaErrorInvalidValue;
+}
 // Every (input kind, channel chunks, N, store mode, auxiliary operands) combination the plans and the self-tests use.
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
+  if (L.c2x) return launch_conv2x(L, s);
   if (L.sftg) {     // in-kernel SFT generator: 32-channel outputs
     if (L.mode == STORE_PS && L.N == 128 && L.kind == IN_NAT3x3 && L.kch == 4)
       return launch_conv_t<IN_NAT3x3, 4, 128, STORE_PS, true, true>(L, s);
@@ -487,6 +510,75 @@ static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
 #undef HDRTV_CONV_P8
 #undef HDRTV_CONV_CASE
   return cudaErrorInvalidValue;
+}
+
+// ---- two chained 3x3 convs (conv2x_p8.cuh) ---------------------------------------------------------
+enum C2xVariant { C2X_C8_SFTG_P8 = 0, C2X_K4_SFTG_P8 = 1, C2X_K4_PLANAR = 2 };
+struct C2xB {             // conv B: weights, width, store mode, epilogue operands
+  const __half* wpk = nullptr;
+  int N = 32;
+  int mode = STORE_P8;
+  int act = ACT_NONE;
+  const P8* res = nullptr;
+  const P8* res2 = nullptr;
+  const P8* raw = nullptr;
+};
+static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int variant, const P8& in,
+                       const __half* wpkA, const Epi& ea, const C2xB& b, const P8& out, int H, int Wd) {
+  ConvLaunch L;
+  memset(&L.p, 0, sizeof(L.p));
+  L.c2x = std::make_shared<Conv2xParams>();
+  Conv2xParams& p = *L.c2x;
+  memset(&p, 0, sizeof(p));
+  const bool c8 = variant == C2X_C8_SFTG_P8;
+  const bool sftg = variant != C2X_K4_PLANAR;
+  if (in.parity) return fail(c, "conv2x " + name + ": natural-layout input required");
+  p.in = reinterpret_cast<const uint4*>(in.base);
+  p.in_row_entries = in.row_entries();
+  p.copy_src0 = 0;
+  p.copy_src_stride = static_cast<uint32_t>(in.Wp);
+  p.H = H;
+  p.W = Wd;
+  p.wpkA = reinterpret_cast<const uint4*>(wpkA);
+  p.wA_bytes = ((c8 ? 6 : 18) + 1) * 32 * 32;
+  if (sftg) {
+    if (!ea.sft_s0 || ea.sft_s0->parity) return fail(c, "conv2x " + name + ": natural-layout stage-0 SFT map required");
+    p.wpk2 = reinterpret_cast<const uint4*>(ea.sft_w2);
+    p.w2_bytes = 3 * 64 * 32;
+    p.s0 = reinterpret_cast<const uint4*>(ea.sft_s0->base);
+    p.s0_row_entries = ea.sft_s0->row_entries();
+    p.s0_src0 = static_cast<uint32_t>(ea.sft_j0) * ea.sft_s0->Wp;
+    p.s0_wp = static_cast<uint32_t>(ea.sft_s0->Wp);
+  }
+  p.wpkB = reinterpret_cast<const uint4*>(b.wpk);
+  p.wB_bytes = (18 + 1) * b.N * 32;
+  p.slopeB = b.act == ACT_RELU ? 0.f : (b.act == ACT_LRELU ? 0.1f : 1.f);
+  if (b.res) { p.has_res = 1; p.res = *b.res; }
+  if (b.res2) { p.has_res2 = 1; p.res2 = *b.res2; }
+  if (b.raw) { p.has_raw = 1; p.raw = *b.raw; }
+  p.out = out;
+  p.planar = b.mode == STORE_PLANAR ? reinterpret_cast<__half*>(1) : nullptr;
+  p.planar_plane = static_cast<long>(H) * Wd;
+  p.planar_W = Wd;
+  p.err = c->d_err;
+  const int strips = (Wd + kC2Strip - 1) / kC2Strip;
+  const int nb = std::max(1, 148 / strips);
+  int band = std::max((H + nb - 1) / nb, 4);
+  band = std::min(band, H);
+  p.band = band;
+  L.grid = dim3(strips, (H + band - 1) / band, 1);
+  L.smem = variant == C2X_C8_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3_C8, 1, true>(p)
+         : variant == C2X_K4_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3, 4, true>(p)
+                                     : conv2x_smem_bytes<IN_NAT3x3, 4, false>(p);
+  if (L.smem > 227 * 1024) return fail(c, "conv2x " + name + ": shared memory budget exceeded");
+  L.c2x_variant = variant;
+  L.N = b.N;
+  L.mode = b.mode;
+  L.name = name;
+  L.p.band = band;
+  L.p.ring = kC2InRing;
+  plan.push_back(L);
+  return 0;
 }
 
 // ---- fused layer chains (chain_p8.cuh) -----------------------------------------------------------
@@ -1107,11 +1199,24 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     }
   };
   // ---- trunk
-  { Epi e = relu; with_sft(e, "LE.SFT_layer1");
-    r |= std_conv(L, "LE.conv_first", IN_NAT3x3_C8, agP8, 8, 32, STORE_P8, T0a, H, Wd, e); }
-  r |= std_conv(L, "LE.HR_conv1", IN_NAT3x3, T0a, 32, 32, STORE_P8, FEA0, H, Wd, relu);
+  const bool use_c2x = use_sftg && env_int("HDRTV_C2X", 1) != 0;   // conv -> conv pairs through a shared-memory row ring
+  if (use_c2x) {
+    Epi ea = relu; with_sft(ea, "LE.SFT_layer1");
+    C2xB b; b.wpk = wk("LE.HR_conv1"); b.N = 32; b.mode = STORE_P8; b.act = ACT_RELU;
+    r |= make_conv2x(c, L, "LE.conv_first+HR_conv1", C2X_C8_SFTG_P8, agP8, wk("LE.conv_first"), ea, b, FEA0, H, Wd);
+  } else {
+    { Epi e = relu; with_sft(e, "LE.SFT_layer1");
+      r |= std_conv(L, "LE.conv_first", IN_NAT3x3_C8, agP8, 8, 32, STORE_P8, T0a, H, Wd, e); }
+    r |= std_conv(L, "LE.HR_conv1", IN_NAT3x3, T0a, 32, 32, STORE_P8, FEA0, H, Wd, relu);
+  }
   auto resblock = [&](const std::string& pre, const P8& xm, const P8& xraw, const P8& ytmp, const P8& out,
                       const P8* res2, const char* next_sft, const P8* next_raw, int h, int w) {
+    if (use_c2x && !next_sft) {     // conv1 -> sft2 -> conv2 + x in one kernel
+      Epi ea = relu; with_sft(ea, pre + ".sft2");
+      C2xB b; b.wpk = wk(pre + ".conv2"); b.N = 32; b.mode = STORE_P8; b.act = ACT_NONE; b.res = &xraw; b.res2 = res2; b.raw = next_raw;
+      r |= make_conv2x(c, L, pre + ".conv1+conv2", C2X_K4_SFTG_P8, xm, wk(pre + ".conv1"), ea, b, out, h, w);
+      return;
+    }
     { Epi e = relu; with_sft(e, pre + ".sft2");
       r |= std_conv(L, pre + ".conv1", IN_NAT3x3, xm, 32, 32, STORE_P8, ytmp, h, w, e); }
     { Epi e; e.res = &xraw; e.res2 = res2; e.raw = next_raw;
@@ -1150,9 +1255,15 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   up("LE.up_conv2.0", U2, FEA1, &X5, "LE.recon_trunk5.0.sft1", X5m, H2, W2);
   resblock("LE.recon_trunk5.0", X5m, X5, Y5, U1, nullptr, nullptr, nullptr, H1, W1);
   up("LE.up_conv3.0", U1, FEA0, nullptr, "LE.SFT_layer2", V0, H1, W1);
-  r |= std_conv(L, "LE.HR_conv2", IN_NAT3x3, V0, 32, 32, STORE_P8, V1, H, Wd, relu);
-  { Epi e; e.res = &agP8; e.planar = reinterpret_cast<__half*>(1);
-    r |= std_conv(L, "LE.conv_last", IN_NAT3x3, V1, 32, 16, STORE_PLANAR, agP8, H, Wd, e); }
+  if (use_c2x) {
+    Epi ea = relu;
+    C2xB b; b.wpk = wk("LE.conv_last"); b.N = 16; b.mode = STORE_PLANAR; b.act = ACT_NONE; b.res = &agP8;
+    r |= make_conv2x(c, L, "LE.HR_conv2+conv_last", C2X_K4_PLANAR, V0, wk("LE.HR_conv2"), ea, b, agP8, H, Wd);
+  } else {
+    r |= std_conv(L, "LE.HR_conv2", IN_NAT3x3, V0, 32, 32, STORE_P8, V1, H, Wd, relu);
+    { Epi e; e.res = &agP8; e.planar = reinterpret_cast<__half*>(1);
+      r |= std_conv(L, "LE.conv_last", IN_NAT3x3, V1, 32, 16, STORE_PLANAR, agP8, H, Wd, e); }
+  }
   if (r) return -1;
 
   dbg_p8(c, "agcm", agP8, 3);
@@ -1338,6 +1449,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
   if (inputs_consumed) CK(c, cudaEventRecord(inputs_consumed, s));   // x, cond and the folded AGCM weights are free again
   for (ConvLaunch& L : c->plan_le) {
     if (L.mode == STORE_PLANAR) L.p.planar = out;
+    if (L.c2x && L.mode == STORE_PLANAR) L.c2x->planar = out;
     CK(c, launch_conv(L, s));
     ++c->launches;
     mark();
