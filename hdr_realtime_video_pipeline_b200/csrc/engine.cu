@@ -561,12 +561,13 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
   p.planar_plane = static_cast<long>(H) * Wd;
   p.planar_W = Wd;
   p.err = c->d_err;
-  const int strips = (Wd + kC2Strip - 1) / kC2Strip;
-  const int nb = std::max(1, 148 / strips);
-  int band = std::max((H + nb - 1) / nb, 4);
-  band = std::min(band, H);
+  p.strips = (Wd + kC2Strip - 1) / kC2Strip;
+  const long items = static_cast<long>(p.strips) * H;
+  // one CTA per SM, each a contiguous range of (strip, row) items; at least 8 rows per CTA so the two halo rows stay cheap
+  const long ctas = std::max<long>(1, std::min<long>(env_int("HDRTV_C2X_CTAS", 148), items / 8));
+  const int band = static_cast<int>((items + ctas - 1) / ctas);
   p.band = band;
-  L.grid = dim3(strips, (H + band - 1) / band, 1);
+  L.grid = dim3(static_cast<unsigned>(ctas), 1, 1);
   L.smem = variant == C2X_C8_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3_C8, 1, true>(p)
          : variant == C2X_K4_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3, 4, true>(p)
                                      : conv2x_smem_bytes<IN_NAT3x3, 4, false>(p);
