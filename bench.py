@@ -40,11 +40,19 @@ KERNEL_MAC_PER_PX = {
     "LE.CondNet{2,3,4}.0": 27648,                         # three 3x3 s2 64->64 convs on cond
     "AGCM.chain": 4480,
     "LE.up_conv3.0": 9216 + 1536,                         # 3x3 32->128 at H/2 + SFT_layer2 stage 1
+    "LE.conv_first+HR_conv1": 864 + 1536 + 9216,          # + SFT_layer1 stage 1
+    "LE.HR_conv2+conv_last": 9216 + 864,
+    "LE.recon_trunk1.0.conv1+conv2": 2304 + 2304 + 384, "LE.recon_trunk5.0.conv1+conv2": 2304 + 2304 + 384,
     "LE.HR_conv1": 9216, "LE.HR_conv2": 9216, "LE.conv_first": 864 + 1536, "LE.conv_last": 864,
-    "LE.down_conv1": 2304 + 96,
+    "LE.down_conv1": 2304 + 384,
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 1920x1080 from profiles/r1_ncu_top_kernels.md (ncu --set full)
-NCU_TRAFFIC_1080P = {"LE.cond_chain+sft0.L0": 54152448 + 556210432, "AGCM.chain": 33399552 + 2764544}
+NCU_TRAFFIC_1080P = {}     # filled from profiles/r1_ncu_top_kernels.json when present (written by scripts/summarise_ncu.py)
+try:
+    with open(os.path.join(REPO, "profiles", "r1_ncu_top_kernels.json")) as _f:
+        NCU_TRAFFIC_1080P = {k: int(v) for k, v in json.load(_f).get("dram_bytes_per_launch_1080p", {}).items()}
+except Exception:
+    pass
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
 
 
@@ -319,7 +327,7 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["tflops"], "traffic": None,
-                         "kernel": "whole hot path of one frame (49 launches: chain_p8_kernel x2, conv_p8_kernel family, "
+                         "kernel": "whole hot path of one frame (chain_p8_kernel x2, conv2x_p8_kernel, conv_p8_kernel family, "
                                    "classifier, pre/pack); CUDA events around the timed steps on the launching stream",
                          "algorithmic": f"{FLOP_PER_PX:.0f} FLOP/px x {px} px per frame", "peak_source": peaks["source"],
                          "ms_per_frame": step_ms, "infer_only_ms": infer_ms,

@@ -398,6 +398,12 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   ring = std::min(ring, env_int(p.ks == 1 ? "HDRTV_RING_1x1" : "HDRTV_RING_3x3", std::max(p.ks == 1 ? 3 : 4, p.ks + prefetch)));
   if (ring < min_ring) ring = min_ring;
   if (ring > kMaxRing) ring = kMaxRing;
+  // Experiment knob (off): give a kernel that is alone on its SM every row slot that still fits.  Measured SLOWER
+  // on B200 (down_conv1 187 -> 227 us at 4K with ring 4 -> 8), so the shallow rings stay.
+  if (env_int("HDRTV_RING_FILL", 0) && fixed + static_cast<size_t>(ring) * p.slot_bytes > 113 * 1024) {
+    const int fill = static_cast<int>((220 * 1024 - fixed) / p.slot_bytes);
+    ring = std::max(ring, std::min(fill, kMaxRing));
+  }
   p.ring = ring;
   L.smem = conv_smem_bytes(p, mode == STORE_PS);
   if (L.smem > 227 * 1024) return fail(c, "conv " + name + ": shared memory budget exceeded");

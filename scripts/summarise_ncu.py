@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Summarise ncu captures into profiles/ (run in the build container after a gpurun profiling call).
+
+    python scripts/summarise_ncu.py gpurun_out/launches_1080p.csv gpurun_out/prof_top_r1.ncu-rep [more .ncu-rep ...]
+
+Writes profiles/r1_launches_1080p.{csv,md}, profiles/r1_ncu_top_kernels.{md,json}."""
+import collections
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(REPO, "profiles")
+os.makedirs(PROF, exist_ok=True)
+launch_csv, reps = sys.argv[1], sys.argv[2:]
+
+# ---- launch list
+rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 5]
+hdr = rows[0]
+iK, iV, iG, iB = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+data = [(r[iK], float(r[iV].replace(",", "")), r[iG], r[iB]) for r in rows[1:]]
+nframes = 4
+per = len(data) // nframes
+last = data[-per:]
+tot = sum(t for _, t, _, _ in last)
+agg = collections.OrderedDict()
+for k, t, g, b in last:
+    k = k.split("(")[0].replace("void ", "")
+    agg.setdefault(k, [0, 0.0])
+    agg[k][0] += 1
+    agg[k][1] += t
+shutil.copy(launch_csv, os.path.join(PROF, "r1_launches_1080p.csv"))
+with open(os.path.join(PROF, "r1_launches_1080p.md"), "w") as f:
+    f.write("# Round 1 — launch list of one 1920x1080 FP16 frame (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n")
+    f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_1080p.csv "
+            "python scripts/profile_frame.py 1080p 1`\n")
+    f.write(f"(raw CSV: r1_launches_1080p.csv, {nframes} frames x {per} launches; table = the last frame).  Times under ncu are "
+            "cold-cache and serialised: shares matter.\n\n")
+    f.write(f"Launches per frame: {per}; sum of kernel durations {tot / 1000:.1f} us.\n\n| share | us | launches | kernel |\n|---|---|---|---|\n")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"| {100 * t / tot:.1f}% | {t / 1000:.1f} | {n} | `{k}` |\n")
+    f.write("\nTemplate arguments: `conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>` (KIND 0 = 3x3, 1 = 1x1, 2 = 3x3 on the 8-channel-padded "
+            "image, 4 = stride-2 3x3 on a parity-split input; KCH = input channels / 8; MODE 0 = P8 store, 1 = PixelShuffle store, 2 = planar "
+            "store; SFTG = in-kernel SFT generator); `conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB>` = two chained 3x3 convs.\n")
+    f.write("\n## Per-launch list (last frame)\n\n| # | us | grid | block | kernel |\n|---|---|---|---|---|\n")
+    for i, (k, t, g, b) in enumerate(last):
+        f.write(f"| {i} | {t / 1000:.1f} | {g} | {b} | `{k.split('(')[0].replace('void ', '')}` |\n")
+
+# ---- full captures
+WANT = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
+        ("dram__bytes_read.sum", "dram_read"), ("dram__bytes_write.sum", "dram_write"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct_of_peak"),
+        ("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "tensor_cycles_active_per_sm"),
+        ("sm__cycles_elapsed.max", "cycles_elapsed"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"), ("smsp__inst_executed.sum", "warp_insts"),
+        ("lts__t_sector_hit_rate.pct", "l2_hit_pct")]
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+md = ["# Round 1 — ncu full captures of the top kernels (key metrics)\n",
+      "Command: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c <n> "
+      "python scripts/profile_frame.py 1080p 1` (1920x1080 FP16 frame).  Per-launch times under ncu are cold-cache and serialised.\n"]
+traffic = {}
+for rep in reps:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rws = list(csv.reader(io.StringIO(txt)))
+    if len(rws) < 3:
+        continue
+    h, units = rws[0], rws[1]
+    md.append(f"\n## {os.path.basename(rep)}\n")
+    for r in rws[2:]:
+        name = r[h.index("Kernel Name")]
+        vals = {}
+        for key, label in WANT:
+            for i, col in enumerate(h):
+                if col.endswith(key):
+                    vals[label] = (r[i], units[i])
+                    break
+        md.append(f"\n**{name}**\n")
+        for k, (v, u) in vals.items():
+            md.append(f"- {k}: {v} {u}")
+        try:
+            ta = float(vals["tensor_cycles_active_per_sm"][0].replace(",", ""))
+            ce = float(vals["cycles_elapsed"][0].replace(",", ""))
+            md.append(f"- tensor pipe active / elapsed: {100 * ta / ce:.1f} %")
+            rd = float(vals["dram_read"][0].replace(",", "")) * SCALE.get(vals["dram_read"][1], 1)
+            wr = float(vals["dram_write"][0].replace(",", "")) * SCALE.get(vals["dram_write"][1], 1)
+            traffic.setdefault(name.split("(")[0].replace("void ", "") + " grid " + vals["grid"][0].strip(), int(rd + wr))
+        except Exception:
+            pass
+open(os.path.join(PROF, "r1_ncu_top_kernels.md"), "w").write("\n".join(md) + "\n")
+# launch-name keyed traffic for bench.py (the two chain programs are unambiguous)
+named = {}
+for k, v in traffic.items():
+    if k.startswith("chain_p8_kernel<ProgCondSft"):
+        named["LE.cond_chain+sft0.L0"] = v
+    elif k.startswith("chain_p8_kernel<ProgAGCM"):
+        named["AGCM.chain"] = v
+    elif k.startswith("conv2x_p8_kernel<2, 1"):
+        named["LE.conv_first+HR_conv1"] = v
+    elif k.startswith("conv2x_p8_kernel<0, 4, 0, 16"):
+        named["LE.HR_conv2+conv_last"] = v
+    elif k.startswith("conv_p8_kernel<4, 8, 64"):
+        named.setdefault("LE.CondNet{2,3,4}.0", v)
+json.dump({"dram_bytes_per_launch_1080p": named, "by_kernel": traffic}, open(os.path.join(PROF, "r1_ncu_top_kernels.json"), "w"), indent=1)
+print("wrote", PROF)
