@@ -27,6 +27,9 @@ _SIGNATURES = {
     "hdrtv_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "hdrtv_destroy": (None, [C.c_void_p]),
     "hdrtv_set_weights": (C.c_int, [C.c_void_p, C.POINTER(TensorDesc), C.c_int]),
+    "hdrtv_set_act_quant": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_int), C.c_int]),
+    "hdrtv_debug_layer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hdrtv_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "hdrtv_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "hdrtv_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -63,6 +63,34 @@ def load_state_dict_any(model_path):
     return state, arch
 
 
+def split_int8_state(state: dict):
+    """Eager INT8 checkpoint (hdrtvnet_torch.py:1748-1963; layers W8Conv2d / W8A8Conv2d / W8A8Linear, :233-410) ->
+    (ordinary fp32 state-dict with de-quantised weights, {layer: (x_scale, x_zero, mode)}).
+
+    weight = weight_int8 * w_scale per output channel (:361); a layer with ``x_scale`` fake-quantises its input,
+    asymmetrically when it also has ``x_zero`` (:350-360).  Layers stored as plain ``weight`` pass through."""
+    out, quant = {}, {}
+    for k, v in state.items():
+        if k.endswith(".weight_int8"):
+            layer = k[: -len(".weight_int8")]
+            scale = np.asarray(state[layer + ".w_scale"], dtype=np.float32).reshape((-1,) + (1,) * (v.ndim - 1))
+            out[layer + ".weight"] = np.ascontiguousarray(np.asarray(v, dtype=np.float32) * scale)
+        elif k.endswith(".x_scale"):
+            layer = k[: -len(".x_scale")]
+            zero = state.get(layer + ".x_zero")
+            quant[layer] = (float(np.asarray(v).reshape(-1)[0]), float(np.asarray(zero).reshape(-1)[0]) if zero is not None else 0.0,
+                            2 if zero is not None else 1)
+        elif k.endswith(".w_scale") or k.endswith(".x_zero"):
+            continue
+        else:
+            out[k] = v
+    return out, quant
+
+
+def is_int8_state(state: dict) -> bool:
+    return any(k.endswith(".weight_int8") for k in state)
+
+
 class HDRTVNetB200:
     """B200-native backend with the reference wrapper's interface."""
 
@@ -86,6 +114,9 @@ class HDRTVNetB200:
         self.device = self._resolve_device(device)
         self.precision = self._resolve_precision(precision, self.device)
         self._use_cuda = True
+        # INT8 layouts: the reference's eager INT8 model is fake-quantisation around ordinary convolutions
+        # (hdrtvnet_torch.py:350-364); here it runs on the FP32 CUDA-core path with the same quantisers.
+        self._int8 = self.precision in ("int8-full", "int8-mixed")
         self._dtype = torch.float16 if self.precision == "fp16" else torch.float32
         self._np_dtype = np.float16 if self.precision == "fp16" else np.float32
         self._hg_weights_explicit = hg_weights is not None
@@ -108,6 +139,7 @@ class HDRTVNetB200:
         self._lib = _native.load()
         self._handle = C.c_void_p()
         cfg = _native.Config(self.device.index, _native.FP16 if self.precision == "fp16" else _native.FP32)
+        self._is_w8_model = self._int8
         rc = self._lib.hdrtv_create(C.byref(cfg), C.byref(self._handle))
         if rc != 0:
             raise RuntimeError("hdrtv_create failed: " + _native.last_error(None))
@@ -146,13 +178,21 @@ class HDRTVNetB200:
         p = str(precision).lower()
         if p not in _VALID_PRECISIONS:
             raise ValueError("precision must be one of: auto, fp16, fp32, int8-full, int8-mixed")
-        if p in ("int8-full", "int8-mixed"):
-            raise RuntimeError(f"precision={p!r} (QAT layouts) is not implemented by this backend yet")
         return "fp16" if p == "auto" else p
 
     # ------------------------------------------------------------------ weights (hdrtvnet_torch.py:2044-2169)
     def _load_model(self, model_path):
         state, arch = load_state_dict_any(model_path)
+        quant = {}
+        if is_int8_state(state):
+            if not self._int8:
+                raise ValueError(f"{model_path} is an INT8 checkpoint; use precision='int8-full' or 'int8-mixed'")
+            state, quant = split_int8_state(state)
+        elif self._int8:
+            raise ValueError(f"{model_path} is not an INT8 checkpoint.\n"
+                             "  Re-run: python scripts/quantize/quantize_int8_full.py or "
+                             "python scripts/quantize/quantize_int8_mixed.py")      # hdrtvnet_torch.py:1758-1762
+        self._act_quant = quant
         classifier = str(arch.get("classifier", os.environ.get("HDRTVNET_CLASSIFIER", "color_condition"))).strip()
         le_arch = str(arch.get("le_arch", os.environ.get("HDRTVNET_LE_ARCH", "")) or "").strip()
         post = str(arch.get("post_correction", os.environ.get("HDRTVNET_POST_CORRECTION", "")) or "").strip()
@@ -183,6 +223,15 @@ class HDRTVNetB200:
                 descs[i].shape[d] = v.shape[d]
         _native.check(self._lib.hdrtv_set_weights(self._handle, descs, len(state)), self._handle, "hdrtv_set_weights")
         self._n_params = int(sum(v.size for v in keep))
+        self._layer_shapes = {k[: -len(".weight")]: tuple(v.shape) for k, v in state.items() if k.endswith(".weight")}
+        if quant:
+            names = sorted(quant)
+            arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+            arr_s = (C.c_float * len(names))(*[quant[n][0] for n in names])
+            arr_z = (C.c_float * len(names))(*[quant[n][1] for n in names])
+            arr_m = (C.c_int * len(names))(*[quant[n][2] for n in names])
+            _native.check(self._lib.hdrtv_set_act_quant(self._handle, arr_n, arr_s, arr_z, arr_m, len(names)), self._handle,
+                          "hdrtv_set_act_quant")
 
     def _resolve_hg_weights(self, model_path):
         cands = [self._hg_weights]
@@ -428,6 +477,18 @@ class HDRTVNetB200:
         if trace:
             return float(cyc.value), tr.reshape(16, 4, 4)
         return float(cyc.value)
+
+    def debug_layer(self, layer: str, x: np.ndarray, stride: int = 1) -> np.ndarray:
+        """One named conv / linear layer of the FP32 (and INT8 fake-quant) path on host data: (Cin,H,W) -> (Cout,Ho,Wo)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        cin, h, w = x.shape
+        wt = self._layer_shapes[layer]
+        ks = wt[2] if len(wt) == 4 else 1
+        ho, wo = (h + 2 * (ks // 2) - ks) // stride + 1, (w + 2 * (ks // 2) - ks) // stride + 1
+        out = np.empty((wt[0], ho, wo), dtype=np.float32)
+        _native.check(self._lib.hdrtv_debug_layer(self._handle, layer.encode(), x.ctypes.data, cin, h, w, stride, out.ctypes.data),
+                      self._handle, "hdrtv_debug_layer")
+        return out
 
     def chain_trace(self, agcm=False, index=0):
         tr = np.zeros(64 * 8 * 8, dtype=np.int64)

@@ -240,6 +240,11 @@ struct Ctx {
   // packed static weights (device) by layer name
   std::map<std::string, __half*> wpk;
   std::map<std::string, std::vector<__half>> host_pk;   // host copies (chains concatenate them)
+  std::map<std::string, ActQuant> quant;                 // INT8 layouts: static input fake-quantisation per layer (FP32 path)
+  ActQuant q(const std::string& layer) const {
+    auto it = quant.find(layer);
+    return it == quant.end() ? ActQuant{} : it->second;
+  }
   // side branch of the LE plan: the tail of the condition pyramid (small launches) overlaps the full-resolution trunk
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -831,6 +836,7 @@ struct HeadParams {
   float* fea;
   float* fold32;
   __half* pk[3];   // packed B operands of the three folded layers, each followed by its bias step
+  ActQuant qs[3], qt[3];   // input fake-quantisation of the scale / shift linears (INT8 layouts)
 };
 __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
   __shared__ float mean5[128];
@@ -852,8 +858,8 @@ __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
     if (n < nn) {
       float s = p.lsb[l][n], h = p.ltb[l][n];
       for (int k = 0; k < 6; ++k) {
-        s = fmaf(p.ls[l][n * 6 + k], fea[k], s);
-        h = fmaf(p.lt[l][n * 6 + k], fea[k], h);
+        s = fmaf(p.ls[l][n * 6 + k], fake_quant(fea[k], p.qs[l]), s);
+        h = fmaf(p.lt[l][n * 6 + k], fake_quant(fea[k], p.qt[l]), h);
       }
       sc[l][n] = 1.f + s;
       sh[l][n] = h;
@@ -1022,6 +1028,8 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     if (l == 0) pix = std::max(pix, 64);
     p.pix = pix;
     p.in_planar = l == 0 ? 1 : 0;
+    p.q = c->q(pre + std::to_string(convi[l]));
+    p.stat_q = l == 4 ? c->q(pre + "20") : ActQuant{};
     const size_t sm = sizeof(float) * (static_cast<size_t>(L.Cin) * L.Cout + static_cast<size_t>(pix) * L.Cin + 2 * L.Cin + pix);
     const unsigned blocks = static_cast<unsigned>((npix + pix - 1) / pix);
     static bool configured = false;
@@ -1046,6 +1054,8 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     hp.lt[i] = c->wd.at(std::string("AGCM.cond_shift_") + nm[i] + ".weight");
     hp.ltb[i] = c->wd.at(std::string("AGCM.cond_shift_") + nm[i] + ".bias");
     hp.pk[i] = c->d_agpk[i];
+    hp.qs[i] = c->q(std::string("AGCM.cond_scale_") + nm[i]);
+    hp.qt[i] = c->q(std::string("AGCM.cond_shift_") + nm[i]);
   }
   hp.w1 = c->wd.at("AGCM.conv_first.weight"); hp.b1 = c->wd.at("AGCM.conv_first.bias");
   hp.w2 = c->wd.at("AGCM.HRconv.weight");     hp.b2 = c->wd.at("AGCM.HRconv.bias");
@@ -1339,8 +1349,9 @@ static int build_ws_fp32(Ctx* c, int H, int Wd) {
 
 static int conv32(Ctx* c, cudaStream_t s, const float* in, const float* w, const float* b, float* out, int Cin, int Cout,
                   int H, int Wd, int ks, int stride, int act, float slope, const float* res = nullptr, int ps = 0,
-                  int outH = 0, int outW = 0) {
+                  int outH = 0, int outW = 0, ActQuant q = ActQuant{}) {
   ConvF32 p;
+  p.q = q;
   p.in = in; p.w = w; p.b = b; p.out = out; p.res = res;
   p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = Wd;
   p.Ho = (H + 2 * (ks / 2) - ks) / stride + 1;
@@ -1358,7 +1369,8 @@ static int conv32n(Ctx* c, cudaStream_t s, const std::string& name, const float*
                    int act, float slope, const float* res = nullptr, int ps = 0, int outH = 0, int outW = 0) {
   const HostTensor& t = W(c, name + ".weight");
   return conv32(c, s, in, c->wd.at(name + ".weight"), c->wd.at(name + ".bias"), out, static_cast<int>(t.shape[1]),
-                static_cast<int>(t.shape[0]), H, Wd, static_cast<int>(t.shape[2]), stride, act, slope, res, ps, outH, outW);
+                static_cast<int>(t.shape[0]), H, Wd, static_cast<int>(t.shape[2]), stride, act, slope, res, ps, outH, outW,
+                c->q(name));
 }
 
 static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float* agcm_out, cudaStream_t s,
@@ -1369,9 +1381,9 @@ static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float
   if (!skip_classifier && run_classifier(c, cond, false, s)) return -1;
   float* f = c->d_fold32;
   int r = 0;
-  r |= conv32(c, s, x, f, f + 192, B("a1"), 3, 64, H, Wd, 1, 1, ACT_RELU, 0.f);
-  r |= conv32(c, s, B("a1"), f + 256, f + 256 + 4096, B("a2"), 64, 64, H, Wd, 1, 1, ACT_RELU, 0.f);
-  r |= conv32(c, s, B("a2"), f + 4416, f + 4416 + 192, agcm_out, 64, 3, H, Wd, 1, 1, ACT_NONE, 0.f);
+  r |= conv32(c, s, x, f, f + 192, B("a1"), 3, 64, H, Wd, 1, 1, ACT_RELU, 0.f, nullptr, 0, 0, 0, c->q("AGCM.conv_first"));
+  r |= conv32(c, s, B("a1"), f + 256, f + 256 + 4096, B("a2"), 64, 64, H, Wd, 1, 1, ACT_RELU, 0.f, nullptr, 0, 0, 0, c->q("AGCM.HRconv"));
+  r |= conv32(c, s, B("a2"), f + 4416, f + 4416 + 192, agcm_out, 64, 3, H, Wd, 1, 1, ACT_NONE, 0.f, nullptr, 0, 0, 0, c->q("AGCM.conv_last"));
   if (inputs_consumed) CK(c, cudaEventRecord(inputs_consumed, s));   // x, cond and the folded AGCM weights are free again
   const float* img = agcm_out;
   // condition pyramid (LeakyReLU 0.1)
@@ -1660,6 +1672,52 @@ int hdrtv_set_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {
   c->has_weights = true;
   release_workspace(c);
   return 0;
+}
+
+int hdrtv_set_act_quant(hdrtv_t* c, const char* const* layers, const float* scales, const float* zeros, const int* modes, int n) {
+  if (!c || (n > 0 && (!layers || !scales || !zeros || !modes))) return fail(c, "hdrtv_set_act_quant: null argument");
+  if (c->precision != HDRTV_FP32 && n > 0)
+    return fail(c, "hdrtv_set_act_quant: the INT8 layouts run on the FP32 (fake-quantisation) path; create the context with HDRTV_FP32");
+  c->quant.clear();
+  for (int i = 0; i < n; ++i) {
+    if (modes[i] < 0 || modes[i] > 2 || !(scales[i] > 0.f)) return fail(c, std::string("hdrtv_set_act_quant: bad entry for ") + layers[i]);
+    std::string key = layers[i];
+    if (key.rfind("module.", 0) == 0) key = key.substr(7);
+    ActQuant q;
+    q.scale = scales[i];
+    q.zero = zeros[i];
+    q.mode = modes[i];
+    c->quant[key] = q;
+  }
+  return 0;
+}
+
+// One named conv / linear layer of the FP32 path on caller-supplied host data (bias, no activation; the layer's input
+// fake-quantiser applies when one is installed).  Parity hook: INT8 fake-quantised networks amplify fp32 summation-
+// order noise chaotically, so they are pinned layer by layer on inputs recorded from the reference.
+int hdrtv_debug_layer(hdrtv_t* c, const char* layer, const float* in_host, int Cin, int H, int Wd, int stride, float* out_host) {
+  if (!c || !layer || !in_host || !out_host) return fail(c, "hdrtv_debug_layer: null argument");
+  if (c->precision != HDRTV_FP32) return fail(c, "hdrtv_debug_layer: FP32 context required");
+  const std::string name = layer;
+  if (!c->w.count(name + ".weight")) return fail(c, "hdrtv_debug_layer: unknown layer " + name);
+  cudaSetDevice(c->device);
+  const HostTensor& t = c->w.at(name + ".weight");
+  const int Cout = static_cast<int>(t.shape[0]);
+  const int ks = t.shape.size() == 4 ? static_cast<int>(t.shape[2]) : 1;
+  if (static_cast<int>(t.shape[1]) != Cin) return fail(c, "hdrtv_debug_layer: channel mismatch for " + name);
+  const int Ho = (H + 2 * (ks / 2) - ks) / stride + 1, Wo = (Wd + 2 * (ks / 2) - ks) / stride + 1;
+  float *din = nullptr, *dout = nullptr;
+  CK(c, cudaMalloc(&din, sizeof(float) * Cin * H * Wd));
+  CK(c, cudaMalloc(&dout, sizeof(float) * Cout * Ho * Wo));
+  cudaMemcpy(din, in_host, sizeof(float) * Cin * H * Wd, cudaMemcpyHostToDevice);
+  int r = conv32(c, 0, din, c->wd.at(name + ".weight"), c->wd.at(name + ".bias"), dout, Cin, Cout, H, Wd, ks, stride, ACT_NONE, 0.f,
+                 nullptr, 0, 0, 0, c->q(name));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, sizeof(float) * Cout * Ho * Wo, cudaMemcpyDeviceToHost);
+  cudaFree(din);
+  cudaFree(dout);
+  CK(c, e);
+  return r;
 }
 
 int hdrtv_prepare(hdrtv_t* c, int H, int Wd) {

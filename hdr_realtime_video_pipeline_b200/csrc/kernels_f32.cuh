@@ -11,6 +11,27 @@ namespace hdrtv {
 // Weights for the block's COB channels are staged in shared memory as [cin][tap][COB].
 // Epilogue: +bias, activation, optional residual add, optional PixelShuffle(2) scatter with crop.
 // ------------------------------------------------------------------------------------------------
+// Static activation fake-quantisation of a layer input (reference W8A8Conv2d / W8A8Linear.forward,
+// hdrtvnet_torch.py:350-364): mode 2 (asymmetric) q = clamp(round((x - zero) / scale), 0, 255), x^ = q*scale + zero;
+// mode 1 (symmetric) q = clamp(round(x / scale), -128, 127), x^ = q*scale; torch.round = round-half-even = rintf.
+struct ActQuant {
+  float scale = 1.f, zero = 0.f;
+  int mode = 0;
+};
+__device__ __forceinline__ float fake_quant(float x, const ActQuant& q) {
+  if (q.mode == 2) {
+    float v = rintf(__fdiv_rn(__fsub_rn(x, q.zero), q.scale));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    return __fadd_rn(__fmul_rn(v, q.scale), q.zero);
+  }
+  if (q.mode == 1) {
+    float v = rintf(__fdiv_rn(x, q.scale));
+    v = fminf(fmaxf(v, -128.f), 127.f);
+    return __fmul_rn(v, q.scale);
+  }
+  return x;
+}
+
 struct ConvF32 {
   const float* in;   // [Cin][H][W]
   const float* w;    // [Cout][Cin][ks][ks]
@@ -21,6 +42,7 @@ struct ConvF32 {
   float slope;
   int ps;            // 1: PixelShuffle(2) + crop to (outH,outW)
   int outH, outW;
+  ActQuant q;        // fake-quantisation of the input (INT8 layouts)
 };
 
 template <int COB>
@@ -49,7 +71,7 @@ __global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
       for (int kx = 0; kx < p.ks; ++kx) {
         const int ix = ox * p.stride + kx - pad;
         if (ix < 0 || ix >= p.W) continue;
-        const float v = __ldg(ip + static_cast<long>(iy) * p.W + ix);
+        const float v = fake_quant(__ldg(ip + static_cast<long>(iy) * p.W + ix), p.q);
         const float* wp = wsm + ((ci * p.ks + ky) * p.ks + kx) * COB;
 #pragma unroll
         for (int c = 0; c < COB; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
@@ -114,6 +136,9 @@ struct ClsLevel {
   double* out_stats;       // [Cout][2], pre-zeroed
   int Cin, Cout, H, W, Ho, Wo;
   int pix;                 // pooled pixels per block
+  ActQuant q;              // fake-quantisation of this level's conv input (after the IN affine)
+  ActQuant stat_q;         // applied to y before it enters out_stats' SUM (the input quantiser of the conv that follows
+                           // the last level, whose global mean is all that is used); sum^2 then is unused
 };
 
 // One level of the AGCM condition classifier (Condition_arch.py:8-35): IN-affine of the previous level, AvgPool(3,2,1)
@@ -177,7 +202,7 @@ __global__ void __launch_bounds__(256) cls_level_kernel(const ClsLevel p) {
           } else {
             v = reinterpret_cast<const float*>(p.in)[(static_cast<long>(iy) * p.W + ix) * Cin + ci];
           }
-          acc += fmaf(v, a, b);
+          acc += fake_quant(fmaf(v, a, b), p.q);
           ++n;
         }
       }
@@ -204,7 +229,7 @@ __global__ void __launch_bounds__(256) cls_level_kernel(const ClsLevel p) {
     float y = (acc0 + acc1 + nwin[px] * bias) / 9.0f;
     y = y >= 0.f ? y : 0.2f * y;
     p.out[static_cast<long>(idx) * Cout + co] = y;
-    s1 += y;
+    s1 += fake_quant(y, p.stat_q);
     s2 += static_cast<double>(y) * y;
   }
   atomicAdd(&ssum[co][0], s1);

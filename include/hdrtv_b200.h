@@ -42,6 +42,19 @@ int hdrtv_create(const hdrtv_config* cfg, hdrtv_t** out);
 void hdrtv_destroy(hdrtv_t* h);
 int hdrtv_set_weights(hdrtv_t* h, const hdrtv_tensor_desc* tensors, int n);
 
+/* INT8 layouts (W8A8Conv2d / W8A8Linear, hdrtvnet_torch.py:296-410; loader :1748-1963): the reference's eager INT8     */
+/* model is fake-quantisation — int8 weights de-quantised per output channel (pass them to hdrtv_set_weights already  */
+/* de-quantised), and a static per-tensor quantiser on every layer INPUT.  This call installs those input quantisers  */
+/* (mode 0 none, 1 symmetric [-128,127], 2 asymmetric [0,255] with zero point) by layer name ("LE.HR_conv1", ...).    */
+/* Supported on HDRTV_FP32 contexts (CUDA-core path).                                                                  */
+int hdrtv_set_act_quant(hdrtv_t* h, const char* const* layers, const float* scales, const float* zeros, const int* modes,
+                        int n);
+
+/* Parity hook (FP32 contexts): one named conv / linear layer (bias, no activation, the layer's input quantiser) on    */
+/* host data: in (Cin,H,W) fp32 -> out (Cout,Ho,Wo) fp32.                                                             */
+int hdrtv_debug_layer(hdrtv_t* h, const char* layer, const float* in_host, int cin, int height, int width, int stride,
+                      float* out_host);
+
 /* HDRTVNetTorch._ensure_buffers (hdrtvnet_torch.py:2198-2233): (re)allocate the per-resolution workspace.          */
 /* Called implicitly by preprocess/infer; returns bytes held via hdrtv_workspace_bytes.                              */
 int hdrtv_prepare(hdrtv_t* h, int height, int width);

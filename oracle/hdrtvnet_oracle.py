@@ -212,6 +212,42 @@ def align_to(x: np.ndarray, rh: int, rw: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# P8  INT8 layouts: static activation fake-quantisation  (hdrtvnet_torch.py:296-410)
+# --------------------------------------------------------------------------
+
+def split_int8_state(raw: dict):
+    """Eager INT8 checkpoint arrays -> (state-dict with de-quantised fp32 weights + ``<layer>.x_scale`` /
+    ``<layer>.x_zero`` entries kept).  weight = weight_int8 * w_scale per output channel (:361)."""
+    sd = {}
+    for k, v in raw.items():
+        if k.endswith(".weight_int8"):
+            layer = k[: -len(".weight_int8")]
+            scale = np.asarray(raw[layer + ".w_scale"], dtype=F32).reshape((-1,) + (1,) * (v.ndim - 1))
+            sd[layer + ".weight"] = (np.asarray(v, dtype=F32) * scale).astype(F32)
+        elif k.endswith(".w_scale"):
+            continue
+        else:
+            sd[k] = np.asarray(v, dtype=F32)
+    return sd
+
+
+def fake_quant_input(sd: dict, layer: str, x: np.ndarray) -> np.ndarray:
+    """W8A8Conv2d / W8A8Linear.forward (:350-360) on the layer input; identity when the layer has no ``x_scale``."""
+    s = sd.get(layer + ".x_scale")
+    if s is None:
+        return x
+    s = F32(np.asarray(s).reshape(-1)[0])
+    z = sd.get(layer + ".x_zero")
+    xf = x.astype(F32)
+    if z is not None:
+        z = F32(np.asarray(z).reshape(-1)[0])
+        q = np.clip(np.rint((xf - z) / s), 0, 255).astype(F32)          # torch.round = round-half-even = rint
+        return (q * s + z).astype(F32)
+    q = np.clip(np.rint(xf / s), -128, 127).astype(F32)
+    return (q * s).astype(F32)
+
+
+# --------------------------------------------------------------------------
 # P2  AGCM  (Condition_arch.py:8-35, 483-494, 559-585)
 # --------------------------------------------------------------------------
 
@@ -224,12 +260,12 @@ def classifier(sd: dict, cond_chw: np.ndarray, prefix: str = "AGCM.classifier.mo
     Dropout(eval: identity) -> conv1x1 128->6 -> global mean.  Returns fea[6]."""
     x = cond_chw.astype(F32)
     for ci, ni in zip(_CLS_CONV, _CLS_NORM):
-        x = conv2d(x, sd[f"{prefix}{ci}.weight"], sd[f"{prefix}{ci}.bias"], 1, 0)
+        x = conv2d(fake_quant_input(sd, f"{prefix}{ci}", x), sd[f"{prefix}{ci}.weight"], sd[f"{prefix}{ci}.bias"], 1, 0)
         x = avg_pool_3s2p1(x)
         x = leaky_relu(x, 0.2)
         if ni is not None:
             x = instance_norm(x, sd[f"{prefix}{ni}.weight"], sd[f"{prefix}{ni}.bias"])
-    x = conv2d(x, sd[f"{prefix}20.weight"], sd[f"{prefix}20.bias"], 1, 0)
+    x = conv2d(fake_quant_input(sd, f"{prefix}20", x), sd[f"{prefix}20.weight"], sd[f"{prefix}20.bias"], 1, 0)
     return x.astype(np.float64).mean(axis=(1, 2)).astype(F32)
 
 
@@ -240,7 +276,7 @@ def gfm_params(sd: dict, fea: np.ndarray) -> dict:
         for kind in ("scale", "shift"):
             w = sd[f"AGCM.cond_{kind}_{name}.weight"].astype(F32)
             b = sd[f"AGCM.cond_{kind}_{name}.bias"].astype(F32)
-            out[f"{kind}_{name}"] = (w @ fea.astype(F32) + b).astype(F32)
+            out[f"{kind}_{name}"] = (w @ fake_quant_input(sd, f"AGCM.cond_{kind}_{name}", fea.astype(F32)) + b).astype(F32)
     return out
 
 
@@ -252,11 +288,11 @@ def agcm(sd: dict, x_chw: np.ndarray, cond_chw: np.ndarray) -> np.ndarray:
     def mod(o, s, t):
         return o * s[:, None, None] + t[:, None, None] + o
 
-    o = conv2d(x_chw, sd["AGCM.conv_first.weight"], sd["AGCM.conv_first.bias"], 1, 0)
+    o = conv2d(fake_quant_input(sd, "AGCM.conv_first", x_chw), sd["AGCM.conv_first.weight"], sd["AGCM.conv_first.bias"], 1, 0)
     o = relu(mod(o, g["scale_first"], g["shift_first"]))
-    o = conv2d(o, sd["AGCM.HRconv.weight"], sd["AGCM.HRconv.bias"], 1, 0)
+    o = conv2d(fake_quant_input(sd, "AGCM.HRconv", o), sd["AGCM.HRconv.weight"], sd["AGCM.HRconv.bias"], 1, 0)
     o = relu(mod(o, g["scale_HR"], g["shift_HR"]))
-    o = conv2d(o, sd["AGCM.conv_last.weight"], sd["AGCM.conv_last.bias"], 1, 0)
+    o = conv2d(fake_quant_input(sd, "AGCM.conv_last", o), sd["AGCM.conv_last.weight"], sd["AGCM.conv_last.bias"], 1, 0)
     return mod(o, g["scale_last"], g["shift_last"]).astype(F32)
 
 
@@ -265,7 +301,7 @@ def agcm(sd: dict, x_chw: np.ndarray, cond_chw: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------
 
 def _conv(sd, name, x, stride=1):
-    return conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride)
+    return conv2d(fake_quant_input(sd, name, x), sd[name + ".weight"], sd[name + ".bias"], stride)
 
 
 def sft_layer(sd: dict, prefix: str, fea: np.ndarray, cond: np.ndarray) -> np.ndarray:

@@ -109,6 +109,51 @@ def main():
     if os.environ.get("HDRTV_GOLDEN_ONLY") == "bilinear":
         return
 
+    # ---- INT8 Full-QAT layout (BASELINE config 5): the reference's eager INT8 model on CPU (fp32 compute fallback,
+    # hdrtvnet_torch.py:1766-1773) on the shipped checkpoint; the raw checkpoint arrays travel as a fixture.
+    int8_path = os.path.join(REF, "src/models/weights/original/pytorch_int8/hr/HR_original_int8_full_qat.pt")
+    ck = torch.load(int8_path, map_location="cpu", weights_only=False)
+    raw = {}
+    for k, v in ck["state_dict"].items():
+        a = v.detach().cpu()
+        raw[k] = a.numpy() if a.dtype == torch.int8 else a.float().numpy()
+    save("weights_int8_full_qat.npz", **raw)
+    proc8 = HDRTVNetTorch(int8_path, device="cpu", precision="int8-full", compile_model=False, use_hg=False,
+                          warmup_passes=0, predequantize="off")
+    for cls, h, w, idx in (("noise", 64, 96, 0), ("ramps", 72, 100, 1), ("white_salt", 72, 100, 3)):
+        frame = synth_frame(idx, h, w, cls)
+        with torch.inference_mode():
+            t, cnd = proc8.preprocess(frame)
+            res = proc8.infer((t.clone(), cnd.clone()))
+        out, agcm_out = res[0], res[1]
+        save(f"int8_{cls}_{h}x{w}.npz", frame=frame, out=out.float().numpy().copy(), agcm_out=agcm_out.float().numpy().copy())
+    # Fake-quantised networks amplify fp32 summation-order noise chaotically (a single flipped quantisation bucket
+    # spreads through the U-Net), so end-to-end INT8 parity can only be statistical.  The exact pin is per layer:
+    # (input, output) pairs recorded from the reference's own W8A8 modules on a small frame.
+    layers = ["LE.conv_first", "LE.down_conv2", "LE.CondNet4.4", "LE.recon_trunk3.0.conv1", "LE.recon_trunk3.0.sft1.SFT_scale_conv0",
+              "LE.recon_trunk3.0.sft1.SFT_shift_conv1", "LE.up_conv1.0", "AGCM.cond_scale_first", "AGCM.classifier.model.16"]
+    rec = {}
+    mods = dict(proc8.model.named_modules())
+    hooks = []
+    for n in layers:
+        def mk(name):
+            def f(mod, inp, out):
+                rec[name + "|in"] = inp[0].detach().float().numpy().copy()
+                o = out.detach().float().numpy().copy()
+                rec[name + "|out"] = o[..., ::4, ::4] if (o.ndim == 4 and o.size > 60000) else o    # big maps: every 4th pixel
+            return f
+        hooks.append(mods[n].register_forward_hook(mk(n)))
+    frame = synth_frame(0, 64, 96, "noise")
+    with torch.inference_mode():
+        t, cnd = proc8.preprocess(frame)
+        proc8.infer((t.clone(), cnd.clone()))
+    for hk in hooks:
+        hk.remove()
+    rec["layers"] = np.array(layers)
+    save("int8_layers_64x96.npz", **rec)
+    if os.environ.get("HDRTV_GOLDEN_ONLY") == "int8":
+        return
+
     # ---- AA bicubic on awkward sizes -------------------------------------
     rng = np.random.default_rng(7)
     aa = {}
