@@ -29,7 +29,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), *SOURCES, "-o", OUT]
+    extra = os.environ.get("HDRTV_NVCC_EXTRA", "").split()          # e.g. -DHDRTV_CHAIN_TRACE for scripts/chain_trace.py
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), *SOURCES, "-o", OUT]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

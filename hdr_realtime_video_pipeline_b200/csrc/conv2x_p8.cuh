@@ -12,20 +12,37 @@
 // discarded.  The two convs have their own MMA-issuing warps and their own epilogue warpgroups, so with one CTA per SM
 // the tensor pipe still sees two independent instruction streams:
 //
-//   warp 0      TMA producer: input rows (and the SFT stage-0 rows of conv A's output rows)
-//   warp 1      MMA issuer of conv A (+ the SFT stage-1 GEMM)       warp 2      MMA issuer of conv B
+//   warp 0      TMA producer: input rows (+ the SFT stage-0 row of the same mid row, in the same ring slot)
+//   warp 1      MMA issuer of conv A        warp 2   MMA issuer of conv B        warp 12  MMA issuer of the SFT stage-1 GEMM
 //   warps 3-6   epilogue A: TMEM -> ReLU, SFT -> fp16 -> mid ring    warps 7-10  epilogue B: TMEM -> global
+//   warp 11     TMA producer of conv B's residual rows (read from shared memory by epilogue B: no DRAM latency per row)
+//
+// Three issuing warps: one thread issues a tcgen05.mma every ~76 cycles at best and every mbarrier wait / commit /
+// elect costs it another 50-110 cycles even when already satisfied (scripts/sync_probe.py), while an N = 96 MMA
+// occupies the pipe for ~56 cycles: a single issuer cannot keep the pipe busy (measured: 1.3-2.2x slower).
+//
+// Row folding.  A tcgen05.mma with M = 128, K = 16 occupies the tensor pipe for max(~45, N/2) cycles, so a 32-output
+// conv issued tap by tap (N = 32) runs the pipe at a third of its rate and every input row is multiplied three times.
+// Here the three vertical taps are folded into N: input row q is multiplied ONCE by [W(dy=2) | W(dy=1) | W(dy=0)]
+// (N = 96) and the three 32-column results accumulate into the TMEM blocks of output rows q-2, q-1 and q, neighbours in
+// a ring of R accumulator blocks (a window that crosses the end of the ring is issued as two MMAs).  The block of the
+// newest row is initialised by the bias step (accumulate off).  A row costs 1 + 6 MMAs instead of 19, every input row
+// is consumed and released once, and the R - 3 spare blocks hide the commit -> epilogue -> release latency.
 #pragma once
 #include "conv_p8.cuh"
 
 namespace hdrtv {
 
-constexpr int kC2Threads = 32 * 11;
+constexpr int kC2Threads = 32 * 13;
 constexpr int kC2Strip = 126;          // output pixels per strip
-constexpr int kC2MidRing = 6;          // mid rows in flight (3 in use by conv B + 3 so that conv A runs ahead)
+constexpr int kC2MidRing = 5;          // mid rows in flight (each is consumed once by conv B)
 constexpr int kC2MidSlot = 4 * kPlaneBytes;
-constexpr int kC2InRing = 6;           // input rows in flight: 3 in use + prefetch (HBM latency ~ 2 row periods)
-constexpr int kC2SRing = 6;            // SFT stage-0 rows in flight
+constexpr int kC2InRing = 5;           // input (+ stage-0) rows in flight, each consumed once by conv A: covers the HBM latency
+constexpr int kC2ResRing = 4;          // residual rows in flight
+constexpr int kC2ResPlane = kTileM * 16;
+constexpr int kC2OnesOff = 1024;       // barrier table below, constant "ones" operand (bias steps) here
+constexpr int kC2Header = kC2OnesOff + kPlaneBytes;
+static_assert(kC2Header % 128 == 0, "operand alignment");
 
 struct Conv2xParams {
   // conv A input
@@ -34,16 +51,23 @@ struct Conv2xParams {
   uint32_t copy_src0, copy_src_stride;       // source entry of channel-chunk plane c: src0 + c * stride (before the row/x offset)
   int H, W, band;                            // image size (conv A, mid and conv B all share it); band unused (1-D grid)
   int strips;                                // 126-pixel strips per row; CTA b owns items [b*T/G, (b+1)*T/G) of the strip-major (strip, row) list
-  const uint4* wpkA; int wA_bytes;           // conv A packed weights (tap steps + bias step), N = 32
+  const uint4* wpkA; int wA_bytes;           // conv A packed weights, row-folded (N = 96 per step) + bias step (N = 32)
   const uint4* wpk2; int w2_bytes;           // SFT stage-1 weights (SFTG)
   const uint4* s0; long s0_row_entries; uint32_t s0_src0, s0_wp;
-  const uint4* wpkB; int wB_bytes;           // conv B packed weights, N = NB
+  const uint4* wpkB; int wB_bytes;           // conv B packed weights, row-folded (N = 3 NB per step) + bias step (N = NB)
   float slopeB;                              // conv B activation as max(v, slope*v)
   int has_res, has_res2, has_raw;
-  P8 res, res2, raw, out;
+  P8 res, res2, raw, out;                    // res: natural layout (streamed through shared memory)
   __half* planar; long planar_plane; int planar_W;
   int* err;
+  long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [row<64][role<8][8]
 };
+
+#ifdef HDRTV_CHAIN_TRACE
+#define C2X_STAMP(role, row, k) do { if (p.trace && blockIdx.x == 0 && (row) < 64 && lane == 0) p.trace[(((row) * 8) + (role)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define C2X_STAMP(role, row, k) do { } while (0)
+#endif
 
 template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB>
 __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_constant__ Conv2xParams p) {
@@ -52,36 +76,43 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
   constexpr int NA = 32;
   constexpr int SPDA = kind_spd(KINDA, KCHA), NCOPY = kind_copies(KINDA, KCHA);
   constexpr int SPDB = kind_spd(IN_NAT3x3, 4);
-  constexpr uint32_t kTmemCols = 256;                 // A 2 x 32 | B 2 x 32 | scale|shift 2 x 64
-  constexpr uint32_t colA = 0, colB = 64, colS = 128;
+  constexpr int RA = SFTGA ? 6 : 8, RB = SFTGA ? 6 : 8;   // accumulator ring blocks: 3 accumulating + spare ones being drained
+  constexpr int CHR = MODEB == STORE_PLANAR ? 1 : NB / 8;  // residual planes per row
+  constexpr int RES_SLOT = CHR * kC2ResPlane;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t colA = 0, colB = colA + RA * NA, colS = colB + RB * NB;
+  static_assert(colS + (SFTGA ? 128 : 0) <= kTmemCols, "TMEM budget");
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * i; };
   auto in_full = [&](int i) { return bar(i); };
   auto in_empty = [&](int i) { return bar(8 + i); };
-  auto s_full = [&](int i) { return bar(16 + i); };
-  auto s_empty = [&](int i) { return bar(24 + i); };
   auto mid_full = [&](int i) { return bar(32 + i); };
   auto mid_empty = [&](int i) { return bar(40 + i); };
   auto a_tfull = [&](int i) { return bar(48 + i); };
-  auto a_tempty = [&](int i) { return bar(50 + i); };
-  auto b_tfull = [&](int i) { return bar(52 + i); };
-  auto b_tempty = [&](int i) { return bar(54 + i); };
-  const uint32_t wfull_bar = bar(56);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 57);
-  static_assert(kC2InRing <= 8 && kC2SRing <= 8 && kC2MidRing <= 8, "barrier table layout");
-  uint8_t* ones = smem + 512;
-  uint8_t* wsmA = smem + kSmemHeader;
+  auto a_tempty = [&](int i) { return bar(56 + i); };
+  auto b_tfull = [&](int i) { return bar(64 + i); };
+  auto b_tempty = [&](int i) { return bar(72 + i); };
+  auto st_full = [&](int i) { return bar(80 + i); };       // scale|shift accumulator stage written
+  auto st_empty = [&](int i) { return bar(82 + i); };      // ... and read back by epilogue A
+  auto res_full = [&](int i) { return bar(84 + i); };
+  auto res_empty = [&](int i) { return bar(92 + i); };
+  const uint32_t wfull_bar = bar(100);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 102);
+  static_assert(kC2InRing <= 8 && kC2MidRing <= 8 && kC2ResRing <= 8 && RA <= 8 && RB <= 8, "barrier table layout");
+  uint8_t* ones = smem + kC2OnesOff;
+  uint8_t* wsmA = smem + kC2Header;
   uint8_t* wsm2 = wsmA + ((p.wA_bytes + 127) & ~127);
   uint8_t* wsmB = wsm2 + (SFTGA ? ((p.w2_bytes + 127) & ~127) : 0);
   uint8_t* ring = wsmB + ((p.wB_bytes + 127) & ~127);
-  uint8_t* sring = ring + kC2InRing * (NCOPY * kPlaneBytes);
-  uint8_t* mring = sring + (SFTGA ? kC2SRing * kSSlotBytes : 0);
+  constexpr int IN_SLOT = (NCOPY + (SFTGA ? 4 : 0)) * kPlaneBytes;      // input planes, then the four stage-0 planes
+  uint8_t* mring = ring + kC2InRing * IN_SLOT;
+  uint8_t* rring = mring + kC2MidRing * kC2MidSlot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // This CTA's contiguous range of (strip, output row) items, walked as segments that stay inside one strip.  Ring
-  // slots, stage parities and barrier phases simply continue from one segment to the next.
+  // slots, accumulator blocks and barrier phases simply continue from one segment to the next.
   struct Seg { int x0, oy0, n_out, jv0, jv1, n_mid_valid, n_in; };
   long w_lo, w_hi;
   {
@@ -105,13 +136,12 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
   };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kC2InRing; ++i) { mbar_init(in_full(i), 1); mbar_init(in_empty(i), 1); }
-    for (int i = 0; i < kC2SRing; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 1); }
+    for (int i = 0; i < kC2InRing; ++i) { mbar_init(in_full(i), 1); mbar_init(in_empty(i), SFTGA ? 2 : 1); }
     for (int i = 0; i < kC2MidRing; ++i) { mbar_init(mid_full(i), 4); mbar_init(mid_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(a_tfull(i), 1); mbar_init(a_tempty(i), 4);
-      mbar_init(b_tfull(i), 1); mbar_init(b_tempty(i), 4);
-    }
+    for (int i = 0; i < kC2ResRing; ++i) { mbar_init(res_full(i), 1); mbar_init(res_empty(i), 4); }
+    for (int i = 0; i < RA; ++i) { mbar_init(a_tfull(i), 1); mbar_init(a_tempty(i), 4); }
+    for (int i = 0; i < RB; ++i) { mbar_init(b_tfull(i), 1); mbar_init(b_tempty(i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(st_full(i), 1); mbar_init(st_empty(i), 4); }
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
@@ -136,7 +166,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
       bulk_g2s(smem_u32(wsmB), p.wpkB, p.wB_bytes, wfull_bar);
       if constexpr (SFTGA) bulk_g2s(smem_u32(wsm2), p.wpk2, p.w2_bytes, wfull_bar);
       grid_dep_wait();
-      uint32_t slot = 0, ph = 1, sslot = 0, sph = 1;
+      uint32_t slot = 0, ph = 1;
       const long sstride = p.copy_src_stride;
       long lo = w_lo;
       Seg sg;
@@ -149,13 +179,16 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         // first input row: image row (oy0 - 1 + jv0) - 1; tensor row index = image row + 1
         const uint4* src = p.in + static_cast<long>(oy0 - 1 + jv0) * p.in_row_entries + static_cast<long>(p.copy_src0) +
                            (x0 - 1 + static_cast<int>(lead));
+        // stage-0 row of mid row q (image row oy0 - 1 + jv0 + q) travels with input row q: mid pixel e <-> entry x0 + e
         const uint4* ssrc = SFTGA ? p.s0 + static_cast<long>(oy0 - 1 + jv0 + 1) * p.s0_row_entries + static_cast<long>(p.s0_src0) + x0
                                   : nullptr;
-        int ts = 0;
         for (int q = 0; q < sg.n_in; ++q) {
+          C2X_STAMP(0, q, 0);
           mbar_wait(in_empty(slot), ph, p.err, 21);
-          mbar_expect_tx(in_full(slot), NCOPY * row_bytes);
-          const uint32_t dst = smem_u32(ring) + slot * (NCOPY * kPlaneBytes) + 16 * lead;
+          C2X_STAMP(0, q, 1);
+          const bool with_s = SFTGA && q < sg.n_mid_valid;
+          mbar_expect_tx(in_full(slot), NCOPY * row_bytes + (with_s ? 4 * kPlaneBytes : 0));
+          const uint32_t dst = smem_u32(ring) + slot * IN_SLOT + 16 * lead;
 #pragma unroll
           for (int c = 0; c < NCOPY; ++c) {
             unsigned long long a;
@@ -163,152 +196,191 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             bulk_g2s(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), row_bytes, in_full(slot));
           }
           src += p.in_row_entries;
-          if (++slot == kC2InRing) { slot = 0; ph ^= 1; }
           if constexpr (SFTGA) {
-            while (ts < sg.n_mid_valid && ts + 2 <= q) {   // stage-0 row of the mid row whose last input row was just requested
-              mbar_wait(s_empty(sslot), sph, p.err, 22);
-              mbar_expect_tx(s_full(sslot), kSSlotBytes);
-              const uint32_t sdst = smem_u32(sring) + sslot * kSSlotBytes;
+            if (with_s) {
+              const uint32_t sdst = smem_u32(ring) + slot * IN_SLOT + NCOPY * kPlaneBytes;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 unsigned long long a;
                 asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(c * p.s0_wp), "l"(ssrc));
-                bulk_g2s(sdst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, s_full(sslot));
+                bulk_g2s(sdst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, in_full(slot));
               }
               ssrc += p.s0_row_entries;
-              ++ts;
-              if (++sslot == kC2SRing) { sslot = 0; sph ^= 1; }
             }
           }
+          if (++slot == kC2InRing) { slot = 0; ph ^= 1; }
         }
       }
       grid_dep_launch();
     }
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ TMA producer, residual rows of conv B
+    if (lane == 0 && p.has_res) {
+      grid_dep_wait();
+      uint32_t slot = 0, ph = 1;
+      const uint32_t wp = static_cast<uint32_t>(p.res.Wp);
+      const long row_entries = p.res.row_entries();
+      long lo = w_lo;
+      Seg sg;
+      while (next_seg(lo, sg)) {
+        // out pixel m <-> tensor entry x0 + 1 + m; stay inside the plane on the last strip
+        const uint32_t bytes = 16u * static_cast<uint32_t>(min(kTileM, p.res.Wp - (sg.x0 + 1)));
+        const uint4* src = reinterpret_cast<const uint4*>(p.res.base) + static_cast<long>(sg.oy0 + 1) * row_entries + (sg.x0 + 1);
+        for (int t = 0; t < sg.n_out; ++t) {
+          mbar_wait(res_empty(slot), ph, p.err, 36);
+          mbar_expect_tx(res_full(slot), CHR * bytes);
+          const uint32_t dst = smem_u32(rring) + slot * RES_SLOT;
+#pragma unroll
+          for (int c = 0; c < CHR; ++c) {
+            unsigned long long a;
+            asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(c * wp), "l"(src));
+            bulk_g2s(dst + c * kC2ResPlane, reinterpret_cast<const void*>(a), bytes, res_full(slot));
+          }
+          src += row_entries;
+          if (++slot == kC2ResRing) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer, conv A (valid mid rows only)
     mbar_wait(wfull_bar, 0, p.err, 23);
-    constexpr uint32_t idesc = make_idesc_f16_m128(NA);
-    constexpr uint32_t b_lbo = static_cast<uint32_t>(NA) << 16, b_step = NA * 2;
+    constexpr uint32_t b_lbo = static_cast<uint32_t>(3 * NA) << 16, b_step = 3 * NA * 2;
     constexpr uint32_t a_lbo = (kind_a_lbo(KINDA) >> 4) << 16;
     const uint32_t b_lo0 = (smem_u32(wsmA) >> 4) | b_lbo;
-    constexpr uint32_t slot16 = (NCOPY * kPlaneBytes) >> 4;
+    const uint64_t bias_desc = mkdesc(((smem_u32(wsmA) + SPDA * 3 * NA * 32) >> 4) | (static_cast<uint32_t>(NA) << 16));
+    constexpr uint32_t slot16 = IN_SLOT >> 4;
     const uint32_t ring16 = smem_u32(ring) >> 4;
-    int base_slot = 0, base_ph = 0, sslot = 0, sph = 0;
-    int rg = 0;                                        // valid mid rows issued so far (all segments): TMEM stage parity
+    int slot = 0, ph = 0;
+    int g0 = 0;                                        // valid mid rows of earlier segments: ring position / phase origin
     long lo = w_lo;
     Seg sg;
     while (next_seg(lo, sg)) {
-      int waited = -1;
-      for (int r = 0; r < sg.n_mid_valid; ++r, ++rg) {
-        const int stage = rg & 1;
-        mbar_wait(a_tempty(stage), ((rg >> 1) & 1) ^ 1, p.err, 24);
+      const int nmv = sg.n_mid_valid;
+      for (int q = 0; q < sg.n_in; ++q) {              // input row q feeds mid rows q-2 (dy 2), q-1 (dy 1), q (dy 0)
+        const int lo_r = max(q - 2, 0), hi_r = min(q, nmv - 1);
+        const int pos_new = (g0 + q) % RA;
+        C2X_STAMP(1, g0 + q, 0);
+        if (q < nmv) mbar_wait(a_tempty(pos_new), (((g0 + q) / RA) & 1) ^ 1, p.err, 24);   // block of mid row q drained
+        C2X_STAMP(1, g0 + q, 1);
+        mbar_wait(in_full(slot), ph, p.err, 25);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + colA + stage * NA;
-        int slot = base_slot, ph = base_ph;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const int q = r + dy;
-          if (q > waited) {
-            mbar_wait(in_full(slot), ph, p.err, 25);
-            waited = q;
-            tc_fence_after();
-          }
-          const uint32_t a16 = ring16 + slot * slot16;
-          if (elect_one()) {
-            static_for<0, SPDA>([&](auto ic) {
-              constexpr int i = decltype(ic)::value;
-              constexpr uint32_t a_off16 = kind_a_off(KINDA, KCHA, i) >> 4;
-              tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPDA + i) * b_step), idesc, (dy | i) ? 1u : 0u);
-            });
-            // input row r is not needed by later mid rows; the last mid row of a segment also frees the two rows below it
-            if (dy == 0 || r == sg.n_mid_valid - 1) tc_commit(in_empty(slot));
-          }
-          __syncwarp();
-          if (++slot == kC2InRing) { slot = 0; ph ^= 1; }
-        }
-        if constexpr (SFTGA) {
-          mbar_wait(s_full(sslot), sph, p.err, 26);
-          tc_fence_after();
-        }
+        C2X_STAMP(1, g0 + q, 2);
+        const int pos_lo = (g0 + lo_r) % RA, nwin = hi_r - lo_r + 1;
+        const int n1 = min(nwin, RA - pos_lo), n2 = nwin - n1;      // the window may cross the end of the ring
+        const uint32_t d1 = tmem_base + colA + static_cast<uint32_t>(pos_lo) * NA, d2 = tmem_base + colA;
+        const uint32_t idesc1 = make_idesc_f16_m128(static_cast<uint32_t>(NA * n1));
+        const uint32_t idesc2 = make_idesc_f16_m128(static_cast<uint32_t>(NA * max(n2, 1)));
+        const uint32_t b_lo1 = b_lo0 + static_cast<uint32_t>(NA * (2 - (q - lo_r))), b_lo2 = b_lo1 + static_cast<uint32_t>(NA * n1);
+        const uint32_t a16 = ring16 + slot * slot16;
         if (elect_one()) {
-          if constexpr (SFTGA) {
-            constexpr uint32_t idesc64 = make_idesc_f16_m128(64);
-            // mid pixel e <-> stage-0 entry x0 + e: the slot starts at entry x0, operand offset 0
-            const uint32_t sa = ((smem_u32(sring) + sslot * kSSlotBytes) >> 4) | ((kPlaneBytes >> 4) << 16);
-            const uint32_t sb = (smem_u32(wsm2) >> 4) | (64u << 16);
-            const uint32_t s_tmem = tmem_base + colS + stage * 64;
-            tc_mma_f16(s_tmem, mkdesc(sa), mkdesc(sb), idesc64, 0u);
-            tc_mma_f16(s_tmem, mkdesc(sa + ((2 * kPlaneBytes) >> 4)), mkdesc(sb + 128), idesc64, 1u);
-            tc_mma_f16(s_tmem, ones_desc, mkdesc(sb + 256), idesc64, 1u);
-            tc_commit(s_empty(sslot));
-          }
-          tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (3 * SPDA) * b_step), idesc, 1u);      // conv A bias
-          tc_commit(a_tfull(stage));
+          if (q < nmv)                                   // bias step: initialises the accumulator of the newest row
+            tc_mma_f16(tmem_base + colA + static_cast<uint32_t>(pos_new) * NA, ones_desc, bias_desc, make_idesc_f16_m128(NA), 0u);
+          static_for<0, SPDA>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr uint32_t a_off16 = kind_a_off(KINDA, KCHA, i) >> 4;
+            const uint64_t ad = mkdesc((a16 + a_off16) | a_lbo);
+            tc_mma_f16(d1, ad, mkdesc(b_lo1 + i * b_step), idesc1, 1u);
+            if (n2) tc_mma_f16(d2, ad, mkdesc(b_lo2 + i * b_step), idesc2, 1u);
+          });
+          tc_commit(in_empty(slot));                   // every input row is read exactly once
+          if (q >= 2) tc_commit(a_tfull((g0 + q - 2) % RA));          // mid row q-2 is complete
         }
         __syncwarp();
-        if constexpr (SFTGA) { if (++sslot == kC2SRing) { sslot = 0; sph ^= 1; } }
-        if (++base_slot == kC2InRing) { base_slot = 0; base_ph ^= 1; }
+        C2X_STAMP(1, g0 + q, 3);
+        if (++slot == kC2InRing) { slot = 0; ph ^= 1; }
       }
-      // the segment used n_in = n_mid_valid + 2 ring slots: step over the two trailing ones
-      for (int k = 0; k < 2; ++k)
-        if (++base_slot == kC2InRing) { base_slot = 0; base_ph ^= 1; }
+      g0 += nmv;
+    }
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ MMA issuer, SFT stage-1 GEMM (scale | shift)
+    if constexpr (SFTGA) {
+      mbar_wait(wfull_bar, 0, p.err, 23);
+      constexpr uint32_t idesc64 = make_idesc_f16_m128(64);
+      const uint32_t sb16 = (smem_u32(wsm2) >> 4) | (64u << 16);
+      const uint32_t sring16 = (smem_u32(ring) + NCOPY * kPlaneBytes) >> 4;
+      int slot = 0, ph = 0, g = 0;
+      long lo = w_lo;
+      Seg sg;
+      while (next_seg(lo, sg)) {
+        for (int q = 0; q < sg.n_in; ++q) {            // the stage-0 row of mid row q shares the ring slot of input row q
+          if (q < sg.n_mid_valid) {
+            mbar_wait(st_empty(g & 1), ((g >> 1) & 1) ^ 1, p.err, 33);
+            mbar_wait(in_full(slot), ph, p.err, 26);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa16 = (sring16 + slot * (IN_SLOT >> 4)) | ((kPlaneBytes >> 4) << 16);
+              const uint32_t s_tmem = tmem_base + colS + (g & 1) * 64;
+              tc_mma_f16(s_tmem, mkdesc(sa16), mkdesc(sb16), idesc64, 0u);
+              tc_mma_f16(s_tmem, mkdesc(sa16 + ((2 * kPlaneBytes) >> 4)), mkdesc(sb16 + 128), idesc64, 1u);
+              tc_mma_f16(s_tmem, ones_desc, mkdesc(sb16 + 256), idesc64, 1u);
+              tc_commit(st_full(g & 1));
+              tc_commit(in_empty(slot));
+            }
+            __syncwarp();
+            ++g;
+          } else {
+            if (lane == 0) mbar_arrive(in_empty(slot));    // no stage-0 row in this slot
+            __syncwarp();
+          }
+          if (++slot == kC2InRing) { slot = 0; ph ^= 1; }
+        }
+      }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer, conv B (reads the mid ring)
     mbar_wait(wfull_bar, 0, p.err, 27);
-    constexpr uint32_t idesc = make_idesc_f16_m128(NB);
-    constexpr uint32_t b_lbo = static_cast<uint32_t>(NB) << 16, b_step = NB * 2;
+    constexpr uint32_t b_lbo = static_cast<uint32_t>(3 * NB) << 16, b_step = 3 * NB * 2;
     constexpr uint32_t a_lbo = (kPlaneBytes >> 4) << 16;
     const uint32_t b_lo0 = (smem_u32(wsmB) >> 4) | b_lbo;
+    const uint64_t bias_desc = mkdesc(((smem_u32(wsmB) + SPDB * 3 * NB * 32) >> 4) | (static_cast<uint32_t>(NB) << 16));
     const uint32_t mring16 = smem_u32(mring) >> 4;
-    int base_slot = 0, base_ph = 0;
-    int tg = 0;                                        // output rows issued so far (all segments): TMEM stage parity
+    int slot = 0, ph = 0;
+    int g0 = 0;                                        // output rows of earlier segments
     long lo = w_lo;
     Seg sg;
     while (next_seg(lo, sg)) {
-      int waited = -1;
-      for (int t = 0; t < sg.n_out; ++t, ++tg) {
-        const int stage = tg & 1;
-        mbar_wait(b_tempty(stage), ((tg >> 1) & 1) ^ 1, p.err, 28);
+      const int n_out = sg.n_out;
+      for (int j = 0; j < n_out + 2; ++j) {            // mid row j feeds output rows j-2 (dy 2), j-1 (dy 1), j (dy 0)
+        const int lo_t = max(j - 2, 0), hi_t = min(j, n_out - 1);
+        const int pos_new = (g0 + j) % RB;
+        C2X_STAMP(2, g0 + j, 0);
+        if (j < n_out) mbar_wait(b_tempty(pos_new), (((g0 + j) / RB) & 1) ^ 1, p.err, 28);
+        C2X_STAMP(2, g0 + j, 1);
+        mbar_wait(mid_full(slot), ph, p.err, 29);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + colB + stage * 32;
-        int slot = base_slot, ph = base_ph;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const int j = t + dy;                          // mid row
-          if (j > waited) {
-            mbar_wait(mid_full(slot), ph, p.err, 29);
-            waited = j;
-            tc_fence_after();
-          }
-          const uint32_t a16 = mring16 + slot * (kC2MidSlot >> 4);
-          if (elect_one()) {
-            static_for<0, SPDB>([&](auto ic) {
-              constexpr int i = decltype(ic)::value;
-              constexpr uint32_t a_off16 = kind_a_off(IN_NAT3x3, 4, i) >> 4;
-              tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPDB + i) * b_step), idesc, (dy | i) ? 1u : 0u);
-            });
-            // mid row t is not needed by later output rows; the last output row of a segment frees the two rows below it
-            if (dy == 0 || t == sg.n_out - 1) tc_commit(mid_empty(slot));
-            if (dy == 2) {
-              tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (3 * SPDB) * b_step), idesc, 1u);      // conv B bias
-              tc_commit(b_tfull(stage));
-            }
-          }
-          __syncwarp();
-          if (++slot == kC2MidRing) { slot = 0; ph ^= 1; }
+        C2X_STAMP(2, g0 + j, 2);
+        const int pos_lo = (g0 + lo_t) % RB, nwin = hi_t - lo_t + 1;
+        const int n1 = min(nwin, RB - pos_lo), n2 = nwin - n1;
+        const uint32_t d1 = tmem_base + colB + static_cast<uint32_t>(pos_lo) * NB, d2 = tmem_base + colB;
+        const uint32_t idesc1 = make_idesc_f16_m128(static_cast<uint32_t>(NB * n1));
+        const uint32_t idesc2 = make_idesc_f16_m128(static_cast<uint32_t>(NB * max(n2, 1)));
+        const uint32_t b_lo1 = b_lo0 + static_cast<uint32_t>(NB * (2 - (j - lo_t))), b_lo2 = b_lo1 + static_cast<uint32_t>(NB * n1);
+        const uint32_t a16 = mring16 + slot * (kC2MidSlot >> 4);
+        if (elect_one()) {
+          if (j < n_out)
+            tc_mma_f16(tmem_base + colB + static_cast<uint32_t>(pos_new) * NB, ones_desc, bias_desc, make_idesc_f16_m128(NB), 0u);
+          static_for<0, SPDB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr uint32_t a_off16 = kind_a_off(IN_NAT3x3, 4, i) >> 4;
+            const uint64_t ad = mkdesc((a16 + a_off16) | a_lbo);
+            tc_mma_f16(d1, ad, mkdesc(b_lo1 + i * b_step), idesc1, 1u);
+            if (n2) tc_mma_f16(d2, ad, mkdesc(b_lo2 + i * b_step), idesc2, 1u);
+          });
+          tc_commit(mid_empty(slot));
+          if (j >= 2) tc_commit(b_tfull((g0 + j - 2) % RB));
         }
-        if (++base_slot == kC2MidRing) { base_slot = 0; base_ph ^= 1; }
+        __syncwarp();
+        C2X_STAMP(2, g0 + j, 3);
+        if (++slot == kC2MidRing) { slot = 0; ph ^= 1; }
       }
-      for (int k = 0; k < 2; ++k)                      // the segment used n_out + 2 mid slots
-        if (++base_slot == kC2MidRing) { base_slot = 0; base_ph ^= 1; }
+      g0 += n_out;
     }
   } else if (warp < 7) {
     // ------------------------------------------------------------------ epilogue A: accumulator -> mid ring row
     const int lg = warp & 3;
     const int e = lg * 32 + lane;                      // mid pixel index = TMEM lane
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    int r = 0;                                         // valid mid rows seen (all segments)
+    int g = 0;                                         // valid mid rows seen (all segments)
     int slot = 0, ph = 1;                              // mid ring: wait for "empty" with the producer-side parity
     long lo = w_lo;
     Seg sg;
@@ -319,20 +391,31 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         const bool valid = j >= sg.jv0 && j <= sg.jv1;
         uint4 h[4];
         if (valid) {
-          const int stage = r & 1;
-          mbar_wait(a_tfull(stage), (r >> 1) & 1, p.err, 30);
-          tc_fence_after();
-          float v[32];
+          const int pos = g % RA, stage = g & 1;
           float sv[SFTGA ? 32 : 1], tv[SFTGA ? 32 : 1];
-          tmem_ld32_async(tlane + colA + stage * NA, reinterpret_cast<uint32_t*>(v));
-          if constexpr (SFTGA) {
+          if (warp == 3) C2X_STAMP(3, g, 0);
+          if constexpr (SFTGA) {                       // scale|shift first: they were issued two rows ago
+            mbar_wait(st_full(stage), (g >> 1) & 1, p.err, 37);
+            if (warp == 3) C2X_STAMP(3, g, 1);
+            tc_fence_after();
             tmem_ld32_async(tlane + colS + stage * 64, reinterpret_cast<uint32_t*>(sv));
             tmem_ld32_async(tlane + colS + stage * 64 + 32, reinterpret_cast<uint32_t*>(tv));
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(st_empty(stage));
           }
+          if (warp == 3) C2X_STAMP(3, g, 2);
+          mbar_wait(a_tfull(pos), (g / RA) & 1, p.err, 30);
+          tc_fence_after();
+          if (warp == 3) C2X_STAMP(3, g, 3);
+          float v[32];
+          tmem_ld32_async(tlane + colA + pos * NA, reinterpret_cast<uint32_t*>(v));
           tc_wait_ld();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(a_tempty(stage));
+          if (lane == 0) mbar_arrive(a_tempty(pos));
+          if (warp == 3) C2X_STAMP(3, g, 4);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float a[8];
@@ -344,18 +427,21 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             }
             h[c] = pack8(a);
           }
-          ++r;
+          ++g;
         } else {
 #pragma unroll
           for (int c = 0; c < 4; ++c) h[c] = make_uint4(0, 0, 0, 0);                            // row outside the image
         }
+        if (warp == 3 && valid) C2X_STAMP(3, g - 1, 5);
         mbar_wait(mid_empty(slot), ph, p.err, 31);
+        if (warp == 3 && valid) C2X_STAMP(3, g - 1, 6);
         uint4* dst = reinterpret_cast<uint4*>(mring + slot * kC2MidSlot) + e;
 #pragma unroll
         for (int c = 0; c < 4; ++c) dst[c * kPlaneEntries] = h[c];
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(mid_full(slot));
+        if (warp == 3 && valid) C2X_STAMP(3, g - 1, 7);
         if (++slot == kC2MidRing) { slot = 0; ph ^= 1; }
       }
     }
@@ -366,33 +452,53 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
     const int m = lg * 32 + lane;
     const float slope = p.slopeB;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    int tg = 0;                                        // output rows seen (all segments)
+    int g = 0;                                         // output rows seen (all segments)
+    int rslot = 0, rph = 0;                            // residual ring
     long lo = w_lo;
     Seg sg;
     while (next_seg(lo, sg)) {
       const int x = sg.x0 + m;
       const int oy0 = sg.oy0;
       const bool xin = m < kC2Strip && x < p.W;
-      ColRef out, res, res2, raw;
+      ColRef out, res2, raw;
       out.init(p.out, x);
-      if (p.has_res) res.init(p.res, x);
       if (p.has_res2) res2.init(p.res2, x);
       if (p.has_raw) raw.init(p.raw, x);
-      for (int t = 0; t < sg.n_out; ++t, ++tg) {
-        const int stage = tg & 1, oy = oy0 + t;
-        if constexpr (MODEB == STORE_PLANAR) {
-          uint4 r4 = make_uint4(0, 0, 0, 0);
-          if (xin && p.has_res) r4 = *res.at(oy, 0);
-          mbar_wait(b_tfull(stage), (tg >> 1) & 1, p.err, 32);
-          tc_fence_after();
-          float v[8];
-          tmem_ld_cols<8>(tlane + colB + stage * 32, v);
-          tc_fence_before();
+      for (int t = 0; t < sg.n_out; ++t, ++g) {
+        const int pos = g % RB, oy = oy0 + t;
+        constexpr int CH = MODEB == STORE_PLANAR ? 1 : NB / 8;
+        uint4 r4[CH], q4[CH];
+        if (MODEB == STORE_P8 && p.has_res2 && xin) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) q4[c] = *res2.at(oy, c);
+        }
+        if (warp == 7) C2X_STAMP(4, g, 0);
+        if (p.has_res) {
+          mbar_wait(res_full(rslot), rph, p.err, 38);
+          const uint4* rs = reinterpret_cast<const uint4*>(rring + rslot * RES_SLOT) + m;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) r4[c] = rs[c * kTileM];
           __syncwarp();
-          if (lane == 0) mbar_arrive(b_tempty(stage));
+          if (lane == 0) mbar_arrive(res_empty(rslot));
+          if (++rslot == kC2ResRing) { rslot = 0; rph ^= 1; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) r4[c] = make_uint4(0, 0, 0, 0);
+        }
+        if (warp == 7) C2X_STAMP(4, g, 1);
+        mbar_wait(b_tfull(pos), (g / RB) & 1, p.err, 32);
+        tc_fence_after();
+        if (warp == 7) C2X_STAMP(4, g, 2);
+        float v[MODEB == STORE_PLANAR ? 8 : NB];
+        tmem_ld_cols<(MODEB == STORE_PLANAR ? 8 : NB)>(tlane + colB + pos * NB, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_tempty(pos));
+        if (warp == 7) C2X_STAMP(4, g, 3);
+        if constexpr (MODEB == STORE_PLANAR) {
           if (xin) {
             float val[8], rr[8];
-            unpack8(r4, rr);
+            unpack8(r4[0], rr);
 #pragma unroll
             for (int k = 0; k < 8; ++k) val[k] = (k < 3) ? fmaxf(v[k], slope * v[k]) + rr[k] : 0.f;
 #pragma unroll
@@ -401,22 +507,6 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             if (p.has_raw) *raw.at(oy, 0) = pack8(val);
           }
         } else {
-          constexpr int CH = NB / 8;
-          uint4 r4[CH], q4[CH];
-          if (xin) {
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              if (p.has_res) r4[c] = *res.at(oy, c);
-              if (p.has_res2) q4[c] = *res2.at(oy, c);
-            }
-          }
-          mbar_wait(b_tfull(stage), (tg >> 1) & 1, p.err, 32);
-          tc_fence_after();
-          float v[NB];
-          tmem_ld_cols<NB>(tlane + colB + stage * 32, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_tempty(stage));
           if (xin) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
@@ -440,6 +530,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             }
           }
         }
+        if (warp == 7) C2X_STAMP(4, g, 4);
       }
     }
   }
@@ -449,11 +540,12 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int KINDA, int KCHA, bool SFTGA>
+template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB>
 inline size_t conv2x_smem_bytes(const Conv2xParams& p) {
-  return kSmemHeader + ((p.wA_bytes + 127) & ~127) + (SFTGA ? ((p.w2_bytes + 127) & ~127) : 0) + ((p.wB_bytes + 127) & ~127) +
-         static_cast<size_t>(kC2InRing) * kind_copies(KINDA, KCHA) * kPlaneBytes + (SFTGA ? kC2SRing * kSSlotBytes : 0) +
-         static_cast<size_t>(kC2MidRing) * kC2MidSlot;
+  constexpr int CHR = MODEB == STORE_PLANAR ? 1 : NB / 8;
+  return kC2Header + ((p.wA_bytes + 127) & ~127) + (SFTGA ? ((p.w2_bytes + 127) & ~127) : 0) + ((p.wB_bytes + 127) & ~127) +
+         static_cast<size_t>(kC2InRing) * (kind_copies(KINDA, KCHA) + (SFTGA ? 4 : 0)) * kPlaneBytes +
+         static_cast<size_t>(kC2MidRing) * kC2MidSlot + static_cast<size_t>(kC2ResRing) * CHR * kC2ResPlane;
 }
 
 }  // namespace hdrtv

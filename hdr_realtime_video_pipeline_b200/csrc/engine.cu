@@ -569,7 +569,10 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
   p.wpkB = reinterpret_cast<const uint4*>(b.wpk);
   p.wB_bytes = (18 + 1) * b.N * 32;
   p.slopeB = b.act == ACT_RELU ? 0.f : (b.act == ACT_LRELU ? 0.1f : 1.f);
-  if (b.res) { p.has_res = 1; p.res = *b.res; }
+  if (b.res) {
+    if (b.res->parity) return fail(c, "conv2x " + name + ": natural-layout residual required");
+    p.has_res = 1; p.res = *b.res;
+  }
   if (b.res2) { p.has_res2 = 1; p.res2 = *b.res2; }
   if (b.raw) { p.has_raw = 1; p.raw = *b.raw; }
   p.out = out;
@@ -584,9 +587,9 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
   const int band = static_cast<int>((items + ctas - 1) / ctas);
   p.band = band;
   L.grid = dim3(static_cast<unsigned>(ctas), 1, 1);
-  L.smem = variant == C2X_C8_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3_C8, 1, true>(p)
-         : variant == C2X_K4_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3, 4, true>(p)
-                                     : conv2x_smem_bytes<IN_NAT3x3, 4, false>(p);
+  L.smem = variant == C2X_C8_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3_C8, 1, true, 32, STORE_P8>(p)
+         : variant == C2X_K4_SFTG_P8 ? conv2x_smem_bytes<IN_NAT3x3, 4, true, 32, STORE_P8>(p)
+                                     : conv2x_smem_bytes<IN_NAT3x3, 4, false, 16, STORE_PLANAR>(p);
   if (L.smem > 227 * 1024) return fail(c, "conv2x " + name + ": shared memory budget exceeded");
   L.c2x_variant = variant;
   L.N = b.N;
@@ -699,6 +702,24 @@ static int pack_layer(Ctx* c, const std::string& key, InKind kind, int kchunks, 
   if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
   return 0;
 }
+// Row-folded copy of a packed 3x3 layer for conv2x_p8_kernel: K step i of the fold holds the three vertical taps side by
+// side along N ([dy=2 | dy=1 | dy=0], 3N rows), followed by the unchanged N-row bias step.
+static int pack_fold(Ctx* c, const std::string& name, int spd, int N) {
+  const std::vector<__half>& pk = c->host_pk.at(name);
+  std::vector<__half> out(pk.size(), __float2half(0.f));
+  if (pk.size() != static_cast<size_t>(3 * spd + 1) * N * 16) return fail(c, "pack_fold " + name + ": unexpected packed size");
+  for (int dy = 0; dy < 3; ++dy)
+    for (int i = 0; i < spd; ++i)
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 16; ++k)
+          out[bpack_index(3 * N, i, (2 - dy) * N + n, k)] = pk[bpack_index(N, dy * spd + i, n, k)];
+  const long b_src = static_cast<long>(3 * spd) * N * 16, b_dst = b_src;
+  for (int i = 0; i < N * 16; ++i) out[b_dst + i] = pk[b_src + i];
+  const std::string key = name + ".fold";
+  c->wpk[key] = w_upload(c, out.data(), out.size());
+  if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
+  return 0;
+}
 static std::function<float(int)> bias_fn(Ctx* c, const std::string& name) {
   const HostTensor& t = W(c, name + ".bias");
   const float* d = t.v.data();
@@ -791,6 +812,12 @@ static int pack_all_fp16(Ctx* c) {
   r |= pack_std(c, "LE.HR_conv1", IN_NAT3x3, 32, 32);
   r |= pack_std(c, "LE.HR_conv2", IN_NAT3x3, 32, 32);
   r |= pack_std(c, "LE.conv_last", IN_NAT3x3, 32, 16);
+  if (!r) {
+    r |= pack_fold(c, "LE.conv_first", 2, 32);
+    r |= pack_fold(c, "LE.HR_conv1", 6, 32);
+    r |= pack_fold(c, "LE.HR_conv2", 6, 32);
+    r |= pack_fold(c, "LE.conv_last", 6, 16);
+  }
   for (int i = 1; i <= 3; ++i) {
     r |= pack_std(c, "LE.down_conv" + std::to_string(i), IN_PAR3x3S2, 32, 32);
     r |= pack_std(c, "LE.up_conv" + std::to_string(i) + ".0", IN_NAT3x3, 32, 128);
@@ -801,6 +828,10 @@ static int pack_all_fp16(Ctx* c) {
       const std::string pre = "LE.recon_trunk" + std::to_string(t) + "." + std::to_string(j);
       r |= pack_std(c, pre + ".conv1", IN_NAT3x3, 32, 32);
       r |= pack_std(c, pre + ".conv2", IN_NAT3x3, 32, 32);
+      if (!r) {
+        r |= pack_fold(c, pre + ".conv1", 6, 32);
+        r |= pack_fold(c, pre + ".conv2", 6, 32);
+      }
     }
   r |= pack_sft_stage0(c, "sft0.L0", kSftL0, 2);
   if (!r) {   // cond chain + the stage-0 convs of the two full-resolution SFT layers as its seventh step
@@ -1224,8 +1255,8 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   const bool use_c2x = use_sftg && env_int("HDRTV_C2X", 1) != 0;   // conv -> conv pairs through a shared-memory row ring
   if (use_c2x) {
     Epi ea = relu; with_sft(ea, "LE.SFT_layer1");
-    C2xB b; b.wpk = wk("LE.HR_conv1"); b.N = 32; b.mode = STORE_P8; b.act = ACT_RELU;
-    r |= make_conv2x(c, L, "LE.conv_first+HR_conv1", C2X_C8_SFTG_P8, agP8, wk("LE.conv_first"), ea, b, FEA0, H, Wd);
+    C2xB b; b.wpk = wk("LE.HR_conv1.fold"); b.N = 32; b.mode = STORE_P8; b.act = ACT_RELU;
+    r |= make_conv2x(c, L, "LE.conv_first+HR_conv1", C2X_C8_SFTG_P8, agP8, wk("LE.conv_first.fold"), ea, b, FEA0, H, Wd);
   } else {
     { Epi e = relu; with_sft(e, "LE.SFT_layer1");
       r |= std_conv(L, "LE.conv_first", IN_NAT3x3_C8, agP8, 8, 32, STORE_P8, T0a, H, Wd, e); }
@@ -1235,8 +1266,8 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
                       const P8* res2, const char* next_sft, const P8* next_raw, int h, int w) {
     if (use_c2x && !next_sft) {     // conv1 -> sft2 -> conv2 + x in one kernel
       Epi ea = relu; with_sft(ea, pre + ".sft2");
-      C2xB b; b.wpk = wk(pre + ".conv2"); b.N = 32; b.mode = STORE_P8; b.act = ACT_NONE; b.res = &xraw; b.res2 = res2; b.raw = next_raw;
-      r |= make_conv2x(c, L, pre + ".conv1+conv2", C2X_K4_SFTG_P8, xm, wk(pre + ".conv1"), ea, b, out, h, w);
+      C2xB b; b.wpk = wk(pre + ".conv2.fold"); b.N = 32; b.mode = STORE_P8; b.act = ACT_NONE; b.res = &xraw; b.res2 = res2; b.raw = next_raw;
+      r |= make_conv2x(c, L, pre + ".conv1+conv2", C2X_K4_SFTG_P8, xm, wk(pre + ".conv1.fold"), ea, b, out, h, w);
       return;
     }
     { Epi e = relu; with_sft(e, pre + ".sft2");
@@ -1279,8 +1310,8 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   up("LE.up_conv3.0", U1, FEA0, nullptr, "LE.SFT_layer2", V0, H1, W1);
   if (use_c2x) {
     Epi ea = relu;
-    C2xB b; b.wpk = wk("LE.conv_last"); b.N = 16; b.mode = STORE_PLANAR; b.act = ACT_NONE; b.res = &agP8;
-    r |= make_conv2x(c, L, "LE.HR_conv2+conv_last", C2X_K4_PLANAR, V0, wk("LE.HR_conv2"), ea, b, agP8, H, Wd);
+    C2xB b; b.wpk = wk("LE.conv_last.fold"); b.N = 16; b.mode = STORE_PLANAR; b.act = ACT_NONE; b.res = &agP8;
+    r |= make_conv2x(c, L, "LE.HR_conv2+conv_last", C2X_K4_PLANAR, V0, wk("LE.HR_conv2.fold"), ea, b, agP8, H, Wd);
   } else {
     r |= std_conv(L, "LE.HR_conv2", IN_NAT3x3, V0, 32, 32, STORE_P8, V1, H, Wd, relu);
     { Epi e; e.res = &agP8; e.planar = reinterpret_cast<__half*>(1);
@@ -1872,7 +1903,7 @@ int hdrtv_mma_probe(hdrtv_t* c, int n, int layout, int vary, int iters, int bloc
 
 int hdrtv_probe(hdrtv_t* c, int kind, int n, int iters, int blocks, int nwarps, int nmma, int groups, float* cycles_per_iter,
                 long long* trace_host) {
-  if (!c || !cycles_per_iter || blocks < 1 || iters < 4 || kind < 0 || kind > 7) return fail(c, "hdrtv_probe: bad argument");
+  if (!c || !cycles_per_iter || blocks < 1 || iters < 4 || kind < 0 || kind > 8) return fail(c, "hdrtv_probe: bad argument");
   cudaSetDevice(c->device);
   long long *d = nullptr, *dtrace = nullptr;
   CK(c, cudaMalloc(&d, sizeof(long long) * blocks));
@@ -1890,7 +1921,7 @@ int hdrtv_probe(hdrtv_t* c, int kind, int n, int iters, int blocks, int nwarps, 
     cudaFuncSetAttribute(probe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   \
     probe_kernel<K><<<blocks, threads, 96 * 1024>>>(a);                                               \
     break;
-  switch (kind) { HDRTV_PROBE_K(0) HDRTV_PROBE_K(1) HDRTV_PROBE_K(2) HDRTV_PROBE_K(3) HDRTV_PROBE_K(4) HDRTV_PROBE_K(5) HDRTV_PROBE_K(6) HDRTV_PROBE_K(7) }
+  switch (kind) { HDRTV_PROBE_K(0) HDRTV_PROBE_K(1) HDRTV_PROBE_K(2) HDRTV_PROBE_K(3) HDRTV_PROBE_K(4) HDRTV_PROBE_K(5) HDRTV_PROBE_K(6) HDRTV_PROBE_K(7) HDRTV_PROBE_K(8) }
 #undef HDRTV_PROBE_K
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<long long> h(blocks);
@@ -1909,16 +1940,25 @@ int hdrtv_probe(hdrtv_t* c, int kind, int n, int iters, int blocks, int nwarps, 
 int hdrtv_chain_trace(hdrtv_t* c, int agcm, int index, long long* trace_host) {
   if (!c || !trace_host) return fail(c, "hdrtv_chain_trace: null argument");
   std::vector<ConvLaunch>& plan = agcm ? c->plan_agcm : c->plan_le;
-  if (index < 0 || index >= static_cast<int>(plan.size()) || !plan[index].chain) return fail(c, "hdrtv_chain_trace: not a chain launch");
+  if (index < 0 || index >= static_cast<int>(plan.size()) || (!plan[index].chain && !plan[index].c2x))
+    return fail(c, "hdrtv_chain_trace: not a chain / conv2x launch");
   cudaSetDevice(c->device);
   long long* d = nullptr;
   CK(c, cudaMalloc(&d, sizeof(long long) * 64 * 8 * 8));
   cudaMemset(d, 0, sizeof(long long) * 64 * 8 * 8);
   ConvLaunch L = plan[index];
-  ChainParams cp = *L.chain;
-  cp.trace = d;
-  L.chain = std::make_shared<ChainParams>(cp);
-  cudaError_t e = launch_chain(L, 0);
+  cudaError_t e;
+  if (L.chain) {
+    ChainParams cp = *L.chain;
+    cp.trace = d;
+    L.chain = std::make_shared<ChainParams>(cp);
+    e = launch_chain(L, 0);
+  } else {
+    Conv2xParams cp = *L.c2x;
+    cp.trace = d;
+    L.c2x = std::make_shared<Conv2xParams>(cp);
+    e = launch_conv2x(L, 0);
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(trace_host, d, sizeof(long long) * 64 * 8 * 8, cudaMemcpyDeviceToHost);
   cudaFree(d);

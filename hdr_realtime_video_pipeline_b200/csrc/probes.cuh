@@ -207,10 +207,11 @@ __global__ void __launch_bounds__(1024) probe_kernel(const ProbeArgs a) {
     //   1 commit, 2 try_wait on a completed barrier, 4 tcgen05.fence::after_thread_sync, 8 alternate accumulator,
     //   16 first MMA overwrites, 32 descriptor low words re-read from shared memory every iteration
     if (threadIdx.x == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 64);
-      const uint64_t bd = make_smem_desc(b0, 64 * 16, 128);
+      const uint32_t idesc = make_idesc_f16(128, N);
+      const uint64_t bd = make_smem_desc(b0, N * 16, 128);
       uint64_t ad[4];
-      for (int k = 0; k < 4; ++k) ad[k] = make_smem_desc(a0 + k * 2 * kPlaneBytes, kPlaneBytes, 128);
+      for (int k = 0; k < 4; ++k)
+        ad[k] = make_smem_desc(a0 + (a.nmma == 1 ? 0 : (a.nmma == 2 ? k * 16 : k * 2 * kPlaneBytes)), kPlaneBytes, 128);
       const uint64_t ones = make_smem_desc(a0 + 40960, 16, 128);
       const int f = a.groups;
       volatile uint32_t* lows = reinterpret_cast<volatile uint32_t*>(smem + 90 * 1024);
@@ -234,6 +235,37 @@ __global__ void __launch_bounds__(1024) probe_kernel(const ProbeArgs a) {
       tc_commit(smem_u32(&bars[8]));
       mbar_wait(smem_u32(&bars[8]), 0, nullptr, 0);
       a.cycles[blockIdx.x] = clock64() - t0;
+    }
+  }
+  else if constexpr (KIND == 8) {
+    // latency of the synchronisation primitives an issuing / epilogue warp executes per row (whole warp, dependent
+    // chain of `iters` ops).  a.groups selects the op.
+    if (warp == 0) {
+      const uint32_t done = smem_u32(&bars[13]);       // fresh barrier: parity 1 is "already complete"
+      const int op = a.groups;
+      uint32_t acc = 0;
+      __syncwarp();
+      const long long t0 = clock64();
+      for (int i = 0; i < a.iters; ++i) {
+        if (op == 1) acc += mbar_try_wait(done, 1);
+        else if (op == 2) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(done), "r"(1u) : "memory");
+          acc += ok;
+        } else if (op == 3) tc_fence_after();
+        else if (op == 4) { if (elect_one()) acc += 1; __syncwarp(); }
+        else if (op == 5) mbar_wait(done, 1, nullptr, 0);
+        else if (op == 6) { if (lane == 0 && a.trace) a.trace[i & 63] = clock64(); }
+        else if (op == 7) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&bars[9 + (i & 3)])); }
+        else if (op == 8) { if (elect_one()) tc_commit(smem_u32(&bars[9 + (i & 3)])); __syncwarp(); }
+        else if (op == 9) fence_proxy_async_smem();
+        else if (op == 10) tc_fence_before();
+        else if (op == 11) { if (lane == 0) acc += mbar_try_wait(done, 1); __syncwarp(); }
+      }
+      const long long t1 = clock64();
+      if (lane == 0) a.cycles[blockIdx.x] = t1 - t0;
+      if (acc == 0xFFFFFFFFu) a.cycles[0] = 0;
     }
   }
   tc_fence_before();

@@ -50,7 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 }
 // Bounded wait: a barrier that never completes (bad tx count, lost commit) must not hang the GPU box.
 // On timeout the error word is set and the kernel traps (sticky launch failure instead of a hang).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_word, int code) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_word, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) {
@@ -59,6 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
       __trap();
     }
   }
+}
+// A phase that has already completed (the common case for ring barriers with slack) costs one try_wait; the bounded
+// spin loop lives out of line (measured with scripts/sync_probe.py: 110 cycles for the inlined loop, 55 for try_wait).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_word, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, err_word, code);
 }
 
 // ------------------------------------------------------- programmatic dependent launch
@@ -134,6 +140,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
