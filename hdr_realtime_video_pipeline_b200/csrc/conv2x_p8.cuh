@@ -55,7 +55,6 @@ struct Conv2xParams {
   const uint4* wpk2; int w2_bytes;           // SFT stage-1 weights (SFTG)
   const uint4* s0; long s0_row_entries; uint32_t s0_src0, s0_wp;
   const uint4* wpkB; int wB_bytes;           // conv B packed weights, row-folded (N = 3 NB per step) + bias step (N = NB)
-  float slopeB;                              // conv B activation as max(v, slope*v)
   int has_res, has_res2, has_raw;
   P8 res, res2, raw, out;                    // res: natural layout (streamed through shared memory)
   __half* planar; long planar_plane; int planar_W;
@@ -63,16 +62,38 @@ struct Conv2xParams {
   long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [row<64][role<8][8]
 };
 
+// fp32 x8 -> fp16 x8 (round to nearest), optionally with the ReLU fused into the conversion
+template <int ACT>
+__device__ __forceinline__ uint4 pack8_act(const float* f) {
+  uint4 u;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (ACT == ACT_RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
+  }
+  return u;
+}
+__device__ __forceinline__ void hadd2x4(uint4& a, const uint4& b) {
+  __half2* x = reinterpret_cast<__half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __hadd2(x[i], y[i]);
+}
+
 #ifdef HDRTV_CHAIN_TRACE
 #define C2X_STAMP(role, row, k) do { if (p.trace && blockIdx.x == 0 && (row) < 64 && lane == 0) p.trace[(((row) * 8) + (role)) * 8 + (k)] = clock64(); } while (0)
 #else
 #define C2X_STAMP(role, row, k) do { } while (0)
 #endif
 
-template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB>
+// ACTB: activation of conv B (ACT_NONE / ACT_RELU).  Conv B's epilogue follows the reference's fp16 graph op by op: the
+// conv result is rounded to fp16 (with the ReLU fused into the conversion), then the residuals are added in fp16.
+template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>
 __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_constant__ Conv2xParams p) {
   static_assert(KINDA == IN_NAT3x3 || KINDA == IN_NAT3x3_C8, "conv A: 3x3 stride 1");
   static_assert(MODEB == STORE_P8 || MODEB == STORE_PLANAR, "conv B store mode");
+  static_assert(ACTB == ACT_NONE || ACTB == ACT_RELU, "conv B activation");
   constexpr int NA = 32;
   constexpr int SPDA = kind_spd(KINDA, KCHA), NCOPY = kind_copies(KINDA, KCHA);
   constexpr int SPDB = kind_spd(IN_NAT3x3, 4);
@@ -421,11 +442,10 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             float a[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              float val = fmaxf(v[c * 8 + k], 0.f);                                             // ReLU
-              if constexpr (SFTGA) val = fmaf(val, sv[c * 8 + k], val) + tv[c * 8 + k];       // x*(scale+1)+shift
-              a[k] = inside_x ? val : 0.f;
+              a[k] = fmaxf(v[c * 8 + k], 0.f);                                                  // ReLU
+              if constexpr (SFTGA) a[k] = fmaf(a[k], sv[c * 8 + k], tv[c * 8 + k]);           // x*(scale+1)+shift, +1 in the bias step
             }
-            h[c] = pack8(a);
+            h[c] = inside_x ? pack8(a) : make_uint4(0, 0, 0, 0);
           }
           ++g;
         } else {
@@ -450,7 +470,6 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
     grid_dep_wait();
     const int lg = warp & 3;
     const int m = lg * 32 + lane;
-    const float slope = p.slopeB;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
     int g = 0;                                         // output rows seen (all segments)
     int rslot = 0, rph = 0;                            // residual ring
@@ -497,37 +516,34 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         if (warp == 7) C2X_STAMP(4, g, 3);
         if constexpr (MODEB == STORE_PLANAR) {
           if (xin) {
-            float val[8], rr[8];
-            unpack8(r4[0], rr);
+            uint4 o = pack8_act<ACTB>(v);
+            hadd2x4(o, r4[0]);
+            const __half* oh = reinterpret_cast<const __half*>(&o);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = (k < 3) ? fmaxf(v[k], slope * v[k]) + rr[k] : 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-              p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = __float2half_rn(val[k]);
-            if (p.has_raw) *raw.at(oy, 0) = pack8(val);
+            for (int k = 0; k < 3; ++k) p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = oh[k];
+            if (p.has_raw) {
+              o.y &= 0x0000FFFFu; o.z = 0u; o.w = 0u;                                            // channels 3..7 stay zero
+              *raw.at(oy, 0) = o;
+            }
           }
         } else {
           if (xin) {
+            uint4 o[CH];
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-              float val[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) val[k] = fmaxf(v[c * 8 + k], slope * v[c * 8 + k]);
-              if (p.has_res) {
-                float rr[8];
-                unpack8(r4[c], rr);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) val[k] += rr[k];
-              }
-              if (p.has_res2) {
-                float rr[8];
-                unpack8(q4[c], rr);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) val[k] += rr[k];
-              }
-              if (p.has_raw) *raw.at(oy, c) = pack8(val);
-              *out.at(oy, c) = pack8(val);
+              o[c] = pack8_act<ACTB>(v + c * 8);
+              hadd2x4(o[c], r4[c]);
             }
+            if (p.has_res2) {
+#pragma unroll
+              for (int c = 0; c < CH; ++c) hadd2x4(o[c], q4[c]);
+            }
+            if (p.has_raw) {
+#pragma unroll
+              for (int c = 0; c < CH; ++c) *raw.at(oy, c) = o[c];
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) *out.at(oy, c) = o[c];
           }
         }
         if (warp == 7) C2X_STAMP(4, g, 4);

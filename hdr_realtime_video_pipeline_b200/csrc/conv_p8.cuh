@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
               if (p.has_raw) *raw[j].at(Y, ch) = pack8(val);
               if constexpr (SFTG) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], sv[c * 8 + k], val[k]) + tv[c * 8 + k];
+                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], sv[c * 8 + k], tv[c * 8 + k]);   // sv = scale + 1 (bias step)
               } else if (p.has_sft) {
                 float s[8], tt[8];
                 unpack8(s4[c], s);
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
               if (p.has_raw) *raw.at(oy, j0 + c) = pack8(val);
               if constexpr (SFTG) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], sv[c * 8 + k], val[k]) + tv[c * 8 + k];
+                for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], sv[c * 8 + k], tv[c * 8 + k]);   // sv = scale + 1 (bias step)
               } else if (p.has_sft) {
                 float s[8], tt[8];
                 unpack8(s4[c], s);

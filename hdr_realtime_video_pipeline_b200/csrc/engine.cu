@@ -459,22 +459,22 @@ static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>, L.grid, kConvThreads, L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
-template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB>
+template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>
 static cudaError_t launch_conv2x_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB>,
+    cudaError_t e = cudaFuncSetAttribute(conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB, ACTB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB>, L.grid, kC2Threads, L.smem, s, *L.c2x);
+  return launch_pdl(conv2x_p8_kernel<KINDA, KCHA, SFTGA, NB, MODEB, ACTB>, L.grid, kC2Threads, L.smem, s, *L.c2x);
 }
 static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
   switch (L.c2x_variant) {
-    case 0: return launch_conv2x_t<IN_NAT3x3_C8, 1, true, 32, STORE_P8>(L, s);
-    case 1: return launch_conv2x_t<IN_NAT3x3, 4, true, 32, STORE_P8>(L, s);
-    case 2: return launch_conv2x_t<IN_NAT3x3, 4, false, 16, STORE_PLANAR>(L, s);
+    case 0: return launch_conv2x_t<IN_NAT3x3_C8, 1, true, 32, STORE_P8, ACT_RELU>(L, s);
+    case 1: return launch_conv2x_t<IN_NAT3x3, 4, true, 32, STORE_P8, ACT_NONE>(L, s);
+    case 2: return launch_conv2x_t<IN_NAT3x3, 4, false, 16, STORE_PLANAR, ACT_NONE>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -568,7 +568,7 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
   }
   p.wpkB = reinterpret_cast<const uint4*>(b.wpk);
   p.wB_bytes = (18 + 1) * b.N * 32;
-  p.slopeB = b.act == ACT_RELU ? 0.f : (b.act == ACT_LRELU ? 0.1f : 1.f);
+  if (b.act != (variant == C2X_C8_SFTG_P8 ? ACT_RELU : ACT_NONE)) return fail(c, "conv2x " + name + ": activation not compiled for this variant");
   if (b.res) {
     if (b.res->parity) return fail(c, "conv2x " + name + ": natural-layout residual required");
     p.has_res = 1; p.res = *b.res;
@@ -764,6 +764,9 @@ static int pack_sft_stage1(Ctx* c, const std::string& name) {
     return ci >= 16 ? ft(nn - 32, ci - 16, tap) : 0.f;
   };
   auto bf = [bs, bt](int nn) { return nn < 32 ? bs(nn) : bt(nn - 32); };
+  // ".stage1p": for the in-kernel generators, whose epilogue computes x * scale1 + shift with scale1 = scale + 1
+  auto bf1 = [bs, bt](int nn) { return nn < 32 ? bs(nn) + 1.f : bt(nn - 32); };
+  if (pack_layer(c, name + ".stage1p", IN_NAT1x1, 4, 64, wf, bf1)) return -1;
   return pack_layer(c, name + ".stage1", IN_NAT1x1, 4, 64, wf, bf);
 }
 
@@ -1246,7 +1249,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
       const S0Ref& ref = s0of.at(nm);
       e.sft_s0 = ref.S;
       e.sft_j0 = ref.j0;
-      e.sft_w2 = wk(nm + ".stage1");
+      e.sft_w2 = wk(nm + ".stage1p");
     } else {
       e.sft = &maps.at(nm);
     }
@@ -2144,7 +2147,7 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
     P8 dummy; dummy.Wp = 16; dummy.chunks = 4;
     build_input_side(IN_NAT1x1, dummy, 0, 4, tmp2, wk2);
     WeightFn wf2 = [&](int n2, int ci, int tap) -> float { return (n2 < 64 && ci < 32 && tap == 0) ? hw2[static_cast<size_t>(n2) * 32 + ci] : 0.f; };
-    std::vector<__half> pk2 = pack_weights(64, wk2, wf2, [&](int n2) { return n2 < 64 ? hb2[n2] : 0.f; });
+    std::vector<__half> pk2 = pack_weights(64, wk2, wf2, [&](int n2) { return n2 < 64 ? hb2[n2] + (n2 < 32 ? 1.f : 0.f) : 0.f; });   // scale rows carry the +1
     __half* dpk2 = ws_alloc<__half>(&t, pk2.size());
     cudaMemcpy(dpk2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice);
     e.sft_s0 = &s0p; e.sft_j0 = sj0; e.sft_w2 = dpk2; e.raw = &rawp;

@@ -24,7 +24,7 @@ idx = next(i for i, n in enumerate(names) if which in n and "+" in n) - first
 print("#", names[idx + first], "plan index", idx)
 tr = net.chain_trace(agcm=False, index=idx)
 t0 = tr[tr > 0].min()
-roles = {0: "prod  [top, slot free]", 1: "mmaA  [top, tempty, in_full, issued, s_full, st_empty, S issued]",
+roles = {0: "prod  [top, slot free]", 1: "mmaA  [top, tempty, in_full, issued]",
          2: "mmaB  [top, tempty, mid_full, issued]", 3: "epiA  [top, st_full, S loaded, a_tfull, acc loaded, math, mid_empty, stored]",
          4: "epiB  [top, res_full, b_tfull, acc loaded, stored]"}
 for r, d in roles.items():
