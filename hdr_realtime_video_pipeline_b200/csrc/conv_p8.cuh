@@ -167,13 +167,20 @@ constexpr int kSSlotBytes = 4 * kPlaneBytes;      // one 32-channel stage-0 row
 constexpr int kSRingPS = 2;                       // PixelShuffle consumers: 4 sub-pixel rows (2 fine rows x 2 column
 constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels per coarse output row
 
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false>
+// FOLD (stride-2 3x3 only): the vertical taps are folded into N as in conv2x_p8.cuh.  Output row m reads input rows
+// 2m (dy 0), 2m+1 (dy 1), 2m+2 (dy 2), so an even input row 2m is multiplied once by [W(dy=2) | W(dy=0)] into the
+// neighbouring accumulator blocks of output rows m-1 and m, an odd one by W(dy=1) into block m: 2/3 of the MMAs, every
+// input row consumed (and its ring slot released) once, and a ring of kFoldR accumulator blocks instead of two stages.
+constexpr int kFoldR = 8;
+
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
 __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
   static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
                 "in-kernel SFT generator: 32-channel outputs only");
+  static_assert(!FOLD || (KIND == IN_PAR3x3S2 && !SFTG && MODE == STORE_P8 && N <= 64), "row folding: plain stride-2 3x3 convs");
   constexpr bool PSG = SFTG && MODE == STORE_PS;
   // SFTG: 2 x 32 conv + 2 x 64 scale|shift columns; PixelShuffle: 2 x 128 conv + 4 sub-pixels x 64 (single-buffered)
-  constexpr uint32_t kTmemCols = SFTG ? (PSG ? 512 : 256) : ((2 * N < 32) ? 32 : 2 * N);
+  constexpr uint32_t kTmemCols = FOLD ? (kFoldR * N < 32 ? 32 : kFoldR * N) : SFTG ? (PSG ? 512 : 256) : ((2 * N < 32) ? 32 : 2 * N);
   constexpr int SRING = PSG ? kSRingPS : kSRing;
   constexpr int SSLOT = PSG ? kSSlotBytesPS : kSSlotBytes;
   constexpr int KS = kind_ks(KIND), STRIDE = kind_stride(KIND), SPD = kind_spd(KIND, KCH), NCOPY = kind_copies(KIND, KCH);
@@ -183,8 +190,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int i) { return bar0 + 8u * i; };
   auto empty_bar = [&](int i) { return bar0 + 8u * (kMaxRing + i); };
-  auto tfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + i); };
-  auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 2 + i); };
+  auto tfull_bar = [&](int i) { return bar0 + 8u * ((FOLD ? 32 : 2 * kMaxRing) + i); };
+  auto tempty_bar = [&](int i) { return bar0 + 8u * ((FOLD ? 40 : 2 * kMaxRing + 2) + i); };
+  static_assert(2 * kMaxRing + 8 + 2 * kSRing <= 32 && 40 + kFoldR <= 64, "barrier table layout");
   const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxRing + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
   auto sfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       mbar_init(full_bar(i), 1);
       mbar_init(empty_bar(i), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (FOLD ? kFoldR : 2); ++i) {
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 8);
     }
@@ -319,6 +327,46 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     constexpr uint32_t slot16 = (NCOPY * kPlaneBytes) >> 4;
     const uint32_t ring16 = smem_u32(ring) >> 4;
     const int ring_n = p.ring;
+    if constexpr (FOLD) {
+      constexpr int R = kFoldR;
+      constexpr uint32_t bE_lbo = static_cast<uint32_t>(2 * N) << 16, bE_step = 2 * N * 2;      // even rows: [dy=2 | dy=0]
+      constexpr uint32_t bO_lbo = static_cast<uint32_t>(N) << 16, bO_step = N * 2;              // odd rows: dy=1
+      const uint32_t bE0 = (smem_u32(wsm) >> 4) | bE_lbo;
+      const uint32_t bO0 = ((smem_u32(wsm) + SPD * 2 * N * 32) >> 4) | bO_lbo;
+      const uint64_t bias_desc = mkdesc(((smem_u32(wsm) + SPD * 3 * N * 32) >> 4) | (static_cast<uint32_t>(N) << 16));
+      int slot = 0, ph = 0;
+      for (int q = 0; q < nrows_in; ++q) {
+        const int m = q >> 1;
+        const bool even = (q & 1) == 0;
+        const bool has_new = even && m < nrows_out;          // first contribution to output row m
+        const int lo = even ? (m >= 1 ? m - 1 : m) : m, hi = even ? (m < nrows_out ? m : m - 1) : m;
+        if (has_new) mbar_wait(tempty_bar(m % R), ((m / R) & 1) ^ 1, p.err, 3);
+        mbar_wait(full_bar(slot), ph, p.err, 4);
+        tc_fence_after();
+        const int pos_lo = lo % R, nwin = hi - lo + 1;
+        const int n1 = min(nwin, R - pos_lo), n2 = nwin - n1;      // the window may cross the end of the ring
+        const uint32_t d1 = tmem_base + static_cast<uint32_t>(pos_lo) * N, d2 = tmem_base;
+        const uint32_t idesc1 = make_idesc_f16_m128(static_cast<uint32_t>(N * n1));
+        const uint32_t b1 = even ? bE0 + static_cast<uint32_t>(lo == m ? N : 0) : bO0, b2 = b1 + static_cast<uint32_t>(N * n1);
+        const uint32_t bstep = even ? bE_step : bO_step;
+        const uint32_t a16 = ring16 + slot * slot16;
+        if (elect_one()) {
+          if (has_new)                                         // bias step: initialises the accumulator of the newest row
+            tc_mma_f16(tmem_base + static_cast<uint32_t>(m % R) * N, ones_desc, bias_desc, idesc, 0u);
+          static_for<0, SPD>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr uint32_t a_off16 = kind_a_off(KIND, KCH, i) >> 4;
+            const uint64_t ad = mkdesc((a16 + a_off16) | a_lbo);
+            tc_mma_f16(d1, ad, mkdesc(b1 + i * bstep), idesc1, 1u);
+            if (n2) tc_mma_f16(d2, ad, mkdesc(b2 + i * bstep), idesc, 1u);
+          });
+          tc_commit(empty_bar(slot));                          // every input row is read exactly once
+          if (even && m >= 1) tc_commit(tfull_bar((m - 1) % R));       // output row m-1 is complete
+        }
+        __syncwarp();
+        if (++slot == ring_n) { slot = 0; ph ^= 1; }
+      }
+    } else {
     int waited = -1;
     int base_slot = 0, base_ph = 0;              // ring slot / phase of input row t*stride
     int sslot = 0, sph = 0;                      // stage-0 ring (SFTG)
@@ -379,6 +427,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       }
       base_slot += STRIDE;
       if (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
+    }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant
@@ -517,7 +566,8 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         if (p.has_raw) raw.init(p.raw, x);
       }
       for (int t = 0; t < nrows_out; ++t) {
-        const int stage = t & 1, oy = oy0 + t;
+        const int stage = FOLD ? t % kFoldR : t & 1, oy = oy0 + t;
+        const uint32_t tpar = FOLD ? (t / kFoldR) & 1 : (t >> 1) & 1;
         uint4 r4[AUX ? CH : 1], q4[AUX ? CH : 1], s4[AUX ? CH : 1], t4[AUX ? CH : 1];
         if constexpr (AUX) {
           if (xin) {       // request the row's auxiliary operands before waiting for the accumulator
@@ -529,7 +579,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
             }
           }
         }
-        mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
+        mbar_wait(tfull_bar(stage), tpar, p.err, 5);
         tc_fence_after();
         float v[COLS];
         float sv[SFTG ? COLS : 1], tv[SFTG ? COLS : 1];

@@ -181,6 +181,7 @@ struct ConvLaunch {
   ConvParams p;
   int kind = 0, kch = 0;
   bool sftg = false;
+  bool fold = false;                    // row-folded stride-2 3x3 (conv_p8_kernel<..., FOLD>); weights are the ".fold2" pack
   int N;
   int mode;
   dim3 grid;
@@ -344,6 +345,7 @@ struct Epi {
   __half* planar = nullptr;
   int out_split = 0;                // output chunks >= out_split are stored to out2 instead
   const P8* out2 = nullptr;
+  bool fold = false;                // weights are row-folded (".fold2"): plain stride-2 3x3 convs
   int zsplit = 0;                   // > 1: this launch runs `zsplit` convs on the same input (weights / outputs below)
   const __half* wpk_z[3] = {nullptr, nullptr, nullptr};
   const P8* out_z[3] = {nullptr, nullptr, nullptr};
@@ -391,8 +393,13 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   p.planar_plane = static_cast<long>(Ho) * Wo;
   p.planar_W = Wo;
   p.err = c->d_err;
-  const int min_ring = p.ks + 1;
-  const size_t budget = (mode == STORE_PS && p.wpk2) ? 224 * 1024 : 200 * 1024;
+  if (e.fold) {
+    if (kind != IN_PAR3x3S2 || mode != STORE_P8 || e.sft_s0 || N > 64 || e.res || e.res2 || e.sft || e.raw)
+      return fail(c, "conv " + name + ": row folding needs a plain stride-2 3x3 conv");
+    L.fold = true;
+  }
+  const int min_ring = e.fold ? 2 : p.ks + 1;
+  const size_t budget = (e.fold || (mode == STORE_PS && p.wpk2)) ? 224 * 1024 : 200 * 1024;
   const size_t fixed = kSmemHeader + ((p.w_bytes + 127) & ~127) + conv_sftg_bytes(p, mode == STORE_PS);
   int ring = static_cast<int>((budget - fixed) / p.slot_bytes);
   // ring depth: rows in use (ks) + prefetch; shallow rings keep shared memory small so that more CTAs share an SM
@@ -401,6 +408,7 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   // share an SM.
   const int prefetch = std::max(1, std::min(5, (24 * 1024) / p.slot_bytes));
   ring = std::min(ring, env_int(p.ks == 1 ? "HDRTV_RING_1x1" : "HDRTV_RING_3x3", std::max(p.ks == 1 ? 3 : 4, p.ks + prefetch)));
+  if (e.fold) ring = std::min(static_cast<int>((budget - fixed) / p.slot_bytes), env_int("HDRTV_RING_FOLD", 6));   // all prefetch
   if (ring < min_ring) ring = min_ring;
   if (ring > kMaxRing) ring = kMaxRing;
   // Experiment knob (off): give a kernel that is alone on its SM every row slot that still fits.  Measured SLOWER
@@ -447,16 +455,16 @@ static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false>
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>,
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG>, L.grid, kConvThreads, L.smem, s, L.p);
+  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>, L.grid, kConvThreads, L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>
@@ -482,6 +490,11 @@ static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
   if (L.c2x) return launch_conv2x(L, s);
+  if (L.fold) {     // row-folded stride-2 3x3 convs of the condition pyramid
+    if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 64) return launch_conv_t<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, true>(L, s);
+    if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 16) return launch_conv_t<IN_PAR3x3S2, 8, 16, STORE_P8, false, false, true>(L, s);
+    return cudaErrorInvalidValue;
+  }
   if (L.sftg) {     // in-kernel SFT generator: 32-channel outputs
     if (L.mode == STORE_PS && L.N == 128 && L.kind == IN_NAT3x3 && L.kch == 4)
       return launch_conv_t<IN_NAT3x3, 4, 128, STORE_PS, true, true>(L, s);
@@ -720,6 +733,26 @@ static int pack_fold(Ctx* c, const std::string& name, int spd, int N) {
   if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
   return 0;
 }
+// Row-folded copy of a packed stride-2 3x3 layer for conv_p8_kernel<..., FOLD>: even input rows use SPD steps of
+// [dy=2 | dy=0] (2N rows each), odd input rows SPD steps of dy=1 (N rows), then the unchanged bias step.
+static int pack_fold2(Ctx* c, const std::string& name, int spd, int N) {
+  const std::vector<__half>& pk = c->host_pk.at(name);
+  if (pk.size() != static_cast<size_t>(3 * spd + 1) * N * 16) return fail(c, "pack_fold2 " + name + ": unexpected packed size");
+  std::vector<__half> out(pk.size(), __float2half(0.f));
+  const long odd0 = static_cast<long>(spd) * 2 * N * 16, bias0 = static_cast<long>(spd) * 3 * N * 16;
+  for (int i = 0; i < spd; ++i)
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < 16; ++k) {
+        out[bpack_index(2 * N, i, n, k)] = pk[bpack_index(N, 2 * spd + i, n, k)];
+        out[bpack_index(2 * N, i, N + n, k)] = pk[bpack_index(N, i, n, k)];
+        out[odd0 + bpack_index(N, i, n, k)] = pk[bpack_index(N, spd + i, n, k)];
+      }
+  for (int i = 0; i < N * 16; ++i) out[bias0 + i] = pk[bias0 + i];
+  const std::string key = name + ".fold2";
+  c->wpk[key] = w_upload(c, out.data(), out.size());
+  if (!c->wpk[key]) return fail(c, "weight upload failed for " + key);
+  return 0;
+}
 static std::function<float(int)> bias_fn(Ctx* c, const std::string& name) {
   const HostTensor& t = W(c, name + ".bias");
   const float* d = t.v.data();
@@ -811,6 +844,10 @@ static int pack_all_fp16(Ctx* c) {
   r |= pack_std(c, "LE.CondNet4.0", IN_PAR3x3S2, 64, 64);
   r |= pack_std(c, "LE.CondNet4.2", IN_PAR3x3S2, 64, 64);
   r |= pack_std(c, "LE.CondNet4.4", IN_PAR3x3S2, 64, 16);
+  if (!r) {
+    for (const char* n : {"LE.CondNet2.0", "LE.CondNet3.0", "LE.CondNet3.2", "LE.CondNet4.0", "LE.CondNet4.2"}) r |= pack_fold2(c, n, 12, 64);
+    r |= pack_fold2(c, "LE.CondNet4.4", 12, 16);
+  }
   r |= pack_std(c, "LE.conv_first", IN_NAT3x3_C8, 8, 32);
   r |= pack_std(c, "LE.HR_conv1", IN_NAT3x3, 32, 32);
   r |= pack_std(c, "LE.HR_conv2", IN_NAT3x3, 32, 32);
@@ -1144,9 +1181,19 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   if (!V0.base || !U1.base) return fail(c, "workspace allocation failed (P8)");
 
   auto wk = [&](const std::string& k) { return c->wpk.at(k); };
+  // Row-folded stride-2 convs of the condition pyramid: experiment, off.  A third fewer MMAs, but these kernels are bound
+  // by the input ring (35 KB rows, 4 slots next to 74 KB of weights: bytes in flight / loaded HBM latency), not by the
+  // tensor pipe: CondNet{2,3,4}.0 571 -> 662 us under ncu at 4K (same DRAM bytes, same tensor-active cycles), the
+  // single convs unchanged (already at 5.2 TB/s).
+  const bool use_fold2 = env_int("HDRTV_FOLD2", 0) != 0;
   auto std_conv = [&](std::vector<ConvLaunch>& plan, const std::string& name, InKind kind, const P8& in, int cin, int N,
                       int mode, const P8& out, int Ho, int Wo, const Epi& e) {
     return make_conv(c, plan, name, kind, in, 0, std::max(1, cin / 8), N, mode, wk(name), out, Ho, Wo, e);
+  };
+  auto fold_conv = [&](std::vector<ConvLaunch>& plan, const std::string& name, const P8& in, int N, const P8& out, int Ho,
+                       int Wo, Epi e) {       // plain stride-2 3x3 on 64 channels
+    e.fold = use_fold2;
+    return make_conv(c, plan, name, IN_PAR3x3S2, in, 0, 8, N, STORE_P8, wk(use_fold2 ? name + ".fold2" : name), out, Ho, Wo, e);
   };
   int r = 0;
   Epi relu; relu.act = ACT_RELU;
@@ -1197,15 +1244,17 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     // the three stride-2 3x3 convs that read `cond` share one launch (cond is fetched from HBM once)
     Epi e = lrelu;
     e.zsplit = 3;
-    e.wpk_z[0] = wk("LE.CondNet2.0"); e.wpk_z[1] = wk("LE.CondNet3.0"); e.wpk_z[2] = wk("LE.CondNet4.0");
+    e.fold = use_fold2;
+    const std::string fs = use_fold2 ? ".fold2" : "";
+    e.wpk_z[0] = wk("LE.CondNet2.0" + fs); e.wpk_z[1] = wk("LE.CondNet3.0" + fs); e.wpk_z[2] = wk("LE.CondNet4.0" + fs);
     e.out_z[0] = &D1; e.out_z[1] = &E1; e.out_z[2] = &E1b;
     r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, e);
     L.back().name = "LE.CondNet{2,3,4}.0";
     r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
     r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
-    r |= std_conv(L, "LE.CondNet3.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, E2, H2, W2, lrelu);
+    r |= fold_conv(L, "LE.CondNet3.2", E1, 64, E2, H2, W2, lrelu);
     r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
-    r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1b, 64, 64, STORE_P8, F2, H2, W2, lrelu);
+    r |= fold_conv(L, "LE.CondNet4.2", E1b, 64, F2, H2, W2, lrelu);
   } else {
     r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
     r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
@@ -1216,7 +1265,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     r |= std_conv(L, "LE.CondNet4.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
     r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, F2, H2, W2, lrelu);
   }
-  r |= std_conv(L, "LE.CondNet4.4", IN_PAR3x3S2, F2, 64, 16, STORE_P8, cond4, H3, W3, none);
+  r |= fold_conv(L, "LE.CondNet4.4", F2, 16, cond4, H3, W3, none);
   // ---- SFT: stage 0 of every SFT layer of a level stacked into one 1x1 conv (LeakyReLU).  Stage 1 (32 -> 64, block
   // diagonal scale|shift) runs inside the consuming conv kernel (SFTG) from the stage-0 map; only the PixelShuffle
   // consumers (up-convs) still read a precomputed scale|shift map.
@@ -1906,7 +1955,7 @@ int hdrtv_mma_probe(hdrtv_t* c, int n, int layout, int vary, int iters, int bloc
 
 int hdrtv_probe(hdrtv_t* c, int kind, int n, int iters, int blocks, int nwarps, int nmma, int groups, float* cycles_per_iter,
                 long long* trace_host) {
-  if (!c || !cycles_per_iter || blocks < 1 || iters < 4 || kind < 0 || kind > 8) return fail(c, "hdrtv_probe: bad argument");
+  if (!c || !cycles_per_iter || blocks < 1 || iters < 4 || kind < 0 || kind > 9) return fail(c, "hdrtv_probe: bad argument");
   cudaSetDevice(c->device);
   long long *d = nullptr, *dtrace = nullptr;
   CK(c, cudaMalloc(&d, sizeof(long long) * blocks));
@@ -1924,7 +1973,7 @@ int hdrtv_probe(hdrtv_t* c, int kind, int n, int iters, int blocks, int nwarps, 
     cudaFuncSetAttribute(probe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   \
     probe_kernel<K><<<blocks, threads, 96 * 1024>>>(a);                                               \
     break;
-  switch (kind) { HDRTV_PROBE_K(0) HDRTV_PROBE_K(1) HDRTV_PROBE_K(2) HDRTV_PROBE_K(3) HDRTV_PROBE_K(4) HDRTV_PROBE_K(5) HDRTV_PROBE_K(6) HDRTV_PROBE_K(7) HDRTV_PROBE_K(8) }
+  switch (kind) { HDRTV_PROBE_K(0) HDRTV_PROBE_K(1) HDRTV_PROBE_K(2) HDRTV_PROBE_K(3) HDRTV_PROBE_K(4) HDRTV_PROBE_K(5) HDRTV_PROBE_K(6) HDRTV_PROBE_K(7) HDRTV_PROBE_K(8) HDRTV_PROBE_K(9) }
 #undef HDRTV_PROBE_K
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<long long> h(blocks);

@@ -225,12 +225,34 @@ __global__ void __launch_bounds__(1024) probe_kernel(const ProbeArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) ad[k] = (ad[k] & 0xFFFFFFFF00000000ull) | lows[k];
         }
+        const uint32_t d2 = (f & 64) ? d + 128 : d;        // flag 64: consecutive MMAs alternate between two accumulators
         tc_mma_f16(d, ad[0], bd, idesc, (f & 16) ? 0u : 1u);
-        tc_mma_f16(d, ad[1], bd, idesc, 1u);
+        tc_mma_f16(d2, ad[1], bd, idesc, 1u);
         tc_mma_f16(d, ad[2], bd, idesc, 1u);
-        tc_mma_f16(d, ad[3], bd, idesc, 1u);
+        tc_mma_f16(d2, ad[3], bd, idesc, 1u);
         tc_mma_f16(d, ones, bd, idesc, 1u);
         if (f & 1) tc_commit(smem_u32(&bars[9 + (i & 3)]));
+      }
+      tc_commit(smem_u32(&bars[8]));
+      mbar_wait(smem_u32(&bars[8]), 0, nullptr, 0);
+      a.cycles[blockIdx.x] = clock64() - t0;
+    }
+  }
+  else if constexpr (KIND == 9) {
+    // operand-stream cost: an unrolled batch of 12 MMAs per iteration whose A tiles (a.nmma & 1) and B tiles
+    // (a.nmma & 2) are all DIFFERENT shared-memory regions, as in a real K loop; accumulators alternate when a.nmma & 4.
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc_f16(128, N);
+      const int f = a.nmma;
+      const uint32_t astep = (f & 1) ? ((2 * kPlaneBytes) >> 4) : 0u;          // 12 x 4352 B = 52 KB
+      const uint32_t bstep = (f & 2) ? static_cast<uint32_t>((N * 32) >> 4) : 0u;   // 6 distinct tiles of N*32 B (N=128: 24 KB)
+      const uint64_t ad0 = make_smem_desc(a0, kPlaneBytes, 128);
+      const uint64_t bd0 = make_smem_desc(smem_u32(smem) + 54 * 1024, N * 16, 128);
+      const uint32_t dalt = (f & 4) ? 128u : 0u;
+      const long long t0 = clock64();
+      for (int i = 0; i < a.iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) tc_mma_f16(tm + ((k & 1) ? dalt : 0u), ad0 + k * astep, bd0 + (k % 6) * bstep, idesc, 1u);
       }
       tc_commit(smem_u32(&bars[8]));
       mbar_wait(smem_u32(&bars[8]), 0, nullptr, 0);

@@ -22,3 +22,10 @@ for n in (16, 32, 48, 64, 96, 128, 192, 256):
     for pat in (0, 1, 2):
         row.append(net.probe(7, n=n, iters=2000, nmma=pat, groups=0) / 5)
     print(f"  N={n:3d}: " + "  ".join(f"{v:6.1f}" for v in row))
+print("same, but consecutive MMAs alternate between two accumulators (no accumulate-after-accumulate dependency)")
+for n in (16, 32, 64, 96, 128):
+    print(f"  N={n:3d}: {net.probe(7, n=n, iters=2000, nmma=0, groups=64) / 5:6.1f}")
+print("unrolled batches of 12 MMAs, cycles per MMA: same A,B / distinct A / distinct B / distinct A and B / distinct A,B + alternating accumulators")
+for n in (16, 32, 48, 64, 96, 128):
+    row = [net.probe(9, n=n, iters=500, nmma=f) / 12 for f in (0, 1, 2, 3, 7)]
+    print(f"  N={n:3d}: " + "  ".join(f"{v:6.1f}" for v in row))
