@@ -327,7 +327,7 @@ static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   const int zs = p.zsplit > 1 ? p.zsplit : 1;
   int nb = std::max(1, slots / (strips * z * zs));
   int band = (p.Ho + nb - 1) / nb;
-  band = std::max(band, env_int("HDRTV_MIN_BAND", 4));
+  band = std::max(band, env_int("HDRTV_MIN_BAND", 2));
   band = std::min(band, p.Ho);
   p.band = band;
   L.grid = dim3(strips * zs, (p.Ho + band - 1) / band, z);
@@ -596,7 +596,7 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
   p.strips = (Wd + kC2Strip - 1) / kC2Strip;
   const long items = static_cast<long>(p.strips) * H;
   // one CTA per SM, each a contiguous range of (strip, row) items; at least 8 rows per CTA so the two halo rows stay cheap
-  const long ctas = std::max<long>(1, std::min<long>(env_int("HDRTV_C2X_CTAS", 148), items / 8));
+  const long ctas = std::max<long>(1, std::min<long>(env_int("HDRTV_C2X_CTAS", 148), items / env_int("HDRTV_C2X_MIN_ROWS", 8)));
   const int band = static_cast<int>((items + ctas - 1) / ctas);
   p.band = band;
   L.grid = dim3(static_cast<unsigned>(ctas), 1, 1);
