@@ -34,7 +34,7 @@ constexpr int kSlotCols = 96;                    // TMEM columns per row slot: 6
 // ---- chain programs (compile-time layer tables) -------------------------------------------------------------------
 // store: 0 none, 1 P8, 2 planar fp16 (3 channels) + single-chunk P8.   act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).
 struct ProgAGCM {
-  static constexpr int L = 3, KS = 1;
+  static constexpr int L = 3, KS = 1, IN_PLANES = 1;
   static constexpr int N[L] = {64, 64, 16};
   static constexpr int STEPS[L] = {1, 4, 4};          // K/16 MMAs per layer (layer 0: the input side's tap steps)
   static constexpr int APLANE[L] = {0, 0, 0};
@@ -46,7 +46,7 @@ struct ProgAGCM {
   static constexpr int A0_LBO[1] = {16};
 };
 struct ProgCond {
-  static constexpr int L = 6, KS = 3;
+  static constexpr int L = 6, KS = 3, IN_PLANES = 1;
   static constexpr int N[L] = {64, 64, 64, 64, 64, 16};
   static constexpr int STEPS[L] = {6, 4, 4, 4, 4, 4};
   static constexpr int APLANE[L] = {0, 0, 0, 0, 0, 0};
@@ -62,7 +62,7 @@ struct ProgCond {
 // C1STORE = 1 also stores cond1 (only a debugging output once its sole consumer, the SFT stage 0, is the next step).
 template <int S0STORE, int C1STORE = 0>
 struct ProgCondSft {
-  static constexpr int L = 7, KS = 3;
+  static constexpr int L = 7, KS = 3, IN_PLANES = 1;
   static constexpr int N[L] = {64, 64, 64, 64, 64, 16, 64};
   static constexpr int STEPS[L] = {6, 4, 4, 4, 4, 4, 1};
   static constexpr int APLANE[L] = {0, 0, 0, 0, 0, 0, 0};
@@ -71,6 +71,33 @@ struct ProgCondSft {
   static constexpr int ACT[L] = {2, 2, 2, 2, 2, 0, 2};
   static constexpr int A0_OFF[2] = {0, 32};
   static constexpr int A0_LBO[2] = {16, 16};
+};
+// Tails of the condition pyramid, one launch per level: the 1x1 convs that follow the stride-2 conv of CondNet2 / CondNet3
+// and stage 0 of the level's four SFT layers (16 -> 4 x 32 channels, LeakyReLU), split into two 64-channel steps that both
+// read the 16-channel condition map left in the slot's operand columns.  Layer 0 is a 1x1 conv on the 64-channel row in
+// the ring (eight channel-chunk planes per slot).  The last step stores chunks 0-3 next to the first half and chunks
+// 4-7 to the parity-split home of the layer an up-conv applies (STORE 3).        (HDRUNet3T1_arch.py:40-62, arch_util.py:63-72)
+struct ProgTail2 {            // CondNet2.2 (64->64, LeakyReLU) -> CondNet2.4 (64->16) -> stage 0 a -> stage 0 b
+  static constexpr int L = 4, KS = 1, IN_PLANES = 8;
+  static constexpr int N[L] = {64, 16, 64, 64};
+  static constexpr int STEPS[L] = {4, 4, 1, 1};
+  static constexpr int APLANE[L] = {0, 0, 0, 0};
+  static constexpr int WRITE[L] = {1, 1, 0, 0};
+  static constexpr int STORE[L] = {0, 0, 1, 3};
+  static constexpr int ACT[L] = {2, 0, 2, 2};
+  static constexpr int A0_OFF[4] = {16, 16 + 2 * kPlaneBytes, 16 + 4 * kPlaneBytes, 16 + 6 * kPlaneBytes};
+  static constexpr int A0_LBO[4] = {kPlaneBytes, kPlaneBytes, kPlaneBytes, kPlaneBytes};
+};
+struct ProgTail3 {            // CondNet3.4 (64->16) -> stage 0 a -> stage 0 b
+  static constexpr int L = 3, KS = 1, IN_PLANES = 8;
+  static constexpr int N[L] = {16, 64, 64};
+  static constexpr int STEPS[L] = {4, 1, 1};
+  static constexpr int APLANE[L] = {0, 0, 0};
+  static constexpr int WRITE[L] = {1, 0, 0};
+  static constexpr int STORE[L] = {0, 1, 3};
+  static constexpr int ACT[L] = {0, 2, 2};
+  static constexpr int A0_OFF[4] = {16, 16 + 2 * kPlaneBytes, 16 + 4 * kPlaneBytes, 16 + 6 * kPlaneBytes};
+  static constexpr int A0_LBO[4] = {kPlaneBytes, kPlaneBytes, kPlaneBytes, kPlaneBytes};
 };
 template <class P>
 __host__ __device__ constexpr int prog_w_off(int l) {   // byte offset of layer l's packed weights (steps + bias step)

@@ -615,7 +615,7 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
 }
 
 // ---- fused layer chains (chain_p8.cuh) -----------------------------------------------------------
-enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3, PROG_COND_SFT3_DBG = 4 };
+enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3, PROG_COND_SFT3_DBG = 4, PROG_TAIL2 = 5, PROG_TAIL3 = 6 };
 
 template <class Prog>
 static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int prog_id, InKind kind, const P8& in,
@@ -629,7 +629,7 @@ static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string
   std::vector<StepK> wk;
   build_input_side(kind, in, 0, kchunks, cp.base, wk);
   ConvParams& p = cp.base;
-  if (p.n_steps != Prog::STEPS[0] || p.ks != Prog::KS || p.stride != 1 || p.slot_bytes != kPlaneBytes)
+  if (p.n_steps != Prog::STEPS[0] || p.ks != Prog::KS || p.stride != 1 || p.slot_bytes != Prog::IN_PLANES * kPlaneBytes)
     return fail(c, "chain " + name + ": input side does not match the chain program");
   if (static_cast<int>(outs.size()) != Prog::L) return fail(c, "chain " + name + ": one output slot per layer expected");
   bool planar = false;
@@ -690,6 +690,8 @@ static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
     case PROG_COND_SFT1: return launch_chain_t<ProgCondSft<1, 1>>(L, s);
     case PROG_COND_SFT3: return launch_chain_t<ProgCondSft<3>>(L, s);
     case PROG_COND_SFT3_DBG: return launch_chain_t<ProgCondSft<3, 1>>(L, s);
+    case PROG_TAIL2: return launch_chain_t<ProgTail2>(L, s);
+    case PROG_TAIL3: return launch_chain_t<ProgTail3>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -883,6 +885,29 @@ static int pack_all_fp16(Ctx* c) {
   }
   r |= pack_sft_stage0(c, "sft0.L1", kSftL1, 4);
   r |= pack_sft_stage0(c, "sft0.L2", kSftL2, 4);
+  if (!r) {   // pyramid tails as chains: [CondNet2.2, CondNet2.4 | CondNet3.4] + the level's stage 0 as two 64-channel halves
+    auto half = [&](const char* const* names) {     // stage 0 of two SFT layers: [scale0 | shift0] x 2 = 64 outputs on 16 channels
+      std::vector<WeightFn> fs;
+      std::vector<std::function<float(int)>> bs;
+      for (int i = 0; i < 2; ++i) {
+        fs.push_back(conv_weight_fn(c, std::string(names[i]) + ".SFT_scale_conv0"));
+        fs.push_back(conv_weight_fn(c, std::string(names[i]) + ".SFT_shift_conv0"));
+        bs.push_back(bias_fn(c, std::string(names[i]) + ".SFT_scale_conv0"));
+        bs.push_back(bias_fn(c, std::string(names[i]) + ".SFT_shift_conv0"));
+      }
+      WeightFn wf = [fs](int nn, int ci, int tap) { return fs[nn / 16](nn % 16, ci, tap); };
+      auto bf = [bs](int nn) { return bs[nn / 16](nn % 16); };
+      return pack_layer_host(IN_NAT1x1, 2, 64, wf, bf);
+    };
+    auto cat = [&](const std::string& key, std::vector<std::vector<__half>> parts) {
+      std::vector<__half> all;
+      for (auto& v : parts) all.insert(all.end(), v.begin(), v.end());
+      c->wpk[key] = w_upload(c, all.data(), all.size());
+      if (!c->wpk[key]) r |= fail(c, "weight upload failed for " + key);
+    };
+    cat("chain.tail2", {c->host_pk.at("LE.CondNet2.2"), c->host_pk.at("LE.CondNet2.4"), half(kSftL1), half(kSftL1 + 2)});
+    cat("chain.tail3", {c->host_pk.at("LE.CondNet3.4"), half(kSftL2), half(kSftL2 + 2)});
+  }
   r |= pack_sft_stage0(c, "sft0.L3a", kSftL3, 4);
   r |= pack_sft_stage0(c, "sft0.L3b", kSftL3 + 4, 4);
   for (auto n : kSftL0) r |= pack_sft_stage1(c, n);
@@ -1201,6 +1226,9 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   Epi none;
   // ---- AGCM MLP (weights folded per frame by agcm_head_kernel)
   const bool use_chain = env_int("HDRTV_CHAIN", 1) != 0;
+  // pyramid tails (1x1 convs after the stride-2 conv + the level's SFT stage 0) as one chain launch per level
+  const bool use_tail = use_chain && use_sftg && env_int("HDRTV_ZFUSE", 1) != 0 && env_int("HDRTV_CHAIN_TAIL", 1) != 0;
+  P8 S1hi, S2hi;
   if (use_chain) {
     r |= make_chain_t<ProgAGCM>(c, c->plan_agcm, "AGCM.chain", PROG_AGCM, IN_NAT1x1_C8, c->xP8, 1, {nullptr, nullptr, &agP8},
                                 c->d_agpk[0], H, Wd);
@@ -1250,10 +1278,22 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     e.out_z[0] = &D1; e.out_z[1] = &E1; e.out_z[2] = &E1b;
     r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, e);
     L.back().name = "LE.CondNet{2,3,4}.0";
-    r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
-    r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
+    if (use_tail) {   // CondNet2.2 -> CondNet2.4 -> stage 0 of the four level-1 SFT layers in one launch (cond2 is never stored)
+      S1hi = S1; S1hi.base = S1.base + static_cast<long>(8) * S1.Wp * 8;       // view: chunk planes 8.. of every row
+      r |= make_chain_t<ProgTail2>(c, L, "LE.CondNet2.2+2.4+sft0.L1", PROG_TAIL2, IN_NAT1x1, D1, 8, {nullptr, nullptr, &S1, &S1hi},
+                                   wk("chain.tail2"), H1, W1, &S1ps);
+    } else {
+      r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
+      r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
+    }
     r |= fold_conv(L, "LE.CondNet3.2", E1, 64, E2, H2, W2, lrelu);
-    r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
+    if (use_tail) {
+      S2hi = S2; S2hi.base = S2.base + static_cast<long>(8) * S2.Wp * 8;
+      r |= make_chain_t<ProgTail3>(c, L, "LE.CondNet3.4+sft0.L2", PROG_TAIL3, IN_NAT1x1, E2, 8, {nullptr, &S2, &S2hi},
+                                   wk("chain.tail3"), H2, W2, &S2ps);
+    } else {
+      r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
+    }
     r |= fold_conv(L, "LE.CondNet4.2", E1b, 64, F2, H2, W2, lrelu);
   } else {
     r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
@@ -1276,7 +1316,8 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     // Sps: parity-split home of the group's last layer (the one an up-conv applies through its PixelShuffle store)
     Epi e0 = lrelu;
     if (use_sftg && Sps) { e0.out_split = 4 * (n - 1); e0.out2 = Sps; }
-    if (!(use_chain && key == "sft0.L0"))     // the full-resolution stage 0 is the last step of the cond chain
+    // the full-resolution stage 0 is the last step of the cond chain, levels 1 and 2 the last steps of the pyramid tails
+    if (!(use_chain && key == "sft0.L0") && !(use_tail && (key == "sft0.L1" || key == "sft0.L2")))
       r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), S, h, w, e0);
     for (int i = 0; i < n; ++i) {
       const std::string nm = names[i];
@@ -1377,7 +1418,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     const std::string& n = A.name;
     const bool tail = n == "LE.CondNet2.2" || n == "LE.CondNet2.4" || n == "LE.CondNet3.2" || n == "LE.CondNet3.4" ||
                       n == "LE.CondNet4.2" || n == "LE.CondNet4.4" || n == "sft0.L1" || n == "sft0.L2" || n == "sft0.L3a" ||
-                      n == "sft0.L3b";
+                      n == "sft0.L3b" || n == "LE.CondNet2.2+2.4+sft0.L1" || n == "LE.CondNet3.4+sft0.L2";
     if (tail && env_int("HDRTV_ZFUSE", 1)) A.branch = 1;
     if (n == "LE.down_conv1") A.join = true;
   }
