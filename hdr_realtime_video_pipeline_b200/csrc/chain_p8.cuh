@@ -99,6 +99,17 @@ struct ProgTail3 {            // CondNet3.4 (64->16) -> stage 0 a -> stage 0 b
   static constexpr int A0_OFF[4] = {16, 16 + 2 * kPlaneBytes, 16 + 4 * kPlaneBytes, 16 + 6 * kPlaneBytes};
   static constexpr int A0_LBO[4] = {kPlaneBytes, kPlaneBytes, kPlaneBytes, kPlaneBytes};
 };
+struct ProgTail4 {            // level 3: stage 0 of its eight SFT layers (16 -> 8 x 32) as four 64-channel steps.  Layer 0 is an
+  static constexpr int L = 5, KS = 1, IN_PLANES = 2;   // identity 1x1 that moves the 16-channel map from the ring into the operand columns
+  static constexpr int N[L] = {16, 64, 64, 64, 64};
+  static constexpr int STEPS[L] = {1, 1, 1, 1, 1};
+  static constexpr int APLANE[L] = {0, 0, 0, 0, 0};
+  static constexpr int WRITE[L] = {1, 0, 0, 0, 0};
+  static constexpr int STORE[L] = {0, 1, 1, 1, 1};
+  static constexpr int ACT[L] = {0, 2, 2, 2, 2};
+  static constexpr int A0_OFF[1] = {16};
+  static constexpr int A0_LBO[1] = {kPlaneBytes};
+};
 template <class P>
 __host__ __device__ constexpr int prog_w_off(int l) {   // byte offset of layer l's packed weights (steps + bias step)
   int off = 0;

@@ -615,7 +615,7 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
 }
 
 // ---- fused layer chains (chain_p8.cuh) -----------------------------------------------------------
-enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3, PROG_COND_SFT3_DBG = 4, PROG_TAIL2 = 5, PROG_TAIL3 = 6 };
+enum ChainProgId { PROG_AGCM = 0, PROG_COND = 1, PROG_COND_SFT1 = 2, PROG_COND_SFT3 = 3, PROG_COND_SFT3_DBG = 4, PROG_TAIL2 = 5, PROG_TAIL3 = 6, PROG_TAIL4 = 7 };
 
 template <class Prog>
 static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int prog_id, InKind kind, const P8& in,
@@ -692,6 +692,7 @@ static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
     case PROG_COND_SFT3_DBG: return launch_chain_t<ProgCondSft<3, 1>>(L, s);
     case PROG_TAIL2: return launch_chain_t<ProgTail2>(L, s);
     case PROG_TAIL3: return launch_chain_t<ProgTail3>(L, s);
+    case PROG_TAIL4: return launch_chain_t<ProgTail4>(L, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -907,6 +908,9 @@ static int pack_all_fp16(Ctx* c) {
     };
     cat("chain.tail2", {c->host_pk.at("LE.CondNet2.2"), c->host_pk.at("LE.CondNet2.4"), half(kSftL1), half(kSftL1 + 2)});
     cat("chain.tail3", {c->host_pk.at("LE.CondNet3.4"), half(kSftL2), half(kSftL2 + 2)});
+    WeightFn ident = [](int nn, int ci, int) { return nn == ci ? 1.f : 0.f; };
+    cat("chain.tail4", {pack_layer_host(IN_NAT1x1, 2, 16, ident, [](int) { return 0.f; }), half(kSftL3), half(kSftL3 + 2),
+                        half(kSftL3 + 4), half(kSftL3 + 6)});
   }
   r |= pack_sft_stage0(c, "sft0.L3a", kSftL3, 4);
   r |= pack_sft_stage0(c, "sft0.L3b", kSftL3 + 4, 4);
@@ -1228,7 +1232,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   const bool use_chain = env_int("HDRTV_CHAIN", 1) != 0;
   // pyramid tails (1x1 convs after the stride-2 conv + the level's SFT stage 0) as one chain launch per level
   const bool use_tail = use_chain && use_sftg && env_int("HDRTV_ZFUSE", 1) != 0 && env_int("HDRTV_CHAIN_TAIL", 1) != 0;
-  P8 S1hi, S2hi;
+  P8 S1hi, S2hi, S3ahi, S3bhi;
   if (use_chain) {
     r |= make_chain_t<ProgAGCM>(c, c->plan_agcm, "AGCM.chain", PROG_AGCM, IN_NAT1x1_C8, c->xP8, 1, {nullptr, nullptr, &agP8},
                                 c->d_agpk[0], H, Wd);
@@ -1317,7 +1321,13 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     Epi e0 = lrelu;
     if (use_sftg && Sps) { e0.out_split = 4 * (n - 1); e0.out2 = Sps; }
     // the full-resolution stage 0 is the last step of the cond chain, levels 1 and 2 the last steps of the pyramid tails
-    if (!(use_chain && key == "sft0.L0") && !(use_tail && (key == "sft0.L1" || key == "sft0.L2")))
+    if (use_tail && key == "sft0.L3a") {      // both level-3 groups in one chain launch
+      S3ahi = S3a; S3ahi.base = S3a.base + static_cast<long>(8) * S3a.Wp * 8;
+      S3bhi = S3b; S3bhi.base = S3b.base + static_cast<long>(8) * S3b.Wp * 8;
+      r |= make_chain_t<ProgTail4>(c, L, "sft0.L3", PROG_TAIL4, IN_NAT1x1, cond, 2, {nullptr, &S3a, &S3ahi, &S3b, &S3bhi},
+                                   wk("chain.tail4"), h, w);
+    }
+    if (!(use_chain && key == "sft0.L0") && !(use_tail && (key == "sft0.L1" || key == "sft0.L2" || key == "sft0.L3a" || key == "sft0.L3b")))
       r |= make_conv(c, L, key, IN_NAT1x1, cond, 0, 2, 32 * n, STORE_P8, wk(key), S, h, w, e0);
     for (int i = 0; i < n; ++i) {
       const std::string nm = names[i];
@@ -1418,7 +1428,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     const std::string& n = A.name;
     const bool tail = n == "LE.CondNet2.2" || n == "LE.CondNet2.4" || n == "LE.CondNet3.2" || n == "LE.CondNet3.4" ||
                       n == "LE.CondNet4.2" || n == "LE.CondNet4.4" || n == "sft0.L1" || n == "sft0.L2" || n == "sft0.L3a" ||
-                      n == "sft0.L3b" || n == "LE.CondNet2.2+2.4+sft0.L1" || n == "LE.CondNet3.4+sft0.L2";
+                      n == "sft0.L3b" || n == "LE.CondNet2.2+2.4+sft0.L1" || n == "LE.CondNet3.4+sft0.L2" || n == "sft0.L3";
     if (tail && env_int("HDRTV_ZFUSE", 1)) A.branch = 1;
     if (n == "LE.down_conv1") A.join = true;
   }
