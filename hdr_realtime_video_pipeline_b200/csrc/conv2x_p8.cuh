@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
   constexpr int NA = 32;
   constexpr int SPDA = kind_spd(KINDA, KCHA), NCOPY = kind_copies(KINDA, KCHA);
   constexpr int SPDB = kind_spd(IN_NAT3x3, 4);
-  constexpr int RA = SFTGA ? 6 : 8, RB = SFTGA ? 6 : 8;   // accumulator ring blocks: 3 accumulating + spare ones being drained
+  // accumulator ring blocks: 3 accumulating + spare ones being drained.  With the SFT GEMM's 128 columns TMEM holds 12
+  // blocks of 32: the cheap 3-channel conv A gets by with one spare block, conv B gets the rest.
+  constexpr int RA = !SFTGA ? 8 : (KINDA == IN_NAT3x3_C8 ? 4 : 6), RB = !SFTGA ? 8 : (KINDA == IN_NAT3x3_C8 ? 8 : 6);
   constexpr int CHR = MODEB == STORE_PLANAR ? 1 : NB / 8;  // residual planes per row
   constexpr int RES_SLOT = CHR * kC2ResPlane;
   constexpr uint32_t kTmemCols = 512;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         uint4 r4[CH], q4[CH];
         if (MODEB == STORE_P8 && p.has_res2 && xin) {
 #pragma unroll
-          for (int c = 0; c < CH; ++c) q4[c] = *res2.at(oy, c);
+          for (int c = 0; c < CH; ++c) q4[c] = __ldcg(res2.at(oy, c));
         }
         if (warp == 7) C2X_STAMP(4, g, 0);
         if (p.has_res) {
@@ -497,8 +499,16 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
           const uint4* rs = reinterpret_cast<const uint4*>(rring + rslot * RES_SLOT) + m;
 #pragma unroll
           for (int c = 0; c < CH; ++c) r4[c] = rs[c * kTileM];
+          // Release the slot only once the loads have RETURNED: the barrier address below depends on the loaded
+          // registers (a warp-wide ld.shared completes for all lanes at once).  With a plain arrive the slot could be
+          // refilled by the residual producer's TMA while the ld.shared was still queued behind other shared-memory
+          // traffic: rare rows then carried the residual of row t + 4 (found by scripts/stress_determinism.py when
+          // other kernels share the SM).
+          uint32_t dep = 0;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) dep |= r4[c].x | r4[c].w;
           __syncwarp();
-          if (lane == 0) mbar_arrive(res_empty(rslot));
+          if (lane == 0) mbar_arrive_after(res_empty(rslot), dep);
           if (++rslot == kC2ResRing) { rslot = 0; rph ^= 1; }
         } else {
 #pragma unroll

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       for (int t = 0; t < nrows_out; ++t) {
         const int stage = t & 1, oy = oy0 + t;
         uint4 r4 = make_uint4(0, 0, 0, 0);
-        if (half == 0 && xin && p.has_res) r4 = *res.at(oy, 0);
+        if (half == 0 && xin && p.has_res) r4 = __ldcg(res.at(oy, 0));
         mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
         tc_fence_after();
         float v[8];
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             r4[sub][c] = make_uint4(0, 0, 0, 0);
-            if (p.has_res && ok[sub]) r4[sub][c] = *res[j].at(Y, 2 * half + c);
+            if (p.has_res && ok[sub]) r4[sub][c] = __ldcg(res[j].at(Y, 2 * half + c));
           }
         }
         mbar_wait(tfull_bar(stage), (t >> 1) & 1, p.err, 5);
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
             uint4 s4[2], t4[2];
             if (!SFTG && p.has_sft) {
 #pragma unroll
-              for (int c = 0; c < 2; ++c) { s4[c] = *sft[j].at(Y, 2 * half + c); t4[c] = *sft[j].at(Y, 2 * half + c + 4); }
+              for (int c = 0; c < 2; ++c) { s4[c] = __ldcg(sft[j].at(Y, 2 * half + c)); t4[c] = __ldcg(sft[j].at(Y, 2 * half + c + 4)); }
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -573,9 +573,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
           if (xin) {       // request the row's auxiliary operands before waiting for the accumulator
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-              if (p.has_res) r4[c] = *res.at(oy, j0 + c);
-              if (p.has_res2) q4[c] = *res2.at(oy, j0 + c);
-              if (p.has_sft) { s4[c] = *sft.at(oy, j0 + c); t4[c] = *sft.at(oy, j0 + c + N / 8); }
+              if (p.has_res) r4[c] = __ldcg(res.at(oy, j0 + c));
+              if (p.has_res2) q4[c] = __ldcg(res2.at(oy, j0 + c));
+              if (p.has_sft) { s4[c] = __ldcg(sft.at(oy, j0 + c)); t4[c] = __ldcg(sft.at(oy, j0 + c + N / 8)); }
             }
           }
         }

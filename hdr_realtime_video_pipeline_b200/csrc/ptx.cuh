@@ -21,6 +21,15 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive that is data-dependent on `dep`: used to release a shared-memory slot only after the loads that produced
+// `dep` have returned (a plain arrive is not held back by the warp's outstanding ld.shared instructions).
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep) {
+  // a select on a value that never occurs: ptxas cannot fold it, so the address is not available before `dep` is
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tsetp.eq.u32 q, %1, 0x7FC17FC3;\n\tselp.b32 t, 8, 0, q;\n\tadd.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t}" ::"r"(bar), "r"(dep)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
