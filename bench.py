@@ -48,9 +48,12 @@ KERNEL_MAC_PER_PX = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 1920x1080 from profiles/r1_ncu_top_kernels.md (ncu --set full)
 NCU_TRAFFIC_1080P = {}     # filled from profiles/r1_ncu_top_kernels.json when present (written by scripts/summarise_ncu.py)
+NCU_FRAME_TRAFFIC_1080P = None   # dram read + write bytes of every launch of one 1080p frame (profiles/r1_traffic_1080p.csv)
 try:
     with open(os.path.join(REPO, "profiles", "r1_ncu_top_kernels.json")) as _f:
-        NCU_TRAFFIC_1080P = {k: int(v) for k, v in json.load(_f).get("dram_bytes_per_launch_1080p", {}).items()}
+        _j = json.load(_f)
+        NCU_TRAFFIC_1080P = {k: int(v) for k, v in _j.get("dram_bytes_per_launch_1080p", {}).items()}
+        NCU_FRAME_TRAFFIC_1080P = _j.get("frame_dram_bytes_1080p", {}).get("total")
 except Exception:
     pass
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
@@ -326,13 +329,20 @@ def run_b200_arm(args):
                            "what": "pinned u8 in -> RGB48 in pinned ring slot ready, one frame in flight"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / peaks["tflops"], "traffic": None,
+                         "frac": achieved_tf / peaks["tflops"],
+                         "traffic": (NCU_FRAME_TRAFFIC_1080P if (h, w) == (1080, 1920) and precision == "fp16" else None),
+                         "traffic_note": "DRAM read + write bytes of all launches of one frame (ncu, profiles/r1_traffic_1080p.csv): "
+                                         "inter-layer activations; the frame's algorithmic I/O is 9 B/px",
+                         "hbm": ({"achieved_GBps": NCU_FRAME_TRAFFIC_1080P / (step_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
+                                  "frac": (NCU_FRAME_TRAFFIC_1080P / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None}
+                                 if NCU_FRAME_TRAFFIC_1080P and (h, w) == (1080, 1920) and precision == "fp16" else None),
                          "kernel": "whole hot path of one frame (chain_p8_kernel x2, conv2x_p8_kernel, conv_p8_kernel family, "
                                    "classifier, pre/pack); CUDA events around the timed steps on the launching stream",
                          "algorithmic": f"{FLOP_PER_PX:.0f} FLOP/px x {px} px per frame", "peak_source": peaks["source"],
                          "ms_per_frame": step_ms, "infer_only_ms": infer_ms,
-                         "note": "tcgen05.mma K=16 costs >= 44.6 pipe cycles for any N <= 64 (profiles/r1_tensor_probe.log): "
-                                 "with C_out in {16,32,64} the pipe-bound ceiling of this network is ~0.65 of dense peak",
+                         "note": "tcgen05.mma M=128 K=16 occupies the pipe for max(N/2, 32 + N/4) cycles (operand fetch; "
+                                 "profiles/r1_sync_probe.log): with C_out in {16,32,64} the pipe-bound ceiling of this network is ~0.65 "
+                                 "of dense peak",
                          "top_kernels": top_kernels},
             "clocks": clocks,
             "ranks": [{"rank": r["rank"], "first_frame": r["first_frame"], "n_frames": r["n_frames"]} for r in records],
