@@ -15,6 +15,7 @@ A "step" is one frame through the hot path: uint8 BGR24 -> normalise -> AGCM -> 
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -201,7 +202,8 @@ def run_b200_arm(args):
 
     h, w = WORKLOADS[args.workload]
     precision = "fp32" if args.precision == "fp32" else "fp16"
-    net = hb.HDRTVNetB200(WEIGHTS, device=f"cuda:{local_rank}", precision=precision, warmup_passes=0, use_hg=False)
+    with contextlib.redirect_stdout(sys.stderr):     # the wrapper prints the reference's load banner: stdout carries the JSON line only
+        net = hb.HDRTVNetB200(WEIGHTS, device=f"cuda:{local_rank}", precision=precision, warmup_passes=0, use_hg=False)
     packer = hb.RGB48Packer(dev, ring_frames=3)
     K, Wm = args.steps, max(3, args.warmup)
     n_distinct = 16
@@ -244,39 +246,49 @@ def run_b200_arm(args):
     infer_ms = float(np.mean([a.elapsed_time(b) for a, b in infer_ev]))
 
     # ---- end to end through the public API, host buffers --------------------------------------------
+    # (a) the one-call frame path (HDRTVNetB200.process_rgb48 -> hdrtv_process): pinned u8 frame in, RGB48 in a pinned
+    #     ring slot out, H2D and D2H inside the timed region, two frames in flight
+    # (b) the reference's three calls (preprocess -> infer -> _tensor_to_rgb48_bytes), same buffers
     state = {}
-    pending = []
-    for i in range(Wm):
-        fr = hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(host_frames[i % n_distinct].numpy())), state)
-        fr.release()
-    barrier()
-    e0 = time.perf_counter()
-    checks = []
-    for i in range(K):
-        out = net.infer(net.preprocess(host_frames[i % n_distinct].numpy()))
-        pending.append(hb.tensor_to_rgb48_bytes(out, state))
-        if len(pending) >= 2:                                    # consumer side of the ring: wait + release in order
-            fr = pending.pop(0)
+
+    def e2e_run(submit, in_flight):
+        pending, checks = [], []
+        for i in range(Wm):
+            submit(i).release()
+        barrier()
+        e0 = time.perf_counter()
+        for i in range(K):
+            pending.append(submit(i))
+            if len(pending) >= in_flight:                            # consumer side of the ring: wait + release in order
+                fr = pending.pop(0)
+                checks.append(int(fr.numpy()[h // 2, w // 2, 0]))
+                fr.release()
+        for fr in pending:
             checks.append(int(fr.numpy()[h // 2, w // 2, 0]))
             fr.release()
-    for fr in pending:
-        checks.append(int(fr.numpy()[h // 2, w // 2, 0]))
-        fr.release()
-    barrier()
-    e2e_s = time.perf_counter() - e0
+        barrier()
+        return time.perf_counter() - e0, checks
 
-    # ---- batch-1 latency (config 2 is latency-bound): serial frames, event-timed H2D..D2H ------------
-    lat = []
-    for i in range(min(K, 60)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        a.record()
-        out = net.infer(net.preprocess(host_frames[i % n_distinct].numpy()))
-        fr = hb.tensor_to_rgb48_bytes(out, state)
-        fr.wait_ready()
-        lat.append((time.perf_counter() - t0) * 1000.0)
-        fr.release()
+    host_np = [f.numpy() for f in host_frames]
+    e2e_s, checks = e2e_run(lambda i: net.process_rgb48(host_np[i % n_distinct]), 3)
+    e2e3_s, checks3 = e2e_run(lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(host_np[i % n_distinct])), state), 2)
+    if checks != checks3:
+        raise RuntimeError("one-call and three-call frame paths disagree")
+
+    # ---- batch-1 latency (config 2 is latency-bound): serial frames, host-timed submit .. RGB48 slot ready --------
+    def latency_run(submit):
+        lat = []
+        for i in range(min(K, 60)):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fr = submit(i)
+            fr.wait_ready()
+            lat.append((time.perf_counter() - t0) * 1000.0)
+            fr.release()
+        return lat
+
+    lat = latency_run(lambda i: net.process_rgb48(host_np[i % n_distinct], serial=True))
+    lat3 = latency_run(lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(host_np[i % n_distinct])), state))
 
     # ---- per-launch device times of one frame (CUDA events between launches, median of 5) -> top-kernel rooflines
     top_kernels = []
@@ -299,10 +311,10 @@ def run_b200_arm(args):
             top_kernels.append(entry)
 
     # ---- max over ranks ------------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1000.0, infer_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, infer_ms, e2e3_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, infer_ms = (float(v) for v in t.tolist())
+    dev_ms, e2e_ms, infer_ms, e2e3_ms = (float(v) for v in t.tolist())
     record = {"rank": rank, "first_frame": first, "n_frames": K, "elapsed_s": dev_ms / 1000.0,
               "descriptors": [(first + i, c) for i, c in enumerate(checks)]}
     records = hb.gather_run_records(record)
@@ -324,9 +336,14 @@ def run_b200_arm(args):
                        "sharding": f"contiguous frame chunks, {world} rank(s), no data-path collective"},
             "pixels_per_s": fps * px,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 6,
+                    "api": "HDRTVNetB200.process_rgb48 (one C-ABI call per frame: hdrtv_process), pinned u8 frame in, RGB48 in a "
+                           "pinned ring slot out",
+                    "three_call_api": {"value": world * K / (e2e3_ms / 1000.0), "unit": "frames/s",
+                                       "api": "preprocess -> infer -> tensor_to_rgb48_bytes (the reference's call sequence)"},
                     "timing": "wall clock between device synchronisations, includes host-side launch cost"},
             "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
-                           "what": "pinned u8 in -> RGB48 in pinned ring slot ready, one frame in flight"},
+                           "three_call_api_p50": float(np.percentile(lat3, 50)),
+                           "what": "pinned u8 in -> RGB48 in pinned ring slot ready, one frame in flight (process_rgb48 serial=True)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["tflops"],

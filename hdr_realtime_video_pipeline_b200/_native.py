@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libhdrtv_b200.so")
 FP32, FP16 = 0, 1
 COND_BICUBIC_AA, COND_ZERO, COND_BILINEAR = 0, 1, 2
 TRANSFER_IDENTITY, TRANSFER_LUT = 0, 1
+PROCESS_SERIAL, PROCESS_INPUT_READY, PROCESS_RESYNC = 1, 2, 4
 
 
 class Config(C.Structure):
@@ -38,6 +39,10 @@ _SIGNATURES = {
     "hdrtv_infer_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "hdrtv_pack_rgb48": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "hdrtv_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p]),
+    "hdrtv_process_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hdrtv_process_output": (C.c_void_p, [C.c_void_p, C.c_int]),
     "hdrtv_set_transfer_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hdrtv_pack_bgr24": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hdrtv_last_error": (C.c_char_p, [C.c_void_p]),

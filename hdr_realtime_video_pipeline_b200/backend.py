@@ -150,6 +150,9 @@ class HDRTVNetB200:
         # infer() then skips the classifier.  Results are identical; HDRTV_B200_PIPELINE=0 keeps everything in-stream.
         self._pipeline = _env_bool("HDRTV_B200_PIPELINE", True)
         self._side = None
+        self._rgb48_ring = None
+        self._lut_set = False
+        self._proc_dirty = False          # hdrtv_process frames in flight on the context's own streams
         self._ev_inputs_free = self._ev_pre_done = None
         self._cls_ready = False
         self._buf_hw = None
@@ -281,6 +284,15 @@ class HDRTVNetB200:
         self._ev_pre_done.record(torch.cuda.current_stream(dev))
         self._cls_ready = False
 
+    def _leave_process_mode(self):
+        """preprocess()/infer() after process_rgb48(): order them behind the one-call path's internal streams."""
+        if self._proc_dirty:
+            cur = torch.cuda.current_stream(self.device)
+            _native.check(self._lib.hdrtv_process_flush(self._handle, C.c_void_p(cur.cuda_stream)), self._handle, "hdrtv_process_flush")
+            if self._side is not None:
+                self._side.wait_stream(cur)
+            self._proc_dirty = False
+
     # ------------------------------------------------------------------ preprocess (hdrtvnet_torch.py:2239-2296)
     def _launch_preprocess(self, raw_dev, h, w, stream):
         # hdrtvnet_torch.py:2265-2294: zero condition > bilinear (fast_condition_resize) > antialiased bicubic
@@ -300,6 +312,7 @@ class HDRTVNetB200:
         h, w = frame_bgr.shape[:2]
         with torch.cuda.device(self.device):
             self._ensure_buffers(h, w)
+            self._leave_process_mode()
             slot = self._pin_idx
             self._pin_idx ^= 1
             if self._pin_events[slot] is not None:
@@ -331,6 +344,7 @@ class HDRTVNetB200:
         h, w = int(frame_u8_dev.shape[0]), int(frame_u8_dev.shape[1])
         with torch.cuda.device(self.device):
             self._ensure_buffers(h, w)
+            self._leave_process_mode()
             src = frame_u8_dev.contiguous()
             cur = torch.cuda.current_stream(self.device)
             work = self._side if self._pipeline else cur
@@ -357,6 +371,7 @@ class HDRTVNetB200:
         h, w = int(tensor.shape[2]), int(tensor.shape[3])
         with torch.cuda.device(self.device):
             self._ensure_buffers(h, w)
+            self._leave_process_mode()
             t = tensor.to(device=self.device, dtype=self._dtype).contiguous()
             c = cond.to(device=self.device, dtype=self._dtype).contiguous()
             if tuple(c.shape) != (1, 3, max(1, h // 4), max(1, w // 4)):
@@ -411,6 +426,59 @@ class HDRTVNetB200:
         output = self.postprocess(out)
         t3 = time.perf_counter()
         return output, (t1 - t0) * 1000.0, (t2 - t1) * 1000.0, (t3 - t2) * 1000.0
+
+    # ------------------------------------------------------------------ one-call frame path (extension)
+    @torch.inference_mode()
+    def process_rgb48(self, frame_bgr, serial: bool = False, transfer: str = "identity", input_ready: bool = False):
+        """BGR24 frame -> RGB48 frame in a pinned ring slot through ONE C-ABI call (``hdrtv_process``): what the
+        playback / export loops do per frame with ``preprocess`` -> ``infer`` -> ``_tensor_to_rgb48_bytes``
+        (gui_pipeline_worker_frame_processing.py:168-331, gui_pipeline_worker_feeders.py:193-249), bit-identical to
+        that sequence.  ``frame_bgr``: uint8 HxWx3 numpy array (pinned memory is DMA-copied straight from the array,
+        which must stay untouched until the returned frame is ready) or a CUDA uint8 tensor.  Returns a
+        ``PinnedFrame`` (wait_ready / buffer_view / release).  ``serial=True`` keeps every stage on the current
+        stream (lowest single-frame latency); the default overlaps frame k+1's copy-in / preprocess / classifier and
+        frame k-1's copy-out with frame k's network."""
+        from .feeders import PinnedFrame, PinnedRing, pq_code_table
+        if isinstance(frame_bgr, torch.Tensor):
+            if frame_bgr.device.type != "cuda" or frame_bgr.dtype != torch.uint8 or frame_bgr.dim() != 3 or frame_bgr.shape[2] != 3:
+                raise ValueError("frame_bgr must be a CUDA uint8 HxWx3 tensor or a uint8 HxWx3 numpy array")
+            src = frame_bgr.contiguous()
+            ptr = src.data_ptr()
+        else:
+            if not isinstance(frame_bgr, np.ndarray) or frame_bgr.dtype != np.uint8 or frame_bgr.ndim != 3 or frame_bgr.shape[2] != 3:
+                raise ValueError("frame_bgr must be a uint8 HxWx3 BGR array")
+            src = np.ascontiguousarray(frame_bgr)
+            ptr = src.ctypes.data
+        if transfer not in ("identity", "pq1000"):
+            raise ValueError("transfer must be 'identity' or 'pq1000'")
+        h, w = int(src.shape[0]), int(src.shape[1])
+        with torch.cuda.device(self.device):
+            self._ensure_buffers(h, w)
+            if transfer == "pq1000" and not self._lut_set:
+                lut = np.ascontiguousarray(pq_code_table(1000.0))
+                _native.check(self._lib.hdrtv_set_transfer_lut(self._handle, lut.ctypes.data, lut.size), self._handle,
+                              "hdrtv_set_transfer_lut")
+                self._lut_set = True
+            if self._rgb48_ring is None:
+                self._rgb48_ring = PinnedRing(self.device)
+            slot = self._rgb48_ring.acquire((h, w, 3))
+            slot["source"] = src                       # keeps the input frame alive until the slot is reused
+            mode = (_native.COND_ZERO if self._fast_zero_condition else
+                    (_native.COND_BILINEAR if self._fast_condition_resize else _native.COND_BICUBIC_AA))
+            flags = (_native.PROCESS_SERIAL if serial else 0) | (_native.PROCESS_INPUT_READY if input_ready else 0)
+            if not self._proc_dirty:                   # first one-call frame after preprocess()/infer() used the context
+                flags |= _native.PROCESS_RESYNC
+                if self._side is not None:
+                    torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._proc_dirty = True
+            tr = _native.TRANSFER_LUT if transfer == "pq1000" else _native.TRANSFER_IDENTITY
+            self._cls_ready = False
+            rc = self._lib.hdrtv_process(self._handle, ptr, h, w, slot["tensor"].data_ptr(), mode, tr, flags,
+                                         C.c_void_p(slot["event"].cuda_event), self._stream())
+            if rc != 0:
+                slot["free"].set()
+                raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle))
+        return PinnedFrame(slot, slot["event"])
 
     def _warmup(self):
         h, w = self.expected_hw or (1080, 1920)

@@ -249,6 +249,19 @@ struct Ctx {
   // side branch of the LE plan: the tail of the condition pyramid (small launches) overlaps the full-resolution trunk
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // hdrtv_process: context-owned frame buffers of the current resolution and the copy-in / copy-out streams of its
+  // three-stage frame pipeline (H2D + preprocess + classifier | AGCM + LE + pack | D2H)
+  struct Proc {
+    int H = 0, W = 0;
+    uint8_t* bgr = nullptr;
+    void *x = nullptr, *cond = nullptr, *out = nullptr, *agcm = nullptr;
+    uint16_t* rgb[2] = {nullptr, nullptr};
+    long frames = 0;
+    bool primed = false;
+  } proc;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in_free = nullptr, ev_pre_done = nullptr, ev_packed = nullptr, ev_user = nullptr;
+  cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
 };
 
 static int fail(Ctx* c, const std::string& m) {
@@ -1056,6 +1069,7 @@ static void release_workspace(Ctx* c) {
   c->plan_le.clear();
   c->f32.clear();
   c->H = c->W = 0;
+  c->proc = Ctx::Proc();       // its buffers were workspace allocations
 }
 
 static void dbg_p8(Ctx* c, const std::string& n, const P8& t, int C, int j0 = 0) {
@@ -1763,6 +1777,10 @@ void hdrtv_destroy(hdrtv_t* c) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  for (cudaEvent_t e : {c->ev_in_free, c->ev_pre_done, c->ev_packed, c->ev_user, c->ev_d2h[0], c->ev_d2h[1]})
+    if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -2105,6 +2123,111 @@ int hdrtv_pack_bgr24(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint
   CK(c, cudaGetLastError());
   ++c->launches;
   return 0;
+}
+
+// ---- SURVEY §8b `hdrtv_process`: BGR24 frame in -> RGB48 frame out, one call ------------------------------------
+static int pointer_on_device(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+static int ensure_proc(Ctx* c, int H, int Wd) {
+  if (hdrtv_prepare(static_cast<hdrtv_t*>(c), H, Wd)) return -1;
+  if (!c->s_in) {
+    CK(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_in_free, &c->ev_pre_done, &c->ev_packed, &c->ev_user, &c->ev_d2h[0], &c->ev_d2h[1]})
+      CK(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  Ctx::Proc& P = c->proc;
+  if (P.H == H && P.W == Wd) return 0;
+  const size_t npix = static_cast<size_t>(H) * Wd, es = c->precision == HDRTV_FP16 ? 2 : 4;
+  const size_t ncond = static_cast<size_t>(std::max(1, H / 4)) * std::max(1, Wd / 4);
+  P.bgr = ws_alloc<uint8_t>(c, npix * 3, false);
+  P.x = ws_alloc<uint8_t>(c, npix * 3 * es, false);
+  P.cond = ws_alloc<uint8_t>(c, ncond * 3 * es, false);
+  P.out = ws_alloc<uint8_t>(c, npix * 3 * es, false);
+  P.agcm = ws_alloc<uint8_t>(c, npix * 3 * es, false);
+  P.rgb[0] = ws_alloc<uint16_t>(c, npix * 3, false);
+  P.rgb[1] = ws_alloc<uint16_t>(c, npix * 3, false);
+  if (!P.bgr || !P.x || !P.cond || !P.out || !P.agcm || !P.rgb[0] || !P.rgb[1]) return fail(c, "hdrtv_process: frame buffer allocation failed");
+  P.H = H;
+  P.W = Wd;
+  P.frames = 0;
+  P.primed = false;
+  return 0;
+}
+
+int hdrtv_process(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rgb48, int cond_mode, int transfer, int flags,
+                  void* done_event, void* stream) {
+  if (!c || !bgr || !rgb48) return fail(c, "hdrtv_process: null argument");
+  cudaSetDevice(c->device);
+  if (ensure_proc(c, H, Wd)) return -1;
+  Ctx::Proc& P = c->proc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t npix = static_cast<size_t>(H) * Wd;
+  const bool serial = (flags & HDRTV_PROCESS_SERIAL) != 0;
+  const bool in_dev = pointer_on_device(bgr) != 0, out_dev = pointer_on_device(rgb48) != 0;
+  cudaStream_t si = serial ? s : c->s_in, so = serial ? s : c->s_out;
+  const int slot = static_cast<int>(P.frames & 1);
+  // ---- stage 1 (copy-in stream): H2D, normalise + condition image, P8 staging + AGCM classifier + GFM fold
+  const uint8_t* src = bgr;
+  if (flags & HDRTV_PROCESS_RESYNC) P.primed = false;
+  if (!serial && (!P.primed || (in_dev && !(flags & HDRTV_PROCESS_INPUT_READY)))) {
+    // first pipelined frame (whatever ran on the caller's stream before may still use the buffers), or a device frame
+    // that is produced on the caller's stream: order the copy-in stream behind the caller's stream
+    CK(c, cudaEventRecord(c->ev_user, s));
+    CK(c, cudaStreamWaitEvent(si, c->ev_user, 0));
+  }
+  if (!in_dev) {
+    CK(c, cudaMemcpyAsync(P.bgr, bgr, npix * 3, cudaMemcpyHostToDevice, si));
+    src = P.bgr;
+  }
+  if (!serial && P.primed) CK(c, cudaStreamWaitEvent(si, c->ev_in_free, 0));   // previous frame's AGCM MLP has read x / cond / fold
+  if (hdrtv_preprocess(c, src, H, Wd, P.x, P.cond, cond_mode, si)) return -1;
+  if (hdrtv_classify(c, P.x, P.cond, H, Wd, si)) return -1;
+  if (!serial) {
+    CK(c, cudaEventRecord(c->ev_pre_done, si));
+    CK(c, cudaStreamWaitEvent(s, c->ev_pre_done, 0));
+  }
+  // ---- stage 2 (caller's stream): AGCM MLP + LE network + RGB48 pack
+  if (hdrtv_infer_ex(c, P.x, P.cond, H, Wd, P.out, P.agcm, 1, serial ? nullptr : c->ev_in_free, s)) return -1;
+  uint16_t* dst = rgb48;
+  if (!out_dev) {
+    dst = P.rgb[slot];
+    if (P.frames >= 2) CK(c, cudaStreamWaitEvent(s, c->ev_d2h[slot], 0));   // staging slot drained (frame k-2; no-op if never recorded)
+  }
+  if (hdrtv_pack_rgb48(c, P.out, c->precision == HDRTV_FP16 ? HDRTV_FP16 : HDRTV_FP32, H, Wd, dst, transfer, s)) return -1;
+  // ---- stage 3 (copy-out stream): D2H into the caller's (pinned) frame
+  cudaStream_t last = s;
+  if (!out_dev) {
+    if (!serial) {
+      CK(c, cudaEventRecord(c->ev_packed, s));
+      CK(c, cudaStreamWaitEvent(so, c->ev_packed, 0));
+    }
+    CK(c, cudaMemcpyAsync(rgb48, dst, npix * 6, cudaMemcpyDeviceToHost, so));
+    if (!serial) CK(c, cudaEventRecord(c->ev_d2h[slot], so));
+    last = so;
+  }
+  if (done_event) CK(c, cudaEventRecord(static_cast<cudaEvent_t>(done_event), last));
+  P.primed = !serial;
+  ++P.frames;
+  return 0;
+}
+
+/* Joins the copy-out stream of hdrtv_process back into `stream` (end of a clip, or before the buffers are reused). */
+int hdrtv_process_flush(hdrtv_t* c, void* stream) {
+  if (!c) return fail(c, "hdrtv_process_flush: null context");
+  if (!c->s_out) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < 2; ++i)
+    if (c->proc.frames > i) CK(c, cudaStreamWaitEvent(s, c->ev_d2h[(c->proc.frames - 1 - i) & 1], 0));
+  return 0;
+}
+
+const void* hdrtv_process_output(const hdrtv_t* c, int which) {
+  if (!c || !c->proc.H) return nullptr;
+  return which == 0 ? c->proc.out : (which == 1 ? c->proc.agcm : nullptr);
 }
 
 int hdrtv_debug_tensor_count(const hdrtv_t* c) { return c ? static_cast<int>(c->dbg.size()) : 0; }

@@ -81,6 +81,52 @@ def pq_code_table(peak_nits: float = 1000.0) -> np.ndarray:
     return np.clip((pq * 65535.0) + 0.5, 0.0, 65535.0).astype(np.uint16)
 
 
+class PinnedRing:
+    """Ring of pinned uint16 (H,W,3) host frames with the reference's free/claim protocol
+    (gui_pipeline_worker_feeders.py:125-170).  Each slot carries a reusable CUDA event whose raw handle is stable, so
+    that the C ABI can record it on one of its own streams (hdrtv_process)."""
+
+    def __init__(self, device, ring_frames: int | None = None):
+        self.device = torch.device(device)
+        self.ring_frames = ring_frames or _gpu_rgb48_ring_frames()
+        self._shape = None
+        self._slots = []
+        self._index = 0
+
+    def _ring(self, shape):
+        if self._shape == shape and self._slots:
+            return self._slots
+        self._slots = []
+        with torch.cuda.device(self.device):
+            for _ in range(self.ring_frames):
+                host = torch.empty(shape, dtype=torch.uint16, pin_memory=True)
+                free = threading.Event()
+                free.set()
+                ev = torch.cuda.Event(enable_timing=False)
+                ev.record(torch.cuda.current_stream(self.device))       # materialise the handle
+                self._slots.append({"tensor": host, "numpy": host.numpy(), "free": free, "event": ev, "source": None})
+        self._shape = shape
+        self._index = 0
+        return self._slots
+
+    def acquire(self, shape, timeout=0.25):
+        slots = self._ring(shape)
+        start = self._index % len(slots)
+        for off in range(len(slots)):
+            idx = (start + off) % len(slots)
+            if slots[idx]["free"].is_set():
+                slots[idx]["free"].clear()
+                self._index = (idx + 1) % len(slots)
+                return slots[idx]
+        slot = slots[start]
+        if not slot["free"].wait(timeout=timeout):
+            raise RuntimeError("RGB48 ring exhausted: no pinned slot was released within "
+                               f"{timeout:.2f}s (ring={len(slots)}); the consumer is not calling release()")
+        slot["free"].clear()
+        self._index = (start + 1) % len(slots)
+        return slot
+
+
 class RGB48Packer:
     """Owns the pack stream, the device staging slots and the pinned ring for one device."""
 

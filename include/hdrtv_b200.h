@@ -86,6 +86,23 @@ int hdrtv_pack_rgb48(hdrtv_t* h, const void* src, int dtype, int height, int wid
                      void* stream);
 int hdrtv_set_transfer_lut(hdrtv_t* h, const uint16_t* lut_host, int n);
 
+/* The whole hot path of one frame in one call (SURVEY §8b `hdrtv_process`): what the playback / export loops do per  */
+/* frame with preprocess -> infer -> _tensor_to_rgb48_bytes (gui_pipeline_worker_frame_processing.py:168-331,         */
+/* gui_pipeline_worker_feeders.py:193-249, gui_export.py:1034-1104).  bgr = uint8 HxWx3 BGR and rgb48 = uint16 HxWx3  */
+/* RGB may each be device memory or (pinned) host memory - detected with cudaPointerGetAttributes; host frames are    */
+/* DMA-copied to / from context-owned device buffers.  Three-stage frame pipeline on context-owned streams: copy-in   */
+/* (H2D, normalise, condition image, AGCM classifier) | caller's `stream` (AGCM MLP, LE network, pack) | copy-out     */
+/* (D2H), so frame k+1's input side and frame k-1's output copy overlap frame k's network.  Nothing synchronises the  */
+/* host: `done_event` (cudaEvent_t, optional) is recorded when rgb48 is complete; the bgr frame must stay untouched   */
+/* until then.  Results are bit-identical to hdrtv_preprocess + hdrtv_infer + hdrtv_pack_rgb48.                       */
+enum { HDRTV_PROCESS_SERIAL = 1,        /* everything on `stream`, no overlap between frames (lowest single-frame latency) */
+       HDRTV_PROCESS_INPUT_READY = 2,   /* device frame already complete: the copy-in stream need not wait for `stream`   */
+       HDRTV_PROCESS_RESYNC = 4 };      /* other entry points used the context since the last hdrtv_process on `stream`   */
+int hdrtv_process(hdrtv_t* h, const uint8_t* bgr, int height, int width, uint16_t* rgb48, int cond_mode, int transfer,
+                  int flags, void* done_event, void* stream);
+int hdrtv_process_flush(hdrtv_t* h, void* stream);          /* `stream` waits for the copy-out stream's pending copies */
+const void* hdrtv_process_output(const hdrtv_t* h, int which); /* device (1,3,H,W) out (0) / agcm_out (1) of the last frame */
+
 /* HDRTVNetTorch.postprocess (hdrtvnet_torch.py:2352-2368): planar -> uint8 HxWx3 BGR, arithmetic in `dtype`.       */
 int hdrtv_pack_bgr24(hdrtv_t* h, const void* src, int dtype, int height, int width, uint8_t* dst, void* stream);
 

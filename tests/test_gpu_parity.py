@@ -334,6 +334,58 @@ def test_frame_pipelining_is_transparent(monkeypatch, precision):
     piped.close()
 
 
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_one_call_frame_path_matches_the_three_calls(nets, precision):
+    """hdrtv_process (HDRTVNetB200.process_rgb48): BGR24 frame -> RGB48 frame in a pinned ring slot in one C-ABI call, with
+    its own three-stage frame pipeline.  Must be bit-identical to preprocess -> infer -> tensor_to_rgb48_bytes for host
+    (pinned and pageable) and device frames, pipelined and serial, back to back without host synchronisation, and keep
+    working when the two APIs are interleaved on one context."""
+    net = nets("hr", precision)
+    frames = [hb.synth_frame(i, 136, 248) for i in range(7)]
+    state = {}
+    want = []
+    for f in frames:
+        fr = hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(f)), state)
+        want.append(fr.numpy().copy())
+        fr.release()
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    for serial in (False, True):
+        got = []
+        for i, f in enumerate(frames):                 # no host synchronisation between submissions
+            src = pinned[i].numpy() if i % 3 == 0 else (f if i % 3 == 1 else torch.from_numpy(f).cuda())
+            got.append(net.process_rgb48(src, serial=serial))
+            if len(got) >= 3:                          # consumer side: in-order wait + release
+                j = len(got) - 3
+                assert np.array_equal(got[j].numpy(), want[j]), (serial, j)
+                got[j].release()
+        for j in range(len(frames) - 2, len(frames)):
+            assert np.array_equal(got[j].numpy(), want[j]), (serial, j)
+            got[j].release()
+    # interleave the two APIs on the same context
+    a = net.process_rgb48(pinned[2].numpy())
+    out, _ = net.infer(net.preprocess(frames[4]))
+    fr = hb.tensor_to_rgb48_bytes(out, state)
+    b = net.process_rgb48(pinned[5].numpy())
+    assert np.array_equal(a.numpy(), want[2]) and np.array_equal(fr.numpy(), want[4]) and np.array_equal(b.numpy(), want[5])
+    for x in (a, fr, b):
+        x.release()
+    # resolution change through the one-call path, and the PQ code-table transfer
+    f2 = hb.synth_frame(1, 72, 100)
+    w2 = hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(f2)), state)
+    g2 = net.process_rgb48(f2)
+    assert np.array_equal(g2.numpy(), w2.numpy())
+    w2.release(), g2.release()
+    if precision == "fp16":
+        pq = hb.RGB48Packer("cuda", transfer="pq1000")
+        w3 = pq.pack(net.infer(net.preprocess(f2)))
+        g3 = net.process_rgb48(f2, transfer="pq1000")
+        assert np.array_equal(g3.numpy(), w3.numpy())
+        w3.release(), g3.release()
+        pq.close()
+    with pytest.raises(ValueError):
+        net.process_rgb48(np.zeros((8, 8), dtype=np.uint8))
+
+
 @pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840)])
 def test_full_size_properties_fp16(nets, hw):
     """BASELINE configs 2/3 sizes: size-independent properties instead of a CPU oracle run —
