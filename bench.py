@@ -49,12 +49,14 @@ KERNEL_MAC_PER_PX = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 1920x1080 from profiles/r1_ncu_top_kernels.md (ncu --set full)
 NCU_TRAFFIC_1080P = {}     # filled from profiles/r1_ncu_top_kernels.json when present (written by scripts/summarise_ncu.py)
-NCU_FRAME_TRAFFIC_1080P = None   # dram read + write bytes of every launch of one 1080p frame (profiles/r1_traffic_1080p.csv)
+NCU_FRAME_TRAFFIC = {}     # workload -> dram read + write bytes of every launch of one frame (profiles/r1_traffic_1080p.csv, r1_launches_4k.csv)
 try:
     with open(os.path.join(REPO, "profiles", "r1_ncu_top_kernels.json")) as _f:
         _j = json.load(_f)
         NCU_TRAFFIC_1080P = {k: int(v) for k, v in _j.get("dram_bytes_per_launch_1080p", {}).items()}
-        NCU_FRAME_TRAFFIC_1080P = _j.get("frame_dram_bytes_1080p", {}).get("total")
+        for _wl in ("1080p", "4k"):
+            if _j.get(f"frame_dram_bytes_{_wl}", {}).get("total"):
+                NCU_FRAME_TRAFFIC[_wl] = int(_j[f"frame_dram_bytes_{_wl}"]["total"])
 except Exception:
     pass
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
@@ -326,6 +328,7 @@ def run_b200_arm(args):
         e2e_fps = world * K / (e2e_ms / 1000.0)
         step_ms = dev_ms / K                                   # whole step: preprocess + infer + pack, device-timed
         achieved_tf = FLOP_PER_PX * px / (step_ms / 1000.0) / 1e12
+        frame_traffic = NCU_FRAME_TRAFFIC.get(args.workload) if precision == "fp16" else None
         line = {
             "metric": "HDRTVNet++ frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -347,12 +350,12 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["tflops"],
-                         "traffic": (NCU_FRAME_TRAFFIC_1080P if (h, w) == (1080, 1920) and precision == "fp16" else None),
-                         "traffic_note": "DRAM read + write bytes of all launches of one frame (ncu, profiles/r1_traffic_1080p.csv): "
-                                         "inter-layer activations; the frame's algorithmic I/O is 9 B/px",
-                         "hbm": ({"achieved_GBps": NCU_FRAME_TRAFFIC_1080P / (step_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
-                                  "frac": (NCU_FRAME_TRAFFIC_1080P / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None}
-                                 if NCU_FRAME_TRAFFIC_1080P and (h, w) == (1080, 1920) and precision == "fp16" else None),
+                         "traffic": frame_traffic,
+                         "traffic_note": "DRAM read + write bytes of all launches of one frame (ncu, profiles/r1_traffic_1080p.csv / "
+                                         "r1_launches_4k.md): inter-layer activations; the frame's algorithmic I/O is 9 B/px",
+                         "hbm": ({"achieved_GBps": frame_traffic / (step_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
+                                  "frac": (frame_traffic / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None}
+                                 if frame_traffic else None),
                          "kernel": "whole hot path of one frame (chain_p8_kernel x2, conv2x_p8_kernel, conv_p8_kernel family, "
                                    "classifier, pre/pack); CUDA events around the timed steps on the launching stream",
                          "algorithmic": f"{FLOP_PER_PX:.0f} FLOP/px x {px} px per frame", "peak_source": peaks["source"],

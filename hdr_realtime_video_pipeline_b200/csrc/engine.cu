@@ -956,6 +956,8 @@ __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
   __shared__ float fea[6];
   __shared__ float sc[3][64], sh[3][64];
   const int t = threadIdx.x;
+  grid_dep_launch();          // the AGCM MLP kernel loads these folded weights only after its own dependency wait
+  grid_dep_wait();
   if (t < 128) mean5[t] = static_cast<float>(p.stats5[2 * t] / p.cnt5);
   __syncthreads();
   if (t < 6) {
@@ -1151,8 +1153,7 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
       CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured = true;
     }
-    cls_level_kernel<<<blocks, 256, sm, s>>>(p);
-    CK(c, cudaGetLastError());
+    CK(c, launch_pdl(cls_level_kernel, dim3(blocks), 256, sm, s, p));
     ++c->launches;
     mark();
   }
@@ -1176,8 +1177,7 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
   hp.w3 = c->wd.at("AGCM.conv_last.weight");  hp.b3 = c->wd.at("AGCM.conv_last.bias");
   hp.fea = c->d_fea;
   hp.fold32 = c->d_fold32;
-  agcm_head_kernel<<<1, 256, 0, s>>>(hp);
-  CK(c, cudaGetLastError());
+  CK(c, launch_pdl(agcm_head_kernel, dim3(1), 256, 0, s, hp));
   ++c->launches;
   return 0;
 }
