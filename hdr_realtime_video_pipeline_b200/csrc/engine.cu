@@ -477,7 +477,7 @@ static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>, L.grid, kConvThreads, L.smem, s, L.p);
+  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>, L.grid, conv_threads(AUX, SFTG, FOLD), L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>
