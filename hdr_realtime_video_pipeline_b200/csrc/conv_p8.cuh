@@ -93,6 +93,7 @@ struct ConvParams {
   ConvCopy copies[kMaxCopies];
   uint32_t copy_src0, copy_src_stride, copy_par_off;   // source entry of copy c: src0 + (c / npar) * stride + (c % npar) * par_off
   int slot_bytes, ring;
+  int l2_prefetch;     // > 0: the producer prefetches input row q + l2_prefetch into L2 when it requests row q
   int n_steps;         // tap steps; the weight buffer holds n_steps + 1 (the last one is the bias step)
   ConvStep steps[kMaxSteps];
   const uint4* wpk;
@@ -184,8 +185,14 @@ constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels pe
 // input row consumed (and its ring slot released) once, and a ring of kFoldR accumulator blocks instead of two stages.
 constexpr int kFoldR = 8;
 
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
+// MC (zsplit = 3 launches only): the three CTAs that run the three weight variants of one strip / band form a cluster
+// (consecutive blockIdx.x) and share every input row: each producer requests a third of the row's planes and the TMA
+// multicasts them into all three rings, so a row crosses L2 -> SM once instead of three times and every CTA issues a
+// third of the copies.  A slot is refilled once all readers of all three CTAs have released it (multicast commits).
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool MC = false>
 __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!MC || conv_dual(AUX, SFTG, FOLD), "multicast variant: plain dual-issuer instances");
+  constexpr uint16_t kMcMask = 0x7;
   static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
                 "in-kernel SFT generator: 32-channel outputs only");
   static_assert(!FOLD || (KIND == IN_PAR3x3S2 && !SFTG && MODE == STORE_P8 && N <= 64), "row folding: plain stride-2 3x3 convs");
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) {
       mbar_init(full_bar(i), 1);
-      mbar_init(empty_bar(i), DUAL ? 2 : 1);
+      mbar_init(empty_bar(i), (DUAL ? 2 : 1) * (MC ? 3 : 1));
     }
     for (int i = 0; i < (FOLD ? kFoldR : 2); ++i) {
       mbar_init(tfull_bar(i), 1);
@@ -249,8 +256,10 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();      // every CTA's barriers are initialised before any peer signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -275,7 +284,31 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
       const uint4* ssrc = SFTG ? p.s0 + (static_cast<long>(oy0) * (PSG ? 2 : 1) + 1) * p.s0_row_entries +
                                      static_cast<long>(p.s0_src0) + x0
                                : nullptr;
+      // L2 prefetch distance: the ring holds only ks + 1..2 rows of the fat (64-channel) inputs, far less than the loaded
+      // HBM latency; rows requested `pf` rows ahead are in L2 by the time their slot frees up.
+      const int pf = p.l2_prefetch;
+      const uint4* psrc = src + static_cast<long>(pf) * row_entries;
+      if (pf > 0) {
+        const uint4* s0p = src + static_cast<long>(ring_n) * row_entries;
+        for (int q = static_cast<int>(ring_n); q < pf && q < nrows_in; ++q, s0p += row_entries) {
+#pragma unroll
+          for (int c = 0; c < NCOPY; ++c) {
+            unsigned long long a;
+            asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(s0p));
+            bulk_prefetch_l2(reinterpret_cast<const void*>(a), kPlaneBytes);
+          }
+        }
+      }
       for (int q = 0; q < nrows_in; ++q) {
+        if (pf > 0 && q + pf < nrows_in) {
+#pragma unroll
+          for (int c = 0; c < NCOPY; ++c) {
+            unsigned long long a;
+            asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(psrc));
+            bulk_prefetch_l2(reinterpret_cast<const void*>(a), kPlaneBytes);
+          }
+        }
+        psrc += row_entries;
         mbar_wait(empty_bar(slot), ph, p.err, 1);
         mbar_expect_tx(full_bar(slot), row_tx);
         const uint32_t dst = smem_u32(ring) + slot * slot_bytes;
@@ -283,7 +316,12 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
         for (int c = 0; c < NCOPY; ++c) {
           unsigned long long a;
           asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(src));
-          bulk_g2s(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot));
+          if constexpr (MC) {
+            if (static_cast<uint32_t>(c % 3) == crank)
+              bulk_g2s_multicast(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot), kMcMask);
+          } else {
+            bulk_g2s(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot));
+          }
         }
         src += row_entries;
         if (++slot == ring_n) { slot = 0; ph ^= 1; }
@@ -409,8 +447,13 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
             tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
           });
           if (my_last) {
-            tc_commit(empty_bar(slot));
-            if (!other_reads) mbar_arrive(empty_bar(slot));      // sole reader: supply the second arrival
+            if constexpr (MC) {
+              tc_commit_multicast(empty_bar(slot), kMcMask);
+              if (!other_reads) tc_commit_multicast(empty_bar(slot), kMcMask);
+            } else {
+              tc_commit(empty_bar(slot));
+              if (!other_reads) mbar_arrive(empty_bar(slot));      // sole reader: supply the second arrival
+            }
           }
           if (dy == KS - 1) {
             tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
@@ -690,6 +733,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (MC) cluster_sync_all();      // no CTA leaves while a peer may still write its ring or signal its barriers
 }
 
 inline size_t conv_sftg_bytes(const ConvParams& p, bool ps) {

@@ -182,6 +182,7 @@ struct ConvLaunch {
   int kind = 0, kch = 0;
   bool sftg = false;
   bool fold = false;                    // row-folded stride-2 3x3 (conv_p8_kernel<..., FOLD>); weights are the ".fold2" pack
+  bool mc = false;                      // zsplit = 3 launch as clusters of three CTAs with TMA-multicast input rows (conv_p8_kernel<..., MC>)
   int N;
   int mode;
   dim3 grid;
@@ -346,6 +347,27 @@ static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   L.grid = dim3(strips * zs, (p.Ho + band - 1) / band, z);
 }
 
+// Co-resident clusters of `cluster_x` CTAs the device can hold for this kernel configuration (0 on error).
+template <typename Kernel>
+static int max_active_clusters(Kernel kernel, int threads, size_t smem, int cluster_x) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(cluster_x) * 64);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 struct Epi {
   int act = ACT_NONE;
   const P8* res = nullptr;
@@ -431,6 +453,9 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
     ring = std::max(ring, std::min(fill, kMaxRing));
   }
   p.ring = ring;
+  // L2 prefetch distance of the input rows (experiment knob HDRTV_L2PF: rows ahead, fat slots only by default)
+  p.l2_prefetch = env_int("HDRTV_L2PF", 0);
+  if (p.slot_bytes < env_int("HDRTV_L2PF_MIN_SLOT", 16 * 1024)) p.l2_prefetch = 0;
   L.smem = conv_smem_bytes(p, mode == STORE_PS);
   if (L.smem > 227 * 1024) return fail(c, "conv " + name + ": shared memory budget exceeded");
   L.N = N;
@@ -440,6 +465,26 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   L.name = name;
   const int wstrip = (p.xmul == 2) ? down2(Wo) : Wo;
   choose_grid(L, (wstrip + kTileM - 1) / kTileM);
+  if (e.zsplit == 3 && !e.fold && kind == IN_PAR3x3S2 && kchunks == 8 && N == 64 && mode == STORE_P8 && !e.res && !e.res2 &&
+      !e.sft && !e.sft_s0 && !e.raw && env_int("HDRTV_MC", 0)) {
+    // clusters of three must all be resident at once (single wave): ask the device how many fit
+    const int fit = max_active_clusters(conv_p8_kernel<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, false, true>,
+                                        conv_threads(false, false, false), L.smem, 3);
+    int need = static_cast<int>(L.grid.x / 3 * L.grid.y * L.grid.z);
+    const int strips3 = static_cast<int>(L.grid.x / 3);
+    if (fit < need && fit >= strips3 && L.grid.z == 1) {     // a few clusters too many: slightly taller bands instead of unicast
+      const int nb = fit / strips3;
+      const int band = (p.Ho + nb - 1) / nb;
+      const int gy = (p.Ho + band - 1) / band;
+      if (strips3 * gy <= fit && strips3 * gy * 100 >= need * 85) {
+        p.band = band;
+        L.grid.y = static_cast<unsigned>(gy);
+        need = strips3 * gy;
+      }
+    }
+    L.mc = fit >= need;
+    if (env_int("HDRTV_MC_VERBOSE", 0)) fprintf(stderr, "[hdrtv] %s: clusters needed %d, resident %d -> %s\n", name.c_str(), need, fit, L.mc ? "multicast" : "unicast");
+  }
   plan.push_back(L);
   return 0;
 }
@@ -453,21 +498,32 @@ static bool use_pdl() {
   return v < 0 ? g_pdl_small_frame : v != 0;
 }
 template <typename Kernel, typename Params>
-static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, const Params& params) {
+static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, const Params& params,
+                              int cluster_x = 1) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (use_pdl()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
-
 template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
@@ -503,6 +559,16 @@ static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
   if (L.c2x) return launch_conv2x(L, s);
+  if (L.mc) {       // CondNet{2,3,4}.0: three weight variants of one strip as a cluster with multicast input rows
+    static bool configured = false;
+    auto k = conv_p8_kernel<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, false, true>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    return launch_pdl(k, L.grid, conv_threads(false, false, false), L.smem, s, L.p, 3);
+  }
   if (L.fold) {     // row-folded stride-2 3x3 convs of the condition pyramid
     if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 64) return launch_conv_t<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, true>(L, s);
     if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 16) return launch_conv_t<IN_PAR3x3S2, 8, 16, STORE_P8, false, false, true>(L, s);

@@ -73,13 +73,16 @@ class Rgb48RawWriter:
 
 
 def export_clip(processor, frames, n_frames: int, out_path: str, rank: int = 0, world_size: int = 1, pack=None,
-                barrier=None) -> dict:
+                barrier=None, one_call: bool = True) -> dict:
     """Export this rank's contiguous chunk of an ``n_frames`` clip.
 
     processor : an ``HDRTVNetB200`` (anything with preprocess / infer)
     frames    : callable ``frames(i) -> uint8 HxWx3 BGR`` (decode or synthetic source), called only for this rank's frames
     pack      : ``pack(out) -> payload`` with wait_ready()/buffer_view()/release(); defaults to tensor_to_rgb48_bytes
     barrier   : optional callable run after rank 0 created the file and before anyone writes (dist.barrier)
+    one_call  : with the default pack, use ``processor.process_rgb48`` (one C-ABI call per frame, ``hdrtv_process``: the
+                frame is DMA-copied straight from the array ``frames(i)`` returned, which must not be rewritten before
+                the frame has been written out) instead of preprocess -> infer -> pack; the bytes are identical
     Returns the per-rank record; gather with ``sharding.gather_run_records`` and check with ``sharding.merge_descriptors``.
     """
     from .feeders import tensor_to_rgb48_bytes
@@ -87,6 +90,7 @@ def export_clip(processor, frames, n_frames: int, out_path: str, rank: int = 0, 
     first, last = sharding.frame_chunk(n_frames, rank, world_size)
     probe = frames(first) if last > first else None
     state: dict = {}
+    use_one_call = bool(one_call) and pack is None and hasattr(processor, "process_rgb48")
     if pack is None:
         def pack(out):
             return tensor_to_rgb48_bytes(out, state)
@@ -112,8 +116,10 @@ def export_clip(processor, frames, n_frames: int, out_path: str, rank: int = 0, 
 
     for i in range(first, last):
         frame = probe if i == first else frames(i)
-        out = processor.infer(processor.preprocess(frame))
-        pending.append((i, pack(out)))
+        if use_one_call:
+            pending.append((i, processor.process_rgb48(frame)))
+        else:
+            pending.append((i, pack(processor.infer(processor.preprocess(frame)))))
         if len(pending) >= 2:                             # keep one frame in flight behind the writer (ring >= 3 slots)
             drain(pending.pop(0))
     for entry in pending:

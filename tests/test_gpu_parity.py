@@ -247,7 +247,8 @@ def test_resolution_change_and_determinism(nets):
     assert np.array_equal(o1, o2)                                                # bitwise repeatable across re-allocation
 
 
-@pytest.mark.parametrize("knobs", [{"HDRTV_FOLD2": "1"}, {"HDRTV_CHAIN_TAIL": "0"}, {"HDRTV_C2X": "0"}, {"HDRTV_ZFUSE": "0"}])
+@pytest.mark.parametrize("knobs", [{"HDRTV_FOLD2": "1"}, {"HDRTV_CHAIN_TAIL": "0"}, {"HDRTV_C2X": "0"}, {"HDRTV_ZFUSE": "0"},
+                                   {"HDRTV_MC": "1"}, {"HDRTV_L2PF": "6", "HDRTV_L2PF_MIN_SLOT": "0"}])
 @pytest.mark.parametrize("name", ["net_hr_noise_136x248.npz", "net_hr_ramps_72x100.npz"])
 def test_alternative_launch_plans_keep_parity(monkeypatch, knobs, name):
     """The plan builder has opt-in / opt-out kernels (row-folded stride-2 convs, pyramid-tail chains, two-conv kernel,
@@ -414,13 +415,14 @@ def test_export_clip_matches_per_frame_pack(nets, tmp_path):
     net = nets("hr", "fp16")
     frames = [hb.synth_frame(i, 72, 100) for i in range(5)]
     out = tmp_path / "clip.rgb48"
-    rec = hb.export_clip(net, lambda i: frames[i], 5, str(out))
-    data = np.fromfile(out, dtype=np.uint16).reshape(5, 72, 100, 3)
-    for i, f in enumerate(frames):
-        o, _ = net.infer(net.preprocess(f))
-        torch.cuda.synchronize()
-        assert np.array_equal(data[i], O.pack_rgb48(o.cpu().numpy()))
-    assert [d[0] for d in rec["descriptors"]] == list(range(5))
+    for one_call in (True, False):               # hdrtv_process per frame / preprocess -> infer -> pack: same bytes
+        rec = hb.export_clip(net, lambda i: frames[i], 5, str(out), one_call=one_call)
+        data = np.fromfile(out, dtype=np.uint16).reshape(5, 72, 100, 3)
+        for i, f in enumerate(frames):
+            o, _ = net.infer(net.preprocess(f))
+            torch.cuda.synchronize()
+            assert np.array_equal(data[i], O.pack_rgb48(o.cpu().numpy())), (one_call, i)
+        assert [d[0] for d in rec["descriptors"]] == list(range(5))
 
 
 # ------------------------------------------------------------------------------------------- P8 INT8 Full-QAT layout
