@@ -33,6 +33,30 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.hdrtv_version()
 
 
+def test_header_constants_match_the_binding():
+    """The enum values of include/hdrtv_b200.h are restated in _native.py (ctypes has no header parser): keep them equal."""
+    header = open(os.path.join(REPO, "include", "hdrtv_b200.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"\b(HDRTV_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    want = {"HDRTV_FP32": _native.FP32, "HDRTV_FP16": _native.FP16, "HDRTV_COND_BICUBIC_AA": _native.COND_BICUBIC_AA,
+            "HDRTV_COND_ZERO": _native.COND_ZERO, "HDRTV_COND_BILINEAR": _native.COND_BILINEAR,
+            "HDRTV_TRANSFER_IDENTITY": _native.TRANSFER_IDENTITY, "HDRTV_TRANSFER_LUT": _native.TRANSFER_LUT,
+            "HDRTV_PROCESS_SERIAL": _native.PROCESS_SERIAL, "HDRTV_PROCESS_INPUT_READY": _native.PROCESS_INPUT_READY,
+            "HDRTV_PROCESS_RESYNC": _native.PROCESS_RESYNC}
+    for k, v in want.items():
+        assert consts.get(k) == v, k
+    # hdrtv_process is the one-call entry of SURVEY §8b: BGR24 in, RGB48 out
+    lib = _native.load()
+    assert lib.hdrtv_process.argtypes is not None and len(lib.hdrtv_process.argtypes) == 10
+
+
+def test_one_call_path_needs_cuda_and_valid_frames():
+    """process_rgb48 has no CPU path either: constructing the backend without CUDA raises (hdrtvnet_torch.py:1678-1690)."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        hb.HDRTVNetB200(os.path.join(REPO, "tests", "golden", "weights_hr.npz"), device="cuda", precision="fp16")
+
+
 def test_library_contains_blackwell_sass():
     """tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, cp.async.bulk -> UBLKCP (B200_PROFILING.md)."""
     cuobjdump = "/usr/local/cuda/bin/cuobjdump"
