@@ -207,11 +207,6 @@ def run_b200_arm(args):
     with contextlib.redirect_stdout(sys.stderr):     # the wrapper prints the reference's load banner: stdout carries the JSON line only
         net = hb.HDRTVNetB200(WEIGHTS, device=f"cuda:{local_rank}", precision=precision, warmup_passes=0, use_hg=False)
     packer = hb.RGB48Packer(dev, ring_frames=3)
-    # The caller's stream carries the network; the backend's own side streams (next frame's copy-in / preprocess /
-    # classifier, copy-out) are created with the default (lowest) priority.  A high-priority caller stream lets the
-    # single-wave network kernels claim SMs before the side-stream blocks do (--stream-priority high; off unless asked for).
-    if args.stream_priority == "high":
-        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     K, Wm = args.steps, max(3, args.warmup)
     n_distinct = 16
     first, _ = hb.frame_chunk(world * K, rank, world)            # contiguous chunk of the (weak-scaled) clip
@@ -341,8 +336,7 @@ def run_b200_arm(args):
             "config": {"workload": CONFIG_NAME[args.workload], "height": h, "width": w, "weights": "HR.pt (fixture copy)",
                        "frames": "4 synthetic content classes cycled, 16 distinct frames per rank",
                        "l2": "per-frame activation working set (>= 1 GB at 1080p) exceeds the 126 MB L2; no explicit flush",
-                       "sharding": f"contiguous frame chunks, {world} rank(s), no data-path collective",
-                       "caller_stream_priority": args.stream_priority},
+                       "sharding": f"contiguous frame chunks, {world} rank(s), no data-path collective"},
             "pixels_per_s": fps * px,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 6,
                     "api": "HDRTVNetB200.process_rgb48 (one C-ABI call per frame: hdrtv_process), pinned u8 frame in, RGB48 in a "
@@ -395,8 +389,6 @@ def main():
     ap.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stream-priority", choices=["high", "default"], default="default",
-                    help="priority of the stream the frames are submitted on (the backend's side streams use the default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -185,14 +185,8 @@ constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels pe
 // input row consumed (and its ring slot released) once, and a ring of kFoldR accumulator blocks instead of two stages.
 constexpr int kFoldR = 8;
 
-// MC (zsplit = 3 launches only): the three CTAs that run the three weight variants of one strip / band form a cluster
-// (consecutive blockIdx.x) and share every input row: each producer requests a third of the row's planes and the TMA
-// multicasts them into all three rings, so a row crosses L2 -> SM once instead of three times and every CTA issues a
-// third of the copies.  A slot is refilled once all readers of all three CTAs have released it (multicast commits).
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool MC = false>
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
 __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
-  static_assert(!MC || conv_dual(AUX, SFTG, FOLD), "multicast variant: plain dual-issuer instances");
-  constexpr uint16_t kMcMask = 0x7;
   static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
                 "in-kernel SFT generator: 32-channel outputs only");
   static_assert(!FOLD || (KIND == IN_PAR3x3S2 && !SFTG && MODE == STORE_P8 && N <= 64), "row folding: plain stride-2 3x3 convs");
@@ -233,7 +227,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) {
       mbar_init(full_bar(i), 1);
-      mbar_init(empty_bar(i), (DUAL ? 2 : 1) * (MC ? 3 : 1));
+      mbar_init(empty_bar(i), DUAL ? 2 : 1);
     }
     for (int i = 0; i < (FOLD ? kFoldR : 2); ++i) {
       mbar_init(tfull_bar(i), 1);
@@ -256,10 +250,8 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();      // every CTA's barriers are initialised before any peer signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -316,12 +308,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
         for (int c = 0; c < NCOPY; ++c) {
           unsigned long long a;
           asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(src));
-          if constexpr (MC) {
-            if (static_cast<uint32_t>(c % 3) == crank)
-              bulk_g2s_multicast(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot), kMcMask);
-          } else {
-            bulk_g2s(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot));
-          }
+          bulk_g2s(dst + c * kPlaneBytes, reinterpret_cast<const void*>(a), kPlaneBytes, full_bar(slot));
         }
         src += row_entries;
         if (++slot == ring_n) { slot = 0; ph ^= 1; }
@@ -447,13 +434,8 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
             tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
           });
           if (my_last) {
-            if constexpr (MC) {
-              tc_commit_multicast(empty_bar(slot), kMcMask);
-              if (!other_reads) tc_commit_multicast(empty_bar(slot), kMcMask);
-            } else {
-              tc_commit(empty_bar(slot));
-              if (!other_reads) mbar_arrive(empty_bar(slot));      // sole reader: supply the second arrival
-            }
+            tc_commit(empty_bar(slot));
+            if (!other_reads) mbar_arrive(empty_bar(slot));      // sole reader: supply the second arrival
           }
           if (dy == KS - 1) {
             tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
@@ -733,7 +715,6 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-  if constexpr (MC) cluster_sync_all();      // no CTA leaves while a peer may still write its ring or signal its barriers
 }
 
 inline size_t conv_sftg_bytes(const ConvParams& p, bool ps) {

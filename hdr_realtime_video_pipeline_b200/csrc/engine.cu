@@ -182,7 +182,6 @@ struct ConvLaunch {
   int kind = 0, kch = 0;
   bool sftg = false;
   bool fold = false;                    // row-folded stride-2 3x3 (conv_p8_kernel<..., FOLD>); weights are the ".fold2" pack
-  bool mc = false;                      // zsplit = 3 launch as clusters of three CTAs with TMA-multicast input rows (conv_p8_kernel<..., MC>)
   int N;
   int mode;
   dim3 grid;
@@ -347,27 +346,6 @@ static void choose_grid(ConvLaunch& L, int strips, int max_occ = 8) {
   L.grid = dim3(strips * zs, (p.Ho + band - 1) / band, z);
 }
 
-// Co-resident clusters of `cluster_x` CTAs the device can hold for this kernel configuration (0 on error).
-template <typename Kernel>
-static int max_active_clusters(Kernel kernel, int threads, size_t smem, int cluster_x) {
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 0;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>(cluster_x) * 64);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster_x);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return n;
-}
-
 struct Epi {
   int act = ACT_NONE;
   const P8* res = nullptr;
@@ -465,26 +443,6 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   L.name = name;
   const int wstrip = (p.xmul == 2) ? down2(Wo) : Wo;
   choose_grid(L, (wstrip + kTileM - 1) / kTileM);
-  if (e.zsplit == 3 && !e.fold && kind == IN_PAR3x3S2 && kchunks == 8 && N == 64 && mode == STORE_P8 && !e.res && !e.res2 &&
-      !e.sft && !e.sft_s0 && !e.raw && env_int("HDRTV_MC", 0)) {
-    // clusters of three must all be resident at once (single wave): ask the device how many fit
-    const int fit = max_active_clusters(conv_p8_kernel<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, false, true>,
-                                        conv_threads(false, false, false), L.smem, 3);
-    int need = static_cast<int>(L.grid.x / 3 * L.grid.y * L.grid.z);
-    const int strips3 = static_cast<int>(L.grid.x / 3);
-    if (fit < need && fit >= strips3 && L.grid.z == 1) {     // a few clusters too many: slightly taller bands instead of unicast
-      const int nb = fit / strips3;
-      const int band = (p.Ho + nb - 1) / nb;
-      const int gy = (p.Ho + band - 1) / band;
-      if (strips3 * gy <= fit && strips3 * gy * 100 >= need * 85) {
-        p.band = band;
-        L.grid.y = static_cast<unsigned>(gy);
-        need = strips3 * gy;
-      }
-    }
-    L.mc = fit >= need;
-    if (env_int("HDRTV_MC_VERBOSE", 0)) fprintf(stderr, "[hdrtv] %s: clusters needed %d, resident %d -> %s\n", name.c_str(), need, fit, L.mc ? "multicast" : "unicast");
-  }
   plan.push_back(L);
   return 0;
 }
@@ -498,32 +456,21 @@ static bool use_pdl() {
   return v < 0 ? g_pdl_small_frame : v != 0;
 }
 template <typename Kernel, typename Params>
-static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, const Params& params,
-                              int cluster_x = 1) {
+static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, const Params& params) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  int n = 0;
-  if (cluster_x > 1) {
-    attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
-    ++n;
-  }
-  if (use_pdl()) {
-    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = n;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
+
 template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
@@ -559,16 +506,6 @@ static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
   if (L.c2x) return launch_conv2x(L, s);
-  if (L.mc) {       // CondNet{2,3,4}.0: three weight variants of one strip as a cluster with multicast input rows
-    static bool configured = false;
-    auto k = conv_p8_kernel<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, false, true>;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return e;
-      configured = true;
-    }
-    return launch_pdl(k, L.grid, conv_threads(false, false, false), L.smem, s, L.p, 3);
-  }
   if (L.fold) {     // row-folded stride-2 3x3 convs of the condition pyramid
     if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 64) return launch_conv_t<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, true>(L, s);
     if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 16) return launch_conv_t<IN_PAR3x3S2, 8, 16, STORE_P8, false, false, true>(L, s);
@@ -1022,8 +959,6 @@ __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
   __shared__ float fea[6];
   __shared__ float sc[3][64], sh[3][64];
   const int t = threadIdx.x;
-  grid_dep_launch();          // the AGCM MLP kernel loads these folded weights only after its own dependency wait
-  grid_dep_wait();
   if (t < 128) mean5[t] = static_cast<float>(p.stats5[2 * t] / p.cnt5);
   __syncthreads();
   if (t < 6) {
@@ -1186,6 +1121,10 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     cudaEventRecord(e, s);
     evs->push_back(e);
   };
+  // The classifier kernels are ordinary launches.  Launching them programmatically (each level staging its weights while
+  // the previous one drains) gained 1.5 % frames/s at 1080p but the first one or two frames of a pipelined burst on an
+  // idle GPU then came out with regions of stale data (scripts/check_paths.py: the blocked dependent blocks perturb the
+  // placement of the network's single-wave grids); removed.
   CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
   static const int convi[6] = {0, 4, 8, 12, 16, 20};
   static const int normi[5] = {3, 7, 11, 15, -1};
@@ -1219,7 +1158,8 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
       CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured = true;
     }
-    CK(c, launch_pdl(cls_level_kernel, dim3(blocks), 256, sm, s, p));
+    cls_level_kernel<<<blocks, 256, sm, s>>>(p);
+    CK(c, cudaGetLastError());
     ++c->launches;
     mark();
   }
@@ -1243,7 +1183,8 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
   hp.w3 = c->wd.at("AGCM.conv_last.weight");  hp.b3 = c->wd.at("AGCM.conv_last.bias");
   hp.fea = c->d_fea;
   hp.fold32 = c->d_fold32;
-  CK(c, launch_pdl(agcm_head_kernel, dim3(1), 256, 0, s, hp));
+  agcm_head_kernel<<<1, 256, 0, s>>>(hp);
+  CK(c, cudaGetLastError());
   ++c->launches;
   return 0;
 }
