@@ -272,7 +272,8 @@ def run_b200_arm(args):
         return time.perf_counter() - e0, checks
 
     host_np = [f.numpy() for f in host_frames]
-    e2e_s, checks = e2e_run(lambda i: net.process_rgb48(host_np[i % n_distinct]), 3)
+    one_call_serial = os.environ.get("BENCH_ONE_CALL_SERIAL", "0") == "1"       # diagnostic knob
+    e2e_s, checks = e2e_run(lambda i: net.process_rgb48(host_np[i % n_distinct], serial=one_call_serial), 3)
     e2e3_s, checks3 = e2e_run(lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(host_np[i % n_distinct])), state), 2)
     if checks != checks3:
         raise RuntimeError("one-call and three-call frame paths disagree")

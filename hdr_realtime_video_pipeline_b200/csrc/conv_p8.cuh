@@ -10,17 +10,9 @@
 // The bias is added by the tensor core too: one extra K=16 step multiplies a constant [1,1,0,..] operand with
 // [bias_hi, bias_lo, 0,..] (fp16 hi/lo split, ~22-bit bias), so the epilogue has no per-channel loads.
 //
-// Warp roles (320 threads, 352 for DUAL instances): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 = epilogue:
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 = epilogue:
 // two warps per TMEM lane quadrant, each draining one half of the N columns.  Residual / SFT operands of a row
 // are requested BEFORE the wait on the accumulator so their HBM latency hides behind the MMAs.
-//
-// Two MMA issuers (DUAL: instances without auxiliary epilogue operands, the in-kernel SFT generator or row folding).  tcgen05.mma issue blocks
-// until the pipe accepts the instruction, and each output row costs the issuing warp three mbarrier waits, three
-// elections and three commits (50-110 cycles apiece, scripts/sync_probe.py): with one issuer the stride-2 64 -> 64
-// convs ran at 73 cycles per MMA against the 48 the pipe needs (profiles/r1_ncu_top_kernels_4k.md: 37 MMAs in 2 708
-// cycles per row).  Warp 1 issues the even output rows (TMEM stage 0), warp 10 the odd ones (stage 1); an input-row
-// slot is released by two arrivals, one from each issuer after its last read of the row (an issuer that is the
-// row's only reader arrives twice).
 //
 // Replaces the cuDNN conv2d calls of the reference's eager path (Condition_arch.py:571-583,
 // HDRUNet3T1_arch.py:160-205, arch_util.py:68-95) with bias / activation / residual / SFT / PixelShuffle fused.
@@ -38,10 +30,7 @@ constexpr int kPlaneBytes = kPlaneEntries * 16;    // 2176
 constexpr int kMaxSteps = 40;
 constexpr int kMaxCopies = 16;
 constexpr int kMaxRing = 8;
-constexpr int kConvThreads = 320;                // 10 warps: producer, MMA issuer, 8 epilogue warps
-// DUAL instances (no auxiliary epilogue operands, no SFT generator, no row folding) run a second MMA-issuing warp
-__host__ __device__ constexpr bool conv_dual(bool aux, bool sftg, bool fold) { return !aux && !sftg && !fold; }
-__host__ __device__ constexpr int conv_threads(bool aux, bool sftg, bool fold) { return conv_dual(aux, sftg, fold) ? kConvThreads + 32 : kConvThreads; }
+constexpr int kConvThreads = 320;
 constexpr int kSmemHeader = 512 + kPlaneBytes + 128;   // barriers, step-descriptor table, constant "ones" operand (bias step)
 
 enum StoreMode : int { STORE_P8 = 0, STORE_PS = 1, STORE_PLANAR = 2 };
@@ -93,7 +82,6 @@ struct ConvParams {
   ConvCopy copies[kMaxCopies];
   uint32_t copy_src0, copy_src_stride, copy_par_off;   // source entry of copy c: src0 + (c / npar) * stride + (c % npar) * par_off
   int slot_bytes, ring;
-  int l2_prefetch;     // > 0: the producer prefetches input row q + l2_prefetch into L2 when it requests row q
   int n_steps;         // tap steps; the weight buffer holds n_steps + 1 (the last one is the bias step)
   ConvStep steps[kMaxSteps];
   const uint4* wpk;
@@ -186,12 +174,11 @@ constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels pe
 constexpr int kFoldR = 8;
 
 template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
-__global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
   static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
                 "in-kernel SFT generator: 32-channel outputs only");
   static_assert(!FOLD || (KIND == IN_PAR3x3S2 && !SFTG && MODE == STORE_P8 && N <= 64), "row folding: plain stride-2 3x3 convs");
   constexpr bool PSG = SFTG && MODE == STORE_PS;
-  constexpr bool DUAL = conv_dual(AUX, SFTG, FOLD);
   // SFTG: 2 x 32 conv + 2 x 64 scale|shift columns; PixelShuffle: 2 x 128 conv + 4 sub-pixels x 64 (single-buffered)
   constexpr uint32_t kTmemCols = FOLD ? (kFoldR * N < 32 ? 32 : kFoldR * N) : SFTG ? (PSG ? 512 : 256) : ((2 * N < 32) ? 32 : 2 * N);
   constexpr int SRING = PSG ? kSRingPS : kSRing;
@@ -227,7 +214,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) {
       mbar_init(full_bar(i), 1);
-      mbar_init(empty_bar(i), DUAL ? 2 : 1);
+      mbar_init(empty_bar(i), 1);
     }
     for (int i = 0; i < (FOLD ? kFoldR : 2); ++i) {
       mbar_init(tfull_bar(i), 1);
@@ -276,31 +263,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
       const uint4* ssrc = SFTG ? p.s0 + (static_cast<long>(oy0) * (PSG ? 2 : 1) + 1) * p.s0_row_entries +
                                      static_cast<long>(p.s0_src0) + x0
                                : nullptr;
-      // L2 prefetch distance: the ring holds only ks + 1..2 rows of the fat (64-channel) inputs, far less than the loaded
-      // HBM latency; rows requested `pf` rows ahead are in L2 by the time their slot frees up.
-      const int pf = p.l2_prefetch;
-      const uint4* psrc = src + static_cast<long>(pf) * row_entries;
-      if (pf > 0) {
-        const uint4* s0p = src + static_cast<long>(ring_n) * row_entries;
-        for (int q = static_cast<int>(ring_n); q < pf && q < nrows_in; ++q, s0p += row_entries) {
-#pragma unroll
-          for (int c = 0; c < NCOPY; ++c) {
-            unsigned long long a;
-            asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(s0p));
-            bulk_prefetch_l2(reinterpret_cast<const void*>(a), kPlaneBytes);
-          }
-        }
-      }
       for (int q = 0; q < nrows_in; ++q) {
-        if (pf > 0 && q + pf < nrows_in) {
-#pragma unroll
-          for (int c = 0; c < NCOPY; ++c) {
-            unsigned long long a;
-            asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c / NPAR) * sstride + (c % NPAR) * spar), "l"(psrc));
-            bulk_prefetch_l2(reinterpret_cast<const void*>(a), kPlaneBytes);
-          }
-        }
-        psrc += row_entries;
         mbar_wait(empty_bar(slot), ph, p.err, 1);
         mbar_expect_tx(full_bar(slot), row_tx);
         const uint32_t dst = smem_u32(ring) + slot * slot_bytes;
@@ -347,7 +310,7 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
       // earlier lets them pile onto whichever SMs drain first and unbalances the single-wave grids.)
       grid_dep_launch();
     }
-  } else if (warp == 1 || (DUAL && warp == 10)) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp runs this (warp-uniform) loop so that descriptor arithmetic stays in uniform registers; one
     // elected lane issues.  Tap-step offsets are compile-time constants: the issuing warp looks nothing up while
@@ -403,51 +366,6 @@ __global__ void __launch_bounds__(conv_threads(AUX, SFTG, FOLD), (MODE == STORE_
         __syncwarp();
         if (++slot == ring_n) { slot = 0; ph ^= 1; }
       }
-    } else if constexpr (DUAL) {
-    // this warp issues output rows widx, widx + 2, ... into TMEM stage widx
-    const int widx = warp == 1 ? 0 : 1;
-    int waited = -1;
-    int base_slot = (widx * STRIDE) % ring_n, base_ph = ((widx * STRIDE) / ring_n) & 1;   // slot / phase of input row t*stride
-    for (int t = widx; t < nrows_out; t += 2) {
-      const int stage = widx;
-      mbar_wait(tempty_bar(stage), ((t >> 1) & 1) ^ 1, p.err, 3);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + stage * N;
-      int slot = base_slot, ph = base_ph;
-#pragma unroll
-      for (int dy = 0; dy < KS; ++dy) {
-        const int q = t * STRIDE + dy;
-        if (q > waited) {
-          mbar_wait(full_bar(slot), ph, p.err, 4);
-          waited = q;
-          tc_fence_after();
-        }
-        // release bookkeeping: my last read of row q?  does the other issuer (rows of the other parity) read it at all?
-        const bool my_last = q < (t + 2) * STRIDE || t + 2 >= nrows_out;
-        const int r_lo = max(0, (q - KS + STRIDE) / STRIDE), r_hi = min(nrows_out - 1, q / STRIDE);   // output rows reading q
-        const bool other_reads = r_hi > r_lo || ((r_lo ^ t) & 1);
-        const uint32_t a16 = ring16 + slot * slot16;
-        if (elect_one()) {
-          static_for<0, SPD>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            constexpr uint32_t a_off16 = kind_a_off(KIND, KCH, i) >> 4;
-            tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
-          });
-          if (my_last) {
-            tc_commit(empty_bar(slot));
-            if (!other_reads) mbar_arrive(empty_bar(slot));      // sole reader: supply the second arrival
-          }
-          if (dy == KS - 1) {
-            tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
-            tc_commit(tfull_bar(stage));
-          }
-        }
-        __syncwarp();
-        if (++slot == ring_n) { slot = 0; ph ^= 1; }
-      }
-      base_slot += 2 * STRIDE;
-      while (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
-    }
     } else {
     int waited = -1;
     int base_slot = 0, base_ph = 0;              // ring slot / phase of input row t*stride

@@ -431,9 +431,6 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
     ring = std::max(ring, std::min(fill, kMaxRing));
   }
   p.ring = ring;
-  // L2 prefetch distance of the input rows (experiment knob HDRTV_L2PF: rows ahead, fat slots only by default)
-  p.l2_prefetch = env_int("HDRTV_L2PF", 0);
-  if (p.slot_bytes < env_int("HDRTV_L2PF_MIN_SLOT", 16 * 1024)) p.l2_prefetch = 0;
   L.smem = conv_smem_bytes(p, mode == STORE_PS);
   if (L.smem > 227 * 1024) return fail(c, "conv " + name + ": shared memory budget exceeded");
   L.N = N;
@@ -480,7 +477,7 @@ static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>, L.grid, conv_threads(AUX, SFTG, FOLD), L.smem, s, L.p);
+  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>, L.grid, kConvThreads, L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>

@@ -247,8 +247,7 @@ def test_resolution_change_and_determinism(nets):
     assert np.array_equal(o1, o2)                                                # bitwise repeatable across re-allocation
 
 
-@pytest.mark.parametrize("knobs", [{"HDRTV_FOLD2": "1"}, {"HDRTV_CHAIN_TAIL": "0"}, {"HDRTV_C2X": "0"}, {"HDRTV_ZFUSE": "0"},
-                                   {"HDRTV_L2PF": "6", "HDRTV_L2PF_MIN_SLOT": "0"}])
+@pytest.mark.parametrize("knobs", [{"HDRTV_FOLD2": "1"}, {"HDRTV_CHAIN_TAIL": "0"}, {"HDRTV_C2X": "0"}, {"HDRTV_ZFUSE": "0"}])
 @pytest.mark.parametrize("name", ["net_hr_noise_136x248.npz", "net_hr_ramps_72x100.npz"])
 def test_alternative_launch_plans_keep_parity(monkeypatch, knobs, name):
     """The plan builder has opt-in / opt-out kernels (row-folded stride-2 convs, pyramid-tail chains, two-conv kernel,
