@@ -177,7 +177,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- B200 arm
@@ -376,12 +376,21 @@ def run_b200_arm(args):
                 "sample": f"{len(times)} synthetic 960x540 frames (BASELINE configs[0]) through oracle/torch_port.py "
                           f"(torch CPU eager fp32, the reference's setup_cpu path), first frame discarded, "
                           f"{float(np.mean(times)) * 1000:.0f} ms/frame; frames/s scaled by pixel count to {w}x{h}"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+JSON_OUT = sys.stdout
+
+
 def main():
+    # stdout carries the JSON line and nothing else: library banners written to file descriptor 1 (NCCL's version line,
+    # the wrapper's load banner) are sent to stderr
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
