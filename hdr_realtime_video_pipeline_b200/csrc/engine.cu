@@ -1118,10 +1118,10 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     cudaEventRecord(e, s);
     evs->push_back(e);
   };
-  // The classifier kernels are ordinary launches.  Launching them programmatically (each level staging its weights while
-  // the previous one drains) gained 1.5 % frames/s at 1080p but the first one or two frames of a pipelined burst on an
-  // idle GPU then came out with regions of stale data (scripts/check_paths.py: the blocked dependent blocks perturb the
-  // placement of the network's single-wave grids); removed.
+  // The classifier levels are launched programmatically (HDRTV_CLS_PDL=0: ordinary launches): a level stages its weights
+  // in shared memory while the previous one drains (+1.5 % frames/s at 1080p).  The head stays an ordinary launch: the
+  // event that hands its results to another stream is recorded right behind it.
+  static const bool cls_pdl = env_int("HDRTV_CLS_PDL", 1) != 0;
   CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
   static const int convi[6] = {0, 4, 8, 12, 16, 20};
   static const int normi[5] = {3, 7, 11, 15, -1};
@@ -1155,7 +1155,8 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
       CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured = true;
     }
-    cls_level_kernel<<<blocks, 256, sm, s>>>(p);
+    if (cls_pdl) CK(c, launch_pdl(cls_level_kernel, dim3(blocks), 256, sm, s, p));
+    else cls_level_kernel<<<blocks, 256, sm, s>>>(p);
     CK(c, cudaGetLastError());
     ++c->launches;
     mark();

@@ -3,6 +3,7 @@
 // Activations are planar NCHW fp32.  Reference: Condition_arch.py:8-35, 559-585; HDRUNet3T1_arch.py:152-206.
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace hdrtv {
 
@@ -158,7 +159,11 @@ __global__ void __launch_bounds__(256) cls_level_kernel(const ClsLevel p) {
   int* nwin = reinterpret_cast<int*>(nb + Cin);   // [PIX]
   __shared__ double ssum[128][2];
   const int tid = threadIdx.x;
+  // Programmatic dependent launch: the next level may start its prologue (static weights -> shared memory) while this
+  // level drains; everything below the wait reads what the previous launch wrote (input map, its statistics).
+  grid_dep_launch();
   for (int i = tid; i < Cin * Cout; i += 256) Wsm[i] = __ldg(p.w + i);
+  grid_dep_wait();
   const double cnt = static_cast<double>(p.H) * p.W;
   for (int ci = tid; ci < Cin; ci += 256) {
     if (p.in_stats) {
