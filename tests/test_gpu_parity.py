@@ -387,10 +387,12 @@ def test_one_call_frame_path_matches_the_three_calls(nets, precision):
 
 
 def test_frame_paths_agree_on_bursts_from_an_idle_gpu():
-    """Regression test: with the AGCM classifier launched programmatically (dependent levels resident early, blocked in
-    griddepcontrol.wait) the first one or two frames of a burst submitted to an idle GPU came out with regions of stale
-    data at 1920x1080, in about two runs out of three.  Every frame of every path (one-call pipelined / serial, three
-    calls), submitted back to back, must equal the frame produced with a device synchronisation after every call."""
+    """Regression test: a dual-issuer variant of the conv kernel had a race that only showed when the placement of the
+    network's single-wave grids was perturbed (the programmatically launched AGCM classifier levels of the next frame,
+    resident early and blocked in griddepcontrol.wait): the first one or two frames of a burst submitted to an idle GPU
+    came out with regions of stale data at 1920x1080 in about two runs out of three.  Every frame of every path
+    (one-call pipelined / serial, three calls), submitted back to back, must equal the frame produced with a device
+    synchronisation after every call."""
     import subprocess
     import sys
     for _ in range(2):
