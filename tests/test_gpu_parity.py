@@ -182,10 +182,30 @@ def test_fp32_network_matches_reference(nets, name):
     assert np.abs(codes.astype(np.int32) - g["rgb48"].astype(np.int32)).max() <= 7     # 1e-4 ~ 6.6 codes
 
 
+FP16_REF_NOISE = 1.5e-3
+
+
+def fp16_gate(d16, d32, dref, what):
+    """BASELINE.json: FP16 output within 2e-3 max-abs of the reference's FP16 path (d16).
+
+    Named exception.  2e-3 is 4 fp16 ulps at the network's output range (0.5..1), and the reference's own FP16 path sits
+    1.1e-3..6.7e-3 from its FP32 path (dref; SURVEY A.3, profiles/r2_parity.json) - its CPU and CUDA FP16 paths do not
+    even agree with each other on flat frames, where a frame-global bias enters through the InstanceNorm statistics of the
+    AGCM classifier (kept in FP32 here).  Two correct FP16 implementations can therefore be d32 + dref apart.  Where
+    d16 > 2e-3 the case must be one in which the reference's own FP16 error uses up at least three of those four ulps
+    (dref >= 1.5e-3) AND this build must be at least as close to the reference's FP32 output as the reference's FP16 path
+    is (d32 <= dref).  Every exception is recorded by name with its triangle in profiles/r2_parity.json."""
+    if d16 <= FP16_TOL:
+        return "d16<=2e-3"
+    assert dref >= FP16_REF_NOISE, (f"{what}: |ours-ref16| = {d16:.3e} > 2e-3 although the reference's own FP16 error is only "
+                                    f"{dref:.3e}")
+    assert d32 <= dref, f"{what}: |ours-ref32| = {d32:.3e} must not exceed the reference's own |ref16-ref32| = {dref:.3e}"
+    return "exception: reference FP16 noise dref>=1.5e-3, d32<=dref"
+
+
 @pytest.mark.parametrize("name", NET_CASES)
-def test_fp16_network_matches_reference(nets, name):
-    """Triangle ours16 / ref16 / ref32: the reference's own FP16 output sits 1.5e-3..4e-3 from its FP32
-    output, so the gate is: within 2e-3 of the reference FP16 path OR at least as close to FP32 as the reference is."""
+def test_fp16_network_matches_reference(nets, parity_log, name):
+    """Triangle ours16 / ref16 / ref32, strict gate: see fp16_gate."""
     g = load_golden(name)
     wname = "hr" if name.startswith("net_hr_") else "rand0"
     out, agcm = _run(nets(wname, "fp16"), g["frame"])
@@ -193,9 +213,56 @@ def test_fp16_network_matches_reference(nets, name):
     d16 = np.abs(out - ref16).max()
     d32 = np.abs(out - ref32).max()
     dref = np.abs(ref16 - ref32).max()
+    a16 = np.abs(agcm - g["agcm_fp16"].astype(np.float32)).max()
     print(f"{name}: |ours-ref16|={d16:.2e} |ours-ref32|={d32:.2e} |ref16-ref32|={dref:.2e}")
-    assert d16 <= FP16_TOL or d32 <= max(dref, FP16_TOL)
-    assert d32 <= 2 * max(dref, FP16_TOL)
+    how = fp16_gate(d16, d32, dref, name)
+    parity_log.add(test="fp16_small", case=name[:-4], ours_vs_ref16=d16, ours_vs_ref32=d32, ref16_vs_ref32=dref, agcm_vs_ref16=a16,
+                   gate=how, reference="Ensemble_AGCM_LE.half() on CPU (fixture)")
+
+
+LARGE_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "net540_*_*.npz")) +
+                     glob.glob(os.path.join(GOLDEN, "net1080_*.npz")) + glob.glob(os.path.join(GOLDEN, "net2160_*.npz")))
+
+
+def _sampled(out, g):
+    s = int(g["step"])
+    return np.concatenate([out[:, ::s, ::s].ravel(), out[:, g["rows"], :].ravel(), out[:, :, g["cols"]].ravel()])
+
+
+@pytest.mark.parametrize("name", LARGE_CASES)
+def test_fp16_config_sizes_match_reference(nets, parity_log, name):
+    """BASELINE configs 1-3 sizes (960x540, 1920x1080, 3840x2160), noise / ramps / white frames, HR.pt and seeded random
+    weights: the FP16 tcgen05 path against the reference's FP32 and FP16 (model.half()) outputs recorded by
+    scripts/make_golden_large.py at every 8th (16th at 4K) pixel, the border rows / columns and the columns around the
+    kernels' 126- / 128-pixel strip seams.  Through infer() and through the one-call process_rgb48() path."""
+    g = load_golden(name)
+    h, w = (int(v) for v in g["hw"])
+    wname = name.split("_")[1]
+    net = nets(wname, "fp16")
+    frame = hb.synth_frame(int(g["idx"]), h, w, str(g["cls"]))
+    out, agcm = _run(net, frame)
+    ours = _sampled(out[0], g)
+    ref32 = np.concatenate([g["sub32"].ravel(), g["rows32"].ravel(), g["cols32"].ravel()])
+    ref16 = np.concatenate([g["sub16"].ravel(), g["rows16"].ravel(), g["cols16"].ravel()]).astype(np.float32)
+    d16, d32 = np.abs(ours - ref16).max(), np.abs(ours - ref32).max()
+    dref = float(g["dref"][0])                                    # the reference's own FP16 error over the FULL frame
+    s = int(g["step"])
+    a16 = np.abs(agcm[0][:, ::s, ::s] - g["agcm16"].astype(np.float32)).max()
+    print(f"{name}: |ours-ref16|={d16:.2e} |ours-ref32|={d32:.2e} |ref16-ref32|={dref:.2e} agcm {a16:.2e}")
+    how = fp16_gate(d16, d32, dref, name)
+    assert a16 <= FP16_TOL or dref >= FP16_REF_NOISE
+    assert abs(float(out.mean()) - float(g["stats"][3])) <= 5e-4
+    # the one-call path must produce exactly the codes of this output, i.e. the same distance to the reference
+    fr = net.process_rgb48(frame)
+    codes = fr.numpy().copy()
+    fr.release()
+    assert np.array_equal(codes, O.pack_rgb48(out.astype(np.float16)))
+    ref_codes = O.pack_rgb48(g["sub16"][None])
+    dcodes = np.abs(codes[::s, ::s].astype(np.int32) - ref_codes.astype(np.int32)).max()
+    assert dcodes <= int(max(d16, FP16_TOL) * 65535) + 2
+    parity_log.add(test="fp16_config_sizes", case=name[:-4], height=h, width=w, ours_vs_ref16=d16, ours_vs_ref32=d32,
+                   ref16_vs_ref32=dref, agcm_vs_ref16=a16, rgb48_codes_vs_ref16=int(dcodes), samples=int(ours.size), gate=how,
+                   reference="Ensemble_AGCM_LE.half() / .float() on CPU (fixture, scripts/make_golden_large.py)")
 
 
 @pytest.mark.parametrize("wname", ["hr", "rand0"])
@@ -264,7 +331,7 @@ def test_alternative_launch_plans_keep_parity(monkeypatch, knobs, name):
     net.close()
     ref16, ref32 = g["out_fp16"].astype(np.float32), g["out"]
     d16, d32, dref = np.abs(out - ref16).max(), np.abs(out - ref32).max(), np.abs(ref16 - ref32).max()
-    assert d16 <= FP16_TOL or d32 <= max(dref, FP16_TOL), (knobs, d16, d32, dref)
+    fp16_gate(d16, d32, dref, f"{knobs} {name}")
 
 
 def test_outputs_are_deterministic_when_other_kernels_share_the_gpu(monkeypatch):
@@ -384,6 +451,80 @@ def test_one_call_frame_path_matches_the_three_calls(nets, precision):
         pq.close()
     with pytest.raises(ValueError):
         net.process_rgb48(np.zeros((8, 8), dtype=np.uint8))
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_p7_caller_sequence_replayed(nets, precision):
+    """P7: the reference's caller glue replayed in behaviour (gui_pipeline_worker_frame_processing.py:118-156, 255-309 and
+    the feeder thread gui_pipeline_worker_feeders.py:438-496), for boxes without the reference copy
+    (tests/test_gpu_reference_live.py runs the reference's own functions when it is installed):
+      producer thread : CUDA timing events on torch.cuda.current_stream() around preprocess + infer, end_event.synchronize(),
+                        a 4-deep torch.empty_like pool filled with copy_(non_blocking=True), ready_event.record(current stream),
+                        bounded queue;
+      feeder thread   : own host thread, ready_event.synchronize() -> tensor_to_rgb48_bytes (private stream) ->
+                        wait_ready()/buffer_view()/release().
+    200 frames, every frame byte-equal to serial execution and to process_rgb48."""
+    import queue
+    import threading
+    net = nets("hr", precision)
+    h, w = 136, 248
+    frames = [hb.synth_frame(i, h, w) for i in range(200)]
+    want = []
+    for f in frames:
+        out, _ = net.infer(net.preprocess(f))
+        torch.cuda.synchronize()
+        want.append(O.pack_rgb48(out.cpu().numpy()).tobytes())
+    q = queue.Queue(maxsize=2)
+    got, errors = [], []
+
+    def feeder():
+        state = {}
+        try:
+            while True:
+                item = q.get(timeout=30)
+                if item is None:
+                    return
+                _present_t, tensor, ready_event = item
+                ready_event.synchronize()
+                payload = hb.tensor_to_rgb48_bytes(tensor, state)
+                payload.wait_ready()
+                got.append(bytes(payload.buffer_view()))
+                payload.release()
+        except Exception as exc:                       # surfaced by the assert below
+            errors.append(exc)
+
+    th = threading.Thread(target=feeder, daemon=True)
+    th.start()
+    pool, pool_idx = None, 0
+    start_ev, end_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lat = []
+    for f in frames:
+        start_ev.record(torch.cuda.current_stream())
+        with torch.inference_mode():
+            tensor, cond = net.preprocess(f)
+            raw_out = net.infer((tensor, cond))
+        end_ev.record(torch.cuda.current_stream())
+        end_ev.synchronize()
+        lat.append(start_ev.elapsed_time(end_ev))
+        prepared = raw_out[0] if isinstance(raw_out, (tuple, list)) else raw_out
+        if pool is None:
+            pool = [torch.empty_like(prepared, memory_format=torch.contiguous_format) for _ in range(4)]
+        staged = pool[pool_idx]
+        pool_idx = (pool_idx + 1) % len(pool)
+        staged.copy_(prepared, non_blocking=True)
+        ready = torch.cuda.Event(enable_timing=False)
+        ready.record(torch.cuda.current_stream())
+        q.put((None, staged, ready), timeout=30)
+    q.put(None)
+    th.join(timeout=120)
+    assert not th.is_alive() and not errors, errors
+    assert len(got) == len(frames) and min(lat) > 0.0
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, bad[:8]
+    for i in (0, 1, 2, 3, 101):
+        fr = net.process_rgb48(frames[i])
+        assert bytes(fr.buffer_view()) == want[i]
+        fr.release()
 
 
 def test_frame_paths_agree_on_bursts_from_an_idle_gpu():
