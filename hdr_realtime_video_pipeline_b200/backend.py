@@ -68,23 +68,41 @@ def split_int8_state(state: dict):
     (ordinary fp32 state-dict with de-quantised weights, {layer: (x_scale, x_zero, mode)}).
 
     weight = weight_int8 * w_scale per output channel (:361); a layer with ``x_scale`` fake-quantises its input,
-    asymmetrically when it also has ``x_zero`` (:350-360).  Layers stored as plain ``weight`` pass through."""
-    out, quant = {}, {}
+    asymmetrically when it also has ``x_zero`` (:350-360).  Layers stored as plain ``weight`` pass through.
+    ``raw8`` (third result): {"<layer>.weight_int8": int8 weights as fp32, "<layer>.w_scale": scales} of the W8A8 layers, for
+    the kind::i8 tensor-core kernels."""
+    out, quant, raw8 = {}, {}, {}
     for k, v in state.items():
         if k.endswith(".weight_int8"):
             layer = k[: -len(".weight_int8")]
-            scale = np.asarray(state[layer + ".w_scale"], dtype=np.float32).reshape((-1,) + (1,) * (v.ndim - 1))
+            # W8A8 layers carry ".w_scale" (:361), weight-only W8 layers ".scale" (W8Conv2d / W8Linear, :233-291)
+            sc = state[layer + ".w_scale"] if (layer + ".w_scale") in state else state[layer + ".scale"]
+            scale = np.asarray(sc, dtype=np.float32).reshape((-1,) + (1,) * (v.ndim - 1))
             out[layer + ".weight"] = np.ascontiguousarray(np.asarray(v, dtype=np.float32) * scale)
+            if (layer + ".x_scale") in state:
+                raw8[layer + ".weight_int8"] = np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+                raw8[layer + ".w_scale"] = np.ascontiguousarray(np.asarray(sc, dtype=np.float32).reshape(-1))
         elif k.endswith(".x_scale"):
             layer = k[: -len(".x_scale")]
             zero = state.get(layer + ".x_zero")
             quant[layer] = (float(np.asarray(v).reshape(-1)[0]), float(np.asarray(zero).reshape(-1)[0]) if zero is not None else 0.0,
                             2 if zero is not None else 1)
-        elif k.endswith(".w_scale") or k.endswith(".x_zero"):
+        elif k.endswith(".w_scale") or k.endswith(".x_zero") or (k.endswith(".scale") and (k[: -len(".scale")] + ".weight_int8") in state):
             continue
         else:
             out[k] = v
-    return out, quant
+    return out, quant, raw8
+
+
+# The W8A8 layers of the reference's shipping INT8 layout, "INT8 Mixed QAT" (configs/qat_layouts/original_nohg_mixed_w8a8.txt):
+# the layers whose input quantisers the tensor-core path implements (kind::i8 launches for the stand-alone 3x3 convs, f16 MMAs
+# on values de-quantised by the producer for the ones inside fused kernels).
+MIXED_W8A8_LAYERS = frozenset(
+    ["LE.down_conv1", "LE.down_conv2", "LE.down_conv3", "LE.up_conv1.0", "LE.up_conv2.0", "LE.up_conv3.0",
+     "LE.recon_trunk1.0.conv1", "LE.recon_trunk1.0.conv2", "LE.recon_trunk2.0.conv1", "LE.recon_trunk2.0.conv2",
+     "LE.recon_trunk4.0.conv1", "LE.recon_trunk4.0.conv2", "LE.recon_trunk5.0.conv2",
+     "LE.CondNet1.4", "LE.CondNet2.4", "LE.CondNet3.0", "LE.CondNet3.2", "LE.CondNet3.4", "LE.CondNet4.0", "LE.CondNet4.2",
+     "LE.CondNet4.4"] + [f"LE.recon_trunk3.{j}.conv{k}" for j in range(4) for k in (1, 2)])
 
 
 def is_int8_state(state: dict) -> bool:
@@ -101,7 +119,7 @@ class HDRTVNetB200:
                  warmup_passes=3, fast_condition_resize=False,
                  # HDRTVNetTensorRT extras (hdrtvnet_torch.py:8172-8189): accepted and ignored
                  engine_width=None, engine_height=None, mode_name=None, qdq_fusion=None, keep_onnx=None,
-                 **ignored_tensorrt_kwargs):
+                 debug_library=False, **ignored_tensorrt_kwargs):
         self.model_path = model_path
         self._warmup_passes = warmup_passes
         self._fast_condition_resize = bool(fast_condition_resize) or _env_bool("HDRTVNET_FAST_COND_RESIZE", False)
@@ -117,8 +135,15 @@ class HDRTVNetB200:
         # INT8 layouts: the reference's eager INT8 model is fake-quantisation around ordinary convolutions
         # (hdrtvnet_torch.py:350-364); here it runs on the FP32 CUDA-core path with the same quantisers.
         self._int8 = self.precision in ("int8-full", "int8-mixed")
-        self._dtype = torch.float16 if self.precision == "fp16" else torch.float32
-        self._np_dtype = np.float16 if self.precision == "fp16" else np.float32
+        state, arch, quant, raw8 = self._read_checkpoint(model_path)
+        # INT8 checkpoints whose quantised layers are those of the mixed layout run on the FP16 tensor-core path with
+        # tcgen05.mma.kind::i8 launches for the W8A8 convs; any other layout (Full-QAT: all 128 layers) runs the reference's
+        # fake-quantisation arithmetic on the FP32 CUDA-core path.  HDRTV_B200_INT8_FP32=1 forces the latter.
+        self._int8_tensor_path = bool(quant) and set(quant) <= MIXED_W8A8_LAYERS and all(q[2] == 2 for q in quant.values()) \
+            and not _env_bool("HDRTV_B200_INT8_FP32", False)
+        half = self.precision == "fp16" or self._int8_tensor_path
+        self._dtype = torch.float16 if half else torch.float32
+        self._np_dtype = np.float16 if half else np.float32
         self._hg_weights_explicit = hg_weights is not None
         self._hg_weights = hg_weights
         self._use_hg = bool(use_hg)
@@ -136,14 +161,17 @@ class HDRTVNetB200:
         self.expected_hw = None
         self.is_static_input_model = False
 
-        self._lib = _native.load()
+        # debug_library=True (tests / scripts): the test build of the engine, which adds the debug, self-test and probe
+        # entry points of include/hdrtv_b200_test.h to the product ABI
+        self._debug_library = bool(debug_library) or _env_bool("HDRTV_B200_TEST_LIB", False)
+        self._lib = _native.load_test() if self._debug_library else _native.load()
         self._handle = C.c_void_p()
-        cfg = _native.Config(self.device.index, _native.FP16 if self.precision == "fp16" else _native.FP32)
+        cfg = _native.Config(self.device.index, _native.FP16 if half else _native.FP32)
         self._is_w8_model = self._int8
         rc = self._lib.hdrtv_create(C.byref(cfg), C.byref(self._handle))
         if rc != 0:
-            raise RuntimeError("hdrtv_create failed: " + _native.last_error(None))
-        self._load_model(model_path)
+            raise RuntimeError("hdrtv_create failed: " + _native.last_error(None, self._lib))
+        self._load_model(model_path, state, arch, quant, raw8)
 
         # Frame pipelining: preprocess() puts the H2D copy, the normalise / condition kernels and the AGCM condition
         # classifier (which depends on `cond` alone) on a side stream, so they overlap the previous frame's LE network;
@@ -151,6 +179,7 @@ class HDRTVNetB200:
         self._pipeline = _env_bool("HDRTV_B200_PIPELINE", True)
         self._side = None
         self._rgb48_ring = None
+        self._rgb48_ring_frames = None     # None: the reference's default / HDRTVNET_FEEDER_GPU_RGB48_RING_FRAMES
         self._lut_set = False
         self._proc_dirty = False          # hdrtv_process frames in flight on the context's own streams
         self._ev_inputs_free = self._ev_pre_done = None
@@ -184,17 +213,20 @@ class HDRTVNetB200:
         return "fp16" if p == "auto" else p
 
     # ------------------------------------------------------------------ weights (hdrtvnet_torch.py:2044-2169)
-    def _load_model(self, model_path):
+    def _read_checkpoint(self, model_path):
         state, arch = load_state_dict_any(model_path)
-        quant = {}
+        quant, raw8 = {}, {}
         if is_int8_state(state):
             if not self._int8:
                 raise ValueError(f"{model_path} is an INT8 checkpoint; use precision='int8-full' or 'int8-mixed'")
-            state, quant = split_int8_state(state)
+            state, quant, raw8 = split_int8_state(state)
         elif self._int8:
             raise ValueError(f"{model_path} is not an INT8 checkpoint.\n"
                              "  Re-run: python scripts/quantize/quantize_int8_full.py or "
                              "python scripts/quantize/quantize_int8_mixed.py")      # hdrtvnet_torch.py:1758-1762
+        return state, arch, quant, raw8
+
+    def _load_model(self, model_path, state, arch, quant, raw8):
         self._act_quant = quant
         classifier = str(arch.get("classifier", os.environ.get("HDRTVNET_CLASSIFIER", "color_condition"))).strip()
         le_arch = str(arch.get("le_arch", os.environ.get("HDRTVNET_LE_ARCH", "")) or "").strip()
@@ -214,9 +246,19 @@ class HDRTVNetB200:
             else:
                 print("WARNING: HG weights not found; continuing with no-HG model.")
             self._use_hg = False
-        descs = (_native.TensorDesc * len(state))()
+        if quant:          # before the weights: on the tensor-core path the weight pack builds the kind::i8 operands from them
+            names = sorted(quant)
+            arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+            arr_s = (C.c_float * len(names))(*[quant[n][0] for n in names])
+            arr_z = (C.c_float * len(names))(*[quant[n][1] for n in names])
+            arr_m = (C.c_int * len(names))(*[quant[n][2] for n in names])
+            self._check(self._lib.hdrtv_set_act_quant(self._handle, arr_n, arr_s, arr_z, arr_m, len(names)), "hdrtv_set_act_quant")
+        tensors = dict(state)
+        if self._int8_tensor_path:
+            tensors.update(raw8)
+        descs = (_native.TensorDesc * len(tensors))()
         keep = []
-        for i, (k, v) in enumerate(state.items()):
+        for i, (k, v) in enumerate(tensors.items()):
             v = np.ascontiguousarray(v, dtype=np.float32)
             keep.append(v)
             descs[i].name = k.encode()
@@ -224,17 +266,16 @@ class HDRTVNetB200:
             descs[i].ndim = v.ndim
             for d in range(v.ndim):
                 descs[i].shape[d] = v.shape[d]
-        _native.check(self._lib.hdrtv_set_weights(self._handle, descs, len(state)), self._handle, "hdrtv_set_weights")
-        self._n_params = int(sum(v.size for v in keep))
+        self._check(self._lib.hdrtv_set_weights(self._handle, descs, len(tensors)), "hdrtv_set_weights")
+        self._n_params = int(sum(v.size for v in state.values()))
         self._layer_shapes = {k[: -len(".weight")]: tuple(v.shape) for k, v in state.items() if k.endswith(".weight")}
-        if quant:
-            names = sorted(quant)
-            arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
-            arr_s = (C.c_float * len(names))(*[quant[n][0] for n in names])
-            arr_z = (C.c_float * len(names))(*[quant[n][1] for n in names])
-            arr_m = (C.c_int * len(names))(*[quant[n][2] for n in names])
-            _native.check(self._lib.hdrtv_set_act_quant(self._handle, arr_n, arr_s, arr_z, arr_m, len(names)), self._handle,
-                          "hdrtv_set_act_quant")
+
+    def _check(self, rc, what):
+        _native.check(rc, self._handle, what, self._lib)
+
+    def _need_debug_library(self):
+        if not self._debug_library:
+            raise RuntimeError("this call needs the test build of the engine: HDRTVNetB200(..., debug_library=True)")
 
     def _resolve_hg_weights(self, model_path):
         cands = [self._hg_weights]
@@ -261,7 +302,7 @@ class HDRTVNetB200:
         if h < 16 or w < 16:
             raise ValueError("frames must be at least 16x16")
         torch.cuda.synchronize(self.device)
-        _native.check(self._lib.hdrtv_prepare(self._handle, h, w), self._handle, "hdrtv_prepare")
+        self._check(self._lib.hdrtv_prepare(self._handle, h, w), "hdrtv_prepare")
         self._buf_hw = (h, w)
         ch, cw = max(1, h // 4), max(1, w // 4)
         dev, dt = self.device, self._dtype
@@ -288,7 +329,7 @@ class HDRTVNetB200:
         """preprocess()/infer() after process_rgb48(): order them behind the one-call path's internal streams."""
         if self._proc_dirty:
             cur = torch.cuda.current_stream(self.device)
-            _native.check(self._lib.hdrtv_process_flush(self._handle, C.c_void_p(cur.cuda_stream)), self._handle, "hdrtv_process_flush")
+            self._check(self._lib.hdrtv_process_flush(self._handle, C.c_void_p(cur.cuda_stream)), "hdrtv_process_flush")
             if self._side is not None:
                 self._side.wait_stream(cur)
             self._proc_dirty = False
@@ -299,11 +340,12 @@ class HDRTVNetB200:
         mode = (_native.COND_ZERO if self._fast_zero_condition else
                 (_native.COND_BILINEAR if self._fast_condition_resize else _native.COND_BICUBIC_AA))
         sp = C.c_void_p(stream.cuda_stream)
-        _native.check(self._lib.hdrtv_preprocess(self._handle, raw_dev.data_ptr(), h, w, self._gpu_input.data_ptr(),
-                                                 self._gpu_cond.data_ptr(), mode, sp), self._handle, "hdrtv_preprocess")
-        if self._pipeline:
-            _native.check(self._lib.hdrtv_classify(self._handle, self._gpu_input.data_ptr(), self._gpu_cond.data_ptr(), h, w, sp),
-                          self._handle, "hdrtv_classify")
+        if self._pipeline:       # fused front end: normalise (+ tensor-core staging) + condition image + AGCM classifier
+            self._check(self._lib.hdrtv_preprocess_classify(self._handle, raw_dev.data_ptr(), h, w, self._gpu_input.data_ptr(),
+                                                            self._gpu_cond.data_ptr(), mode, sp), "hdrtv_preprocess_classify")
+        else:
+            self._check(self._lib.hdrtv_preprocess(self._handle, raw_dev.data_ptr(), h, w, self._gpu_input.data_ptr(),
+                                                   self._gpu_cond.data_ptr(), mode, sp), "hdrtv_preprocess")
 
     @torch.inference_mode()
     def preprocess(self, frame_bgr):
@@ -386,7 +428,7 @@ class HDRTVNetB200:
                                           self._gpu_agcm.data_ptr(), 1 if skip else 0,
                                           C.c_void_p(self._ev_inputs_free.cuda_event), self._stream())
             if rc != 0:
-                raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle))
+                raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle, self._lib))
         return self._gpu_out, self._gpu_agcm
 
     # ------------------------------------------------------------------ postprocess (hdrtvnet_torch.py:2352-2368)
@@ -401,8 +443,8 @@ class HDRTVNetB200:
             self._ensure_buffers(h, w) if self._buf_hw != (h, w) else None
             src = output.contiguous()
             dt = _native.FP16 if src.dtype == torch.float16 else _native.FP32
-            _native.check(self._lib.hdrtv_pack_bgr24(self._handle, src.data_ptr(), dt, h, w, self._gpu_u8.data_ptr(),
-                                                     self._stream()), self._handle, "hdrtv_pack_bgr24")
+            self._check(self._lib.hdrtv_pack_bgr24(self._handle, src.data_ptr(), dt, h, w, self._gpu_u8.data_ptr(),
+                                                   self._stream()), "hdrtv_pack_bgr24")
             self._pin_output.copy_(self._gpu_u8, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
         return self._pin_output.numpy()
@@ -429,7 +471,8 @@ class HDRTVNetB200:
 
     # ------------------------------------------------------------------ one-call frame path (extension)
     @torch.inference_mode()
-    def process_rgb48(self, frame_bgr, serial: bool = False, transfer: str = "identity", input_ready: bool = False):
+    def process_rgb48(self, frame_bgr, serial: bool = False, transfer: str = "identity", input_ready: bool = False,
+                      checksum: bool = False):
         """BGR24 frame -> RGB48 frame in a pinned ring slot through ONE C-ABI call (``hdrtv_process``): what the
         playback / export loops do per frame with ``preprocess`` -> ``infer`` -> ``_tensor_to_rgb48_bytes``
         (gui_pipeline_worker_frame_processing.py:168-331, gui_pipeline_worker_feeders.py:193-249), bit-identical to
@@ -437,7 +480,8 @@ class HDRTVNetB200:
         which must stay untouched until the returned frame is ready) or a CUDA uint8 tensor.  Returns a
         ``PinnedFrame`` (wait_ready / buffer_view / release).  ``serial=True`` keeps every stage on the current
         stream (lowest single-frame latency); the default overlaps frame k+1's copy-in / preprocess / classifier and
-        frame k-1's copy-out with frame k's network."""
+        frame k-1's copy-out with frame k's network.  ``checksum=True``: the pack kernel also computes the frame's descriptor
+        checksum (``sharding.frame_checksum``) on the device; read it with ``PinnedFrame.checksum()``."""
         from .feeders import PinnedFrame, PinnedRing, pq_code_table
         if isinstance(frame_bgr, torch.Tensor):
             if frame_bgr.device.type != "cuda" or frame_bgr.dtype != torch.uint8 or frame_bgr.dim() != 3 or frame_bgr.shape[2] != 3:
@@ -456,11 +500,10 @@ class HDRTVNetB200:
             self._ensure_buffers(h, w)
             if transfer == "pq1000" and not self._lut_set:
                 lut = np.ascontiguousarray(pq_code_table(1000.0))
-                _native.check(self._lib.hdrtv_set_transfer_lut(self._handle, lut.ctypes.data, lut.size), self._handle,
-                              "hdrtv_set_transfer_lut")
+                self._check(self._lib.hdrtv_set_transfer_lut(self._handle, lut.ctypes.data, lut.size), "hdrtv_set_transfer_lut")
                 self._lut_set = True
             if self._rgb48_ring is None:
-                self._rgb48_ring = PinnedRing(self.device)
+                self._rgb48_ring = PinnedRing(self.device, self._rgb48_ring_frames)
             slot = self._rgb48_ring.acquire((h, w, 3))
             slot["source"] = src                       # keeps the input frame alive until the slot is reused
             mode = (_native.COND_ZERO if self._fast_zero_condition else
@@ -473,12 +516,23 @@ class HDRTVNetB200:
             self._proc_dirty = True
             tr = _native.TRANSFER_LUT if transfer == "pq1000" else _native.TRANSFER_IDENTITY
             self._cls_ready = False
-            rc = self._lib.hdrtv_process(self._handle, ptr, h, w, slot["tensor"].data_ptr(), mode, tr, flags,
-                                         C.c_void_p(slot["event"].cuda_event), self._stream())
+            slot["has_checksum"] = bool(checksum)
+            rc = self._lib.hdrtv_process_ex(self._handle, ptr, h, w, slot["tensor"].data_ptr(), mode, tr, flags,
+                                            C.c_void_p(slot["checksum"].data_ptr()) if checksum else None,
+                                            C.c_void_p(slot["event"].cuda_event), self._stream())
             if rc != 0:
                 slot["free"].set()
-                raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle))
+                raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle, self._lib))
         return PinnedFrame(slot, slot["event"])
+
+    def set_rgb48_ring_frames(self, n: int):
+        """Depth of process_rgb48's pinned RGB48 ring (frames that may be in flight + 1); takes effect when the ring is
+        (re)created.  The reference's ring holds 3 frames (gui_pipeline_worker_feeders.py:28-36)."""
+        n = max(2, min(16, int(n)))
+        if self._rgb48_ring is not None and self._rgb48_ring.ring_frames != n:
+            torch.cuda.synchronize(self.device)
+            self._rgb48_ring = None
+        self._rgb48_ring_frames = n
 
     def _warmup(self):
         h, w = self.expected_hw or (1080, 1920)
@@ -507,6 +561,7 @@ class HDRTVNetB200:
 
     def debug_tensors(self) -> dict:
         """Named intermediates of the last infer() as (C,H,W) fp32 numpy arrays (synchronises)."""
+        self._need_debug_library()
         out = {}
         n = self._lib.hdrtv_debug_tensor_count(self._handle)
         name = C.create_string_buffer(128)
@@ -514,7 +569,7 @@ class HDRTVNetB200:
         for i in range(n):
             self._lib.hdrtv_debug_tensor_info(self._handle, i, name, 128, C.byref(c), C.byref(h), C.byref(w))
             arr = np.empty((c.value, h.value, w.value), dtype=np.float32)
-            _native.check(self._lib.hdrtv_debug_tensor_read(self._handle, i, arr.ctypes.data), self._handle, "debug read")
+            self._check(self._lib.hdrtv_debug_tensor_read(self._handle, i, arr.ctypes.data), "debug read")
             out[name.value.decode()] = arr
         return out
 
@@ -528,46 +583,62 @@ class HDRTVNetB200:
         n = self._lib.hdrtv_time_plan(self._handle, tensor.data_ptr(), cond.data_ptr(), h, w, self._gpu_out.data_ptr(),
                                       self._gpu_agcm.data_ptr(), ms, 256, names, 32768, self._stream())
         if n < 0:
-            raise RuntimeError("hdrtv_time_plan failed: " + _native.last_error(self._handle))
+            raise RuntimeError("hdrtv_time_plan failed: " + _native.last_error(self._handle, self._lib))
         return list(zip(names.value.decode().strip().split("\n"), [float(ms[i]) for i in range(n)]))
 
     def mma_probe(self, n, layout=0, vary=1, iters=2000, blocks=1, nacc=1):
+        self._need_debug_library()
         cyc = C.c_float()
-        _native.check(self._lib.hdrtv_mma_probe(self._handle, n, layout, vary, iters, blocks, nacc, C.byref(cyc)), self._handle,
-                      "hdrtv_mma_probe")
+        self._check(self._lib.hdrtv_mma_probe(self._handle, n, layout, vary, iters, blocks, nacc, C.byref(cyc)), "hdrtv_mma_probe")
         return float(cyc.value)
 
     def probe(self, kind, n=64, iters=2000, blocks=1, nwarps=4, nmma=4, groups=1, trace=False):
+        self._need_debug_library()
         cyc = C.c_float()
         tr = np.zeros(256, dtype=np.int64) if trace else None
-        _native.check(self._lib.hdrtv_probe(self._handle, kind, n, iters, blocks, nwarps, nmma, groups, C.byref(cyc),
-                                            tr.ctypes.data if trace else None), self._handle, "hdrtv_probe")
+        self._check(self._lib.hdrtv_probe(self._handle, kind, n, iters, blocks, nwarps, nmma, groups, C.byref(cyc),
+                                          tr.ctypes.data if trace else None), "hdrtv_probe")
         if trace:
             return float(cyc.value), tr.reshape(16, 4, 4)
         return float(cyc.value)
 
     def debug_layer(self, layer: str, x: np.ndarray, stride: int = 1) -> np.ndarray:
         """One named conv / linear layer of the FP32 (and INT8 fake-quant) path on host data: (Cin,H,W) -> (Cout,Ho,Wo)."""
+        self._need_debug_library()
         x = np.ascontiguousarray(x, dtype=np.float32)
         cin, h, w = x.shape
         wt = self._layer_shapes[layer]
         ks = wt[2] if len(wt) == 4 else 1
         ho, wo = (h + 2 * (ks // 2) - ks) // stride + 1, (w + 2 * (ks // 2) - ks) // stride + 1
         out = np.empty((wt[0], ho, wo), dtype=np.float32)
-        _native.check(self._lib.hdrtv_debug_layer(self._handle, layer.encode(), x.ctypes.data, cin, h, w, stride, out.ctypes.data),
-                      self._handle, "hdrtv_debug_layer")
+        self._check(self._lib.hdrtv_debug_layer(self._handle, layer.encode(), x.ctypes.data, cin, h, w, stride, out.ctypes.data),
+                    "hdrtv_debug_layer")
         return out
 
+    def debug_conv_i8(self, layer: str, q: np.ndarray, stride: int = 1):
+        """One W8A8 layer through its kind::i8 launch on uint8 codes (C,H,W): (raw int32 accumulators (N,Ho,Wo), float output)."""
+        self._need_debug_library()
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        cin, h, w = q.shape
+        n = self._layer_shapes[layer][0]
+        ho, wo = ((h - 1) // 2 + 1, (w - 1) // 2 + 1) if stride == 2 else (h, w)
+        acc = np.empty((n, ho, wo), dtype=np.int32)
+        out = np.empty((n // 4, 2 * ho, 2 * wo) if n == 128 else (n, ho, wo), dtype=np.float32)
+        self._check(self._lib.hdrtv_debug_conv_i8(self._handle, layer.encode(), q.ctypes.data, cin, h, w, stride, acc.ctypes.data,
+                                                  out.ctypes.data), "hdrtv_debug_conv_i8")
+        return acc, out
+
     def chain_trace(self, agcm=False, index=0):
+        self._need_debug_library()
         tr = np.zeros(64 * 8 * 8, dtype=np.int64)
-        _native.check(self._lib.hdrtv_chain_trace(self._handle, 1 if agcm else 0, index, tr.ctypes.data), self._handle,
-                      "hdrtv_chain_trace")
+        self._check(self._lib.hdrtv_chain_trace(self._handle, 1 if agcm else 0, index, tr.ctypes.data), "hdrtv_chain_trace")
         return tr.reshape(64, 8, 8)
 
     def conv_selftest(self, kind, cin, cout, h, w, flags=0):
+        self._need_debug_library()
         mx, ref = C.c_float(), C.c_float()
-        _native.check(self._lib.hdrtv_conv_selftest(self._handle, kind, cin, cout, h, w, flags, C.byref(mx), C.byref(ref)),
-                      self._handle, "hdrtv_conv_selftest")
+        self._check(self._lib.hdrtv_conv_selftest(self._handle, kind, cin, cout, h, w, flags, C.byref(mx), C.byref(ref)),
+                    "hdrtv_conv_selftest")
         return float(mx.value), float(ref.value)
 
     def close(self):

@@ -123,6 +123,8 @@ struct ChainParams {
   int strips;                // 128-pixel strips per row; the grid is 1-D, each CTA takes a contiguous (strip, row) range
   P8 outs[kMaxChain];        // per layer, where STORE != 0
   P8 outs2;                  // second home of a split store (STORE == 3)
+  ActQuant opq[kMaxChain];   // INT8 layouts: layer l+1 is a W8A8 layer -> its input quantiser is applied to layer l's operand
+                             // (only for layers whose output is not also stored: the stored tensor would be the raw one)
   long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [step<64][slot<8][8]
 };
 
@@ -130,10 +132,14 @@ __device__ __forceinline__ void group_barrier(int id) {
   asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 // Parked wait for the epilogue side (long suspend hint: fewer polling instructions competing with working warps).
+// Bounded by a poll COUNT (2^27 polls of >= ~30 ns each, up to 2 us when parked: between ~4 s and a few minutes): a loaded
+// box only makes polls slower, so it cannot trip the bound early, and the loop carries no 64-bit timer state - this wait sits
+// in the hottest loop of the chain kernels, which run at their register cap (the %globaltimer variant lives in the out-of-line
+// mbar_wait_slow).
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, int* err_word, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait_hint(bar, parity, 2000)) {
-    if (++spins > (1u << 20)) {
+    if (++spins > (1u << 27)) {
       if (err_word) atomicExch(err_word, code);
       __threadfence_system();
       __trap();
@@ -166,7 +172,9 @@ struct ChainWalk {
 #define CHAIN_STAMP(k) do { } while (0)
 #endif
 
-template <class Prog>
+// QOP: INT8 layouts - cp.opq[l] (the input quantiser of a W8A8 layer l+1) is applied to layer l's operand.  Compile-time, so
+// that the FP16 instances carry none of it.
+template <class Prog, bool QOP = false>
 __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid_constant__ ChainParams cp) {
   const ConvParams& p = cp.base;
   constexpr int G = kChainGroups;
@@ -332,6 +340,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
               float a[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) a[k] = act(v[c * 8 + k]);
+              if constexpr (QOP && kWrite != 0 && kStore == 0) {
+                if (cp.opq[l].mode) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) a[k] = fake_quant_h(a[k], cp.opq[l]);
+                }
+              }
               h[c] = pack8(a);
             }
             CHAIN_STAMP(4);

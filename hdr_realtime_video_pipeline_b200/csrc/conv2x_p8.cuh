@@ -58,7 +58,18 @@ struct Conv2xParams {
   int has_res, has_res2, has_raw;
   P8 res, res2, raw, out;                    // res: natural layout (streamed through shared memory)
   __half* planar; long planar_plane; int planar_W;
+  // STORE_PLANAR only, optional: the RGB48 feeder pack fused into this epilogue (gui_pipeline_worker_feeders.py:193-249:
+  // fp32 clamp * 65535 + 0.5, truncate, RGB order, HWC interleave) so that the one-call frame path needs no pack launch
+  // INT8 layouts (Type B: f16 MMAs on de-quantised values, the reference's eager INT8 semantics): qmid = input quantiser of
+  // conv B, applied to the mid rows; outq = uint8 copy of the output through `out_q` for an INT8 (kind::i8) consumer
+  ActQuant qmid, out_q;
+  int has_outq, skip_out;                    // skip_out: the fp16 `out` tensor has no reader
+  P8 outq;                                   // uint8 tensor: 16 channels per 16-byte entry (chunks = C / 16)
+  uint16_t* rgb48;                           // uint16 (H, W, 3), device memory
+  const uint16_t* rgb48_lut;                 // optional transfer code table indexed by the half bit pattern of the clamped value
+  unsigned long long* rgb48_cksum;           // optional descriptor checksum accumulator (kernels_io.cuh: cks_term)
   int* err;
+  uint32_t opaque_zero;      // 0 at run time, unknown to ptxas: data-dependent slot release (ptx.cuh, mbar_arrive_after)
   long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [row<64][role<8][8]
 };
 
@@ -446,6 +457,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             for (int k = 0; k < 8; ++k) {
               a[k] = fmaxf(v[c * 8 + k], 0.f);                                                  // ReLU
               if constexpr (SFTGA) a[k] = fmaf(a[k], sv[c * 8 + k], tv[c * 8 + k]);           // x*(scale+1)+shift, +1 in the bias step
+              a[k] = fake_quant_h(a[k], p.qmid);                                                // conv B is a W8A8 layer (INT8 layouts)
             }
             h[c] = inside_x ? pack8(a) : make_uint4(0, 0, 0, 0);
           }
@@ -481,8 +493,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
       const int x = sg.x0 + m;
       const int oy0 = sg.oy0;
       const bool xin = m < kC2Strip && x < p.W;
-      ColRef out, res2, raw;
+      ColRef out, res2, raw, outq;
       out.init(p.out, x);
+      if (p.has_outq) outq.init(p.outq, x);
       if (p.has_res2) res2.init(p.res2, x);
       if (p.has_raw) raw.init(p.raw, x);
       for (int t = 0; t < sg.n_out; ++t, ++g) {
@@ -508,7 +521,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
 #pragma unroll
           for (int c = 0; c < CH; ++c) dep |= r4[c].x | r4[c].w;
           __syncwarp();
-          if (lane == 0) mbar_arrive_after(res_empty(rslot), dep);
+          if (lane == 0) mbar_arrive_after(res_empty(rslot), dep, p.opaque_zero);
           if (++rslot == kC2ResRing) { rslot = 0; rph ^= 1; }
         } else {
 #pragma unroll
@@ -525,16 +538,34 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         if (lane == 0) mbar_arrive(b_tempty(pos));
         if (warp == 7) C2X_STAMP(4, g, 3);
         if constexpr (MODEB == STORE_PLANAR) {
+          unsigned long long cks = 0;
           if (xin) {
             uint4 o = pack8_act<ACTB>(v);
             hadd2x4(o, r4[0]);
             const __half* oh = reinterpret_cast<const __half*>(&o);
 #pragma unroll
             for (int k = 0; k < 3; ++k) p.planar[k * p.planar_plane + static_cast<long>(oy) * p.planar_W + x] = oh[k];
+            if (p.rgb48) {                                   // fused feeder pack: same arithmetic as pack_rgb48_kernel
+              const long e0 = (static_cast<long>(oy) * p.planar_W + x) * 3;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                float f = fminf(fmaxf(__half2float(oh[k]), 0.f), 1.f);
+                uint32_t code;
+                if (p.rgb48_lut) code = p.rgb48_lut[__half_as_ushort(__float2half_rn(f))];
+                else code = static_cast<uint32_t>(__fadd_rn(__fmul_rn(f, 65535.0f), 0.5f));
+                p.rgb48[e0 + k] = static_cast<uint16_t>(code);
+                cks += static_cast<unsigned long long>(code) * static_cast<unsigned long long>(static_cast<uint32_t>((e0 + k) % 65521) + 1u);
+              }
+            }
             if (p.has_raw) {
               o.y &= 0x0000FFFFu; o.z = 0u; o.w = 0u;                                            // channels 3..7 stay zero
               *raw.at(oy, 0) = o;
             }
+          }
+          if (p.rgb48_cksum) {                               // warp-uniform branch
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) cks += __shfl_xor_sync(0xffffffffu, cks, off);
+            if (lane == 0 && cks) atomicAdd(p.rgb48_cksum, cks);
           }
         } else {
           if (xin) {
@@ -552,8 +583,21 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
 #pragma unroll
               for (int c = 0; c < CH; ++c) *raw.at(oy, c) = o[c];
             }
+            if (!p.skip_out) {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) *out.at(oy, c) = o[c];
+              for (int c = 0; c < CH; ++c) *out.at(oy, c) = o[c];
+            }
+            if constexpr (CH >= 2) {
+              if (p.has_outq) {                    // uint8 codes of the (fp16) output for an INT8 consumer
+#pragma unroll
+                for (int c = 0; c < CH; c += 2) {
+                  float f0[8], f1[8];
+                  unpack8(o[c], f0);
+                  unpack8(o[c + 1], f1);
+                  *outq.at(oy, c >> 1) = pack16_u8(f0, f1, p.out_q);
+                }
+              }
+            }
           }
         }
         if (warp == 7) C2X_STAMP(4, g, 4);

@@ -111,6 +111,24 @@ struct ConvParams {
   long planar_plane;
   int planar_W;
   int* err;
+  // ---- INT8 layouts (W8A8Conv2d, hdrtvnet_torch.py:296-364) -------------------------------------------------------
+  // I8 instances: `in` is a uint8 tensor (16 channels per 16-byte entry: the P8 geometry of C/2 fp16 channels) holding the
+  // codes q of the layer's input quantiser, the weights are int8, the accumulator is S32 (tcgen05.mma.kind::i8) and the
+  // epilogue de-quantises:  conv(x^, w)[n] + b[n] = acc[n] * (x_scale * w_scale[n]) + beta[cls][n]   with
+  // beta[cls][n] = b[n] + x_zero * w_scale[n] * sum over the taps that are INSIDE the image for border class cls of
+  // sum_c w_int8[n, c, tap]  (zero padding is applied to x^, not to q: a padded tap contributes nothing, not x_zero).
+  const float* i8_alpha;      // [N]
+  const float* i8_beta;       // [16][N], cls = cy * 4 + cx, bit 0: first tap outside, bit 1: last tap outside
+  int i8_H, i8_W;             // input size
+  int* i8_acc_dump;           // test build: raw S32 accumulators, planar [N][Ho][Wo]
+  // Producer side of a W8A8 consumer: the values stored to `out` pass through that consumer's input quantiser, either as
+  // fp16 x^ (the consumer runs f16 MMAs on de-quantised values, like the reference's eager INT8 path) or, out_u8 = 1, as
+  // the uint8 codes themselves (`out` is then a uint8 tensor for an I8 consumer).  `raw` / `out2` stay unquantised.
+  ActQuant out_q;
+  int out_u8;
+  ActQuant in_q_z[3];         // XFORM instances: input quantiser of each fused variant (mode 0: none)
+  ActQuant out_q_z[3];        // zsplit launches: per-variant out_q / out_u8
+  int out_u8_z[3];
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -173,12 +191,43 @@ constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels pe
 // input row consumed (and its ring slot released) once, and a ring of kFoldR accumulator blocks instead of two stages.
 constexpr int kFoldR = 8;
 
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
-__global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
+// 16 uint8 codes (two 8-channel groups of one pixel) -> one 16-byte entry
+__device__ __forceinline__ uint4 pack16_u8(const float* a, const float* b, const ActQuant& q) {
+  uint4 u;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    w[i] = quant_u8_h(a[4 * i], q) | (quant_u8_h(a[4 * i + 1], q) << 8) | (quant_u8_h(a[4 * i + 2], q) << 16) | (quant_u8_h(a[4 * i + 3], q) << 24);
+    w[2 + i] = quant_u8_h(b[4 * i], q) | (quant_u8_h(b[4 * i + 1], q) << 8) | (quant_u8_h(b[4 * i + 2], q) << 16) | (quant_u8_h(b[4 * i + 3], q) << 24);
+  }
+  return u;
+}
+__device__ __forceinline__ uint4 pack8_fq(const float* f, const ActQuant& q) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = fake_quant_h(f[i], q);
+  return pack8(t);
+}
+// border class of an output coordinate o of a 3-tap window with the given stride over an input of `size`
+__device__ __forceinline__ int tap_class(int o, int stride, int size) {
+  return ((o * stride - 1 < 0) ? 1 : 0) | ((o * stride + 1 >= size) ? 2 : 0);
+}
+
+// XFORM (INT8 layouts, stride-2 3x3 on a parity-split fp16 input): four extra warps fake-quantise every input row IN PLACE in
+// its ring slot between the TMA arrival and the MMAs, with the input quantiser of this CTA's conv (p.in_q_z[variant]).  Used by
+// the launch that runs CondNet2.0 (weight-only INT8: no quantiser), CondNet3.0 and CondNet4.0 (W8A8, each with its own input
+// quantiser) on the same `cond` rows: the three convs keep sharing one fetch of `cond` instead of three pre-quantised copies.
+constexpr int kXformThreads = 128;
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool I8 = false, bool XFORM = false>
+__global__ void __launch_bounds__(kConvThreads + (XFORM ? kXformThreads : 0), (MODE == STORE_PS) ? 1 : 2)
+conv_p8_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!I8 || (!FOLD && kind_ks(KIND) == 3 && MODE != STORE_PLANAR), "INT8 instances: plain 3x3 convs");
+  static_assert(!XFORM || (KIND == IN_PAR3x3S2 && !SFTG && !FOLD && !I8), "in-place input quantiser: stride-2 3x3 on fp16 rows");
   static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
                 "in-kernel SFT generator: 32-channel outputs only");
   static_assert(!FOLD || (KIND == IN_PAR3x3S2 && !SFTG && MODE == STORE_P8 && N <= 64), "row folding: plain stride-2 3x3 convs");
   constexpr bool PSG = SFTG && MODE == STORE_PS;
+  constexpr bool OQ = I8 || XFORM;      // output quantisers (out_q / out_u8) exist only in the INT8-layout instances
   // SFTG: 2 x 32 conv + 2 x 64 scale|shift columns; PixelShuffle: 2 x 128 conv + 4 sub-pixels x 64 (single-buffered)
   constexpr uint32_t kTmemCols = FOLD ? (kFoldR * N < 32 ? 32 : kFoldR * N) : SFTG ? (PSG ? 512 : 256) : ((2 * N < 32) ? 32 : 2 * N);
   constexpr int SRING = PSG ? kSRingPS : kSRing;
@@ -197,6 +246,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
   auto sfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };
   auto sempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + kSRing + i); };   // kSRing >= kSRingPS
+  auto xready_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };            // XFORM (never with SFTG): kMaxRing slots
   uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
   uint8_t* wsm2 = wsm + ((p.w_bytes + 127) & ~127);
@@ -226,6 +276,9 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         mbar_init(sfull_bar(i), 1);
         mbar_init(sempty_bar(i), 1);
       }
+    }
+    if constexpr (XFORM) {
+      for (int i = 0; i < p.ring; ++i) mbar_init(xready_bar(i), kXformThreads / 32);
     }
     mbar_fence_init();
   }
@@ -317,6 +370,8 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     // the tensor pipe waits (an M=128 x N<=64 x K=16 MMA costs the pipe only ~45 cycles).
     mbar_wait(wfull_bar, 0, p.err, 2);
     constexpr uint32_t idesc = make_idesc_f16_m128(N);
+    constexpr uint32_t idesc_i8 = make_idesc_i8_m128(N);
+    (void)idesc_i8;
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
     auto mkdesc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
     const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 128);
@@ -380,7 +435,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       for (int dy = 0; dy < KS; ++dy) {
         const int q = t * STRIDE + dy;
         if (q > waited) {
-          mbar_wait(full_bar(slot), ph, p.err, 4);
+          mbar_wait(XFORM ? xready_bar(slot) : full_bar(slot), ph, p.err, 4);
           waited = q;
           tc_fence_after();
         }
@@ -389,11 +444,14 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
           static_for<0, SPD>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr uint32_t a_off16 = kind_a_off(KIND, KCH, i) >> 4;
-            tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
+            if constexpr (I8)
+              tc_mma_i8(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc_i8, (dy | i) ? 1u : 0u);
+            else
+              tc_mma_f16(d_tmem, mkdesc((a16 + a_off16) | a_lbo), mkdesc(b_lo0 + (dy * SPD + i) * b_step), idesc, (dy | i) ? 1u : 0u);
           });
           if (dy < STRIDE) tc_commit(empty_bar(slot));      // this input row is not needed by later output rows
           if (!SFTG && dy == KS - 1) {
-            tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
+            if constexpr (!I8) tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // + bias
             tc_commit(tfull_bar(stage));
           }
         }
@@ -419,7 +477,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
             tc_mma_f16(s_tmem, ones_desc, mkdesc(sb + 256), idesc64, 1u);
           }
           tc_commit(sempty_bar(sslot));
-          tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // conv bias
+          if constexpr (!I8) tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + (KS * SPD) * b_step), idesc, 1u);      // conv bias
           tc_commit(tfull_bar(stage));
         }
         __syncwarp();
@@ -428,6 +486,36 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       base_slot += STRIDE;
       if (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
     }
+    }
+  } else if (warp >= kConvThreads / 32) {
+    // ------------------------------------------------------------------ in-place input quantiser (XFORM)
+    if constexpr (XFORM) {
+      const ActQuant q = p.in_q_z[zsel];
+      const int tw = threadIdx.x - kConvThreads;
+      const uint32_t ring_n = p.ring;
+      uint32_t slot = 0, ph = 0;
+      for (int qrow = 0; qrow < nrows_in; ++qrow) {
+        mbar_wait(full_bar(slot), ph, p.err, 9);
+        const int iy = oy0 * STRIDE + qrow - 1;                  // image row held by this ring row (pad rows stay zero)
+        if (q.mode && iy >= 0 && iy < p.i8_H) {
+          uint4* base = reinterpret_cast<uint4*>(ring + slot * (NCOPY * kPlaneBytes));
+          for (int e = tw; e < NCOPY * kPlaneEntries; e += kXformThreads) {
+            const int plane = e / kPlaneEntries, k = e - plane * kPlaneEntries;
+            const int xx = 2 * (x0 + k - 1) + (plane & 1);       // pixel of entry k of a parity half-plane (pad entries stay zero)
+            if (xx >= 0 && xx < p.i8_W) {
+              float f[8];
+              unpack8(base[e], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fake_quant_h(f[i], q);
+              base[e] = pack8(f);
+            }
+          }
+          fence_proxy_async_smem();                              // generic-proxy writes -> visible to the MMAs' async-proxy reads
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xready_bar(slot));
+        if (++slot == ring_n) { slot = 0; ph ^= 1; }
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant
@@ -496,6 +584,24 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         tc_fence_after();
         float v[64];
         tmem_ld_cols<64>(tlane + stage * N + half * 64, v);
+        if constexpr (I8) {        // de-quantise: S32 accumulator -> conv + bias (border class of this pixel)
+          const int cls = tap_class(oy, STRIDE, p.i8_H) * 4 + tap_class(x, STRIDE, p.i8_W);
+          const float4* al = reinterpret_cast<const float4*>(p.i8_alpha + half * 64);
+          const float4* be = reinterpret_cast<const float4*>(p.i8_beta + cls * N + half * 64);
+#pragma unroll
+          for (int k4 = 0; k4 < 16; ++k4) {
+            const float4 a4 = __ldg(al + k4), b4 = __ldg(be + k4);
+            if (p.i8_acc_dump && xin) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                p.i8_acc_dump[(static_cast<long>(half * 64 + 4 * k4 + e) * p.Ho + oy) * p.Wo + x] = __float_as_int(v[4 * k4 + e]);
+            }
+            v[4 * k4 + 0] = fmaf(__int2float_rn(__float_as_int(v[4 * k4 + 0])), a4.x, b4.x);
+            v[4 * k4 + 1] = fmaf(__int2float_rn(__float_as_int(v[4 * k4 + 1])), a4.y, b4.y);
+            v[4 * k4 + 2] = fmaf(__int2float_rn(__float_as_int(v[4 * k4 + 2])), a4.z, b4.z);
+            v[4 * k4 + 3] = fmaf(__int2float_rn(__float_as_int(v[4 * k4 + 3])), a4.w, b4.w);
+          }
+        }
         if constexpr (!SFTG) {
           tc_fence_before();
           __syncwarp();
@@ -523,10 +629,11 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
 #pragma unroll
               for (int c = 0; c < 2; ++c) { s4[c] = __ldcg(sft[j].at(Y, 2 * half + c)); t4[c] = __ldcg(sft[j].at(Y, 2 * half + c + 4)); }
             }
+            float fin[OQ ? 2 : 1][8];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               const int ch = 2 * half + c;
-              float val[8];
+              float* val = fin[OQ ? c : 0];
 #pragma unroll
               for (int cc = 0; cc < 8; ++cc) val[cc] = v[32 * c + 4 * cc + sub];
               if (p.has_res) {
@@ -546,7 +653,14 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
 #pragma unroll
                 for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], s[k], val[k]) + tt[k];
               }
-              *out[j].at(Y, ch) = pack8(val);
+              if constexpr (OQ) {
+                if (!p.out_u8) *out[j].at(Y, ch) = p.out_q.mode ? pack8_fq(val, p.out_q) : pack8(val);
+              } else {
+                *out[j].at(Y, ch) = pack8(val);
+              }
+            }
+            if constexpr (OQ) {
+              if (p.out_u8) *out[j].at(Y, half) = pack16_u8(fin[0], fin[1], p.out_q);   // 16 channels = one uint8 entry
             }
           }
         }
@@ -558,6 +672,8 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
       ColRef out, out2, res, res2, sft, raw;
       if (zs > 1) out.init(p.out_zp[zsel], x);
       else out.init(p.out, x);
+      const ActQuant oq = !OQ ? ActQuant{} : (zs > 1 ? p.out_q_z[zsel] : p.out_q);
+      const bool ou8 = OQ && (zs > 1 ? p.out_u8_z[zsel] : p.out_u8) != 0;
       if (p.out_split > 0) out2.init(p.out2, x);
       if constexpr (AUX) {
         if (p.has_res) res.init(p.res, x);
@@ -591,10 +707,22 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(stage));
+        if constexpr (I8) {        // de-quantise: S32 accumulator -> conv + bias (border class of this pixel)
+          const int cls = tap_class(oy, STRIDE, p.i8_H) * 4 + tap_class(x, STRIDE, p.i8_W);
+          const float* al = p.i8_alpha + half * COLS;
+          const float* be = p.i8_beta + cls * N + half * COLS;
+#pragma unroll
+          for (int k = 0; k < COLS; ++k) {
+            if (p.i8_acc_dump && xin)
+              p.i8_acc_dump[(static_cast<long>(half * COLS + k) * p.Ho + oy) * p.Wo + x] = __float_as_int(v[k]);
+            v[k] = fmaf(__int2float_rn(__float_as_int(v[k])), __ldg(al + k), __ldg(be + k));
+          }
+        }
         if (xin) {
+          float fin[OQ ? CH : 1][8];
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
-            float val[8];
+            float* val = fin[OQ ? c : 0];
 #pragma unroll
             for (int k = 0; k < 8; ++k) val[k] = fmaxf(v[c * 8 + k], slope * v[c * 8 + k]);
             if constexpr (AUX) {
@@ -623,7 +751,17 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
               }
             }
             if (p.out_split > 0 && j0 + c >= p.out_split) *out2.at(oy, j0 + c - p.out_split) = pack8(val);
-            else *out.at(oy, j0 + c) = pack8(val);
+            else if constexpr (OQ) {
+              if (!ou8) *out.at(oy, j0 + c) = oq.mode ? pack8_fq(val, oq) : pack8(val);
+            } else {
+              *out.at(oy, j0 + c) = pack8(val);
+            }
+          }
+          if constexpr (OQ && CH >= 2) {
+            if (ou8) {               // 16 channels = one uint8 entry; chunk index in units of 16 channels
+#pragma unroll
+              for (int c = 0; c < CH; c += 2) *out.at(oy, (j0 + c) >> 1) = pack16_u8(fin[c], fin[c + 1], oq);
+            }
           }
         }
       }

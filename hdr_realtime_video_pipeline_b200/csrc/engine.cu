@@ -9,6 +9,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -17,7 +18,10 @@
 #include "conv_p8.cuh"
 #include "chain_p8.cuh"
 #include "conv2x_p8.cuh"
+#ifdef HDRTV_TEST_EXPORTS
+#include "../../include/hdrtv_b200_test.h"
 #include "probes.cuh"
+#endif
 #include <memory>
 #include "kernels_f32.cuh"
 #include "kernels_io.cuh"
@@ -182,6 +186,8 @@ struct ConvLaunch {
   int kind = 0, kch = 0;
   bool sftg = false;
   bool fold = false;                    // row-folded stride-2 3x3 (conv_p8_kernel<..., FOLD>); weights are the ".fold2" pack
+  bool i8 = false;                      // W8A8 layer on tcgen05.mma.kind::i8 (uint8 input tensor, int8 weights)
+  bool xform = false;                   // in-place input quantiser warps (CondNet{2,3,4}.0 launch of the INT8 layouts)
   int N;
   int mode;
   dim3 grid;
@@ -240,6 +246,7 @@ struct Ctx {
   uint16_t* d_lut = nullptr;
   // packed static weights (device) by layer name
   std::map<std::string, __half*> wpk;
+  std::map<std::string, float*> i8tab;                   // W8A8 layers on kind::i8: alpha[N] | beta[16][N] (device)
   std::map<std::string, std::vector<__half>> host_pk;   // host copies (chains concatenate them)
   std::map<std::string, ActQuant> quant;                 // INT8 layouts: static input fake-quantisation per layer (FP32 path)
   ActQuant q(const std::string& layer) const {
@@ -262,6 +269,7 @@ struct Ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in_free = nullptr, ev_pre_done = nullptr, ev_packed = nullptr, ev_user = nullptr;
   cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
+  unsigned long long* d_cksum = nullptr;      // [2] frame checksums of the two RGB48 staging slots (hdrtv_process_ex)
 };
 
 static int fail(Ctx* c, const std::string& m) {
@@ -359,6 +367,15 @@ struct Epi {
   int out_split = 0;                // output chunks >= out_split are stored to out2 instead
   const P8* out2 = nullptr;
   bool fold = false;                // weights are row-folded (".fold2"): plain stride-2 3x3 convs
+  // INT8 layouts
+  bool i8 = false;                  // kind::i8 instance: `in` is a uint8 tensor, wpk the int8 pack, i8_tab = alpha[N] | beta[16][N]
+  const float* i8_tab = nullptr;
+  int i8_H = 0, i8_W = 0;           // input size (tap validity)
+  ActQuant out_q;                   // quantiser applied to the `out` store (input quantiser of a W8A8 consumer)
+  bool out_u8 = false;              // ... stored as uint8 codes
+  ActQuant in_q_z[3];               // per-variant in-place input quantisers (XFORM)
+  ActQuant out_q_z[3];              // per-variant output quantisers of a zsplit launch
+  bool out_u8_z[3] = {false, false, false};
   int zsplit = 0;                   // > 1: this launch runs `zsplit` convs on the same input (weights / outputs below)
   const __half* wpk_z[3] = {nullptr, nullptr, nullptr};
   const P8* out_z[3] = {nullptr, nullptr, nullptr};
@@ -406,6 +423,26 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
   p.planar_plane = static_cast<long>(Ho) * Wo;
   p.planar_W = Wo;
   p.err = c->d_err;
+  p.out_q = e.out_q;
+  p.out_u8 = e.out_u8 ? 1 : 0;
+  if (e.out_u8 && (e.out_q.mode != 2 || N < 32 || mode == STORE_PLANAR)) return fail(c, "conv " + name + ": uint8 output needs an asymmetric quantiser and >= 32 output channels");
+  p.i8_H = e.i8_H;
+  p.i8_W = e.i8_W;
+  if (e.i8) {
+    if (!e.i8_tab || p.ks != 3 || e.fold || e.zsplit > 1) return fail(c, "conv " + name + ": INT8 instance needs its de-quantisation table and a plain 3x3 conv");
+    p.i8_alpha = e.i8_tab;
+    p.i8_beta = e.i8_tab + N;
+    L.i8 = true;
+  }
+  bool any_oq = e.out_q.mode != 0;
+  for (int z = 0; z < 3; ++z) {
+    p.in_q_z[z] = e.in_q_z[z];
+    p.out_q_z[z] = e.out_q_z[z];
+    p.out_u8_z[z] = e.out_u8_z[z] ? 1 : 0;
+    if (e.in_q_z[z].mode) L.xform = true;
+    any_oq |= e.out_q_z[z].mode != 0;
+  }
+  if (any_oq && !(L.i8 || L.xform)) return fail(c, "conv " + name + ": output quantisers are compiled into the INT8-layout instances only");
   if (e.fold) {
     if (kind != IN_PAR3x3S2 || mode != STORE_P8 || e.sft_s0 || N > 64 || e.res || e.res2 || e.sft || e.raw)
       return fail(c, "conv " + name + ": row folding needs a plain stride-2 3x3 conv");
@@ -468,16 +505,17 @@ static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false>
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool I8 = false, bool XFORM = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>,
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD, I8, XFORM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD>, L.grid, kConvThreads, L.smem, s, L.p);
+  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD, I8, XFORM>, L.grid, kConvThreads + (XFORM ? kXformThreads : 0),
+                    L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>
@@ -503,6 +541,26 @@ static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
   if (L.c2x) return launch_conv2x(L, s);
+  if (L.xform) {    // CondNet{2,3,4}.0 of the INT8 layouts: per-variant in-place input quantiser
+    if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 64 && L.mode == STORE_P8 && !L.sftg && !L.i8)
+      return launch_conv_t<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, false, false, true>(L, s);
+    return cudaErrorInvalidValue;
+  }
+  if (L.i8) {       // W8A8 layers on tcgen05.mma.kind::i8 (uint8 activations: KCH counts 16-channel planes)
+    const bool aux8 = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
+    if (L.sftg) {
+      if (L.kind == IN_PAR3x3S2 && L.kch == 2 && L.N == 32 && L.mode == STORE_P8) return launch_conv_t<IN_PAR3x3S2, 2, 32, STORE_P8, true, true, false, true>(L, s);
+      if (L.kind == IN_NAT3x3 && L.kch == 2 && L.N == 32 && L.mode == STORE_P8) return launch_conv_t<IN_NAT3x3, 2, 32, STORE_P8, true, true, false, true>(L, s);
+      if (L.kind == IN_NAT3x3 && L.kch == 2 && L.N == 128 && L.mode == STORE_PS) return launch_conv_t<IN_NAT3x3, 2, 128, STORE_PS, true, true, false, true>(L, s);
+      return cudaErrorInvalidValue;
+    }
+    if (L.kind == IN_PAR3x3S2 && L.kch == 2 && L.N == 32 && L.mode == STORE_P8) return aux8 ? launch_conv_t<IN_PAR3x3S2, 2, 32, STORE_P8, true, false, false, true>(L, s) : launch_conv_t<IN_PAR3x3S2, 2, 32, STORE_P8, false, false, false, true>(L, s);
+    if (L.kind == IN_NAT3x3 && L.kch == 2 && L.N == 32 && L.mode == STORE_P8) return aux8 ? launch_conv_t<IN_NAT3x3, 2, 32, STORE_P8, true, false, false, true>(L, s) : launch_conv_t<IN_NAT3x3, 2, 32, STORE_P8, false, false, false, true>(L, s);
+    if (L.kind == IN_NAT3x3 && L.kch == 2 && L.N == 128 && L.mode == STORE_PS && !aux8) return launch_conv_t<IN_NAT3x3, 2, 128, STORE_PS, false, false, false, true>(L, s);
+    if (L.kind == IN_PAR3x3S2 && L.kch == 4 && L.N == 64 && L.mode == STORE_P8 && !aux8) return launch_conv_t<IN_PAR3x3S2, 4, 64, STORE_P8, false, false, false, true>(L, s);
+    if (L.kind == IN_PAR3x3S2 && L.kch == 4 && L.N == 16 && L.mode == STORE_P8 && !aux8) return launch_conv_t<IN_PAR3x3S2, 4, 16, STORE_P8, false, false, false, true>(L, s);
+    return cudaErrorInvalidValue;
+  }
   if (L.fold) {     // row-folded stride-2 3x3 convs of the condition pyramid
     if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 64) return launch_conv_t<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, true>(L, s);
     if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 16) return launch_conv_t<IN_PAR3x3S2, 8, 16, STORE_P8, false, false, true>(L, s);
@@ -564,6 +622,10 @@ struct C2xB {             // conv B: weights, width, store mode, epilogue operan
   const P8* res = nullptr;
   const P8* res2 = nullptr;
   const P8* raw = nullptr;
+  // INT8 layouts: qmid = input quantiser of conv B (applied to the mid rows), outq = uint8 copy of the output through out_q
+  ActQuant qmid, out_q;
+  const P8* outq = nullptr;
+  bool skip_out = false;
 };
 static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& name, int variant, const P8& in,
                        const __half* wpkA, const Epi& ea, const C2xB& b, const P8& out, int H, int Wd) {
@@ -602,6 +664,14 @@ static int make_conv2x(Ctx* c, std::vector<ConvLaunch>& plan, const std::string&
   if (b.res2) { p.has_res2 = 1; p.res2 = *b.res2; }
   if (b.raw) { p.has_raw = 1; p.raw = *b.raw; }
   p.out = out;
+  p.qmid = b.qmid;
+  p.out_q = b.out_q;
+  if (b.outq) {
+    if (b.mode != STORE_P8 || b.out_q.mode != 2) return fail(c, "conv2x " + name + ": uint8 output needs a P8 store and an asymmetric quantiser");
+    p.has_outq = 1;
+    p.outq = *b.outq;
+  }
+  p.skip_out = b.skip_out ? 1 : 0;
   p.planar = b.mode == STORE_PLANAR ? reinterpret_cast<__half*>(1) : nullptr;
   p.planar_plane = static_cast<long>(H) * Wd;
   p.planar_W = Wd;
@@ -686,24 +756,27 @@ static int make_chain_t(Ctx* c, std::vector<ConvLaunch>& plan, const std::string
   plan.push_back(L);
   return 0;
 }
-template <class Prog>
+template <class Prog, bool QOP = false>
 static cudaError_t launch_chain_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain_p8_kernel<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(chain_p8_kernel<Prog, QOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(chain_p8_kernel<Prog>, L.grid, kChainThreads, L.smem, s, *L.chain);
+  return launch_pdl(chain_p8_kernel<Prog, QOP>, L.grid, kChainThreads, L.smem, s, *L.chain);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
+  bool qop = false;                      // INT8 layouts: an operand quantiser is installed on one of the chain's layers
+  for (int l = 0; l < kMaxChain; ++l) qop |= L.chain->opq[l].mode != 0;
+  if (qop && L.chain_prog != PROG_COND_SFT3 && L.chain_prog != PROG_TAIL2) return cudaErrorInvalidValue;
   switch (L.chain_prog) {
     case PROG_AGCM: return launch_chain_t<ProgAGCM>(L, s);
     case PROG_COND: return launch_chain_t<ProgCond>(L, s);
     case PROG_COND_SFT1: return launch_chain_t<ProgCondSft<1, 1>>(L, s);
-    case PROG_COND_SFT3: return launch_chain_t<ProgCondSft<3>>(L, s);
+    case PROG_COND_SFT3: return qop ? launch_chain_t<ProgCondSft<3>, true>(L, s) : launch_chain_t<ProgCondSft<3>>(L, s);
     case PROG_COND_SFT3_DBG: return launch_chain_t<ProgCondSft<3, 1>>(L, s);
-    case PROG_TAIL2: return launch_chain_t<ProgTail2>(L, s);
+    case PROG_TAIL2: return qop ? launch_chain_t<ProgTail2, true>(L, s) : launch_chain_t<ProgTail2>(L, s);
     case PROG_TAIL3: return launch_chain_t<ProgTail3>(L, s);
     case PROG_TAIL4: return launch_chain_t<ProgTail4>(L, s);
   }
@@ -777,6 +850,80 @@ static std::function<float(int)> bias_fn(Ctx* c, const std::string& name) {
 }
 static int pack_std(Ctx* c, const std::string& name, InKind kind, int cin, int N) {
   return pack_layer(c, name, kind, std::max(1, cin / 8), N, conv_weight_fn(c, name), bias_fn(c, name));
+}
+
+// W8A8 layer for tcgen05.mma.kind::i8: int8 weights in the B-operand layout of K = 32 steps (two 16-byte K halves of 16 input
+// channels each), plus the de-quantisation table of its epilogue (conv_p8.cuh, ConvParams::i8_alpha / i8_beta).
+static int pack_i8_layer(Ctx* c, const std::string& name, InKind kind, int kch16, int N) {
+  if (!c->w.count(name + ".weight_int8") || !c->w.count(name + ".w_scale")) return 0;      // not an INT8 layer of this checkpoint
+  const ActQuant q = c->q(name);
+  if (q.mode != 2) return 0;                                                              // W8A16 / symmetric: f16 path
+  const HostTensor& wi = W(c, name + ".weight_int8");
+  const HostTensor& ws = W(c, name + ".w_scale");
+  const HostTensor& bs = W(c, name + ".bias");
+  const int O = static_cast<int>(wi.shape[0]), I = static_cast<int>(wi.shape[1]);
+  if (wi.shape.size() != 4 || wi.shape[2] != 3 || wi.shape[3] != 3 || O > N || I > kch16 * 16)
+    return fail(c, "pack_i8_layer " + name + ": unexpected weight shape");
+  ConvParams tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  std::vector<StepK> wk;
+  P8 dummy;
+  dummy.Wp = 16;
+  dummy.chunks = kch16;
+  build_input_side(kind, dummy, 0, kch16, tmp, wk);
+  std::vector<int8_t> pk(static_cast<size_t>(wk.size() + 1) * N * 32, 0);
+  auto wv = [&](int n, int ci, int tap) -> float { return (n < O && ci < I) ? wi.v[(static_cast<size_t>(n) * I + ci) * 9 + tap] : 0.f; };
+  for (size_t st = 0; st < wk.size(); ++st)
+    for (int h = 0; h < 2; ++h) {
+      const HalfK hk = wk[st][h];
+      if (hk.tap < 0) continue;
+      for (int e = 0; e < 16; ++e)
+        for (int n = 0; n < N; ++n)
+          pk[st * N * 32 + static_cast<size_t>(h) * N * 16 + (n >> 3) * 128 + (n & 7) * 16 + e] =
+              static_cast<int8_t>(lrintf(wv(n, hk.chunk * 16 + e, hk.tap)));
+    }
+  std::vector<float> tab(static_cast<size_t>(17) * N, 0.f);
+  for (int n = 0; n < O; ++n) {
+    tab[n] = q.scale * ws.v[n];
+    double tapsum[9];
+    for (int t = 0; t < 9; ++t) {
+      double a = 0.0;
+      for (int ci = 0; ci < I; ++ci) a += wv(n, ci, t);
+      tapsum[t] = a;
+    }
+    for (int cls = 0; cls < 16; ++cls) {
+      const int cy = cls >> 2, cx = cls & 3;
+      double a = 0.0;
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) {
+          const bool out_y = (dy == 0 && (cy & 1)) || (dy == 2 && (cy & 2));
+          const bool out_x = (dx == 0 && (cx & 1)) || (dx == 2 && (cx & 2));
+          if (!out_y && !out_x) a += tapsum[dy * 3 + dx];
+        }
+      tab[static_cast<size_t>(1 + cls) * N + n] = bs.v[n] + static_cast<float>(static_cast<double>(q.zero) * ws.v[n] * a);
+    }
+  }
+  c->wpk[name + ".i8"] = reinterpret_cast<__half*>(w_upload(c, pk.data(), pk.size()));
+  c->i8tab[name] = w_upload(c, tab.data(), tab.size());
+  if (!c->wpk[name + ".i8"] || !c->i8tab[name]) return fail(c, "weight upload failed for " + name + ".i8");
+  return 0;
+}
+// The W8A8 layers that run as kind::i8 launches when the checkpoint quantises them (INT8 mixed layout:
+// configs/qat_layouts/original_nohg_mixed_w8a8.txt); uint8 inputs count 16-channel planes.
+static int pack_all_i8(Ctx* c) {
+  int r = 0;
+  for (int i = 1; i <= 3; ++i) {
+    r |= pack_i8_layer(c, "LE.down_conv" + std::to_string(i), IN_PAR3x3S2, 2, 32);
+    r |= pack_i8_layer(c, "LE.up_conv" + std::to_string(i) + ".0", IN_NAT3x3, 2, 128);
+  }
+  for (int j = 0; j < 4; ++j) {
+    r |= pack_i8_layer(c, "LE.recon_trunk3." + std::to_string(j) + ".conv1", IN_NAT3x3, 2, 32);
+    r |= pack_i8_layer(c, "LE.recon_trunk3." + std::to_string(j) + ".conv2", IN_NAT3x3, 2, 32);
+  }
+  r |= pack_i8_layer(c, "LE.CondNet3.2", IN_PAR3x3S2, 4, 64);
+  r |= pack_i8_layer(c, "LE.CondNet4.2", IN_PAR3x3S2, 4, 64);
+  r |= pack_i8_layer(c, "LE.CondNet4.4", IN_PAR3x3S2, 4, 16);
+  return r;
 }
 
 static const char* kSftL0[] = {"LE.SFT_layer1", "LE.SFT_layer2"};
@@ -931,6 +1078,7 @@ static int pack_all_fp16(Ctx* c) {
   for (auto n : kSftL1) r |= pack_sft_stage1(c, n);
   for (auto n : kSftL2) r |= pack_sft_stage1(c, n);
   for (auto n : kSftL3) r |= pack_sft_stage1(c, n);
+  r |= pack_all_i8(c);
   return r;
 }
 
@@ -1229,6 +1377,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   if (!V0.base || !U1.base) return fail(c, "workspace allocation failed (P8)");
 
   auto wk = [&](const std::string& k) { return c->wpk.at(k); };
+  const bool qm = !c->quant.empty();     // INT8 layout: some layers carry input quantisers (hdrtv_set_act_quant)
   // Row-folded stride-2 convs of the condition pyramid: experiment, off.  A third fewer MMAs, but these kernels are bound
   // by the input ring (35 KB rows, 4 slots next to 74 KB of weights: bytes in flight / loaded HBM latency), not by the
   // tensor pipe: CondNet{2,3,4}.0 571 -> 662 us under ncu at 4K (same DRAM bytes, same tensor-active cycles), the
@@ -1280,9 +1429,14 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     else if (use_sftg)
       r |= make_chain_t<ProgCondSft<3>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT3, IN_NAT3x3_C8, agP8, 1,
                                         {nullptr, nullptr, &COND, nullptr, nullptr, nullptr, &S0}, wk("chain.cond_sft"), H, Wd, &S0ps);
+
     else
       r |= make_chain_t<ProgCondSft<1, 1>>(c, L, "LE.cond_chain+sft0.L0", PROG_COND_SFT1, IN_NAT3x3_C8, agP8, 1,
                                         {nullptr, nullptr, &COND, nullptr, nullptr, &cond1, &S0}, wk("chain.cond_sft"), H, Wd);
+    if (qm && !r && c->q("LE.CondNet1.4").mode) {                  // CondNet1.4 (W8A8) reads CondNet1.2's output: chain layer 4 -> 5
+      if (!use_sftg || env_int("HDRTV_DEBUG_TENSORS", 0)) return fail(c, "INT8 layouts need the default launch plan");
+      L.back().chain->opq[4] = c->q("LE.CondNet1.4");
+    }
   } else {
   r |= std_conv(L, "LE.cond_first.0", IN_NAT3x3_C8, agP8, 8, 64, STORE_P8, B1, H, Wd, lrelu);
     r |= std_conv(L, "LE.cond_first.2", IN_NAT1x1, B1, 64, 64, STORE_P8, B2, H, Wd, lrelu);
@@ -1291,6 +1445,20 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     r |= std_conv(L, "LE.CondNet1.2", IN_NAT1x1, C1a, 64, 64, STORE_P8, C1b, H, Wd, lrelu);
     r |= std_conv(L, "LE.CondNet1.4", IN_NAT1x1, C1b, 64, 16, STORE_P8, cond1, H, Wd, none);
   }
+  // INT8 layouts: uint8 homes of the tensors read by kind::i8 convs of the pyramid
+  std::set<std::string> q_used;                                     // quantisers this plan honours (checked at the end)
+  auto Qp = [&](const std::string& n) { if (qm && c->q(n).mode) q_used.insert(n); return qm ? c->q(n) : ActQuant{}; };
+  auto is8p = [&](const std::string& n) { const bool y = qm && c->i8tab.count(n) != 0; if (y) q_used.insert(n); return y; };
+  P8 E1q, E1bq, F2q;
+  if (is8p("LE.CondNet3.2")) E1q = make_p8(c, 32, H1, W1, true);    // 64 channels of uint8 = 4 planes
+  if (is8p("LE.CondNet4.2")) E1bq = make_p8(c, 32, H1, W1, true);
+  if (is8p("LE.CondNet4.4")) F2q = make_p8(c, 32, H2, W2, true);
+  auto i8_pyr = [&](const std::string& name, const P8& inq, int N, const P8& out, int ho, int wo, int hin, int win, Epi e) {
+    e.i8 = true; e.i8_tab = c->i8tab.at(name); e.i8_H = hin; e.i8_W = win;
+    return make_conv(c, L, name, IN_PAR3x3S2, inq, 0, 4, N, STORE_P8, wk(name + ".i8"), out, ho, wo, e);
+  };
+  if (qm && !(use_chain && use_sftg && use_tail && env_int("HDRTV_ZFUSE", 1) && !use_fold2))
+    return fail(c, "INT8 layouts need the default launch plan");
   if (env_int("HDRTV_ZFUSE", 1)) {
     // the three stride-2 3x3 convs that read `cond` share one launch (cond is fetched from HBM once)
     Epi e = lrelu;
@@ -1299,17 +1467,30 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     const std::string fs = use_fold2 ? ".fold2" : "";
     e.wpk_z[0] = wk("LE.CondNet2.0" + fs); e.wpk_z[1] = wk("LE.CondNet3.0" + fs); e.wpk_z[2] = wk("LE.CondNet4.0" + fs);
     e.out_z[0] = &D1; e.out_z[1] = &E1; e.out_z[2] = &E1b;
+    if (qm) {
+      // W8A8 variants quantise `cond` in place in their ring slots (conv_p8.cuh, XFORM); their outputs go to the next
+      // layer as uint8 codes when that layer runs on kind::i8
+      e.in_q_z[0] = Qp("LE.CondNet2.0"); e.in_q_z[1] = Qp("LE.CondNet3.0"); e.in_q_z[2] = Qp("LE.CondNet4.0");
+      e.i8_H = H; e.i8_W = Wd;
+      if (is8p("LE.CondNet3.2")) { e.out_z[1] = &E1q; e.out_q_z[1] = Qp("LE.CondNet3.2"); e.out_u8_z[1] = true; }
+      else e.out_q_z[1] = Qp("LE.CondNet3.2");
+      if (is8p("LE.CondNet4.2")) { e.out_z[2] = &E1bq; e.out_q_z[2] = Qp("LE.CondNet4.2"); e.out_u8_z[2] = true; }
+      else e.out_q_z[2] = Qp("LE.CondNet4.2");
+      e.out_q_z[0] = Qp("LE.CondNet2.2");
+    }
     r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, e);
     L.back().name = "LE.CondNet{2,3,4}.0";
     if (use_tail) {   // CondNet2.2 -> CondNet2.4 -> stage 0 of the four level-1 SFT layers in one launch (cond2 is never stored)
       S1hi = S1; S1hi.base = S1.base + static_cast<long>(8) * S1.Wp * 8;       // view: chunk planes 8.. of every row
       r |= make_chain_t<ProgTail2>(c, L, "LE.CondNet2.2+2.4+sft0.L1", PROG_TAIL2, IN_NAT1x1, D1, 8, {nullptr, nullptr, &S1, &S1hi},
                                    wk("chain.tail2"), H1, W1, &S1ps);
+      if (qm && !r) L.back().chain->opq[0] = Qp("LE.CondNet2.4");               // CondNet2.4 reads CondNet2.2's output
     } else {
       r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
       r |= std_conv(L, "LE.CondNet2.4", IN_NAT1x1, D2, 64, 16, STORE_P8, cond2, H1, W1, none);
     }
-    r |= fold_conv(L, "LE.CondNet3.2", E1, 64, E2, H2, W2, lrelu);
+    if (is8p("LE.CondNet3.2")) { Epi e2 = lrelu; e2.out_q = Qp("LE.CondNet3.4"); r |= i8_pyr("LE.CondNet3.2", E1q, 64, E2, H2, W2, H1, W1, e2); }
+    else { Epi e2 = lrelu; e2.out_q = Qp("LE.CondNet3.4"); r |= fold_conv(L, "LE.CondNet3.2", E1, 64, E2, H2, W2, e2); }
     if (use_tail) {
       S2hi = S2; S2hi.base = S2.base + static_cast<long>(8) * S2.Wp * 8;
       r |= make_chain_t<ProgTail3>(c, L, "LE.CondNet3.4+sft0.L2", PROG_TAIL3, IN_NAT1x1, E2, 8, {nullptr, &S2, &S2hi},
@@ -1317,7 +1498,13 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     } else {
       r |= std_conv(L, "LE.CondNet3.4", IN_NAT1x1, E2, 64, 16, STORE_P8, cond3, H2, W2, none);
     }
-    r |= fold_conv(L, "LE.CondNet4.2", E1b, 64, F2, H2, W2, lrelu);
+    if (is8p("LE.CondNet4.2")) {
+      Epi e2 = lrelu; e2.out_q = Qp("LE.CondNet4.4"); e2.out_u8 = is8p("LE.CondNet4.4");
+      r |= i8_pyr("LE.CondNet4.2", E1bq, 64, e2.out_u8 ? F2q : F2, H2, W2, H1, W1, e2);
+    } else {
+      Epi e2 = lrelu; e2.out_q = Qp("LE.CondNet4.4");
+      r |= fold_conv(L, "LE.CondNet4.2", E1b, 64, F2, H2, W2, e2);
+    }
   } else {
     r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
     r |= std_conv(L, "LE.CondNet2.2", IN_NAT1x1, D1, 64, 64, STORE_P8, D2, H1, W1, lrelu);
@@ -1328,6 +1515,8 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     r |= std_conv(L, "LE.CondNet4.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, E1, H1, W1, lrelu);
     r |= std_conv(L, "LE.CondNet4.2", IN_PAR3x3S2, E1, 64, 64, STORE_P8, F2, H2, W2, lrelu);
   }
+  if (is8p("LE.CondNet4.4")) r |= i8_pyr("LE.CondNet4.4", F2q, 16, cond4, H3, W3, H2, W2, none);
+  else
   r |= fold_conv(L, "LE.CondNet4.4", F2, 16, cond4, H3, W3, none);
   // ---- SFT: stage 0 of every SFT layer of a level stacked into one 1x1 conv (LeakyReLU).  Stage 1 (32 -> 64, block
   // diagonal scale|shift) runs inside the consuming conv kernel (SFTG) from the stage-0 map; only the PixelShuffle
@@ -1374,39 +1563,96 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     }
   };
   // ---- trunk
+  // INT8 layouts (qm): a W8A8 layer that is its own launch runs on tcgen05.mma.kind::i8 from a uint8 tensor written by its
+  // producer's epilogue (is8); a W8A8 layer inside a fused kernel keeps f16 MMAs on values its producer has passed through
+  // the layer's input quantiser (the reference's eager INT8 semantics: de-quantise, then an fp16 convolution).
   const bool use_c2x = use_sftg && env_int("HDRTV_C2X", 1) != 0;   // conv -> conv pairs through a shared-memory row ring
+  if (qm && !(use_c2x && use_sftg)) return fail(c, "INT8 layouts need the default launch plan (HDRTV_C2X / HDRTV_SFTG on)");
+  auto Q = Qp;
+  auto is8 = is8p;
+  auto U8 = [&](int C, int h, int w, bool par) { return make_p8(c, C / 2, h, w, par); };    // uint8 tensor: 16 channels per entry
+  P8 FEA0q, FEA1q, FEA2q, U3q, U2q, U1q, Zq, Y3q;
+  if (is8("LE.down_conv1")) FEA0q = U8(32, H, Wd, true);
+  if (is8("LE.down_conv2")) FEA1q = U8(32, H1, W1, true);
+  if (is8("LE.down_conv3")) FEA2q = U8(32, H2, W2, true);
+  if (is8("LE.up_conv1.0")) U3q = U8(32, H3, W3, false);
+  if (is8("LE.up_conv2.0")) U2q = U8(32, H2, W2, false);
+  if (is8("LE.up_conv3.0")) U1q = U8(32, H1, W1, false);
+  bool q3 = qm;                                                     // level 3 (eight 3x3 convs): all of them on kind::i8, or none
+  for (int j = 0; j < 4 && q3; ++j)
+    q3 = is8("LE.recon_trunk3." + std::to_string(j) + ".conv1") && is8("LE.recon_trunk3." + std::to_string(j) + ".conv2");
+  if (q3) { Zq = U8(32, H3, W3, false); Y3q = U8(32, H3, W3, false); }
+  auto i8_epi = [&](Epi& e, const std::string& name, int hin, int win) {
+    e.i8 = true; e.i8_tab = c->i8tab.at(name); e.i8_H = hin; e.i8_W = win;
+  };
   if (use_c2x) {
     Epi ea = relu; with_sft(ea, "LE.SFT_layer1");
     C2xB b; b.wpk = wk("LE.HR_conv1.fold"); b.N = 32; b.mode = STORE_P8; b.act = ACT_RELU;
+    b.qmid = Q("LE.HR_conv1");
+    if (is8("LE.down_conv1")) { b.outq = &FEA0q; b.out_q = Q("LE.down_conv1"); }
     r |= make_conv2x(c, L, "LE.conv_first+HR_conv1", C2X_C8_SFTG_P8, agP8, wk("LE.conv_first.fold"), ea, b, FEA0, H, Wd);
   } else {
     { Epi e = relu; with_sft(e, "LE.SFT_layer1");
       r |= std_conv(L, "LE.conv_first", IN_NAT3x3_C8, agP8, 8, 32, STORE_P8, T0a, H, Wd, e); }
     r |= std_conv(L, "LE.HR_conv1", IN_NAT3x3, T0a, 32, 32, STORE_P8, FEA0, H, Wd, relu);
   }
+  // conv1 -> sft2 -> conv2 + x.  outq / oq: uint8 copy of the block output for an INT8 consumer; skip_out: no fp16 reader.
   auto resblock = [&](const std::string& pre, const P8& xm, const P8& xraw, const P8& ytmp, const P8& out,
-                      const P8* res2, const char* next_sft, const P8* next_raw, int h, int w) {
-    if (use_c2x && !next_sft) {     // conv1 -> sft2 -> conv2 + x in one kernel
+                      const P8* res2, const char* next_sft, const P8* next_raw, int h, int w, const P8* outq = nullptr,
+                      ActQuant oq = ActQuant{}, bool skip_out = false) {
+    if (use_c2x && !next_sft) {     // one kernel
       Epi ea = relu; with_sft(ea, pre + ".sft2");
       C2xB b; b.wpk = wk(pre + ".conv2.fold"); b.N = 32; b.mode = STORE_P8; b.act = ACT_NONE; b.res = &xraw; b.res2 = res2; b.raw = next_raw;
+      b.qmid = Q(pre + ".conv2");
+      b.outq = outq; b.out_q = oq; b.skip_out = skip_out;
       r |= make_conv2x(c, L, pre + ".conv1+conv2", C2X_K4_SFTG_P8, xm, wk(pre + ".conv1.fold"), ea, b, out, h, w);
       return;
     }
-    { Epi e = relu; with_sft(e, pre + ".sft2");
+    { Epi e = relu; with_sft(e, pre + ".sft2"); e.out_q = Q(pre + ".conv2");
       r |= std_conv(L, pre + ".conv1", IN_NAT3x3, xm, 32, 32, STORE_P8, ytmp, h, w, e); }
     { Epi e; e.res = &xraw; e.res2 = res2; e.raw = next_raw;
-      if (next_sft) with_sft(e, next_sft);
+      if (next_sft) { with_sft(e, next_sft); e.out_q = Q(std::string(next_sft).substr(0, std::string(next_sft).size() - 5) + ".conv1"); }
       r |= std_conv(L, pre + ".conv2", IN_NAT3x3, ytmp, 32, 32, STORE_P8, out, h, w, e); }
   };
-  { Epi e = relu; e.raw = &X1; with_sft(e, "LE.recon_trunk1.0.sft1");
-    r |= std_conv(L, "LE.down_conv1", IN_PAR3x3S2, FEA0, 32, 32, STORE_P8, X1m, H1, W1, e); }
-  resblock("LE.recon_trunk1.0", X1m, X1, Y1, FEA1, nullptr, nullptr, nullptr, H1, W1);
-  { Epi e = relu; e.raw = &X2; with_sft(e, "LE.recon_trunk2.0.sft1");
-    r |= std_conv(L, "LE.down_conv2", IN_PAR3x3S2, FEA1, 32, 32, STORE_P8, X2m, H2, W2, e); }
-  resblock("LE.recon_trunk2.0", X2m, X2, Y2, FEA2, nullptr, nullptr, nullptr, H2, W2);
-  { Epi e = relu; e.raw = &FEA3; with_sft(e, "LE.recon_trunk3.0.sft1");
-    r |= std_conv(L, "LE.down_conv3", IN_PAR3x3S2, FEA2, 32, 32, STORE_P8, Zm, H3, W3, e); }
-  {
+  // stride-2 down conv: ReLU, raw copy (residual of the level's first block), SFT -> input of that block's conv1
+  auto down = [&](const std::string& name, const P8& in, const P8& inq, const P8* raw, const std::string& sft, const P8& out,
+                  ActQuant oq, bool out_u8, int ho, int wo, int hin, int win) {
+    Epi e = relu; e.raw = raw; with_sft(e, sft); e.out_q = oq; e.out_u8 = out_u8;
+    if (is8(name)) {
+      i8_epi(e, name, hin, win);
+      r |= make_conv(c, L, name, IN_PAR3x3S2, inq, 0, 2, 32, STORE_P8, wk(name + ".i8"), out, ho, wo, e);
+    } else {
+      r |= std_conv(L, name, IN_PAR3x3S2, in, 32, 32, STORE_P8, out, ho, wo, e);
+    }
+  };
+  down("LE.down_conv1", FEA0, FEA0q, &X1, "LE.recon_trunk1.0.sft1", X1m, Q("LE.recon_trunk1.0.conv1"), false, H1, W1, H, Wd);
+  resblock("LE.recon_trunk1.0", X1m, X1, Y1, FEA1, nullptr, nullptr, nullptr, H1, W1, is8("LE.down_conv2") ? &FEA1q : nullptr,
+           Q("LE.down_conv2"));
+  down("LE.down_conv2", FEA1, FEA1q, &X2, "LE.recon_trunk2.0.sft1", X2m, Q("LE.recon_trunk2.0.conv1"), false, H2, W2, H1, W1);
+  resblock("LE.recon_trunk2.0", X2m, X2, Y2, FEA2, nullptr, nullptr, nullptr, H2, W2, is8("LE.down_conv3") ? &FEA2q : nullptr,
+           Q("LE.down_conv3"));
+  down("LE.down_conv3", FEA2, FEA2q, &FEA3, "LE.recon_trunk3.0.sft1", q3 ? Zq : Zm, Q("LE.recon_trunk3.0.conv1"), q3, H3, W3, H2, W2);
+  if (q3) {
+    // level 3 on kind::i8: Zq / Y3q hold the uint8 codes of conv1's / conv2's input; residual copies stay fp16
+    const P8* xraw = &FEA3;
+    for (int i = 0; i < 4; ++i) {
+      const std::string pre = "LE.recon_trunk3." + std::to_string(i);
+      { Epi e = relu; with_sft(e, pre + ".sft2"); e.out_q = Q(pre + ".conv2"); e.out_u8 = true; i8_epi(e, pre + ".conv1", H3, W3);
+        r |= make_conv(c, L, pre + ".conv1", IN_NAT3x3, Zq, 0, 2, 32, STORE_P8, wk(pre + ".conv1.i8"), Y3q, H3, W3, e); }
+      Epi e; e.res = xraw; i8_epi(e, pre + ".conv2", H3, W3);
+      if (i < 3) {
+        const std::string nxt = "LE.recon_trunk3." + std::to_string(i + 1);
+        e.raw = &Z[i & 1]; with_sft(e, nxt + ".sft1"); e.out_q = Q(nxt + ".conv1"); e.out_u8 = true;
+        r |= make_conv(c, L, pre + ".conv2", IN_NAT3x3, Y3q, 0, 2, 32, STORE_P8, wk(pre + ".conv2.i8"), Zq, H3, W3, e);
+        xraw = &Z[i & 1];
+      } else {                       // out = trunk3(fea3) + fea3 -> up_conv1
+        e.res2 = &FEA3;
+        if (is8("LE.up_conv1.0")) { e.out_q = Q("LE.up_conv1.0"); e.out_u8 = true; }
+        r |= make_conv(c, L, pre + ".conv2", IN_NAT3x3, Y3q, 0, 2, 32, STORE_P8, wk(pre + ".conv2.i8"), is8("LE.up_conv1.0") ? U3q : U3,
+                       H3, W3, e);
+      }
+    }
+  } else {
     const P8* xraw = &FEA3;
     for (int i = 0; i < 4; ++i) {
       const std::string pre = "LE.recon_trunk3." + std::to_string(i);
@@ -1416,28 +1662,44 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
         resblock(pre, Zm, *xraw, Y3, Zm, nullptr, nxt.c_str(), &Z[i & 1], H3, W3);
         xraw = &Z[i & 1];
       } else {
-        resblock(pre, Zm, *xraw, Y3, U3, &FEA3, nullptr, nullptr, H3, W3);   // out = trunk3(fea3) + fea3
+        resblock(pre, Zm, *xraw, Y3, U3, &FEA3, nullptr, nullptr, H3, W3, is8("LE.up_conv1.0") ? &U3q : nullptr,
+                 Q("LE.up_conv1.0"), is8("LE.up_conv1.0"));   // out = trunk3(fea3) + fea3
       }
     }
   }
-  auto up = [&](const std::string& name, const P8& in, const P8& skip, const P8* raw, const char* sft, const P8& out,
-                int hin, int win) {
-    Epi e = relu; e.res = &skip; e.raw = raw; with_sft(e, sft);
-    r |= std_conv(L, name, IN_NAT3x3, in, 32, 128, STORE_PS, out, hin, win, e);
+  auto up = [&](const std::string& name, const P8& in, const P8& inq, const P8& skip, const P8* raw, const char* sft, const P8& out,
+                ActQuant oq, int hin, int win) {
+    Epi e = relu; e.res = &skip; e.raw = raw; with_sft(e, sft); e.out_q = oq;
+    if (is8(name)) {
+      i8_epi(e, name, hin, win);
+      r |= make_conv(c, L, name, IN_NAT3x3, inq, 0, 2, 128, STORE_PS, wk(name + ".i8"), out, hin, win, e);
+    } else {
+      r |= std_conv(L, name, IN_NAT3x3, in, 32, 128, STORE_PS, out, hin, win, e);
+    }
   };
-  up("LE.up_conv1.0", U3, FEA2, &X4, "LE.recon_trunk4.0.sft1", X4m, H3, W3);
-  resblock("LE.recon_trunk4.0", X4m, X4, Y4, U2, nullptr, nullptr, nullptr, H2, W2);
-  up("LE.up_conv2.0", U2, FEA1, &X5, "LE.recon_trunk5.0.sft1", X5m, H2, W2);
-  resblock("LE.recon_trunk5.0", X5m, X5, Y5, U1, nullptr, nullptr, nullptr, H1, W1);
-  up("LE.up_conv3.0", U1, FEA0, nullptr, "LE.SFT_layer2", V0, H1, W1);
+  up("LE.up_conv1.0", U3, U3q, FEA2, &X4, "LE.recon_trunk4.0.sft1", X4m, Q("LE.recon_trunk4.0.conv1"), H3, W3);
+  resblock("LE.recon_trunk4.0", X4m, X4, Y4, U2, nullptr, nullptr, nullptr, H2, W2, is8("LE.up_conv2.0") ? &U2q : nullptr,
+           Q("LE.up_conv2.0"), is8("LE.up_conv2.0"));
+  up("LE.up_conv2.0", U2, U2q, FEA1, &X5, "LE.recon_trunk5.0.sft1", X5m, Q("LE.recon_trunk5.0.conv1"), H2, W2);
+  resblock("LE.recon_trunk5.0", X5m, X5, Y5, U1, nullptr, nullptr, nullptr, H1, W1, is8("LE.up_conv3.0") ? &U1q : nullptr,
+           Q("LE.up_conv3.0"), is8("LE.up_conv3.0"));
+  up("LE.up_conv3.0", U1, U1q, FEA0, nullptr, "LE.SFT_layer2", V0, Q("LE.HR_conv2"), H1, W1);
   if (use_c2x) {
     Epi ea = relu;
     C2xB b; b.wpk = wk("LE.conv_last.fold"); b.N = 16; b.mode = STORE_PLANAR; b.act = ACT_NONE; b.res = &agP8;
+    b.qmid = Q("LE.conv_last");
     r |= make_conv2x(c, L, "LE.HR_conv2+conv_last", C2X_K4_PLANAR, V0, wk("LE.HR_conv2.fold"), ea, b, agP8, H, Wd);
   } else {
     r |= std_conv(L, "LE.HR_conv2", IN_NAT3x3, V0, 32, 32, STORE_P8, V1, H, Wd, relu);
     { Epi e; e.res = &agP8; e.planar = reinterpret_cast<__half*>(1);
       r |= std_conv(L, "LE.conv_last", IN_NAT3x3, V1, 32, 16, STORE_PLANAR, agP8, H, Wd, e); }
+  }
+  if (qm && !r) {
+    q_used.insert("LE.CondNet1.4");
+    for (const auto& kv : c->quant)
+      if (kv.second.mode && !q_used.count(kv.first))
+        return fail(c, "INT8 layout: the input quantiser of " + kv.first + " is not supported on the tensor-core path (supported: the "
+                       "W8A8 layers of configs/qat_layouts/original_nohg_mixed_w8a8.txt); use the FP32 fake-quantisation path");
   }
   if (r) return -1;
   // Side branch: everything downstream of CondNet{2,3,4}.0 in the condition pyramid (1x1 / stride-2 tails and the SFT
@@ -1607,8 +1869,14 @@ static int run_fp32(Ctx* c, const float* x, const float* cond, float* out, float
   return r;
 }
 
+struct FusedPack {            // RGB48 pack fused into the last kernel of the FP16 plan (one-call frame path)
+  uint16_t* rgb48 = nullptr;
+  const uint16_t* lut = nullptr;
+  unsigned long long* cksum = nullptr;
+};
 static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __half* agcm_out, cudaStream_t s,
-                    std::vector<cudaEvent_t>* evs = nullptr, bool skip_classifier = false, cudaEvent_t inputs_consumed = nullptr) {
+                    std::vector<cudaEvent_t>* evs = nullptr, bool skip_classifier = false, cudaEvent_t inputs_consumed = nullptr,
+                    const FusedPack* fused = nullptr) {
   const int H = c->H, Wd = c->W;
   g_pdl_small_frame = static_cast<long>(H) * Wd < 4000000L;
   auto mark = [&]() {
@@ -1643,7 +1911,12 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
   bool forked = false, side_dirty = false;
   for (ConvLaunch& L : c->plan_le) {
     if (L.mode == STORE_PLANAR) L.p.planar = out;
-    if (L.c2x && L.mode == STORE_PLANAR) L.c2x->planar = out;
+    if (L.c2x && L.mode == STORE_PLANAR) {
+      L.c2x->planar = out;
+      L.c2x->rgb48 = fused ? fused->rgb48 : nullptr;
+      L.c2x->rgb48_lut = fused ? fused->lut : nullptr;
+      L.c2x->rgb48_cksum = fused ? fused->cksum : nullptr;
+    }
     cudaStream_t ls = s;
     if (branching && L.branch == 1) {
       if (!forked) {
@@ -1671,6 +1944,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
 }
 
 
+#ifdef HDRTV_TEST_EXPORTS
 // ------------------------------------------------------------------------------------------------
 // tcgen05 issue-rate probe: `iters` back-to-back accumulating M=128 x N x K=16 MMAs from one thread, timed with
 // clock64 around issue..commit-complete.  Operand contents are irrelevant (zeros); only descriptors matter.
@@ -1732,6 +2006,8 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(int iters, int layout, i
   if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+#endif  // HDRTV_TEST_EXPORTS
+
 }  // namespace hdrtv
 
 // ================================================================================================
@@ -1742,7 +2018,11 @@ struct hdrtv_ctx : public Ctx {};
 
 extern "C" {
 
-const char* hdrtv_version(void) { return "hdrtv_b200 0.1 (sm_100a)"; }
+#ifdef HDRTV_TEST_EXPORTS
+const char* hdrtv_version(void) { return "hdrtv_b200 0.2 (sm_100a, test build: product ABI + debug / probe entry points)"; }
+#else
+const char* hdrtv_version(void) { return "hdrtv_b200 0.2 (sm_100a)"; }
+#endif
 
 const char* hdrtv_last_error(const hdrtv_t* h) { return h ? h->err.c_str() : g_err; }
 
@@ -1779,6 +2059,7 @@ void hdrtv_destroy(hdrtv_t* c) {
   for (void* p : c->weight_allocs) cudaFree(p);
   if (c->d_err) cudaFree(c->d_err);
   if (c->d_lut) cudaFree(c->d_lut);
+  if (c->d_cksum) cudaFree(c->d_cksum);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1810,7 +2091,16 @@ int hdrtv_set_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {
                                "LE.up_conv3.0.weight", "LE.recon_trunk3.3.sft2.SFT_shift_conv1.bias", "LE.SFT_layer2.SFT_scale_conv0.weight"};
   for (auto k : must)
     if (!c->w.count(k)) return fail(c, std::string("hdrtv_set_weights: missing key ") + k);
-  if (c->w.size() != 264) return fail(c, "hdrtv_set_weights: expected 264 tensors, got " + std::to_string(c->w.size()));
+  // INT8 checkpoints may pass the raw int8 weights and their per-channel scales of the W8A8 layers next to the de-quantised
+  // fp32 weights ("<layer>.weight_int8" as integral floats, "<layer>.w_scale"): the kind::i8 kernels multiply those
+  size_t n_model = 0;
+  for (const auto& kv : c->w) {
+    const std::string& k = kv.first;
+    const bool extra = (k.size() > 12 && k.compare(k.size() - 12, 12, ".weight_int8") == 0) ||
+                       (k.size() > 8 && k.compare(k.size() - 8, 8, ".w_scale") == 0);
+    if (!extra) ++n_model;
+  }
+  if (n_model != 264) return fail(c, "hdrtv_set_weights: expected 264 tensors, got " + std::to_string(n_model));
   for (int ci : {0, 4, 8, 12, 16}) {   // classifier 1x1 weights, transposed to [Cin][Cout] for coalesced reads
     const std::string k = "AGCM.classifier.model." + std::to_string(ci) + ".weight";
     const HostTensor& t0 = c->w.at(k);
@@ -1833,8 +2123,11 @@ int hdrtv_set_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {
 
 int hdrtv_set_act_quant(hdrtv_t* c, const char* const* layers, const float* scales, const float* zeros, const int* modes, int n) {
   if (!c || (n > 0 && (!layers || !scales || !zeros || !modes))) return fail(c, "hdrtv_set_act_quant: null argument");
-  if (c->precision != HDRTV_FP32 && n > 0)
-    return fail(c, "hdrtv_set_act_quant: the INT8 layouts run on the FP32 (fake-quantisation) path; create the context with HDRTV_FP32");
+  // HDRTV_FP32 contexts: every layer may carry a quantiser (fake-quantisation on the CUDA-core path, any layout).
+  // HDRTV_FP16 contexts: the tensor-core path of the INT8 MIXED layout; call this BEFORE hdrtv_set_weights (the weight pack
+  // builds the int8 operands and de-quantisation tables of the quantised layers); unsupported layers fail in hdrtv_prepare.
+  if (c->precision == HDRTV_FP16 && c->has_weights && n > 0)
+    return fail(c, "hdrtv_set_act_quant: on an FP16 context the quantisers must be installed before hdrtv_set_weights");
   c->quant.clear();
   for (int i = 0; i < n; ++i) {
     if (modes[i] < 0 || modes[i] > 2 || !(scales[i] > 0.f)) return fail(c, std::string("hdrtv_set_act_quant: bad entry for ") + layers[i]);
@@ -1849,6 +2142,7 @@ int hdrtv_set_act_quant(hdrtv_t* c, const char* const* layers, const float* scal
   return 0;
 }
 
+#ifdef HDRTV_TEST_EXPORTS
 // One named conv / linear layer of the FP32 path on caller-supplied host data (bias, no activation; the layer's input
 // fake-quantiser applies when one is installed).  Parity hook: INT8 fake-quantised networks amplify fp32 summation-
 // order noise chaotically, so they are pinned layer by layer on inputs recorded from the reference.
@@ -1876,6 +2170,8 @@ int hdrtv_debug_layer(hdrtv_t* c, const char* layer, const float* in_host, int C
   CK(c, e);
   return r;
 }
+
+#endif  // HDRTV_TEST_EXPORTS
 
 int hdrtv_prepare(hdrtv_t* c, int H, int Wd) {
   if (!c) return fail(c, "hdrtv_prepare: null context");
@@ -1918,17 +2214,23 @@ int hdrtv_prepare(hdrtv_t* c, int H, int Wd) {
 size_t hdrtv_workspace_bytes(const hdrtv_t* c) { return c ? c->ws_bytes : 0; }
 long hdrtv_launch_count(const hdrtv_t* c) { return c ? c->launches : 0; }
 
-int hdrtv_preprocess(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out, void* cond_out, int cond_mode, void* stream) {
+// stage_p8: (FP16) the normalise pass also writes the image into the tensor-core layout the AGCM chain reads, so the
+// separate staging launch of hdrtv_classify / hdrtv_infer is not needed for this frame.
+static int preprocess_impl(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out, void* cond_out, int cond_mode,
+                           cudaStream_t s, bool stage_p8, bool* staged) {
+  if (staged) *staged = false;
   if (!c || !bgr || !x_out || !cond_out) return fail(c, "hdrtv_preprocess: null argument");
   if (hdrtv_prepare(c, H, Wd)) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long npix = static_cast<long>(H) * Wd;
   const bool vec = (Wd % 16 == 0) && (reinterpret_cast<uintptr_t>(bgr) % 16 == 0);
   const int Hc = std::max(1, H / 4), Wc = std::max(1, Wd / 4);
   CondTaps tp{c->d_xstart, c->d_xw, c->d_ystart, c->d_yw};
   dim3 cgrid((Wc + kCondTW - 1) / kCondTW, (Hc + kCondTH - 1) / kCondTH);
   if (c->precision == HDRTV_FP16) {
-    if (vec) normalize_vec16_kernel<__half><<<static_cast<unsigned>((npix / 16 + 255) / 256), 256, 0, s>>>(bgr, static_cast<__half*>(x_out), H, Wd);
+    if (vec && stage_p8) {
+      normalize_p8_kernel<<<static_cast<unsigned>((npix + 4095) / 4096), 256, 0, s>>>(bgr, static_cast<__half*>(x_out), c->xP8, H, Wd);
+      if (staged) *staged = true;
+    } else if (vec) normalize_vec16_kernel<__half><<<static_cast<unsigned>((npix / 16 + 255) / 256), 256, 0, s>>>(bgr, static_cast<__half*>(x_out), H, Wd);
     else normalize_scalar_kernel<__half><<<static_cast<unsigned>((npix + 255) / 256), 256, 0, s>>>(bgr, static_cast<__half*>(x_out), H, Wd);
     cond_aa_kernel<__half><<<cgrid, 256, 0, s>>>(bgr, static_cast<__half*>(cond_out), H, Wd, Hc, Wc, tp, cond_mode);
   } else {
@@ -1939,6 +2241,10 @@ int hdrtv_preprocess(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out,
   CK(c, cudaGetLastError());
   c->launches += 2;
   return 0;
+}
+
+int hdrtv_preprocess(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out, void* cond_out, int cond_mode, void* stream) {
+  return preprocess_impl(c, bgr, H, Wd, x_out, cond_out, cond_mode, static_cast<cudaStream_t>(stream), false, nullptr);
 }
 
 int hdrtv_infer_ex(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* out, void* agcm_out, int skip_classifier,
@@ -1962,12 +2268,11 @@ int hdrtv_infer(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void
   return hdrtv_infer_ex(c, x, cond, H, Wd, out, agcm_out, 0, nullptr, stream);
 }
 
-int hdrtv_classify(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* stream) {
+static int classify_impl(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, cudaStream_t s, bool staged) {
   if (!c || !x || !cond) return fail(c, "hdrtv_classify: null argument");
   if (hdrtv_prepare(c, H, Wd)) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   try {
-    if (c->precision == HDRTV_FP16) {     // stage the image into the tensor-core layout (first step of the FP16 network)
+    if (c->precision == HDRTV_FP16 && !staged) {     // stage the image into the tensor-core layout (first step of the FP16 network)
       planar_to_p8_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(static_cast<const __half*>(x), c->xP8, H, Wd);
       CK(c, cudaGetLastError());
       ++c->launches;
@@ -1976,6 +2281,20 @@ int hdrtv_classify(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, v
   } catch (const std::exception& e) {
     return fail(c, std::string("hdrtv_classify: ") + e.what());
   }
+}
+
+int hdrtv_classify(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, void* stream) {
+  return classify_impl(c, x, cond, H, Wd, static_cast<cudaStream_t>(stream), false);
+}
+
+/* Fused front end: hdrtv_preprocess + hdrtv_classify for the same frame in one call; on the FP16 path the normalise pass
+   writes the tensor-core staging copy of the image itself (one launch and one 6 B/px round trip less). */
+int hdrtv_preprocess_classify(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, void* x_out, void* cond_out, int cond_mode,
+                              void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bool staged = false;
+  if (preprocess_impl(c, bgr, H, Wd, x_out, cond_out, cond_mode, s, true, &staged)) return -1;
+  return classify_impl(c, x_out, cond_out, H, Wd, s, staged);
 }
 
 // Per-launch device times of one fp16 infer (CUDA events between launches).  names: '\n'-separated.
@@ -1998,6 +2317,7 @@ int hdrtv_time_plan(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, 
   return n;
 }
 
+#ifdef HDRTV_TEST_EXPORTS
 // cycles per MMA (average over `iters`) on `blocks` concurrently resident CTAs; returns max over CTAs.
 int hdrtv_mma_probe(hdrtv_t* c, int n, int layout, int vary, int iters, int blocks, int nacc, float* cycles_per_mma) {
   if (!c) return -1;
@@ -2092,6 +2412,8 @@ int hdrtv_chain_trace(hdrtv_t* c, int agcm, int index, long long* trace_host) {
   return 0;
 }
 
+#endif  // HDRTV_TEST_EXPORTS
+
 int hdrtv_set_transfer_lut(hdrtv_t* c, const uint16_t* lut, int n) {
   if (!c || !lut || n != 0x3C01) return fail(c, "hdrtv_set_transfer_lut: need 15361 entries (half patterns 0x0000..0x3C00)");
   if (!c->d_lut && cudaMalloc(&c->d_lut, 0x3C01 * sizeof(uint16_t)) != cudaSuccess) return fail(c, "lut alloc");
@@ -2099,9 +2421,9 @@ int hdrtv_set_transfer_lut(hdrtv_t* c, const uint16_t* lut, int n) {
   return 0;
 }
 
-int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint16_t* dst, int transfer, void* stream) {
+static int pack_rgb48_impl(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint16_t* dst, int transfer,
+                           unsigned long long* checksum_dev, cudaStream_t s) {
   if (!c || !src || !dst) return fail(c, "hdrtv_pack_rgb48: null argument");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long npix = static_cast<long>(H) * Wd;
   const unsigned blocks = static_cast<unsigned>(((npix + 7) / 8 + 255) / 256);
   const uint16_t* lut = nullptr;
@@ -2110,11 +2432,16 @@ int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint
     lut = c->d_lut;
   }
   const int vec_ok = (npix % 8 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
-  if (dtype == HDRTV_FP16) pack_rgb48_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix, lut, vec_ok);
-  else pack_rgb48_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix, lut, vec_ok);
+  if (checksum_dev) CK(c, cudaMemsetAsync(checksum_dev, 0, sizeof(unsigned long long), s));
+  if (dtype == HDRTV_FP16) pack_rgb48_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(src), dst, npix, lut, vec_ok, checksum_dev);
+  else pack_rgb48_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), dst, npix, lut, vec_ok, checksum_dev);
   CK(c, cudaGetLastError());
   ++c->launches;
   return 0;
+}
+
+int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint16_t* dst, int transfer, void* stream) {
+  return pack_rgb48_impl(c, src, dtype, H, Wd, dst, transfer, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int hdrtv_pack_bgr24(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint8_t* dst, void* stream) {
@@ -2128,6 +2455,11 @@ int hdrtv_pack_bgr24(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint
   CK(c, cudaGetLastError());
   ++c->launches;
   return 0;
+}
+
+static bool plan_can_fuse_pack(const Ctx* c) {
+  static const bool enabled = env_int("HDRTV_FUSED_PACK", 1) != 0;
+  return enabled && c->precision == HDRTV_FP16 && !c->plan_le.empty() && c->plan_le.back().c2x && c->plan_le.back().mode == STORE_PLANAR;
 }
 
 // ---- SURVEY §8b `hdrtv_process`: BGR24 frame in -> RGB48 frame out, one call ------------------------------------
@@ -2163,8 +2495,8 @@ static int ensure_proc(Ctx* c, int H, int Wd) {
   return 0;
 }
 
-int hdrtv_process(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rgb48, int cond_mode, int transfer, int flags,
-                  void* done_event, void* stream) {
+int hdrtv_process_ex(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rgb48, int cond_mode, int transfer, int flags,
+                     uint64_t* checksum_out, void* done_event, void* stream) {
   if (!c || !bgr || !rgb48) return fail(c, "hdrtv_process: null argument");
   cudaSetDevice(c->device);
   if (ensure_proc(c, H, Wd)) return -1;
@@ -2189,28 +2521,48 @@ int hdrtv_process(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rgb48
     src = P.bgr;
   }
   if (!serial && P.primed) CK(c, cudaStreamWaitEvent(si, c->ev_in_free, 0));   // previous frame's AGCM MLP has read x / cond / fold
-  if (hdrtv_preprocess(c, src, H, Wd, P.x, P.cond, cond_mode, si)) return -1;
-  if (hdrtv_classify(c, P.x, P.cond, H, Wd, si)) return -1;
+  if (hdrtv_preprocess_classify(c, src, H, Wd, P.x, P.cond, cond_mode, si)) return -1;
   if (!serial) {
     CK(c, cudaEventRecord(c->ev_pre_done, si));
     CK(c, cudaStreamWaitEvent(s, c->ev_pre_done, 0));
   }
-  // ---- stage 2 (caller's stream): AGCM MLP + LE network + RGB48 pack
-  if (hdrtv_infer_ex(c, P.x, P.cond, H, Wd, P.out, P.agcm, 1, serial ? nullptr : c->ev_in_free, s)) return -1;
+  // ---- stage 2 (caller's stream): AGCM MLP + LE network + RGB48 pack (fused into the network's last kernel on the
+  // FP16 path: its epilogue writes the codes next to the planar output)
   uint16_t* dst = rgb48;
-  if (!out_dev) {
-    dst = P.rgb[slot];
-    if (P.frames >= 2) CK(c, cudaStreamWaitEvent(s, c->ev_d2h[slot], 0));   // staging slot drained (frame k-2; no-op if never recorded)
+  unsigned long long* cks = nullptr;
+  if (checksum_out && !c->d_cksum) CK(c, cudaMalloc(&c->d_cksum, 2 * sizeof(unsigned long long)));
+  if (!out_dev) dst = P.rgb[slot];
+  // the staging slot / checksum word of frame k-2 must have left the device (no-op if never recorded)
+  if ((!out_dev || checksum_out) && P.frames >= 2) CK(c, cudaStreamWaitEvent(s, c->ev_d2h[slot], 0));
+  if (checksum_out) cks = c->d_cksum + slot;
+  const uint16_t* lut = nullptr;
+  if (transfer == HDRTV_TRANSFER_LUT) {
+    if (!c->d_lut || c->precision != HDRTV_FP16) return fail(c, "hdrtv_process: LUT transfer needs fp16 precision and a table");
+    lut = c->d_lut;
   }
-  if (hdrtv_pack_rgb48(c, P.out, c->precision == HDRTV_FP16 ? HDRTV_FP16 : HDRTV_FP32, H, Wd, dst, transfer, s)) return -1;
+  if (plan_can_fuse_pack(c)) {
+    if (cks) CK(c, cudaMemsetAsync(cks, 0, sizeof(unsigned long long), s));
+    FusedPack fp;
+    fp.rgb48 = dst; fp.lut = lut; fp.cksum = cks;
+    try {
+      if (run_fp16(c, static_cast<const __half*>(P.x), static_cast<const __half*>(P.cond), static_cast<__half*>(P.out),
+                   static_cast<__half*>(P.agcm), s, nullptr, true, serial ? nullptr : c->ev_in_free, &fp)) return -1;
+    } catch (const std::exception& e) {
+      return fail(c, std::string("hdrtv_process: ") + e.what());
+    }
+  } else {
+    if (hdrtv_infer_ex(c, P.x, P.cond, H, Wd, P.out, P.agcm, 1, serial ? nullptr : c->ev_in_free, s)) return -1;
+    if (pack_rgb48_impl(c, P.out, c->precision == HDRTV_FP16 ? HDRTV_FP16 : HDRTV_FP32, H, Wd, dst, transfer, cks, s)) return -1;
+  }
   // ---- stage 3 (copy-out stream): D2H into the caller's (pinned) frame
   cudaStream_t last = s;
-  if (!out_dev) {
+  if (!out_dev || checksum_out) {
     if (!serial) {
       CK(c, cudaEventRecord(c->ev_packed, s));
       CK(c, cudaStreamWaitEvent(so, c->ev_packed, 0));
     }
-    CK(c, cudaMemcpyAsync(rgb48, dst, npix * 6, cudaMemcpyDeviceToHost, so));
+    if (!out_dev) CK(c, cudaMemcpyAsync(rgb48, dst, npix * 6, cudaMemcpyDeviceToHost, so));
+    if (checksum_out) CK(c, cudaMemcpyAsync(checksum_out, cks, sizeof(unsigned long long), cudaMemcpyDefault, so));
     if (!serial) CK(c, cudaEventRecord(c->ev_d2h[slot], so));
     last = so;
   }
@@ -2218,6 +2570,11 @@ int hdrtv_process(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rgb48
   P.primed = !serial;
   ++P.frames;
   return 0;
+}
+
+int hdrtv_process(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rgb48, int cond_mode, int transfer, int flags,
+                  void* done_event, void* stream) {
+  return hdrtv_process_ex(c, bgr, H, Wd, rgb48, cond_mode, transfer, flags, nullptr, done_event, stream);
 }
 
 /* Joins the copy-out stream of hdrtv_process back into `stream` (end of a clip, or before the buffers are reused). */
@@ -2233,6 +2590,64 @@ int hdrtv_process_flush(hdrtv_t* c, void* stream) {
 const void* hdrtv_process_output(const hdrtv_t* c, int which) {
   if (!c || !c->proc.H) return nullptr;
   return which == 0 ? c->proc.out : (which == 1 ? c->proc.agcm : nullptr);
+}
+
+#ifdef HDRTV_TEST_EXPORTS
+// One W8A8 layer through its tcgen05.mma.kind::i8 launch on caller-supplied uint8 codes q [C][H][W] (host): returns the raw
+// S32 accumulators sum(q * w_int8) as planar [N][Ho][Wo] (what the tensor core produced, before any float arithmetic) and the
+// de-quantised layer output (conv + bias, no activation) as planar fp32 [Cout][Ho][Wo] ([Cout/4][2Ho][2Wo] after PixelShuffle
+// for the up-convs).  Parity hook for tests/golden/int8mixed_layers_*.npz.
+int hdrtv_debug_conv_i8(hdrtv_t* c, const char* layer, const uint8_t* q_host, int C, int H, int Wd, int stride, int32_t* acc_host,
+                        float* out_host) {
+  if (!c || !layer || !q_host || !acc_host || !out_host) return fail(c, "hdrtv_debug_conv_i8: null argument");
+  if (c->precision != HDRTV_FP16) return fail(c, "hdrtv_debug_conv_i8: FP16 (tensor-core) context required");
+  const std::string name = layer;
+  if (!c->i8tab.count(name)) return fail(c, "hdrtv_debug_conv_i8: " + name + " is not a kind::i8 layer of this checkpoint");
+  cudaSetDevice(c->device);
+  const HostTensor& wi = c->w.at(name + ".weight_int8");
+  const int O = static_cast<int>(wi.shape[0]);
+  if (static_cast<int>(wi.shape[1]) != C || (C != 32 && C != 64) || (stride != 1 && stride != 2)) return fail(c, "hdrtv_debug_conv_i8: shape");
+  const bool ps = O == 128;
+  const int N = O;
+  const int Ho = stride == 2 ? down2(H) : H, Wo = stride == 2 ? down2(Wd) : Wd;
+  Ctx t;
+  t.device = c->device;
+  t.d_err = c->d_err;
+  P8 in = make_p8(&t, C / 2, H, Wd, stride == 2);                               // uint8: 16 channels per entry
+  P8 outp = ps ? make_p8(&t, 32, 2 * Ho, 2 * Wo, false) : make_p8(&t, std::max(8, N), Ho, Wo, false);
+  int* dacc = ws_alloc<int>(&t, static_cast<size_t>(N) * Ho * Wo);
+  if (!in.base || !outp.base || !dacc) { for (void* p : t.ws_allocs) cudaFree(p); return fail(c, "hdrtv_debug_conv_i8: alloc"); }
+  {
+    std::vector<uint8_t> h(static_cast<size_t>(in.entries()) * 16, 0);
+    for (int ch = 0; ch < C; ++ch)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < Wd; ++x)
+          h[in.entry(y, ch / 16, x) * 16 + ch % 16] = q_host[(static_cast<size_t>(ch) * H + y) * Wd + x];
+    cudaMemcpy(in.base, h.data(), h.size(), cudaMemcpyHostToDevice);
+  }
+  std::vector<ConvLaunch> plan;
+  Epi e;
+  e.i8 = true; e.i8_tab = c->i8tab.at(name); e.i8_H = H; e.i8_W = Wd;
+  int r = make_conv(&t, plan, name, stride == 2 ? IN_PAR3x3S2 : IN_NAT3x3, in, 0, C / 16, N, ps ? STORE_PS : STORE_P8,
+                    c->wpk.at(name + ".i8"), outp, Ho, Wo, e);
+  if (r) c->err = t.err;
+  if (!r) {
+    plan[0].p.i8_acc_dump = dacc;
+    cudaError_t ce = launch_conv(plan[0], 0);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { fail(c, std::string("hdrtv_debug_conv_i8 launch: ") + cudaGetErrorString(ce)); r = -1; }
+  }
+  if (!r) {
+    cudaMemcpy(acc_host, dacc, sizeof(int) * N * Ho * Wo, cudaMemcpyDeviceToHost);
+    const int oc = ps ? 32 : N, oh = ps ? 2 * Ho : Ho, ow = ps ? 2 * Wo : Wo;
+    float* tmpd = ws_alloc<float>(&t, static_cast<size_t>(oc) * oh * ow);
+    p8_to_planar_f32_kernel<<<dim3((ow + 127) / 128, oh), 128>>>(outp, 0, oc, tmpd);
+    if (cudaMemcpy(out_host, tmpd, sizeof(float) * oc * oh * ow, cudaMemcpyDeviceToHost) != cudaSuccess) r = fail(c, "hdrtv_debug_conv_i8: readback");
+  }
+  t.d_err = nullptr;
+  for (void* p : t.ws_allocs) cudaFree(p);
+  t.ws_allocs.clear();
+  return r;
 }
 
 int hdrtv_debug_tensor_count(const hdrtv_t* c) { return c ? static_cast<int>(c->dbg.size()) : 0; }
@@ -2418,5 +2833,7 @@ int hdrtv_conv_selftest(hdrtv_t* c, int kind, int cin, int cout, int H, int Wd, 
   t.ws_allocs.clear();
   return r;
 }
+
+#endif  // HDRTV_TEST_EXPORTS
 
 }  // extern "C"

@@ -12,27 +12,6 @@ namespace hdrtv {
 // Weights for the block's COB channels are staged in shared memory as [cin][tap][COB].
 // Epilogue: +bias, activation, optional residual add, optional PixelShuffle(2) scatter with crop.
 // ------------------------------------------------------------------------------------------------
-// Static activation fake-quantisation of a layer input (reference W8A8Conv2d / W8A8Linear.forward,
-// hdrtvnet_torch.py:350-364): mode 2 (asymmetric) q = clamp(round((x - zero) / scale), 0, 255), x^ = q*scale + zero;
-// mode 1 (symmetric) q = clamp(round(x / scale), -128, 127), x^ = q*scale; torch.round = round-half-even = rintf.
-struct ActQuant {
-  float scale = 1.f, zero = 0.f;
-  int mode = 0;
-};
-__device__ __forceinline__ float fake_quant(float x, const ActQuant& q) {
-  if (q.mode == 2) {
-    float v = rintf(__fdiv_rn(__fsub_rn(x, q.zero), q.scale));
-    v = fminf(fmaxf(v, 0.f), 255.f);
-    return __fadd_rn(__fmul_rn(v, q.scale), q.zero);
-  }
-  if (q.mode == 1) {
-    float v = rintf(__fdiv_rn(x, q.scale));
-    v = fminf(fmaxf(v, -128.f), 127.f);
-    return __fmul_rn(v, q.scale);
-  }
-  return x;
-}
-
 struct ConvF32 {
   const float* in;   // [Cin][H][W]
   const float* w;    // [Cout][Cin][ks][ks]

@@ -56,6 +56,55 @@ __global__ void normalize_scalar_kernel(const uint8_t* __restrict__ bgr, T* __re
   }
 }
 
+// ---- normalise + tensor-core staging in one pass (FP16 path): besides the planar (1,3,H,W) tensor the API returns, the
+// same threads write the image as the single-chunk P8 tensor [R,G,B,0,0,0,0,0] the AGCM chain reads (one 16-byte entry
+// per pixel).  The entries go through shared memory so that consecutive lanes store consecutive entries (128-bit,
+// coalesced); a block covers 4096 consecutive pixels of the frame (needs W % 16 == 0).
+__global__ void __launch_bounds__(256) normalize_p8_kernel(const uint8_t* __restrict__ bgr, __half* __restrict__ x, P8 xp8,
+                                                           int H, int W) {
+  __shared__ uint2 px[4096];                                   // (R,G | B,0) halves of one pixel
+  const long g = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;  // group of 16 pixels
+  const long plane = static_cast<long>(H) * W;
+  const long ngroups = plane / 16;
+  if (g < ngroups) {
+    const uint4* src = reinterpret_cast<const uint4*>(bgr) + g * 3;
+    alignas(16) uint4 q[3];
+    q[0] = __ldg(src);
+    q[1] = __ldg(src + 1);
+    q[2] = __ldg(src + 2);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(q);
+    alignas(16) __half v[3][16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[c][i] = __float2half_rn(__fmul_rn(static_cast<float>(bytes[3 * i + (2 - c)]), 0.003921568859368563f));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint4* dst = reinterpret_cast<uint4*>(x + c * plane + g * 16);
+      dst[0] = reinterpret_cast<const uint4*>(v[c])[0];
+      dst[1] = reinterpret_cast<const uint4*>(v[c])[1];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint2 e;
+      e.x = static_cast<uint32_t>(__half_as_ushort(v[0][i])) | (static_cast<uint32_t>(__half_as_ushort(v[1][i])) << 16);
+      e.y = static_cast<uint32_t>(__half_as_ushort(v[2][i]));
+      px[threadIdx.x * 16 + i] = e;
+    }
+  }
+  __syncthreads();
+  const long p0 = static_cast<long>(blockIdx.x) * 4096;
+  uint4* base = reinterpret_cast<uint4*>(xp8.base);
+#pragma unroll 4
+  for (int k = threadIdx.x; k < 4096; k += 256) {
+    const long pidx = p0 + k;
+    if (pidx >= plane) break;
+    const int y = static_cast<int>(pidx / W), xx = static_cast<int>(pidx - static_cast<long>(y) * W);
+    const uint2 e = px[k];
+    base[xp8.entry(y, 0, xx)] = make_uint4(e.x, e.y, 0u, 0u);
+  }
+}
+
 // ---- condition image: antialiased bicubic x0.25 (separable 16-tap Keys cubic, a = -0.5, normalised taps) ----
 // Tap tables are built on the host per resolution: start index + 16 fp32 weights (zero beyond `count`).
 // One block = 8x32 output pixels; the block's u8 window is normalised once into shared memory, a horizontal
@@ -109,6 +158,34 @@ __global__ void __launch_bounds__(256) cond_aa_kernel(const uint8_t* __restrict_
     return;
   }
   const int ys0 = tp.ystart[min(oy0, Hc - 1)];
+  // Stage the block's u8 window (RH rows x RW pixels, BGR interleaved) in shared memory with coalesced 32-bit loads:
+  // the horizontal pass below reads every byte 4 times (16 taps / stride 4), and byte loads straight from global
+  // memory ran this kernel at 229 GB/s (profiles/r1_launches_1080p.md).
+  __shared__ uint32_t win[RH][(RW * 3 + 3) / 4 + 2];
+  const int xs0 = tp.xstart[min(ox0, Wc - 1)];
+  const long row_bytes = static_cast<long>(W) * 3;
+  const int b0 = xs0 * 3;
+  const int b0a = b0 & ~3;                                    // word-aligned start inside a row (rows are W*3 bytes, W % 4 == 0
+  const int skew = b0 - b0a;                                  //  is not required: alignment is per absolute byte address below)
+  constexpr int WORDS = (RW * 3 + 3) / 4 + 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(bgr) & 3) == 0) && ((row_bytes & 3) == 0);
+  for (int r = ty; r < RH; r += kCondTH) {
+    const int iy = ys0 + r;
+    if (iy >= H) continue;
+    const uint8_t* row = bgr + static_cast<long>(iy) * row_bytes;
+    for (int wd = tx; wd < WORDS; wd += kCondTW) {
+      const long off = static_cast<long>(b0a) + 4 * wd;
+      uint32_t v = 0;
+      if (aligned && off + 4 <= row_bytes) v = __ldg(reinterpret_cast<const uint32_t*>(row + off));
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (off + k < row_bytes) v |= static_cast<uint32_t>(row[off + k]) << (8 * k);
+      }
+      win[r][wd] = v;
+    }
+  }
+  __syncthreads();
   // horizontal pass: thread (row r, out col tx) for r = ty, ty+8, ...
   const int oxc = min(ox, Wc - 1);
   const int xs = tp.xstart[oxc];
@@ -119,11 +196,11 @@ __global__ void __launch_bounds__(256) cond_aa_kernel(const uint8_t* __restrict_
     const int iy = ys0 + r;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (iy < H) {
-      const uint8_t* row = bgr + (static_cast<long>(iy) * W) * 3;
+      const uint8_t* wrow = reinterpret_cast<const uint8_t*>(win[r]) + skew;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const int ix = min(xs + k, W - 1);  // weights beyond `count` are zero
-        const uint8_t* px = row + 3 * ix;
+        const int ix = min(xs + k, W - 1) - xs0;  // weights beyond `count` are zero
+        const uint8_t* px = wrow + 3 * ix;
         a0 = fmaf(wx[k], norm_u8(px[2], sizeof(T) == 2), a0);
         a1 = fmaf(wx[k], norm_u8(px[1], sizeof(T) == 2), a1);
         a2 = fmaf(wx[k], norm_u8(px[0], sizeof(T) == 2), a2);
@@ -166,12 +243,34 @@ __device__ __forceinline__ float ldf(const T* p) {
 }
 // 8 pixels per thread: planar loads, 3 x 128-bit interleaved stores (needs W*H % 8 == 0).  `lut` (optional,
 // fp16 inputs only) maps the half bit pattern of the clamped value to a code (PQ transfer option).
+// `checksum` (optional): the frame descriptor's order-sensitive 64-bit checksum sum_i code[i] * ((i mod 65521) + 1) over the
+// flattened (H,W,3) array (sharding.frame_checksum), accumulated with integer atomics (exact, order-independent).
+__device__ __forceinline__ unsigned long long cks_term(uint32_t code, long elem) {
+  return static_cast<unsigned long long>(code) * static_cast<unsigned long long>(static_cast<uint32_t>(elem % 65521) + 1u);
+}
+__device__ __forceinline__ void cks_block_add(unsigned long long v, unsigned long long* checksum) {
+  __shared__ unsigned long long part[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) t += part[i];
+    if (t) atomicAdd(checksum, t);
+  }
+}
 template <typename T>
 __global__ void __launch_bounds__(256) pack_rgb48_kernel(const T* __restrict__ src, uint16_t* __restrict__ dst, long npix,
-                                                         const uint16_t* __restrict__ lut, int vec_ok) {
+                                                         const uint16_t* __restrict__ lut, int vec_ok,
+                                                         unsigned long long* __restrict__ checksum) {
   const long g = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long i0 = g * 8;
-  if (i0 >= npix) return;
+  unsigned long long cks = 0;
+  if (i0 >= npix) {
+    if (checksum) cks_block_add(0, checksum);
+    return;
+  }
   if (vec_ok && i0 + 8 <= npix) {
     alignas(16) uint16_t o[24];
 #pragma unroll
@@ -198,18 +297,26 @@ __global__ void __launch_bounds__(256) pack_rgb48_kernel(const T* __restrict__ s
     d[0] = os[0];
     d[1] = os[1];
     d[2] = os[2];
+    if (checksum) {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) cks += cks_term(o[k], i0 * 3 + k);
+    }
   } else {
     const long i1 = i0 + 8 < npix ? i0 + 8 : npix;
     for (long i = i0; i < i1; ++i)
       for (int c = 0; c < 3; ++c) {
+        uint16_t code;
         if (lut != nullptr && sizeof(T) == 2) {
           __half h = __float2half_rn(fminf(fmaxf(ldf(src + c * npix + i), 0.f), 1.f));
-          dst[i * 3 + c] = lut[__half_as_ushort(h)];
+          code = lut[__half_as_ushort(h)];
         } else {
-          dst[i * 3 + c] = static_cast<uint16_t>(q16(ldf(src + c * npix + i)));
+          code = static_cast<uint16_t>(q16(ldf(src + c * npix + i)));
         }
+        dst[i * 3 + c] = code;
+        cks += cks_term(code, i * 3 + c);
       }
   }
+  if (checksum) cks_block_add(cks, checksum);
 }
 
 // ---- BGR24 pack: arithmetic IN THE TENSOR'S DTYPE (half: each of mul/add rounds to half), truncate, RGB->BGR ----

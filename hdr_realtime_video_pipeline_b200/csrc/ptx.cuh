@@ -21,13 +21,19 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Arrive that is data-dependent on `dep`: used to release a shared-memory slot only after the loads that produced
-// `dep` have returned (a plain arrive is not held back by the warp's outstanding ld.shared instructions).
-__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep) {
-  // a select on a value that never occurs: ptxas cannot fold it, so the address is not available before `dep` is
+// ---- Cross-proxy write-after-read rule (one place, applies to every ring in this code base) -------------------------
+// A shared-memory slot that is REFILLED by the async proxy (cp.async.bulk / TMA) may only be handed back to the producer
+//   (a) by tcgen05.commit, when its readers were tcgen05.mma instructions (the commit arrives after they completed), or
+//   (b) by an mbarrier.arrive that is DATA-DEPENDENT on the ld.shared results, when its readers were ordinary loads:
+//       a plain arrive is not held back by the warp's outstanding shared loads, so the producer's next bulk copy could land
+//       before a queued load executed (seen as rare rows carrying data of row t + ring depth, only under SM sharing).
+// mbar_arrive_after implements (b): the barrier address is `bar + (dep & zero)`, where `zero` is a kernel parameter that
+// is 0 at run time but opaque to ptxas, so the arrive cannot issue before `dep` (a value derived from every loaded
+// register) is available - and, unlike a select on a "never occurring" constant, no data value can redirect the arrive.
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, uint32_t opaque_zero) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tsetp.eq.u32 q, %1, 0x7FC17FC3;\n\tselp.b32 t, 8, 0, q;\n\tadd.u32 t, t, %0;\n\t"
-      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t}" ::"r"(bar), "r"(dep)
+      "{\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tadd.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t}" ::"r"(bar), "r"(dep), "r"(opaque_zero)
       : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -57,15 +63,27 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a barrier that never completes (bad tx count, lost commit) must not hang the GPU box.
-// On timeout the error word is set and the kernel traps (sticky launch failure instead of a hang).
+// Bounded wait: a barrier that never completes (bad tx count, lost commit) must not hang the GPU box.  The bound is TIME
+// (%globaltimer, seconds), not a spin count: a loaded box (several ranks, profilers, preemption) slows every warp down
+// but cannot trip it.  On timeout the error word is set and the kernel traps (sticky launch failure instead of a hang).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kMbarTimeoutNs = 8ull * 1000ull * 1000ull * 1000ull;      // 8 s
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_word, int code) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err_word) atomicExch(err_word, code);
-      __threadfence_system();
-      __trap();
+    if ((++spins & 0x3FFu) == 0) {                     // look at the clock every 1024 polls
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kMbarTimeoutNs) {
+        if (err_word) atomicExch(err_word, code);
+        __threadfence_system();
+        __trap();
+      }
     }
   }
 }
@@ -130,6 +148,20 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// kind::i8 instruction descriptor: A = unsigned 8 bit (activations), B = signed 8 bit (weights), D = S32, both K-major,
+// M = 128; one instruction covers K = 32 (two 16-byte K halves, same canonical layout as the f16 K = 16 case).
+__host__ __device__ constexpr uint32_t make_idesc_i8_m128(uint32_t n) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -72,8 +72,8 @@ class Rgb48RawWriter:
             self._fd = None
 
 
-def export_clip(processor, frames, n_frames: int, out_path: str, rank: int = 0, world_size: int = 1, pack=None,
-                barrier=None, one_call: bool = True) -> dict:
+def export_clip(processor, frames, n_frames: int, out_path: str | None, rank: int = 0, world_size: int = 1, pack=None,
+                barrier=None, one_call: bool = True, in_flight: int = 3, device_checksums: bool = True) -> dict:
     """Export this rank's contiguous chunk of an ``n_frames`` clip.
 
     processor : an ``HDRTVNetB200`` (anything with preprocess / infer)
@@ -83,6 +83,11 @@ def export_clip(processor, frames, n_frames: int, out_path: str, rank: int = 0, 
     one_call  : with the default pack, use ``processor.process_rgb48`` (one C-ABI call per frame, ``hdrtv_process``: the
                 frame is DMA-copied straight from the array ``frames(i)`` returned, which must not be rewritten before
                 the frame has been written out) instead of preprocess -> infer -> pack; the bytes are identical
+    out_path  : raw rgb48le file shared by all ranks, or None: the frames are delivered to the pinned ring and released
+                (the sink of the benchmark: "decode-to-RGB48 output", BASELINE config 3 / 4 without a disk in the loop)
+    in_flight : frames submitted ahead of the one being drained (the pinned ring is sized in_flight + 1)
+    device_checksums : (one-call path) the descriptor checksum of every frame is computed by the pack kernel on the GPU
+                (``hdrtv_process_ex``) instead of a numpy pass over the 50 MB frame on the host
     Returns the per-rank record; gather with ``sharding.gather_run_records`` and check with ``sharding.merge_descriptors``.
     """
     from .feeders import tensor_to_rgb48_bytes
@@ -96,31 +101,40 @@ def export_clip(processor, frames, n_frames: int, out_path: str, rank: int = 0, 
             return tensor_to_rgb48_bytes(out, state)
     h, w = (probe.shape[0], probe.shape[1]) if probe is not None else (0, 0)
     writer = None
-    if rank == 0:                                         # rank 0 sizes the file; it always owns frame 0 of a non-empty clip
-        if probe is None:
-            raise ValueError("empty clip")
-        writer = Rgb48RawWriter(out_path, n_frames, h, w, create=True)
-    if barrier is not None:
+    if out_path is not None:
+        if rank == 0:                                     # rank 0 sizes the file; it always owns frame 0 of a non-empty clip
+            if probe is None:
+                raise ValueError("empty clip")
+            writer = Rgb48RawWriter(out_path, n_frames, h, w, create=True)
+        if barrier is not None:
+            barrier()
+        if writer is None and probe is not None:
+            writer = Rgb48RawWriter(out_path, n_frames, h, w, create=False)
+    elif barrier is not None:
         barrier()
-    if writer is None and probe is not None:
-        writer = Rgb48RawWriter(out_path, n_frames, h, w, create=False)
+    in_flight = max(1, int(in_flight))
+    if use_one_call and hasattr(processor, "set_rgb48_ring_frames"):
+        processor.set_rgb48_ring_frames(in_flight + 1)
+    dev_cks = bool(device_checksums) and use_one_call
     descriptors, pending = [], []
     t0 = time.perf_counter()
 
     def drain(entry):
         idx, payload = entry
         view = payload.buffer_view()                      # waits for the CUDA event of the ring slot
-        descriptors.append((idx, sharding.frame_checksum(np.frombuffer(view, dtype=np.uint16))))
-        writer.write(idx, view)
+        cks = payload.checksum() if dev_cks else sharding.frame_checksum(np.frombuffer(view, dtype=np.uint16))
+        descriptors.append((idx, cks))
+        if writer is not None:
+            writer.write(idx, view)
         payload.release()
 
     for i in range(first, last):
         frame = probe if i == first else frames(i)
         if use_one_call:
-            pending.append((i, processor.process_rgb48(frame)))
+            pending.append((i, processor.process_rgb48(frame, checksum=dev_cks)))
         else:
             pending.append((i, pack(processor.infer(processor.preprocess(frame)))))
-        if len(pending) >= 2:                             # keep one frame in flight behind the writer (ring >= 3 slots)
+        if len(pending) > in_flight or (not use_one_call and len(pending) >= 2):
             drain(pending.pop(0))
     for entry in pending:
         drain(entry)

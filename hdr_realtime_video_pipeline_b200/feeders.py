@@ -53,6 +53,14 @@ class PinnedFrame:
         self.wait_ready()
         return self._slot["numpy"]
 
+    def checksum(self) -> int:
+        """Descriptor checksum of the frame computed on the device by the pack kernel (process_rgb48(checksum=True));
+        equals sharding.frame_checksum(self.numpy())."""
+        if not self._slot.get("has_checksum"):
+            raise RuntimeError("frame was produced without checksum=True")
+        self.wait_ready()
+        return int(self._slot["checksum"].numpy().view(np.uint64)[0])
+
     def release(self) -> None:
         if self._released:
             return
@@ -104,7 +112,8 @@ class PinnedRing:
                 free.set()
                 ev = torch.cuda.Event(enable_timing=False)
                 ev.record(torch.cuda.current_stream(self.device))       # materialise the handle
-                self._slots.append({"tensor": host, "numpy": host.numpy(), "free": free, "event": ev, "source": None})
+                self._slots.append({"tensor": host, "numpy": host.numpy(), "free": free, "event": ev, "source": None,
+                                    "checksum": torch.zeros(1, dtype=torch.int64).pin_memory(), "has_checksum": False})
         self._shape = shape
         self._index = 0
         return self._slots

@@ -19,6 +19,49 @@ def frame_chunk(n_frames: int, rank: int, world_size: int) -> tuple[int, int]:
     return (rank * n_frames) // world_size, ((rank + 1) * n_frames) // world_size
 
 
+def pin_rank_to_local_cores(local_rank: int, local_world: int, device_of_rank=None) -> list[int]:
+    """One process per GPU: bind this rank to its own share of the host cores BEFORE it allocates pinned frame buffers
+    (first touch places them on the NUMA node of the allocating core).  NVML names the cores close to each GPU; ranks
+    whose GPUs share a core set split that set evenly; without NVML the allowed cores are split evenly over the local
+    ranks.  Returns the cores this process now runs on.  (torchrun starts every rank on the same affinity mask: eight
+    submit loops and all their pinned memory on one NUMA node cost 16 % of the 8-GPU end-to-end throughput in round 1.)"""
+    import os
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return []
+    allowed_set = set(allowed)
+    dev = device_of_rank or (lambda r: r)
+    near = {}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        for r in range(local_world):
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(dev(r)))
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+            cores = tuple(c for c in (64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1)
+                          if c in allowed_set)
+            near[r] = cores
+    except Exception:
+        near = {}
+    mine = None
+    if near.get(local_rank):
+        peers = [r for r in range(local_world) if near.get(r) == near[local_rank]]
+        cores = list(near[local_rank])
+        if len(cores) >= len(peers):
+            share = len(cores) // len(peers)
+            k = peers.index(local_rank)
+            mine = cores[k * share:(k + 1) * share]
+    if not mine:
+        share = max(1, len(allowed) // max(1, local_world))
+        mine = allowed[local_rank * share:(local_rank + 1) * share] or allowed
+    try:
+        os.sched_setaffinity(0, set(mine))
+    except OSError:
+        return allowed
+    return sorted(mine)
+
+
 def frame_checksum(rgb48: np.ndarray) -> int:
     """Order-sensitive 64-bit checksum of one packed frame (descriptor payload, cheap to compare across runs)."""
     a = np.ascontiguousarray(rgb48).view(np.uint16).astype(np.uint64).ravel()

@@ -50,11 +50,6 @@ int hdrtv_set_weights(hdrtv_t* h, const hdrtv_tensor_desc* tensors, int n);
 int hdrtv_set_act_quant(hdrtv_t* h, const char* const* layers, const float* scales, const float* zeros, const int* modes,
                         int n);
 
-/* Parity hook (FP32 contexts): one named conv / linear layer (bias, no activation, the layer's input quantiser) on    */
-/* host data: in (Cin,H,W) fp32 -> out (Cout,Ho,Wo) fp32.                                                             */
-int hdrtv_debug_layer(hdrtv_t* h, const char* layer, const float* in_host, int cin, int height, int width, int stride,
-                      float* out_host);
-
 /* HDRTVNetTorch._ensure_buffers (hdrtvnet_torch.py:2198-2233): (re)allocate the per-resolution workspace.          */
 /* Called implicitly by preprocess/infer; returns bytes held via hdrtv_workspace_bytes.                              */
 int hdrtv_prepare(hdrtv_t* h, int height, int width);
@@ -78,6 +73,11 @@ int hdrtv_infer(hdrtv_t* h, const void* x, const void* cond, int height, int wid
 int hdrtv_classify(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* stream);
 int hdrtv_infer_ex(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
                    int skip_classifier, void* inputs_consumed_event, void* stream);
+/* Fused front end of the pipelined path: hdrtv_preprocess + hdrtv_classify of one frame in one call (preprocess:2239-2296 */
+/* followed by the input-only part of the network).  On the FP16 path the normalise pass also writes the tensor-core      */
+/* staging copy of the image, so the frame is read once and no separate staging launch runs.                              */
+int hdrtv_preprocess_classify(hdrtv_t* h, const uint8_t* bgr, int height, int width, void* x_out, void* cond_out,
+                              int cond_mode, void* stream);
 
 /* _tensor_to_rgb48_bytes (gui_pipeline_worker_feeders.py:193-249): (1,3,H,W) planar of `dtype` -> uint16 HxWx3 RGB */
 /* (rgb48le), FP32 clamp*65535+0.5 truncate.  dst may be device memory or a mapped pinned ring slot.                */
@@ -100,37 +100,24 @@ enum { HDRTV_PROCESS_SERIAL = 1,        /* everything on `stream`, no overlap be
        HDRTV_PROCESS_RESYNC = 4 };      /* other entry points used the context since the last hdrtv_process on `stream`   */
 int hdrtv_process(hdrtv_t* h, const uint8_t* bgr, int height, int width, uint16_t* rgb48, int cond_mode, int transfer,
                   int flags, void* done_event, void* stream);
+/* Same, plus the frame's output descriptor checksum (ordered output descriptors of the frame-sharded export): */
+/* sum_i code[i] * ((i mod 65521) + 1) over the uint16 HxWx3 frame, computed by the pack kernel on the device and copied */
+/* to *checksum_out (pinned host or device memory, may be NULL) before done_event is recorded.                            */
+int hdrtv_process_ex(hdrtv_t* h, const uint8_t* bgr, int height, int width, uint16_t* rgb48, int cond_mode, int transfer,
+                     int flags, uint64_t* checksum_out, void* done_event, void* stream);
 int hdrtv_process_flush(hdrtv_t* h, void* stream);          /* `stream` waits for the copy-out stream's pending copies */
 const void* hdrtv_process_output(const hdrtv_t* h, int which); /* device (1,3,H,W) out (0) / agcm_out (1) of the last frame */
 
 /* HDRTVNetTorch.postprocess (hdrtvnet_torch.py:2352-2368): planar -> uint8 HxWx3 BGR, arithmetic in `dtype`.       */
 int hdrtv_pack_bgr24(hdrtv_t* h, const void* src, int dtype, int height, int width, uint8_t* dst, void* stream);
 
-/* Introspection used by tests, smoke() and bench.py.                                                               */
+/* Introspection used by tests, smoke() and bench.py.  (Debug / probe entry points live in hdrtv_b200_test.h and are  */
+/* exported only by the test build of the library, libhdrtv_b200_test.so.)                                          */
 const char* hdrtv_last_error(const hdrtv_t* h);
 long hdrtv_launch_count(const hdrtv_t* h);               /* kernels launched by this context so far                 */
-int hdrtv_debug_tensor_count(const hdrtv_t* h);
-int hdrtv_debug_tensor_info(const hdrtv_t* h, int idx, char* name, int name_cap, int* c, int* height, int* width);
-int hdrtv_debug_tensor_read(hdrtv_t* h, int idx, float* dst_host); /* (C,H,W) fp32; synchronises                    */
-/* One convolution through both paths on random data: returns max |tcgen05(fp16) - cuda-core(fp32)| in *max_abs.   */
-int hdrtv_conv_selftest(hdrtv_t* h, int kind, int cin, int cout, int height, int width, int flags, float* max_abs,
-                        float* ref_max);
 /* Per-launch device times (ms) of one FP16 hdrtv_infer, CUDA events between launches; returns the count.          */
 int hdrtv_time_plan(hdrtv_t* h, const void* x, const void* cond, int height, int width, void* out, void* agcm_out,
                     float* ms, int cap, char* names, int names_cap, void* stream);
-/* tcgen05 issue-rate probe (design evidence): cycles per M=128 x n x K=16 MMA; layout 0/1 = SWIZZLE_NONE (plane     */
-/* pitch / dense), 2 = SWIZZLE_128B; `blocks` concurrent CTAs.                                                      */
-int hdrtv_mma_probe(hdrtv_t* h, int n, int layout, int vary, int iters, int blocks, int n_accumulators,
-                    float* cycles_per_mma);
-/* Micro-probes of the tensor path (csrc/probes.cuh): 0 MMA SS M=128, 1 MMA with A in TMEM, 2 MMA SS M=64,             */
-/* 3 tcgen05.ld throughput (nwarps warps x 64 columns), 4 layer-chain round trip (nmma K-steps, `groups` row slots).   */
-/* 5 free-running MMA + commit stream.  trace_host (optional, 256 entries): clock64 stamps of probe 4's first 16      */
-/* iterations, [iter][group<4][event<4] = issue start, after commit, epilogue woke, epilogue arrived.                  */
-int hdrtv_probe(hdrtv_t* h, int kind, int n, int iters, int blocks, int nwarps, int nmma, int groups,
-                float* cycles_per_iter, long long* trace_host);
-/* Debug timeline of one fused layer-chain launch (after an hdrtv_infer at the current size): clock64 stamps of CTA 0, */
-/* [step < 64][row slot < 8][8].                                                                                        */
-int hdrtv_chain_trace(hdrtv_t* h, int agcm_plan, int launch_index, long long* trace_host);
 const char* hdrtv_version(void);
 
 #ifdef __cplusplus

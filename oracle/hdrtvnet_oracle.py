@@ -222,9 +222,11 @@ def split_int8_state(raw: dict):
     for k, v in raw.items():
         if k.endswith(".weight_int8"):
             layer = k[: -len(".weight_int8")]
-            scale = np.asarray(raw[layer + ".w_scale"], dtype=F32).reshape((-1,) + (1,) * (v.ndim - 1))
+            # W8A8 layers carry ".w_scale" (:361), weight-only W8 layers ".scale" (W8Conv2d / W8Linear, :233-291)
+            sc = raw[layer + ".w_scale"] if (layer + ".w_scale") in raw else raw[layer + ".scale"]
+            scale = np.asarray(sc, dtype=F32).reshape((-1,) + (1,) * (v.ndim - 1))
             sd[layer + ".weight"] = (np.asarray(v, dtype=F32) * scale).astype(F32)
-        elif k.endswith(".w_scale"):
+        elif k.endswith(".w_scale") or (k.endswith(".scale") and (k[: -len(".scale")] + ".weight_int8") in raw):
             continue
         else:
             sd[k] = np.asarray(v, dtype=F32)

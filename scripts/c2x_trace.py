@@ -13,7 +13,7 @@ import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "1080p"
 which = sys.argv[2] if len(sys.argv) > 2 else "trunk1.0"
 h, w = {"540p": (540, 960), "1080p": (1080, 1920), "4k": (2160, 3840)}[wl]
-net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False)
+net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False, debug_library=True)
 frame = torch.from_numpy(hb.synth_frame(0, h, w)).cuda()
 x, c = net.preprocess_device(frame)
 net.infer((x, c))

@@ -20,7 +20,7 @@ KINDS = {0: "NAT3x3", 1: "NAT1x1", 2: "NAT3x3_C8", 3: "NAT1x1_C8", 4: "PAR3x3S2"
 def _mk(precision="fp16"):
     import hdr_realtime_video_pipeline_b200 as hb
     return hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision=precision, warmup_passes=0,
-                           use_hg=False)
+                           use_hg=False, debug_library=True)
 
 
 def stage_selftest(args):

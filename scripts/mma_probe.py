@@ -6,7 +6,7 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
-net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False)
+net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False, debug_library=True)
 names = {0: "none/plane-pitch", 1: "none/dense", 2: "swizzle128"}
 for blocks in (1, 148, 296):
     for layout in (0, 2):

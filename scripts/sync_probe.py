@@ -7,7 +7,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
 
-net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False)
+net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False, debug_library=True)
 ops = {0: "empty loop", 1: "try_wait (complete barrier, whole warp)", 2: "test_wait (complete barrier)", 3: "tcgen05.fence::after_thread_sync",
        4: "elect.sync + syncwarp", 5: "mbar_wait wrapper", 6: "lane-0 clock64 stamp to global", 7: "syncwarp + lane-0 mbarrier.arrive",
        8: "elected tcgen05.commit (nothing pending)", 9: "fence.proxy.async.shared::cta", 10: "tcgen05.fence::before_thread_sync",

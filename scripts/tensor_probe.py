@@ -10,7 +10,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
 
-net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False)
+net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False, debug_library=True)
 for blocks in (1, 148):
     for kind, label in ((0, "mma SS M=128"), (1, "mma TS (A in TMEM) M=128"), (2, "mma SS M=64")):
         row = []

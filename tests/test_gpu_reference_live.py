@@ -183,7 +183,16 @@ def _play(processor, frames, pack_fn=None):
     if pack_fn is not None:
         REF.feeders._tensor_to_rgb48_bytes = pack_fn          # the one-line integration: INTEGRATION.md
     try:
-        th = threading.Thread(target=wk._hdr_feeder_fn, args=(wk._hdr_queue, widget, False, 60.0, True), daemon=True)
+        errors = []
+
+        def feeder():
+            try:
+                wk._hdr_feeder_fn(wk._hdr_queue, widget, False, 60.0, True)
+            except BaseException as exc:             # a dead feeder must not leave the producer spinning on a full queue
+                errors.append(exc)
+                wk._stop_flag = True
+
+        th = threading.Thread(target=feeder, daemon=True)
         th.start()
         h, w = frames[0].shape[:2]
         lat = []
@@ -192,9 +201,10 @@ def _play(processor, frames, pack_fn=None):
                                                              proc_h=h, lower_res_processing=False, mpv_w=widget, use_cuda=True)
             assert torch.is_tensor(prepared) and tuple(prepared.shape) == (1, 3, h, w) and need_cpu is False and ms > 0.0
             lat.append(ms)
-        wk._hdr_queue.put(None)
+        assert not errors, errors
+        wk._hdr_queue.put(None, timeout=30)
         th.join(timeout=120)
-        assert not th.is_alive()
+        assert not th.is_alive() and not errors, errors
     finally:
         REF.feeders._tensor_to_rgb48_bytes = old
     return widget.frames, lat

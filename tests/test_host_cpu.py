@@ -31,6 +31,22 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/hdrtv_b200.h but not exported"
     assert declared == set(_native.EXPORTED_SYMBOLS)
     assert b"sm_100a" in lib.hdrtv_version()
+    # the product ABI is the path's entry points only: no debug / probe / self-test symbol is exported by the product library
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (hdrtv_[a-z0-9_]+)", out))
+    assert exported == declared, exported ^ declared
+
+
+def test_test_library_exports_the_debug_entry_points():
+    """include/hdrtv_b200_test.h: debug / self-test / probe entry points live in libhdrtv_b200_test.so (same sources,
+    -DHDRTV_TEST_EXPORTS), next to the whole product ABI."""
+    header = open(os.path.join(REPO, "include", "hdrtv_b200_test.h")).read()
+    declared = set(re.findall(r"\b(hdrtv_[a-z0-9_]+)\s*\(", header)) - {"hdrtv_t"}
+    assert declared == set(_native.TEST_EXPORTED_SYMBOLS)
+    lib = _native.load_test()
+    for name in sorted(declared | set(_native.EXPORTED_SYMBOLS)):
+        assert hasattr(lib, name), name
+    assert b"test build" in lib.hdrtv_version()
 
 
 def test_header_constants_match_the_binding():

@@ -182,3 +182,34 @@ def test_int8_network_statistical_parity(name):
     assert np.abs(agcm - g["agcm_out"]).mean() <= 1e-5
     d = np.abs(out - g["out"])
     assert d.mean() <= 8e-3 and d.max() <= 8e-2, (d.mean(), d.max())           # a few activation-quantiser steps (~0.008)
+
+
+@pytest.mark.parametrize("name", ["int8mixed_noise_64x96", "int8mixed_ramps_72x100"])
+def test_int8_mixed_network_statistical_parity(name):
+    """The reference's shipping INT8 layout (INT8 Mixed QAT: 29 W8A8 / 78 W8A16 / 21 FP16 layers): the oracle on the raw
+    checkpoint arrays against the reference's own eager run (scripts/make_golden_int8_mixed.py)."""
+    g = load_golden(name + ".npz")
+    sd = O.split_int8_state(load_golden("weights_int8_mixed_qat.npz"))
+    assert sum(1 for k in sd if k.endswith(".x_scale")) == 29
+    x, cond = O.preprocess(g["frame"], np.float32)
+    out, agcm = O.infer(sd, x, cond)
+    assert np.abs(agcm - g["agcm_out"]).max() <= 1e-4
+    d = np.abs(out - g["out"])
+    assert d.mean() <= 8e-3 and d.max() <= 8e-2
+
+
+def test_int8_mixed_layer_accumulators_fixture_is_self_consistent():
+    """The integer accumulators recorded next to the reference modules' outputs reproduce those outputs through the
+    de-quantisation identity the kind::i8 epilogue uses: conv(x^, w) + b = acc * (s * ws) + b + z * ws * sum_valid(w)."""
+    g = load_golden("int8mixed_layers_64x96.npz")
+    raw = load_golden("weights_int8_mixed_qat.npz")
+    for layer in [str(x) for x in g["layers"]]:
+        q, acc, out = g[layer + "|q"][0].astype(np.float64), g[layer + "|acc"][0].astype(np.float64), g[layer + "|out"][0]
+        w8 = raw[layer + ".weight_int8"].astype(np.float64)
+        ws = raw[layer + ".w_scale"].astype(np.float64).reshape(-1, 1, 1)
+        s, z = float(raw[layer + ".x_scale"]), float(raw[layer + ".x_zero"])
+        stride = int(g[layer + "|stride"])
+        ones = np.ones_like(q)
+        wsum = O.conv2d(ones.astype(np.float32), w8.astype(np.float32), None, stride=stride).astype(np.float64)   # sum of w over VALID taps
+        deq = acc * (s * ws) + raw[layer + ".bias"].astype(np.float64).reshape(-1, 1, 1) + z * ws * wsum
+        assert np.abs(deq - out).max() <= 2e-4 * max(1.0, float(np.abs(out).max())), layer
