@@ -74,7 +74,9 @@ for _name in ("r2_traffic.json", "r1_ncu_top_kernels.json"):
     except Exception:
         continue
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
-W_INT8 = {"int8-full": "HR_original_int8_full_qat.pt", "int8-mixed": "HR_original_int8_mixed_qat.pt"}
+# the reference's INT8 checkpoints (src/models/weights/original/pytorch_int8/hr/*_qat.pt) as raw-array fixtures
+W_INT8 = {"int8-full": os.path.join(REPO, "tests", "golden", "weights_int8_full_qat.npz"),
+          "int8-mixed": os.path.join(REPO, "tests", "golden", "weights_int8_mixed_qat.npz")}
 
 
 def measured_peaks():
@@ -361,7 +363,8 @@ def measure_workload(net, packer, hb, torch, dev, barrier, wl, K, Wm, rank, loca
     e2e_s, checks = e2e_run(lambda i: net.process_rgb48(host_np[i % n_distinct]), 3)
     e2e3_s, checks3 = e2e_run(lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(host_np[i % n_distinct])), state), 2)
     if checks != checks3:
-        raise RuntimeError("one-call and three-call frame paths disagree")
+        bad = [(i, a, b) for i, (a, b) in enumerate(zip(checks, checks3)) if a != b]
+        raise RuntimeError(f"one-call and three-call frame paths disagree on {len(bad)} of {len(checks)} frames: {bad[:8]}")
     res["e2e_s"], res["e2e3_s"], res["checks"] = e2e_s, e2e3_s, checks
 
     # ---- batch-1 latency (config 2 is latency-bound): serial frames, host-timed submit .. RGB48 slot ready --------
@@ -382,7 +385,7 @@ def measure_workload(net, packer, hb, torch, dev, barrier, wl, K, Wm, rank, loca
     # ---- K1 (normalise + condition image) and K8 (RGB48 pack) alone: achieved GB/s over their algorithmic bytes ----
     if rank == 0:
         reps = 40
-        esz = 2 if precision == "fp16" else 4
+        esz = 2 if net._dtype == torch.float16 else 4
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pipeline = net._pipeline
         net._pipeline = False                                        # preprocess alone, on the current stream
@@ -412,7 +415,7 @@ def measure_workload(net, packer, hb, torch, dev, barrier, wl, K, Wm, rank, loca
 
     # ---- per-launch device times of one frame (CUDA events between launches, median of 5) -> top-kernel rooflines
     res["top_kernels"] = []
-    if rank == 0 and precision == "fp16":
+    if rank == 0 and net._dtype == torch.float16:
         x, c = net.preprocess_device(dev_frames[0], assume_ready=True)
         runs = [net.time_plan((x, c)) for _ in range(5)]
         names = [n for n, _ in runs[0]]
@@ -508,14 +511,7 @@ def run_b200_arm(args):
         torch.cuda.synchronize(dev)
 
     precision = args.precision
-    if precision in W_INT8:
-        from oracle import reference_loader as RL
-        ref = RL.load()
-        if ref is None:
-            raise RuntimeError("INT8 checkpoints travel with baseline/_ref (scripts/install_reference.py)")
-        weights = ref.weights(W_INT8[precision])
-    else:
-        weights = WEIGHTS
+    weights = W_INT8.get(precision, WEIGHTS)
     K, Wm = args.steps, max(3, args.warmup)
     wls = ["1080p", "4k"] if args.workload == "both" else [args.workload]
     if world > 1:
@@ -556,13 +552,15 @@ def run_b200_arm(args):
             entries[wl] = workload_entry(wl, raw[wl], world, K, peaks, precision)
         hd = entries[head]
         h, w = WORKLOADS[head]
-        dtype = {"fp16": "f16", "fp32": "f32"}.get(precision, "u8 activations x s8 weights (W8A8 layers) + f16")
+        dtype = {"fp16": "f16", "fp32": "f32", "int8-mixed": "u8 x s8 -> s32 (W8A8 convs, tcgen05.mma.kind::i8) + f16",
+                 "int8-full": "f32 (fake-quantised, CUDA cores)"}[precision]
         line = {
             "metric": "HDRTVNet++ frames/sec", "value": hd["value"], "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": hd["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic",
             "config": {"workload": CONFIG_NAME["4k_export" if (world > 1 and head == "4k") else head], "height": h, "width": w,
-                       "precision": precision, "weights": "HR.pt (fixture copy)" if precision in ("fp16", "fp32") else W_INT8[precision],
+                       "precision": precision,
+                       "weights": "HR.pt (fixture copy)" if precision in ("fp16", "fp32") else os.path.basename(W_INT8[precision]),
                        "headline": "the top-level value / e2e / roofline are the 3840x2160 workload (north-star target >= 60 frames/s); "
                                    "workloads['1080p'] carries BASELINE configs[1] incl. its frame latency",
                        "frames": "4 synthetic content classes cycled (noise / ramps / black / white+salt)",

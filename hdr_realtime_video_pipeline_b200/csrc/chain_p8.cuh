@@ -125,6 +125,10 @@ struct ChainParams {
   P8 outs2;                  // second home of a split store (STORE == 3)
   ActQuant opq[kMaxChain];   // INT8 layouts: layer l+1 is a W8A8 layer -> its input quantiser is applied to layer l's operand
                              // (only for layers whose output is not also stored: the stored tensor would be the raw one)
+  // INT8 layouts: uint8 copies of the stored 64-channel layer (STORE == 1; `cond`) through the input quantisers of its W8A8
+  // consumers that run on kind::i8 (CondNet3.0, CondNet4.0): 16 channels per 16-byte entry
+  ActQuant q8[2];
+  P8 outq8[2];
   long long* trace;          // only read when compiled with HDRTV_CHAIN_TRACE: clock64 stamps of CTA 0 [step<64][slot<8][8]
 };
 
@@ -340,13 +344,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
               float a[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) a[k] = act(v[c * 8 + k]);
-              if constexpr (QOP && kWrite != 0 && kStore == 0) {
-                if (cp.opq[l].mode) {
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) a[k] = fake_quant_h(a[k], cp.opq[l]);
-                }
-              }
               h[c] = pack8(a);
+              if constexpr (QOP && kWrite != 0 && kStore == 0) {
+                if (cp.opq[l].mode) h[c] = fq_entry(h[c], cp.opq[l]);
+              }
             }
             CHAIN_STAMP(4);
             if constexpr (kWrite != 0) {
@@ -361,6 +362,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
                 o.init(cp.outs[l], x);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) *o.at(oy, c) = h[c];
+                if constexpr (QOP) {
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    if (cp.q8[i].mode) {
+                      ColRef oq;
+                      oq.init(cp.outq8[i], x);
+#pragma unroll
+                      for (int c = 0; c < 8; c += 2) {
+                        float f0[8], f1[8];
+                        unpack8(h[c], f0);
+                        unpack8(h[c + 1], f1);
+                        *oq.at(oy, c >> 1) = pack16_u8h(f0, f1, cp.q8[i]);
+                      }
+                    }
+                  }
+                }
               }
             } else if constexpr (kStore == 3) {
               if (xin) {

@@ -41,10 +41,48 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
 struct ActQuant {
   float scale = 1.f, zero = 0.f;
   int mode = 0;
+  float inv = 1.f;          // 1 / scale (host): fast path of quant_code
 };
-__device__ __forceinline__ float quant_code(float x, const ActQuant& q) {      // mode 2: the uint8 code as a float in [0, 255]
-  float v = rintf(__fdiv_rn(__fsub_rn(x, q.zero), q.scale));
-  return fminf(fmaxf(v, 0.f), 255.f);
+// mode 2: the uint8 code as a float in [0, 255] = clamp(rint((x - zero) / scale), 0, 255) bit for bit, without an IEEE division
+// and without the quarter-rate FRND / F2I conversions per element:
+//   * the quotient is formed with the host-computed reciprocal and clamped first (the clamp commutes with rint: its bounds are
+//     integers).  With d = fl(x - zero) common to both forms, fl(d / scale) and fl(d * fl(1 / scale)) differ by at most
+//     3 * 2^-24 * |quotient| <= 4.6e-5 inside the clamp range;
+//   * rint is the magic-number addition (1.5 * 2^23: round-to-nearest-even happens in the FADD, the code is the low mantissa
+//     byte of the sum);
+//   * only when the clamped quotient lands within 1e-4 of a bucket boundary (k + 0.5) is the true division evaluated - out of
+//     line, so that the division's slow path is not inlined dozens of times into the epilogues.
+constexpr float kRintMagic = 12582912.f;
+constexpr float kQuantNear = 0.4999f;
+__device__ __noinline__ float quant_code_exact(float d, float scale) { return fminf(fmaxf(rintf(__fdiv_rn(d, scale)), 0.f), 255.f); }
+// u = clamped quotient + magic (low mantissa byte = the code unless the return value, the distance from the rounded value,
+// exceeds kQuantNear)
+__device__ __forceinline__ float quant_round(float x, const ActQuant& q, float& u) {
+  const float t = __fmul_rn(__fsub_rn(x, q.zero), q.inv);
+  const float tc = fminf(fmaxf(t, 0.f), 255.f);
+  u = __fadd_rn(tc, kRintMagic);
+  return fabsf(__fsub_rn(tc, __fsub_rn(u, kRintMagic)));
+}
+__device__ __forceinline__ float quant_code(float x, const ActQuant& q) {
+  float u;
+  const float e = quant_round(x, q, u);
+  float v = __fsub_rn(u, kRintMagic);
+  if (e > kQuantNear) v = quant_code_exact(__fsub_rn(x, q.zero), q.scale);
+  return v;
+}
+// eight values at once: u[k] - kRintMagic = code k.  One boundary test for the group (a warp takes the branch when any of its
+// 256 values is near a boundary: ~5 %); fully unrolled - a dynamically indexed u[] / x[] would move both arrays to local memory.
+__device__ __forceinline__ void quant_round8(const float* x, const ActQuant& q, float* u) {
+  float e = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) e = fmaxf(e, quant_round(x[k], q, u[k]));
+  if (e > kQuantNear) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float uu;
+      if (quant_round(x[k], q, uu) > kQuantNear) u[k] = __fadd_rn(quant_code_exact(__fsub_rn(x[k], q.zero), q.scale), kRintMagic);
+    }
+  }
 }
 __device__ __forceinline__ float fake_quant(float x, const ActQuant& q) {
   if (q.mode == 2) return __fadd_rn(__fmul_rn(quant_code(x, q), q.scale), q.zero);
@@ -55,16 +93,6 @@ __device__ __forceinline__ float fake_quant(float x, const ActQuant& q) {
   }
   return x;
 }
-// FP16 tensor path: the tensor a W8A8 layer quantises is the fp16 OUTPUT of its producer (the reference calls x.float() on
-// it), and the de-quantised value is cast back to the compute dtype, fp16 (:358).
-__device__ __forceinline__ float fake_quant_h(float x, const ActQuant& q) {
-  if (q.mode == 0) return x;
-  return __half2float(__float2half_rn(fake_quant(__half2float(__float2half_rn(x)), q)));
-}
-__device__ __forceinline__ uint32_t quant_u8_h(float x, const ActQuant& q) {   // uint8 code of the fp16-rounded value
-  return static_cast<uint32_t>(quant_code(__half2float(__float2half_rn(x)), q));
-}
-
 #define HDRTV_CUDA_OK(expr)                                                                    \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \

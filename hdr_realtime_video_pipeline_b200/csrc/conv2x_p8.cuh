@@ -457,9 +457,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             for (int k = 0; k < 8; ++k) {
               a[k] = fmaxf(v[c * 8 + k], 0.f);                                                  // ReLU
               if constexpr (SFTGA) a[k] = fmaf(a[k], sv[c * 8 + k], tv[c * 8 + k]);           // x*(scale+1)+shift, +1 in the bias step
-              a[k] = fake_quant_h(a[k], p.qmid);                                                // conv B is a W8A8 layer (INT8 layouts)
             }
             h[c] = inside_x ? pack8(a) : make_uint4(0, 0, 0, 0);
+            if (p.qmid.mode && inside_x) h[c] = fq_entry(h[c], p.qmid);                         // conv B is a W8A8 layer (INT8 layouts)
           }
           ++g;
         } else {
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
                   float f0[8], f1[8];
                   unpack8(o[c], f0);
                   unpack8(o[c + 1], f1);
-                  *outq.at(oy, c >> 1) = pack16_u8(f0, f1, p.out_q);
+                  *outq.at(oy, c >> 1) = pack16_u8h(f0, f1, p.out_q);
                 }
               }
             }

@@ -126,9 +126,6 @@ struct ConvParams {
   // the uint8 codes themselves (`out` is then a uint8 tensor for an I8 consumer).  `raw` / `out2` stay unquantised.
   ActQuant out_q;
   int out_u8;
-  ActQuant in_q_z[3];         // XFORM instances: input quantiser of each fused variant (mode 0: none)
-  ActQuant out_q_z[3];        // zsplit launches: per-variant out_q / out_u8
-  int out_u8_z[3];
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -191,43 +188,53 @@ constexpr int kSSlotBytesPS = 16 * kPlaneBytes;   // parities) of 32 channels pe
 // input row consumed (and its ring slot released) once, and a ring of kFoldR accumulator blocks instead of two stages.
 constexpr int kFoldR = 8;
 
-// 16 uint8 codes (two 8-channel groups of one pixel) -> one 16-byte entry
+// eight uint8 codes of fp16-representable values -> two 32-bit words
+__device__ __forceinline__ uint2 quant8_u8h(const float* x, const ActQuant& q) {
+  float u[8];
+  quant_round8(x, q, u);
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(u[k]);
+  uint2 r;
+  r.x = __byte_perm(__byte_perm(w[0], w[1], 0x0040), __byte_perm(w[2], w[3], 0x0040), 0x5410);
+  r.y = __byte_perm(__byte_perm(w[4], w[5], 0x0040), __byte_perm(w[6], w[7], 0x0040), 0x5410);
+  return r;
+}
+// 16 uint8 codes (two 8-channel groups of one pixel, fp16-representable values) -> one 16-byte entry
+__device__ __forceinline__ uint4 pack16_u8h(const float* a, const float* b, const ActQuant& q) {
+  const uint2 lo = quant8_u8h(a, q), hi = quant8_u8h(b, q);
+  return make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+// fp16 entry -> the fake-quantised fp16 entry x^ = q * scale + zero (two roundings, like the reference), cast back to fp16
+__device__ __forceinline__ uint4 fq_entry(const uint4& h, const ActQuant& q) {
+  float x[8], u[8];
+  unpack8(h, x);
+  quant_round8(x, q, u);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(__fmul_rn(__fsub_rn(u[k], kRintMagic), q.scale), q.zero);
+  return pack8(x);
+}
+// the same for fp32 epilogue values: rounded to fp16 first (the tensor a W8A8 layer quantises is its producer's fp16 output)
 __device__ __forceinline__ uint4 pack16_u8(const float* a, const float* b, const ActQuant& q) {
-  uint4 u;
-  uint32_t* w = reinterpret_cast<uint32_t*>(&u);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    w[i] = quant_u8_h(a[4 * i], q) | (quant_u8_h(a[4 * i + 1], q) << 8) | (quant_u8_h(a[4 * i + 2], q) << 16) | (quant_u8_h(a[4 * i + 3], q) << 24);
-    w[2 + i] = quant_u8_h(b[4 * i], q) | (quant_u8_h(b[4 * i + 1], q) << 8) | (quant_u8_h(b[4 * i + 2], q) << 16) | (quant_u8_h(b[4 * i + 3], q) << 24);
-  }
-  return u;
+  float fa[8], fb[8];
+  unpack8(pack8(a), fa);
+  unpack8(pack8(b), fb);
+  return pack16_u8h(fa, fb, q);
 }
-__device__ __forceinline__ uint4 pack8_fq(const float* f, const ActQuant& q) {
-  float t[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t[i] = fake_quant_h(f[i], q);
-  return pack8(t);
-}
+__device__ __forceinline__ uint4 pack8_fq(const float* f, const ActQuant& q) { return fq_entry(pack8(f), q); }
 // border class of an output coordinate o of a 3-tap window with the given stride over an input of `size`
 __device__ __forceinline__ int tap_class(int o, int stride, int size) {
   return ((o * stride - 1 < 0) ? 1 : 0) | ((o * stride + 1 >= size) ? 2 : 0);
 }
 
-// XFORM (INT8 layouts, stride-2 3x3 on a parity-split fp16 input): four extra warps fake-quantise every input row IN PLACE in
-// its ring slot between the TMA arrival and the MMAs, with the input quantiser of this CTA's conv (p.in_q_z[variant]).  Used by
-// the launch that runs CondNet2.0 (weight-only INT8: no quantiser), CondNet3.0 and CondNet4.0 (W8A8, each with its own input
-// quantiser) on the same `cond` rows: the three convs keep sharing one fetch of `cond` instead of three pre-quantised copies.
-constexpr int kXformThreads = 128;
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool I8 = false, bool XFORM = false>
-__global__ void __launch_bounds__(kConvThreads + (XFORM ? kXformThreads : 0), (MODE == STORE_PS) ? 1 : 2)
-conv_p8_kernel(const __grid_constant__ ConvParams p) {
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool I8 = false>
+__global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv_p8_kernel(const __grid_constant__ ConvParams p) {
   static_assert(!I8 || (!FOLD && kind_ks(KIND) == 3 && MODE != STORE_PLANAR), "INT8 instances: plain 3x3 convs");
-  static_assert(!XFORM || (KIND == IN_PAR3x3S2 && !SFTG && !FOLD && !I8), "in-place input quantiser: stride-2 3x3 on fp16 rows");
   static_assert(!SFTG || (AUX && ((MODE == STORE_P8 && N == 32) || (MODE == STORE_PS && N == 128))),
                 "in-kernel SFT generator: 32-channel outputs only");
   static_assert(!FOLD || (KIND == IN_PAR3x3S2 && !SFTG && MODE == STORE_P8 && N <= 64), "row folding: plain stride-2 3x3 convs");
   constexpr bool PSG = SFTG && MODE == STORE_PS;
-  constexpr bool OQ = I8 || XFORM;      // output quantisers (out_q / out_u8) exist only in the INT8-layout instances
+  constexpr bool OQ = I8;               // output quantisers (out_q / out_u8) exist only in the INT8-layout instances
   // SFTG: 2 x 32 conv + 2 x 64 scale|shift columns; PixelShuffle: 2 x 128 conv + 4 sub-pixels x 64 (single-buffered)
   constexpr uint32_t kTmemCols = FOLD ? (kFoldR * N < 32 ? 32 : kFoldR * N) : SFTG ? (PSG ? 512 : 256) : ((2 * N < 32) ? 32 : 2 * N);
   constexpr int SRING = PSG ? kSRingPS : kSRing;
@@ -246,7 +253,6 @@ conv_p8_kernel(const __grid_constant__ ConvParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxRing + 5));
   auto sfull_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };
   auto sempty_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + kSRing + i); };   // kSRing >= kSRingPS
-  auto xready_bar = [&](int i) { return bar0 + 8u * (2 * kMaxRing + 8 + i); };            // XFORM (never with SFTG): kMaxRing slots
   uint8_t* ones = smem + 512;
   uint8_t* wsm = smem + kSmemHeader;
   uint8_t* wsm2 = wsm + ((p.w_bytes + 127) & ~127);
@@ -276,9 +282,6 @@ conv_p8_kernel(const __grid_constant__ ConvParams p) {
         mbar_init(sfull_bar(i), 1);
         mbar_init(sempty_bar(i), 1);
       }
-    }
-    if constexpr (XFORM) {
-      for (int i = 0; i < p.ring; ++i) mbar_init(xready_bar(i), kXformThreads / 32);
     }
     mbar_fence_init();
   }
@@ -435,7 +438,7 @@ conv_p8_kernel(const __grid_constant__ ConvParams p) {
       for (int dy = 0; dy < KS; ++dy) {
         const int q = t * STRIDE + dy;
         if (q > waited) {
-          mbar_wait(XFORM ? xready_bar(slot) : full_bar(slot), ph, p.err, 4);
+          mbar_wait(full_bar(slot), ph, p.err, 4);
           waited = q;
           tc_fence_after();
         }
@@ -486,36 +489,6 @@ conv_p8_kernel(const __grid_constant__ ConvParams p) {
       base_slot += STRIDE;
       if (base_slot >= ring_n) { base_slot -= ring_n; base_ph ^= 1; }
     }
-    }
-  } else if (warp >= kConvThreads / 32) {
-    // ------------------------------------------------------------------ in-place input quantiser (XFORM)
-    if constexpr (XFORM) {
-      const ActQuant q = p.in_q_z[zsel];
-      const int tw = threadIdx.x - kConvThreads;
-      const uint32_t ring_n = p.ring;
-      uint32_t slot = 0, ph = 0;
-      for (int qrow = 0; qrow < nrows_in; ++qrow) {
-        mbar_wait(full_bar(slot), ph, p.err, 9);
-        const int iy = oy0 * STRIDE + qrow - 1;                  // image row held by this ring row (pad rows stay zero)
-        if (q.mode && iy >= 0 && iy < p.i8_H) {
-          uint4* base = reinterpret_cast<uint4*>(ring + slot * (NCOPY * kPlaneBytes));
-          for (int e = tw; e < NCOPY * kPlaneEntries; e += kXformThreads) {
-            const int plane = e / kPlaneEntries, k = e - plane * kPlaneEntries;
-            const int xx = 2 * (x0 + k - 1) + (plane & 1);       // pixel of entry k of a parity half-plane (pad entries stay zero)
-            if (xx >= 0 && xx < p.i8_W) {
-              float f[8];
-              unpack8(base[e], f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fake_quant_h(f[i], q);
-              base[e] = pack8(f);
-            }
-          }
-          fence_proxy_async_smem();                              // generic-proxy writes -> visible to the MMAs' async-proxy reads
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(xready_bar(slot));
-        if (++slot == ring_n) { slot = 0; ph ^= 1; }
-      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant
@@ -672,8 +645,8 @@ conv_p8_kernel(const __grid_constant__ ConvParams p) {
       ColRef out, out2, res, res2, sft, raw;
       if (zs > 1) out.init(p.out_zp[zsel], x);
       else out.init(p.out, x);
-      const ActQuant oq = !OQ ? ActQuant{} : (zs > 1 ? p.out_q_z[zsel] : p.out_q);
-      const bool ou8 = OQ && (zs > 1 ? p.out_u8_z[zsel] : p.out_u8) != 0;
+      const ActQuant oq = !OQ ? ActQuant{} : p.out_q;
+      const bool ou8 = OQ && p.out_u8 != 0;
       if (p.out_split > 0) out2.init(p.out2, x);
       if constexpr (AUX) {
         if (p.has_res) res.init(p.res, x);

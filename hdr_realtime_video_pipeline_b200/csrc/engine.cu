@@ -187,7 +187,6 @@ struct ConvLaunch {
   bool sftg = false;
   bool fold = false;                    // row-folded stride-2 3x3 (conv_p8_kernel<..., FOLD>); weights are the ".fold2" pack
   bool i8 = false;                      // W8A8 layer on tcgen05.mma.kind::i8 (uint8 input tensor, int8 weights)
-  bool xform = false;                   // in-place input quantiser warps (CondNet{2,3,4}.0 launch of the INT8 layouts)
   int N;
   int mode;
   dim3 grid;
@@ -373,9 +372,6 @@ struct Epi {
   int i8_H = 0, i8_W = 0;           // input size (tap validity)
   ActQuant out_q;                   // quantiser applied to the `out` store (input quantiser of a W8A8 consumer)
   bool out_u8 = false;              // ... stored as uint8 codes
-  ActQuant in_q_z[3];               // per-variant in-place input quantisers (XFORM)
-  ActQuant out_q_z[3];              // per-variant output quantisers of a zsplit launch
-  bool out_u8_z[3] = {false, false, false};
   int zsplit = 0;                   // > 1: this launch runs `zsplit` convs on the same input (weights / outputs below)
   const __half* wpk_z[3] = {nullptr, nullptr, nullptr};
   const P8* out_z[3] = {nullptr, nullptr, nullptr};
@@ -434,15 +430,7 @@ static int make_conv(Ctx* c, std::vector<ConvLaunch>& plan, const std::string& n
     p.i8_beta = e.i8_tab + N;
     L.i8 = true;
   }
-  bool any_oq = e.out_q.mode != 0;
-  for (int z = 0; z < 3; ++z) {
-    p.in_q_z[z] = e.in_q_z[z];
-    p.out_q_z[z] = e.out_q_z[z];
-    p.out_u8_z[z] = e.out_u8_z[z] ? 1 : 0;
-    if (e.in_q_z[z].mode) L.xform = true;
-    any_oq |= e.out_q_z[z].mode != 0;
-  }
-  if (any_oq && !(L.i8 || L.xform)) return fail(c, "conv " + name + ": output quantisers are compiled into the INT8-layout instances only");
+  if (e.out_q.mode != 0 && !L.i8) return fail(c, "conv " + name + ": output quantisers are compiled into the INT8-layout instances only");
   if (e.fold) {
     if (kind != IN_PAR3x3S2 || mode != STORE_P8 || e.sft_s0 || N > 64 || e.res || e.res2 || e.sft || e.raw)
       return fail(c, "conv " + name + ": row folding needs a plain stride-2 3x3 conv");
@@ -505,17 +493,16 @@ static cudaError_t launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
-template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool I8 = false, bool XFORM = false>
+template <int KIND, int KCH, int N, int MODE, bool AUX, bool SFTG = false, bool FOLD = false, bool I8 = false>
 static cudaError_t launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD, I8, XFORM>,
+    cudaError_t e = cudaFuncSetAttribute(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD, I8>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD, I8, XFORM>, L.grid, kConvThreads + (XFORM ? kXformThreads : 0),
-                    L.smem, s, L.p);
+  return launch_pdl(conv_p8_kernel<KIND, KCH, N, MODE, AUX, SFTG, FOLD, I8>, L.grid, kConvThreads, L.smem, s, L.p);
 }
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s);
 template <int KINDA, int KCHA, bool SFTGA, int NB, int MODEB, int ACTB>
@@ -541,11 +528,6 @@ static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
   if (L.c2x) return launch_conv2x(L, s);
-  if (L.xform) {    // CondNet{2,3,4}.0 of the INT8 layouts: per-variant in-place input quantiser
-    if (L.kind == IN_PAR3x3S2 && L.kch == 8 && L.N == 64 && L.mode == STORE_P8 && !L.sftg && !L.i8)
-      return launch_conv_t<IN_PAR3x3S2, 8, 64, STORE_P8, false, false, false, false, true>(L, s);
-    return cudaErrorInvalidValue;
-  }
   if (L.i8) {       // W8A8 layers on tcgen05.mma.kind::i8 (uint8 activations: KCH counts 16-channel planes)
     const bool aux8 = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
     if (L.sftg) {
@@ -769,6 +751,7 @@ static cudaError_t launch_chain_t(const ConvLaunch& L, cudaStream_t s) {
 static cudaError_t launch_chain(const ConvLaunch& L, cudaStream_t s) {
   bool qop = false;                      // INT8 layouts: an operand quantiser is installed on one of the chain's layers
   for (int l = 0; l < kMaxChain; ++l) qop |= L.chain->opq[l].mode != 0;
+  qop |= L.chain->q8[0].mode != 0 || L.chain->q8[1].mode != 0;
   if (qop && L.chain_prog != PROG_COND_SFT3 && L.chain_prog != PROG_TAIL2) return cudaErrorInvalidValue;
   switch (L.chain_prog) {
     case PROG_AGCM: return launch_chain_t<ProgAGCM>(L, s);
@@ -920,6 +903,8 @@ static int pack_all_i8(Ctx* c) {
     r |= pack_i8_layer(c, "LE.recon_trunk3." + std::to_string(j) + ".conv1", IN_NAT3x3, 2, 32);
     r |= pack_i8_layer(c, "LE.recon_trunk3." + std::to_string(j) + ".conv2", IN_NAT3x3, 2, 32);
   }
+  r |= pack_i8_layer(c, "LE.CondNet3.0", IN_PAR3x3S2, 4, 64);
+  r |= pack_i8_layer(c, "LE.CondNet4.0", IN_PAR3x3S2, 4, 64);
   r |= pack_i8_layer(c, "LE.CondNet3.2", IN_PAR3x3S2, 4, 64);
   r |= pack_i8_layer(c, "LE.CondNet4.2", IN_PAR3x3S2, 4, 64);
   r |= pack_i8_layer(c, "LE.CondNet4.4", IN_PAR3x3S2, 4, 16);
@@ -1460,26 +1445,43 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   if (qm && !(use_chain && use_sftg && use_tail && env_int("HDRTV_ZFUSE", 1) && !use_fold2))
     return fail(c, "INT8 layouts need the default launch plan");
   if (env_int("HDRTV_ZFUSE", 1)) {
-    // the three stride-2 3x3 convs that read `cond` share one launch (cond is fetched from HBM once)
-    Epi e = lrelu;
-    e.zsplit = 3;
-    e.fold = use_fold2;
-    const std::string fs = use_fold2 ? ".fold2" : "";
-    e.wpk_z[0] = wk("LE.CondNet2.0" + fs); e.wpk_z[1] = wk("LE.CondNet3.0" + fs); e.wpk_z[2] = wk("LE.CondNet4.0" + fs);
-    e.out_z[0] = &D1; e.out_z[1] = &E1; e.out_z[2] = &E1b;
-    if (qm) {
-      // W8A8 variants quantise `cond` in place in their ring slots (conv_p8.cuh, XFORM); their outputs go to the next
-      // layer as uint8 codes when that layer runs on kind::i8
-      e.in_q_z[0] = Qp("LE.CondNet2.0"); e.in_q_z[1] = Qp("LE.CondNet3.0"); e.in_q_z[2] = Qp("LE.CondNet4.0");
-      e.i8_H = H; e.i8_W = Wd;
-      if (is8p("LE.CondNet3.2")) { e.out_z[1] = &E1q; e.out_q_z[1] = Qp("LE.CondNet3.2"); e.out_u8_z[1] = true; }
-      else e.out_q_z[1] = Qp("LE.CondNet3.2");
-      if (is8p("LE.CondNet4.2")) { e.out_z[2] = &E1bq; e.out_q_z[2] = Qp("LE.CondNet4.2"); e.out_u8_z[2] = true; }
-      else e.out_q_z[2] = Qp("LE.CondNet4.2");
-      e.out_q_z[0] = Qp("LE.CondNet2.2");
+    const bool c30q = is8p("LE.CondNet3.0"), c40q = is8p("LE.CondNet4.0");
+    if (!c30q && !c40q) {
+      // the three stride-2 3x3 convs that read `cond` share one launch (cond is fetched from HBM once)
+      Epi e = lrelu;
+      e.zsplit = 3;
+      e.fold = use_fold2;
+      const std::string fs = use_fold2 ? ".fold2" : "";
+      e.wpk_z[0] = wk("LE.CondNet2.0" + fs); e.wpk_z[1] = wk("LE.CondNet3.0" + fs); e.wpk_z[2] = wk("LE.CondNet4.0" + fs);
+      e.out_z[0] = &D1; e.out_z[1] = &E1; e.out_z[2] = &E1b;
+      r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, e);
+      L.back().name = "LE.CondNet{2,3,4}.0";
+    } else {
+      // INT8 layouts: the W8A8 convs among the three run on kind::i8 from uint8 copies of `cond` that the cond chain wrote
+      // through their input quantisers (64 B/px each instead of the 128 B/px fp16 tensor); the others keep f16 MMAs on `cond`
+      if (r) return -1;
+      ChainParams& cc = *L.back().chain;      // the cond chain is the launch before this one
+      r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, lrelu);
+      int nq = 0;
+      auto third = [&](const std::string& name, bool q8, const std::string& next, const P8& out16, const P8& out8) {
+        Epi e = lrelu;
+        e.out_q = Qp(next);
+        e.out_u8 = is8p(next);
+        if (q8) {
+          P8 condq = make_p8(c, 32, H, Wd, true);                    // 64 channels of uint8 = 4 planes, parity-split like `cond`
+          if (!condq.base) { r |= fail(c, "workspace allocation failed (uint8 cond)"); return; }
+          cc.q8[nq] = Qp(name);
+          cc.outq8[nq] = condq;
+          ++nq;
+          r |= i8_pyr(name, condq, 64, e.out_u8 ? out8 : out16, H1, W1, H, Wd, e);
+        } else {
+          if (e.out_q.mode) { r |= fail(c, "INT8 layout: " + name + " feeds a W8A8 layer but is not one itself (unsupported mix)"); return; }
+          r |= std_conv(L, name, IN_PAR3x3S2, COND, 64, 64, STORE_P8, out16, H1, W1, e);
+        }
+      };
+      third("LE.CondNet3.0", c30q, "LE.CondNet3.2", E1, E1q);
+      third("LE.CondNet4.0", c40q, "LE.CondNet4.2", E1b, E1bq);
     }
-    r |= std_conv(L, "LE.CondNet2.0", IN_PAR3x3S2, COND, 64, 64, STORE_P8, D1, H1, W1, e);
-    L.back().name = "LE.CondNet{2,3,4}.0";
     if (use_tail) {   // CondNet2.2 -> CondNet2.4 -> stage 0 of the four level-1 SFT layers in one launch (cond2 is never stored)
       S1hi = S1; S1hi.base = S1.base + static_cast<long>(8) * S1.Wp * 8;       // view: chunk planes 8.. of every row
       r |= make_chain_t<ProgTail2>(c, L, "LE.CondNet2.2+2.4+sft0.L1", PROG_TAIL2, IN_NAT1x1, D1, 8, {nullptr, nullptr, &S1, &S1hi},
@@ -2137,6 +2139,7 @@ int hdrtv_set_act_quant(hdrtv_t* c, const char* const* layers, const float* scal
     q.scale = scales[i];
     q.zero = zeros[i];
     q.mode = modes[i];
+    q.inv = 1.0f / scales[i];
     c->quant[key] = q;
   }
   return 0;

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Determinism / path-agreement diagnostic of the INT8-mixed tensor path.   python scripts/check_int8.py [1080p|540p|4k]"""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import torch  # noqa: E402
+import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
+from oracle import hdrtvnet_oracle as O  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "1080p"
+h, w = {"540p": (540, 960), "1080p": (1080, 1920), "4k": (2160, 3840)}[wl]
+net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_int8_mixed_qat.npz"), precision="int8-mixed", warmup_passes=0, use_hg=False,
+                      debug_library=True)
+print("tensor path:", net._int8_tensor_path)
+pinned = [torch.from_numpy(hb.synth_frame(i, h, w)).pin_memory() for i in range(8)]
+frames = [t.numpy() for t in pinned]
+want = []
+for i, f in enumerate(frames):
+    outs = []
+    for rep in range(4):
+        torch.cuda.synchronize()
+        out, _ = net.infer(net.preprocess(f))
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    same = [bool(torch.equal(outs[0], o)) for o in outs[1:]]
+    if not all(same):
+        d = (outs[0].float() - outs[1].float()).abs()
+        dbg = net.debug_tensors()
+        print(f"frame {i}: synchronised repeats differ {same} max {float(d.max()):.3e} n {int((d > 0).sum())}")
+    want.append(O.pack_rgb48(outs[0].cpu().numpy()))
+print("synchronised repeats done")
+state = {}
+for name, fn, infl in (("one-call pipelined", lambda i: net.process_rgb48(frames[i % 8]), 3),
+                       ("one-call serial", lambda i: net.process_rgb48(frames[i % 8], serial=True), 3),
+                       ("three-call", lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(frames[i % 8])), state), 2)):
+    pending, bad = [], []
+    for i in range(32):
+        pending.append((i, fn(i)))
+        if len(pending) >= infl:
+            j, fr = pending.pop(0)
+            if not np.array_equal(fr.numpy(), want[j % 8]):
+                d = np.nonzero((fr.numpy() != want[j % 8]).any(axis=2))
+                bad.append((j, int(d[0].size), int(d[0].min()), int(d[0].max()), int(d[1].min()), int(d[1].max())))
+            fr.release()
+    for j, fr in pending:
+        if not np.array_equal(fr.numpy(), want[j % 8]):
+            bad.append((j,))
+        fr.release()
+    print(f"{wl} {name}: {len(bad)} of 32 frames differ", bad[:6], flush=True)

@@ -695,7 +695,7 @@ def test_int8_mixed_network_statistical_parity(net_int8_mixed, parity_log, name)
     parity_log.add(test="int8_mixed_small", case=name, mean_abs=d.mean(), max_abs=d.max(), agcm_max_abs=da.max(),
                    reference="HDRTVNetTorch(precision='int8-mixed') on CPU (fp32 compute), fixture")
     assert da.max() <= FP16_TOL                                                   # AGCM is FP16 in the mixed layout
-    assert d.mean() <= 8e-3 and d.max() <= 8e-2
+    assert d.mean() <= 1.5e-3 and d.max() <= 2e-2                                 # measured: mean 4-5e-4, max 3-5e-3
     fr = hb.tensor_to_rgb48_bytes(torch.from_numpy(out).cuda().half(), {})
     assert np.array_equal(fr.numpy(), O.pack_rgb48(out.astype(np.float16)))
     fr.release()

@@ -239,3 +239,33 @@ def test_p7_reference_playback_loop_and_feeder_thread_run_unchanged_on_this_back
         fr.release()
     assert one == want[:24]
     assert float(np.median(lat)) < 50.0
+
+
+# ------------------------------------------------------------------------------------------------ INT8 Mixed QAT, live
+@needs_ref
+@pytest.mark.parametrize("hw", [(540, 960), (1080, 1920)])
+def test_int8_mixed_against_the_reference_cuda_int8_path(parity_log, hw):
+    """BASELINE config 5 on the shipping layout: the reference's eager INT8-mixed model on this GPU (W8A8Conv2d with
+    compute_dtype fp16, hdrtvnet_torch.py:296-364, 1748-1963) against the kind::i8 tensor-core path on the same checkpoint."""
+    ckpt = REF.weights("HR_original_int8_mixed_qat.pt")
+    ref = REF.HDRTVNetTorch(ckpt, device="cuda", precision="int8-mixed", compile_model=False, use_hg=False, warmup_passes=0,
+                            predequantize="off")
+    net = hb.HDRTVNetB200(ckpt, device="cuda", precision="int8-mixed", warmup_passes=0, use_hg=False)
+    assert net._int8_tensor_path
+    worst = 0.0
+    for cls, idx in (("noise", 0), ("ramps", 1)):
+        frame = hb.synth_frame(idx, hw[0], hw[1], cls)
+        r16, ragcm, _ = _ref_run(ref, frame)
+        out, agcm = net.infer(net.preprocess(frame))
+        torch.cuda.synchronize()
+        d = np.abs(out.float().cpu().numpy() - r16)
+        da = np.abs(agcm.float().cpu().numpy() - ragcm).max()
+        print(f"INT8-mixed {cls} {hw}: mean {d.mean():.2e} max {d.max():.2e} agcm {da:.2e}")
+        parity_log.add(test="int8_mixed_live", case="%s_%d_%dx%d" % (cls, idx, hw[0], hw[1]), mean_abs=d.mean(), max_abs=d.max(),
+                       agcm_max_abs=da, reference="HDRTVNetTorch(device='cuda', precision='int8-mixed'), unmodified reference, same box")
+        assert da <= FP16_TOL
+        assert d.mean() <= 1.5e-3 and d.max() <= 3e-2
+        worst = max(worst, float(d.max()))
+    net.close()
+    del ref
+    torch.cuda.empty_cache()
