@@ -18,6 +18,7 @@
 #include "conv_p8.cuh"
 #include "chain_p8.cuh"
 #include "conv2x_p8.cuh"
+#include "conv3z_pair.cuh"
 #ifdef HDRTV_TEST_EXPORTS
 #include "../../include/hdrtv_b200_test.h"
 #include "probes.cuh"
@@ -195,6 +196,7 @@ struct ConvLaunch {
   std::shared_ptr<ChainParams> chain;   // set: this launch is a fused layer chain (chain_p8_kernel), `p` is a geometry copy
   int chain_prog = 0;
   std::shared_ptr<Conv2xParams> c2x;    // set: two chained 3x3 convs in one kernel (conv2x_p8_kernel)
+  std::shared_ptr<PairParams> pair;     // set: CondNet{2,3,4}.0 as one N = 192 conv on CTA pairs (conv3z_pair_kernel)
   int c2x_variant = 0;
   int branch = 0;                       // 1: runs on the context's side stream, concurrently with the main-stream launches
   bool join = false;                    // main-stream launch that needs everything queued on the side stream so far
@@ -524,10 +526,60 @@ static cudaError_t launch_conv2x(const ConvLaunch& L, cudaStream_t s) {
   }
   return cudaErrorInvalidValue;
 }
+// ---- CondNet{2,3,4}.0 on CTA pairs (conv3z_pair.cuh) ----------------------------------------------
+static cudaError_t launch_pair(const ConvLaunch& L, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3z_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = L.grid;
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, conv3z_pair_kernel, *L.pair);
+}
+// co-resident clusters of the pair kernel on this device (one CTA per SM: 74 on a full B200)
+static int pair_max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = 0;
+  if (cudaFuncSetAttribute(conv3z_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return cached;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * 74);
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = pair_smem_bytes();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv3z_pair_kernel, &cfg) == cudaSuccess) cached = n;
+  else cudaGetLastError();
+  return cached;
+}
+
 // Every (input kind, channel chunks, N, store mode, auxiliary operands) combination the plans and the self-tests use.
 static cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t s) {
   if (L.chain) return launch_chain(L, s);
   if (L.c2x) return launch_conv2x(L, s);
+  if (L.pair) return launch_pair(L, s);
   if (L.i8) {       // W8A8 layers on tcgen05.mma.kind::i8 (uint8 activations: KCH counts 16-channel planes)
     const bool aux8 = L.p.has_res || L.p.has_res2 || L.p.has_sft || L.p.has_raw;
     if (L.sftg) {
@@ -996,6 +1048,15 @@ static int pack_all_fp16(Ctx* c) {
     for (const char* n : {"LE.CondNet2.0", "LE.CondNet3.0", "LE.CondNet3.2", "LE.CondNet4.0", "LE.CondNet4.2"}) r |= pack_fold2(c, n, 12, 64);
     r |= pack_fold2(c, "LE.CondNet4.4", 12, 16);
   }
+  if (!r) {   // CondNet{2,3,4}.0 stacked along N (192 columns: conv-major) and split into the two 96-column halves of a CTA pair
+    WeightFn f3[3] = {conv_weight_fn(c, "LE.CondNet2.0"), conv_weight_fn(c, "LE.CondNet3.0"), conv_weight_fn(c, "LE.CondNet4.0")};
+    std::function<float(int)> b3[3] = {bias_fn(c, "LE.CondNet2.0"), bias_fn(c, "LE.CondNet3.0"), bias_fn(c, "LE.CondNet4.0")};
+    for (int half = 0; half < 2; ++half) {
+      WeightFn wf = [=](int n, int ci, int tap) { const int g = half * kPairNHalf + n; return f3[g / 64](g % 64, ci, tap); };
+      auto bf = [=](int n) { const int g = half * kPairNHalf + n; return b3[g / 64](g % 64); };
+      r |= pack_layer(c, "LE.CondNet234.0.pair" + std::to_string(half), IN_PAR3x3S2, 8, kPairNHalf, wf, bf);
+    }
+  }
   r |= pack_std(c, "LE.conv_first", IN_NAT3x3_C8, 8, 32);
   r |= pack_std(c, "LE.HR_conv1", IN_NAT3x3, 32, 32);
   r |= pack_std(c, "LE.HR_conv2", IN_NAT3x3, 32, 32);
@@ -1446,7 +1507,36 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
     return fail(c, "INT8 layouts need the default launch plan");
   if (env_int("HDRTV_ZFUSE", 1)) {
     const bool c30q = is8p("LE.CondNet3.0"), c40q = is8p("LE.CondNet4.0");
-    if (!c30q && !c40q) {
+    const int pair_clusters = (!use_fold2 && env_int("HDRTV_PAIR", 1)) ? pair_max_clusters() : 0;
+    if (!c30q && !c40q && pair_clusters > 0) {
+      // the three stride-2 3x3 convs that read `cond` as ONE N = 192 conv on CTA pairs (conv3z_pair.cuh)
+      ConvLaunch P;
+      memset(&P.p, 0, sizeof(P.p));
+      P.pair = std::make_shared<PairParams>();
+      PairParams& pp = *P.pair;
+      memset(&pp, 0, sizeof(pp));
+      pp.in = reinterpret_cast<const uint4*>(COND.base);
+      pp.in_row_entries = COND.row_entries();
+      pp.in_wp = static_cast<uint32_t>(COND.Wp);
+      pp.wpk[0] = reinterpret_cast<const uint4*>(wk("LE.CondNet234.0.pair0"));
+      pp.wpk[1] = reinterpret_cast<const uint4*>(wk("LE.CondNet234.0.pair1"));
+      pp.Ho = H1;
+      pp.Wo = W1;
+      pp.strips = (W1 + kTileM - 1) / kTileM;
+      pp.pairs = (pp.strips + 1) / 2;
+      pp.out[0] = D1; pp.out[1] = E1; pp.out[2] = E1b;
+      pp.err = c->d_err;
+      const long items = static_cast<long>(pp.pairs) * H1;
+      const long clusters = std::max<long>(1, std::min<long>(std::min(pair_clusters, env_int("HDRTV_PAIR_CLUSTERS", 74)), items / 4));
+      P.grid = dim3(static_cast<unsigned>(2 * clusters), 1, 1);
+      P.smem = pair_smem_bytes();
+      P.N = kPairN;
+      P.mode = STORE_P8;
+      P.name = "LE.CondNet{2,3,4}.0";
+      P.p.ring = kPairRing;
+      P.p.band = static_cast<int>((items + clusters - 1) / clusters);
+      L.push_back(P);
+    } else if (!c30q && !c40q) {
       // the three stride-2 3x3 convs that read `cond` share one launch (cond is fetched from HBM once)
       Epi e = lrelu;
       e.zsplit = 3;
