@@ -45,6 +45,7 @@ struct PairParams {
   int Ho, Wo;                  // output size
   int strips, pairs;           // 128-pixel output strips, strip pairs
   P8 out[3];                   // CondNet2.0 / CondNet3.0 / CondNet4.0 outputs (64 channels; layouts may differ)
+  int pf_rows;                 // > 0: input rows requested into L2 this many rows ahead of the ring (cp.async.bulk.prefetch.L2)
   int* err;
 };
 
@@ -68,7 +69,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on the barrier at the same offset in the LEADER CTA of the pair (works from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t result_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_smem), "r"(ncols) : "memory");
@@ -174,7 +175,19 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv3z_pair_kernel(const __gr
         // and stores nothing
         const int strip = min(2 * pair + static_cast<int>(rank), p.strips - 1);
         const uint4* src = p.in + static_cast<long>(2 * r0) * p.in_row_entries + strip * kTileM;
+        auto prefetch_row = [&](int q) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            unsigned long long a;
+            asm volatile("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"((c >> 1) * wp + (c & 1) * half), "l"(p.in + (static_cast<long>(2 * r0 + q) * p.in_row_entries + strip * kTileM)));
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(kPlaneBytes) : "memory");
+          }
+        };
+        const int pf = p.pf_rows;
+        if (pf > 0)
+          for (int q = kPairRing; q < min(kPairRing + pf, 2 * n + 1); ++q) prefetch_row(q);
         for (int q = 0; q < 2 * n + 1; ++q) {
+          if (pf > 0 && q + kPairRing + pf < 2 * n + 1) prefetch_row(q + kPairRing + pf);
           mbar_wait(empty_bar(slot), ph, p.err, 41);
           mbar_expect_tx(full_bar(slot), kPairSlotBytes);
           const uint32_t dst = smem_u32(ring) + slot * kPairSlotBytes;

@@ -1526,6 +1526,7 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
       pp.pairs = (pp.strips + 1) / 2;
       pp.out[0] = D1; pp.out[1] = E1; pp.out[2] = E1b;
       pp.err = c->d_err;
+      pp.pf_rows = env_int("HDRTV_PAIR_PF", 0);
       const long items = static_cast<long>(pp.pairs) * H1;
       const long clusters = std::max<long>(1, std::min<long>(std::min(pair_clusters, env_int("HDRTV_PAIR_CLUSTERS", 74)), items / 4));
       P.grid = dim3(static_cast<unsigned>(2 * clusters), 1, 1);
