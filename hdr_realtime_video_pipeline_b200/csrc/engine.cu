@@ -1145,18 +1145,25 @@ struct HeadParams {
   __half* pk[3];   // packed B operands of the three folded layers, each followed by its bias step
   ActQuant qs[3], qt[3];   // input fake-quantisation of the scale / shift linears (INT8 layouts)
 };
-__global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
+__device__ __forceinline__ void agcm_head_body(const HeadParams& p, const double* stats5) {
   __shared__ float mean5[128];
   __shared__ float fea[6];
   __shared__ float sc[3][64], sh[3][64];
   const int t = threadIdx.x;
-  if (t < 128) mean5[t] = static_cast<float>(p.stats5[2 * t] / p.cnt5);
+  if (t < 128) mean5[t] = static_cast<float>(stats5[2 * t] / p.cnt5);
   __syncthreads();
-  if (t < 6) {
-    float a = p.b6[t];
-    for (int k = 0; k < 128; ++k) a = fmaf(p.w6[t * 128 + k], mean5[k], a);
-    fea[t] = a;
-    p.fea[t] = a;
+  if (t < 6 * 32) {      // one warp per output: four independent loads per lane, then a fixed-order shuffle tree
+    const int o = t >> 5, ln = t & 31;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a = fmaf(__ldg(p.w6 + o * 128 + ln + 32 * k), mean5[ln + 32 * k], a);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (ln == 0) {
+      a += p.b6[o];
+      fea[o] = a;
+      p.fea[o] = a;
+    }
   }
   __syncthreads();
   for (int i = t; i < 3 * 64; i += blockDim.x) {
@@ -1220,6 +1227,8 @@ __global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) {
     }
   }
 }
+
+__global__ void __launch_bounds__(256) agcm_head_kernel(const HeadParams p) { agcm_head_body(p, p.stats5); }
 
 // ------------------------------------------------------------------------------------------------
 // Condition-image tap tables (host): same arithmetic as ATen's _compute_indices_weights_aa for bicubic.
@@ -1316,13 +1325,13 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
   // in shared memory while the previous one drains (+1.5 % frames/s at 1080p).  The head stays an ordinary launch: the
   // event that hands its results to another stream is recorded right behind it.
   static const bool cls_pdl = env_int("HDRTV_CLS_PDL", 1) != 0;
-  CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
   static const int convi[6] = {0, 4, 8, 12, 16, 20};
   static const int normi[5] = {3, 7, 11, 15, -1};
   const std::string pre = "AGCM.classifier.model.";
+  ClsLevel lv[5];
   for (int l = 0; l < 5; ++l) {
     const Ctx::Lvl& L = c->cls[l];
-    ClsLevel p;
+    ClsLevel& p = lv[l];
     p.in = l == 0 ? cond : static_cast<const void*>(c->cls[l - 1].out);
     p.in_is_half = (l == 0 && cond_half) ? 1 : 0;
     p.in_stats = l == 0 ? nullptr : c->cls[l - 1].stats;
@@ -1342,18 +1351,6 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     p.in_planar = l == 0 ? 1 : 0;
     p.q = c->q(pre + std::to_string(convi[l]));
     p.stat_q = l == 4 ? c->q(pre + "20") : ActQuant{};
-    const size_t sm = sizeof(float) * (static_cast<size_t>(L.Cin) * L.Cout + static_cast<size_t>(pix) * L.Cin + 2 * L.Cin + pix);
-    const unsigned blocks = static_cast<unsigned>((npix + pix - 1) / pix);
-    static bool configured = false;
-    if (!configured) {
-      CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      configured = true;
-    }
-    if (cls_pdl) CK(c, launch_pdl(cls_level_kernel, dim3(blocks), 256, sm, s, p));
-    else cls_level_kernel<<<blocks, 256, sm, s>>>(p);
-    CK(c, cudaGetLastError());
-    ++c->launches;
-    mark();
   }
   HeadParams hp;
   hp.stats5 = c->cls[4].stats;
@@ -1375,6 +1372,23 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
   hp.w3 = c->wd.at("AGCM.conv_last.weight");  hp.b3 = c->wd.at("AGCM.conv_last.bias");
   hp.fea = c->d_fea;
   hp.fold32 = c->d_fold32;
+
+  CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
+  for (int l = 0; l < 5; ++l) {
+    const ClsLevel& p = lv[l];
+    const size_t sm = sizeof(float) * (static_cast<size_t>(p.Cin) * p.Cout + static_cast<size_t>(p.pix) * p.Cin + 2 * p.Cin + p.pix);
+    const unsigned blocks = static_cast<unsigned>((p.Ho * p.Wo + p.pix - 1) / p.pix);
+    static bool configured = false;
+    if (!configured) {
+      CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      configured = true;
+    }
+    if (cls_pdl) CK(c, launch_pdl(cls_level_kernel, dim3(blocks), 256, sm, s, p));
+    else cls_level_kernel<<<blocks, 256, sm, s>>>(p);
+    CK(c, cudaGetLastError());
+    ++c->launches;
+    mark();
+  }
   agcm_head_kernel<<<1, 256, 0, s>>>(hp);
   CK(c, cudaGetLastError());
   ++c->launches;
