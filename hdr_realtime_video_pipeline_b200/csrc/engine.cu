@@ -243,6 +243,7 @@ struct Ctx {
   __half* plan_agcm_planar_slot = nullptr;
   // fp32 buffers
   std::map<std::string, float*> f32;
+  long f32_qtmp_elems = 0;      // size of the "qtmp" scratch tensor (pre-quantised layer inputs of the INT8 layouts)
   // lut
   uint16_t* d_lut = nullptr;
   // packed static weights (device) by layer name
@@ -1271,6 +1272,7 @@ static void release_workspace(Ctx* c) {
   c->plan_agcm.clear();
   c->plan_le.clear();
   c->f32.clear();
+  c->f32_qtmp_elems = 0;
   c->H = c->W = 0;
   c->proc = Ctx::Proc();       // its buffers were workspace allocations
 }
@@ -1849,6 +1851,10 @@ static int build_ws_fp32(Ctx* c, int H, int Wd) {
   };
   bool ok = true;
   ok &= A("a1", 64 * P0) && A("a2", 64 * P0) && A("cond", 64 * P0) && A("cond1", 16 * P0);
+  if (!c->quant.empty()) {      // INT8 layouts: scratch for a pre-quantised layer input (largest: 64 channels at full resolution)
+    ok &= A("qtmp", 64 * P0);
+    c->f32_qtmp_elems = ok ? static_cast<long>(64 * P0) : 0;
+  }
   ok &= A("u1a", 64 * P1) && A("u1b", 64 * P1) && A("cond2", 16 * P1);
   ok &= A("u2a", 64 * P2) && A("cond3", 16 * P2) && A("cond4", 16 * P3);
   ok &= A("f0a", 32 * P0) && A("f0b", 32 * P0) && A("fea0", 32 * P0);
@@ -1869,6 +1875,17 @@ static int build_ws_fp32(Ctx* c, int H, int Wd) {
   return 0;
 }
 
+template <int COB>
+static cudaError_t launch_conv32_t(const ConvF32& p, dim3 grid, size_t sm, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_f32_kernel<COB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  conv_f32_kernel<COB><<<grid, 128, sm, s>>>(p);
+  return cudaGetLastError();
+}
 static int conv32(Ctx* c, cudaStream_t s, const float* in, const float* w, const float* b, float* out, int Cin, int Cout,
                   int H, int Wd, int ks, int stride, int act, float slope, const float* res = nullptr, int ps = 0,
                   int outH = 0, int outW = 0, ActQuant q = ActQuant{}) {
@@ -1879,11 +1896,24 @@ static int conv32(Ctx* c, cudaStream_t s, const float* in, const float* w, const
   p.Ho = (H + 2 * (ks / 2) - ks) / stride + 1;
   p.Wo = (Wd + 2 * (ks / 2) - ks) / stride + 1;
   p.ks = ks; p.stride = stride; p.act = act; p.slope = slope; p.ps = ps; p.outH = outH; p.outW = outW;
-  constexpr int COB = 8;
-  dim3 grid((p.Wo + 127) / 128, p.Ho, (Cout + COB - 1) / COB);
-  const size_t sm = sizeof(float) * Cin * ks * ks * COB;
-  conv_f32_kernel<COB><<<grid, 128, sm, s>>>(p);
-  CK(c, cudaGetLastError());
+  // INT8 layouts: quantise the input once into the context's scratch tensor (when it is large enough: the workspace of the
+  // current resolution) instead of per tap inside the convolution
+  const long n_in = static_cast<long>(Cin) * H * Wd;
+  auto it = c->f32.find("qtmp");
+  if (q.mode && it != c->f32.end() && n_in <= c->f32_qtmp_elems) {
+    fake_quant_f32_kernel<<<static_cast<unsigned>((n_in + 255) / 256), 256, 0, s>>>(in, it->second, n_in, q);
+    CK(c, cudaGetLastError());
+    ++c->launches;
+    p.in = it->second;
+    p.q = ActQuant{};
+  }
+  // output channels per thread: 32 where the layer has them (one pass over the input per 32 outputs), 16 / 8 for the narrow ones
+  const int cob = Cout >= 32 ? 32 : (Cout >= 16 ? 16 : 8);
+  dim3 grid((p.Wo + 127) / 128, p.Ho, (Cout + cob - 1) / cob);
+  const size_t sm = sizeof(float) * Cin * ks * ks * cob;
+  if (sm > 100 * 1024) return fail(c, "conv32: weight tile exceeds the shared-memory budget");
+  cudaError_t e = cob == 32 ? launch_conv32_t<32>(p, grid, sm, s) : cob == 16 ? launch_conv32_t<16>(p, grid, sm, s) : launch_conv32_t<8>(p, grid, sm, s);
+  CK(c, e);
   ++c->launches;
   return 0;
 }

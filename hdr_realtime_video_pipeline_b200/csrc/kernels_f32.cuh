@@ -25,9 +25,12 @@ struct ConvF32 {
   ActQuant q;        // fake-quantisation of the input (INT8 layouts)
 };
 
+// COB output channels per thread: the input value (and, for the INT8 layouts, its fake-quantisation - the caller passes a
+// pre-quantised tensor and p.q.mode = 0 whenever it can) is loaded once per COB outputs, the weights come from shared
+// memory as 128-bit broadcasts.  The accumulation order per output (ci, ky, kx) does not depend on COB.
 template <int COB>
 __global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
-  extern __shared__ float wsm[];  // [Cin*ks*ks][COB]
+  extern __shared__ __align__(16) float wsm[];  // [Cin*ks*ks][COB]
   const int co0 = blockIdx.z * COB;
   const int taps = p.ks * p.ks;
   const int kk = p.Cin * taps;
@@ -52,9 +55,15 @@ __global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
         const int ix = ox * p.stride + kx - pad;
         if (ix < 0 || ix >= p.W) continue;
         const float v = fake_quant(__ldg(ip + static_cast<long>(iy) * p.W + ix), p.q);
-        const float* wp = wsm + ((ci * p.ks + ky) * p.ks + kx) * COB;
+        const float4* wp = reinterpret_cast<const float4*>(wsm + ((ci * p.ks + ky) * p.ks + kx) * COB);
 #pragma unroll
-        for (int c = 0; c < COB; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
+        for (int c = 0; c < COB / 4; ++c) {
+          const float4 w4 = wp[c];
+          acc[4 * c + 0] = fmaf(v, w4.x, acc[4 * c + 0]);
+          acc[4 * c + 1] = fmaf(v, w4.y, acc[4 * c + 1]);
+          acc[4 * c + 2] = fmaf(v, w4.z, acc[4 * c + 2]);
+          acc[4 * c + 3] = fmaf(v, w4.w, acc[4 * c + 3]);
+        }
       }
     }
   }
@@ -76,6 +85,12 @@ __global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
     if (p.res) v += __ldg(p.res + o);
     p.out[o] = v;
   }
+}
+// INT8 layouts on the FP32 path: a layer's input passes through its quantiser once, here, instead of once per tap and
+// output-channel block inside the convolution
+__global__ void fake_quant_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long n, ActQuant q) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fake_quant(x[i], q);
 }
 
 // y = x * (scale + 1) + shift   (arch_util.py:72)
