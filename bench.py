@@ -370,6 +370,8 @@ def measure_workload(net, packer, hb, torch, dev, barrier, wl, K, Wm, rank, loca
     # ---- batch-1 latency (config 2 is latency-bound): serial frames, host-timed submit .. RGB48 slot ready --------
     def latency_run(submit):
         lat = []
+        for i in range(5):                                           # warm-up: the first frames after a mode switch are not steady state
+            submit(i).release()
         for i in range(max(30, min(K, 200))):
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()

@@ -227,7 +227,7 @@ struct Ctx {
   std::string err;
   std::vector<DebugTensor> dbg;
   // classifier
-  struct Lvl { int Cin, Cout, H, W, Ho, Wo; float* out; double* stats; };
+  struct Lvl { int Cin, Cout, H, W, Ho, Wo; float* out; double* stats; int pix; unsigned blocks; double* partials; unsigned int* counter; };
   std::vector<Lvl> cls;
   double* cls_stats_all = nullptr;
   size_t cls_stats_bytes = 0;
@@ -1302,6 +1302,17 @@ static int build_classifier(Ctx* c, int Hc, int Wc) {
     if (!L.out) return fail(c, "alloc classifier level");
     L.stats = sp;
     sp += 2 * L.Cout;
+    // ~256 blocks per level; the first (3-channel) level takes more pixels per block
+    const int npix = L.Ho * L.Wo;
+    int pix = 1;
+    while (pix < 128 && (npix + pix - 1) / pix > 296) pix *= 2;
+    if (l == 0) pix = std::max(pix, 64);
+    L.pix = pix;
+    L.blocks = static_cast<unsigned>((npix + pix - 1) / pix);
+    const unsigned groups = (L.blocks + kClsGroup - 1) / kClsGroup;
+    L.partials = ws_alloc<double>(c, static_cast<size_t>(L.blocks + groups) * 2 * L.Cout);
+    L.counter = ws_alloc<unsigned int>(c, groups + 1);     // zeroed at allocation; every launch leaves them at zero
+    if (!L.partials || !L.counter) return fail(c, "alloc classifier partial sums");
     c->cls.push_back(L);
     h = L.Ho; w = L.Wo;
   }
@@ -1344,12 +1355,9 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
     p.out = L.out;
     p.out_stats = L.stats;
     p.Cin = L.Cin; p.Cout = L.Cout; p.H = L.H; p.W = L.W; p.Ho = L.Ho; p.Wo = L.Wo;
-    const int npix = L.Ho * L.Wo;
-    // ~256 blocks per level; the first (3-channel) level takes more pixels per block
-    int pix = 1;
-    while (pix < 128 && (npix + pix - 1) / pix > 296) pix *= 2;
-    if (l == 0) pix = std::max(pix, 64);
-    p.pix = pix;
+    p.pix = L.pix;
+    p.partials = L.partials;
+    p.counter = L.counter;
     p.in_planar = l == 0 ? 1 : 0;
     p.q = c->q(pre + std::to_string(convi[l]));
     p.stat_q = l == 4 ? c->q(pre + "20") : ActQuant{};
@@ -1375,11 +1383,10 @@ static int run_classifier(Ctx* c, const void* cond, bool cond_half, cudaStream_t
   hp.fea = c->d_fea;
   hp.fold32 = c->d_fold32;
 
-  CK(c, cudaMemsetAsync(c->cls_stats_all, 0, c->cls_stats_bytes, s));
   for (int l = 0; l < 5; ++l) {
     const ClsLevel& p = lv[l];
     const size_t sm = sizeof(float) * (static_cast<size_t>(p.Cin) * p.Cout + static_cast<size_t>(p.pix) * p.Cin + 2 * p.Cin + p.pix);
-    const unsigned blocks = static_cast<unsigned>((p.Ho * p.Wo + p.pix - 1) / p.pix);
+    const unsigned blocks = c->cls[l].blocks;
     static bool configured = false;
     if (!configured) {
       CK(c, cudaFuncSetAttribute(cls_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -2445,7 +2452,7 @@ int hdrtv_time_plan(hdrtv_t* c, const void* x, const void* cond, int H, int Wd, 
   if (run_fp16(c, static_cast<const __half*>(x), static_cast<const __half*>(cond), static_cast<__half*>(out),
                static_cast<__half*>(agcm_out), s, &evs)) return -1;
   CK(c, cudaStreamSynchronize(s));
-  std::string nm = "planar_to_p8\ncls.level0 (+memset)\ncls.level1\ncls.level2\ncls.level3\ncls.level4\nagcm_head\n";
+  std::string nm = "planar_to_p8\ncls.level0\ncls.level1\ncls.level2\ncls.level3\ncls.level4\nagcm_head\n";
   for (auto& L : c->plan_agcm) nm += L.name + " N" + std::to_string(L.N) + " grid" + std::to_string(L.grid.x) + "x" + std::to_string(L.grid.y) + "x" + std::to_string(L.grid.z) + " ring" + std::to_string(L.p.ring) + " smem" + std::to_string(L.smem) + "\n";
   for (auto& L : c->plan_le) nm += L.name + " N" + std::to_string(L.N) + " grid" + std::to_string(L.grid.x) + "x" + std::to_string(L.grid.y) + "x" + std::to_string(L.grid.z) + " ring" + std::to_string(L.p.ring) + " smem" + std::to_string(L.smem) + "\n";
   snprintf(names, names_cap, "%s", nm.c_str());

@@ -128,7 +128,9 @@ struct ClsLevel {
   const float* w;          // [Cin][Cout]  (transposed copy made at weight-load time)
   const float* b;          // [Cout]
   float* out;              // pixel-major [Ho][Wo][Cout]
-  double* out_stats;       // [Cout][2], pre-zeroed
+  double* out_stats;       // [Cout][2]: written (not accumulated) by the last block of the level
+  double* partials;        // [blocks][2 * Cout] per-block sums, then [groups][2 * Cout] per-group sums
+  unsigned int* counter;   // [groups] blocks of a group that have published, then [1] groups that have published; self-resetting
   int Cin, Cout, H, W, Ho, Wo;
   int pix;                 // pooled pixels per block
   ActQuant q;              // fake-quantisation of this level's conv input (after the IN affine)
@@ -273,9 +275,11 @@ __device__ __forceinline__ double cls_block_reduce(int Cout, double s1, double s
   return tot;
 }
 
+constexpr unsigned kClsGroup = 32;     // blocks per first-stage group of the level-total reduction
 __global__ void __launch_bounds__(256) cls_level_kernel(const ClsLevel p) {
   extern __shared__ float sm[];
   __shared__ double red[512];
+  __shared__ bool last_block;
   const ClsSmem m = cls_smem(p, sm);
   // Programmatic dependent launch: the next level may start its prologue (static weights -> shared memory) while this
   // level drains; everything below the wait reads what the previous launch wrote (input map, its statistics).
@@ -287,7 +291,44 @@ __global__ void __launch_bounds__(256) cls_level_kernel(const ClsLevel p) {
   double s1 = 0.0, s2 = 0.0;
   cls_tile<256>(p, m, blockIdx.x * p.pix, s1, s2);
   const double tot = cls_block_reduce<256>(p.Cout, s1, s2, red);
-  if (threadIdx.x < 2 * p.Cout) atomicAdd(p.out_stats + threadIdx.x, tot);     // [Cout][2]: index = 2 * channel + statistic
+  // Level totals without atomics on the data (threadfence reduction, two stages): every block publishes its partial sums;
+  // the block that arrives last in its group of kClsGroup blocks adds the group's partials in block order and publishes the
+  // group sum; the group that arrives last adds the group sums in group order.  FP64 atomicAdd in arrival order made the
+  // totals - and through the InstanceNorm's E[x^2] - mean^2 the whole condition vector - differ in the last bit from run to
+  // run on some frames (one fp32 ulp of `fea`: invisible in the FP16 output, amplified by bucket flips in the INT8 layouts).
+  const int tid = threadIdx.x, nq = 2 * p.Cout;                // nq <= 256
+  const unsigned nblk = gridDim.x, ngrp = (nblk + kClsGroup - 1) / kClsGroup;
+  const unsigned grp = blockIdx.x / kClsGroup, b0 = grp * kClsGroup, gsize = min(kClsGroup, nblk - b0);
+  double* gpart = p.partials + static_cast<long>(nblk) * nq;
+  if (tid < nq) p.partials[static_cast<long>(blockIdx.x) * nq + tid] = tot;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_block = atomicAdd(p.counter + grp, 1u) == gsize - 1;
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  if (tid < nq) {
+    double a = 0.0;
+#pragma unroll 8
+    for (unsigned b = 0; b < gsize; ++b) a += __ldcg(p.partials + static_cast<long>(b0 + b) * nq + tid);
+    gpart[static_cast<long>(grp) * nq + tid] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    p.counter[grp] = 0u;                                        // ready for the next frame
+    last_block = atomicAdd(p.counter + ngrp, 1u) == ngrp - 1;
+  }
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  if (tid < nq) {
+    double a = 0.0;
+#pragma unroll 8
+    for (unsigned g = 0; g < ngrp; ++g) a += __ldcg(gpart + static_cast<long>(g) * nq + tid);
+    p.out_stats[tid] = a;                                       // [Cout][2]: index = 2 * channel + statistic
+  }
+  if (tid == 0) p.counter[ngrp] = 0u;
 }
 
 }  // namespace hdrtv

@@ -16,7 +16,8 @@ h, w = {"540p": (540, 960), "1080p": (1080, 1920), "4k": (2160, 3840)}[wl]
 net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_int8_mixed_qat.npz"), precision="int8-mixed", warmup_passes=0, use_hg=False,
                       debug_library=True)
 print("tensor path:", net._int8_tensor_path)
-pinned = [torch.from_numpy(hb.synth_frame(i, h, w)).pin_memory() for i in range(8)]
+ND = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+pinned = [torch.from_numpy(hb.synth_frame(i, h, w)).pin_memory() for i in range(ND)]
 frames = [t.numpy() for t in pinned]
 want = []
 for i, f in enumerate(frames):
@@ -34,20 +35,20 @@ for i, f in enumerate(frames):
     want.append(O.pack_rgb48(outs[0].cpu().numpy()))
 print("synchronised repeats done")
 state = {}
-for name, fn, infl in (("one-call pipelined", lambda i: net.process_rgb48(frames[i % 8]), 3),
-                       ("one-call serial", lambda i: net.process_rgb48(frames[i % 8], serial=True), 3),
-                       ("three-call", lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(frames[i % 8])), state), 2)):
+for name, fn, infl in (("one-call pipelined", lambda i: net.process_rgb48(frames[i % ND]), 3),
+                       ("one-call serial", lambda i: net.process_rgb48(frames[i % ND], serial=True), 3),
+                       ("three-call", lambda i: hb.tensor_to_rgb48_bytes(net.infer(net.preprocess(frames[i % ND])), state), 2)):
     pending, bad = [], []
-    for i in range(32):
+    for i in range(2 * ND + 16):
         pending.append((i, fn(i)))
         if len(pending) >= infl:
             j, fr = pending.pop(0)
-            if not np.array_equal(fr.numpy(), want[j % 8]):
-                d = np.nonzero((fr.numpy() != want[j % 8]).any(axis=2))
+            if not np.array_equal(fr.numpy(), want[j % ND]):
+                d = np.nonzero((fr.numpy() != want[j % ND]).any(axis=2))
                 bad.append((j, int(d[0].size), int(d[0].min()), int(d[0].max()), int(d[1].min()), int(d[1].max())))
             fr.release()
     for j, fr in pending:
-        if not np.array_equal(fr.numpy(), want[j % 8]):
+        if not np.array_equal(fr.numpy(), want[j % ND]):
             bad.append((j,))
         fr.release()
-    print(f"{wl} {name}: {len(bad)} of 32 frames differ", bad[:6], flush=True)
+    print(f"{wl} {name}: {len(bad)} of {2 * ND + 16} frames differ", bad[:6], flush=True)

