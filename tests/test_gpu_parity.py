@@ -560,6 +560,25 @@ def test_frame_paths_agree_on_bursts_from_an_idle_gpu():
             assert ": 0 of " in ln, ln
 
 
+def test_condition_vector_is_bit_reproducible(nets):
+    """Regression test: the classifier's InstanceNorm statistics were FP64 atomicAdd totals in block-arrival order; on some
+    frames (synthetic 4K frame 12: E[x^2] - mean^2 amplifies the last bit of the sums) the condition vector `fea` then came out
+    with two different values, about one pass in two, which the INT8 layout turned into whole-frame differences.  The totals
+    are now added in block order: every pass over the frame, interleaved with other frames, gives the same AGCM output bits
+    (1017 of its values moved with the condition vector before) and the same network output."""
+    import hashlib
+    net = nets("hr", "fp16")
+    frames = {i: hb.synth_frame(i, 2160, 3840) for i in (11, 12, 13)}
+    seen = set()
+    for rep in range(12):
+        for i in (11, 12, 13):
+            out, agcm = net.infer(net.preprocess(frames[i]))
+            if i == 12:
+                torch.cuda.synchronize()
+                seen.add((hashlib.md5(agcm.cpu().numpy().tobytes()).hexdigest(), hashlib.md5(out.cpu().numpy().tobytes()).hexdigest()))
+    assert len(seen) == 1
+
+
 @pytest.mark.parametrize("hw", [(1080, 1920), (2160, 3840)])
 def test_full_size_properties_fp16(nets, hw):
     """BASELINE configs 2/3 sizes: size-independent properties instead of a CPU oracle run —
