@@ -92,7 +92,7 @@ def do_launches(tag, wl, src, nframes=4):
     named = {}
     if names:
         plan = [n for n in names if n.split(" ")[0] not in ("planar_to_p8", "agcm_head") and not n.startswith("cls.")]
-        tens = [d for d in last if d["kernel"].startswith(("chain_p8_kernel", "conv_p8_kernel", "conv2x_p8_kernel"))]
+        tens = [d for d in last if d["kernel"].startswith(("chain_p8_kernel", "conv_p8_kernel", "conv2x_p8_kernel", "conv3z_pair_kernel"))]
         if len(plan) == len(tens):
             for n, d in zip(plan, tens):
                 named[n.split(" ")[0]] = int(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0))
