@@ -1531,6 +1531,11 @@ static int build_plan_fp16(Ctx* c, int H, int Wd) {
   if (env_int("HDRTV_ZFUSE", 1)) {
     const bool c30q = is8p("LE.CondNet3.0"), c40q = is8p("LE.CondNet4.0");
     const int pair_clusters = (!use_fold2 && env_int("HDRTV_PAIR", 1)) ? pair_max_clusters() : 0;
+    // the fp16 launches of these three convs have no output quantisers: a layout that quantises the input of CondNet2.2 /
+    // 3.2 / 4.2 without making CondNet3.0 / 4.0 W8A8 itself is refused instead of being run unquantised
+    if (qm && !c30q && !c40q && (c->q("LE.CondNet2.2").mode || c->q("LE.CondNet3.2").mode || c->q("LE.CondNet4.2").mode))
+      return fail(c, "INT8 layout: CondNet2.2 / 3.2 / 4.2 are quantised but CondNet3.0 / 4.0 are not W8A8 (unsupported mix on the "
+                     "tensor-core path); use the FP32 fake-quantisation path");
     if (!c30q && !c40q && pair_clusters > 0) {
       // the three stride-2 3x3 convs that read `cond` as ONE N = 192 conv on CTA pairs (conv3z_pair.cuh)
       ConvLaunch P;
