@@ -1887,15 +1887,16 @@ static int build_ws_fp32(Ctx* c, int H, int Wd) {
   return 0;
 }
 
+constexpr int kF32Pxt = 4;        // output pixels per thread of conv_f32_kernel
 template <int COB>
 static cudaError_t launch_conv32_t(const ConvF32& p, dim3 grid, size_t sm, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_f32_kernel<COB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_f32_kernel<COB, kF32Pxt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_f32_kernel<COB><<<grid, 128, sm, s>>>(p);
+  conv_f32_kernel<COB, kF32Pxt><<<grid, 64, sm, s>>>(p);
   return cudaGetLastError();
 }
 static int conv32(Ctx* c, cudaStream_t s, const float* in, const float* w, const float* b, float* out, int Cin, int Cout,
@@ -1919,12 +1920,12 @@ static int conv32(Ctx* c, cudaStream_t s, const float* in, const float* w, const
     p.in = it->second;
     p.q = ActQuant{};
   }
-  // output channels per thread: 32 where the layer has them (one pass over the input per 32 outputs), 16 / 8 for the narrow ones
-  const int cob = Cout >= 32 ? 32 : (Cout >= 16 ? 16 : 8);
-  dim3 grid((p.Wo + 127) / 128, p.Ho, (Cout + cob - 1) / cob);
+  // register tile: 4 pixels x 16 output channels per thread (8 for the 3-channel outputs)
+  const int cob = Cout >= 16 ? 16 : 8;
+  dim3 grid((p.Wo + 64 * kF32Pxt - 1) / (64 * kF32Pxt), p.Ho, (Cout + cob - 1) / cob);
   const size_t sm = sizeof(float) * Cin * ks * ks * cob;
-  if (sm > 100 * 1024) return fail(c, "conv32: weight tile exceeds the shared-memory budget");
-  cudaError_t e = cob == 32 ? launch_conv32_t<32>(p, grid, sm, s) : cob == 16 ? launch_conv32_t<16>(p, grid, sm, s) : launch_conv32_t<8>(p, grid, sm, s);
+  if (sm > 100 * 1024 || ks > 3 || stride > 2) return fail(c, "conv32: unsupported shape");
+  cudaError_t e = cob == 16 ? launch_conv32_t<16>(p, grid, sm, s) : launch_conv32_t<8>(p, grid, sm, s);
   CK(c, e);
   ++c->launches;
   return 0;

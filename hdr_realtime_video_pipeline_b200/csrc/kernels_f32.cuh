@@ -25,11 +25,14 @@ struct ConvF32 {
   ActQuant q;        // fake-quantisation of the input (INT8 layouts)
 };
 
-// COB output channels per thread: the input value (and, for the INT8 layouts, its fake-quantisation - the caller passes a
-// pre-quantised tensor and p.q.mode = 0 whenever it can) is loaded once per COB outputs, the weights come from shared
-// memory as 128-bit broadcasts.  The accumulation order per output (ci, ky, kx) does not depend on COB.
-template <int COB>
-__global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
+// Register tile: PXT consecutive output pixels x COB output channels per thread.  Per (ci, ky) the thread loads the input
+// row segment its PXT pixels need once (stride * (PXT - 1) + ks values) and per tap COB weights from shared memory as
+// 128-bit broadcasts, so PXT * COB FMAs stand against COB / 4 shared loads: the loop is FMA-bound.  For the INT8 layouts the
+// caller passes a pre-quantised tensor and p.q.mode = 0 whenever it can.  The accumulation order per output (ci, ky, kx)
+// does not depend on the tile, and a tap outside the image adds an exact zero, so results are identical to a one-pixel,
+// skip-the-tap kernel.
+template <int COB, int PXT>
+__global__ void __launch_bounds__(64) conv_f32_kernel(const ConvF32 p) {
   extern __shared__ __align__(16) float wsm[];  // [Cin*ks*ks][COB]
   const int co0 = blockIdx.z * COB;
   const int taps = p.ks * p.ks;
@@ -39,51 +42,73 @@ __global__ void __launch_bounds__(128) conv_f32_kernel(const ConvF32 p) {
     wsm[i] = (co0 + c < p.Cout) ? p.w[static_cast<long>(co0 + c) * kk + k] : 0.f;
   }
   __syncthreads();
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * PXT;
   const int oy = blockIdx.y;
-  if (ox >= p.Wo) return;
-  float acc[COB];
+  if (ox0 >= p.Wo) return;
+  float acc[PXT][COB];
 #pragma unroll
-  for (int c = 0; c < COB; ++c) acc[c] = 0.f;
+  for (int q = 0; q < PXT; ++q)
+#pragma unroll
+    for (int c = 0; c < COB; ++c) acc[q][c] = 0.f;
   const int pad = p.ks / 2;
+  constexpr int SEG = 2 * (PXT - 1) + 3;          // widest segment: stride 2, 3 taps
+  const int seg = p.stride * (PXT - 1) + p.ks;
+  const int ix0 = ox0 * p.stride - pad;
   for (int ci = 0; ci < p.Cin; ++ci) {
     const float* ip = p.in + static_cast<long>(ci) * p.H * p.W;
     for (int ky = 0; ky < p.ks; ++ky) {
       const int iy = oy * p.stride + ky - pad;
-      if (iy < 0 || iy >= p.H) continue;
-      for (int kx = 0; kx < p.ks; ++kx) {
-        const int ix = ox * p.stride + kx - pad;
-        if (ix < 0 || ix >= p.W) continue;
-        const float v = fake_quant(__ldg(ip + static_cast<long>(iy) * p.W + ix), p.q);
-        const float4* wp = reinterpret_cast<const float4*>(wsm + ((ci * p.ks + ky) * p.ks + kx) * COB);
+      if (iy < 0 || iy >= p.H) continue;           // the whole row of taps is padding: adds nothing
+      const float* row = ip + static_cast<long>(iy) * p.W;
+      float v[SEG];
 #pragma unroll
-        for (int c = 0; c < COB / 4; ++c) {
-          const float4 w4 = wp[c];
-          acc[4 * c + 0] = fmaf(v, w4.x, acc[4 * c + 0]);
-          acc[4 * c + 1] = fmaf(v, w4.y, acc[4 * c + 1]);
-          acc[4 * c + 2] = fmaf(v, w4.z, acc[4 * c + 2]);
-          acc[4 * c + 3] = fmaf(v, w4.w, acc[4 * c + 3]);
+      for (int j = 0; j < SEG; ++j) {
+        const int ix = ix0 + j;
+        v[j] = (j < seg && ix >= 0 && ix < p.W) ? fake_quant(__ldg(row + ix), p.q) : 0.f;
+      }
+      const float* wrow = wsm + (ci * p.ks + ky) * p.ks * COB;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (kx < p.ks) {
+          const float4* wp = reinterpret_cast<const float4*>(wrow + kx * COB);
+#pragma unroll
+          for (int c = 0; c < COB / 4; ++c) {
+            const float4 w4 = wp[c];
+#pragma unroll
+            for (int q = 0; q < PXT; ++q) {
+              const float x = p.stride == 2 ? v[2 * q + kx] : v[q + kx];
+              acc[q][4 * c + 0] = fmaf(x, w4.x, acc[q][4 * c + 0]);
+              acc[q][4 * c + 1] = fmaf(x, w4.y, acc[q][4 * c + 1]);
+              acc[q][4 * c + 2] = fmaf(x, w4.z, acc[q][4 * c + 2]);
+              acc[q][4 * c + 3] = fmaf(x, w4.w, acc[q][4 * c + 3]);
+            }
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < COB; ++c) {
-    const int co = co0 + c;
-    if (co >= p.Cout) break;
-    float v = acc[c] + __ldg(p.b + co);
-    if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
-    else if (p.act == ACT_LRELU) v = v >= 0.f ? v : v * p.slope;
-    long o;
-    if (p.ps) {
-      const int Y = 2 * oy + ((co & 3) >> 1), X = 2 * ox + (co & 1);
-      if (Y >= p.outH || X >= p.outW) continue;
-      o = (static_cast<long>(co >> 2) * p.outH + Y) * p.outW + X;
-    } else {
-      o = (static_cast<long>(co) * p.Ho + oy) * p.Wo + ox;
+  for (int q = 0; q < PXT; ++q) {
+    const int ox = ox0 + q;
+    if (ox >= p.Wo) break;
+#pragma unroll
+    for (int c = 0; c < COB; ++c) {
+      const int co = co0 + c;
+      if (co >= p.Cout) break;
+      float v = acc[q][c] + __ldg(p.b + co);
+      if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+      else if (p.act == ACT_LRELU) v = v >= 0.f ? v : v * p.slope;
+      long o;
+      if (p.ps) {
+        const int Y = 2 * oy + ((co & 3) >> 1), X = 2 * ox + (co & 1);
+        if (Y >= p.outH || X >= p.outW) continue;
+        o = (static_cast<long>(co >> 2) * p.outH + Y) * p.outW + X;
+      } else {
+        o = (static_cast<long>(co) * p.Ho + oy) * p.Wo + ox;
+      }
+      if (p.res) v += __ldg(p.res + o);
+      p.out[o] = v;
     }
-    if (p.res) v += __ldg(p.res + o);
-    p.out[o] = v;
   }
 }
 // INT8 layouts on the FP32 path: a layer's input passes through its quantiser once, here, instead of once per tap and
