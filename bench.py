@@ -429,8 +429,9 @@ def measure_workload(net, packer, hb, torch, dev, barrier, wl, K, Wm, rank, loca
             if mac is not None:
                 entry.update({"algorithmic_mac_per_px": mac, "achieved_tflops": 2.0 * mac * px / (med[i] / 1000.0) / 1e12})
             traffic = NCU_KERNEL_TRAFFIC.get(wl, {}).get(name)
-            if traffic is not None:
+            if traffic is not None:      # DRAM bytes of this launch (ncu, profiles/) over its CUDA-event time here
                 entry["traffic_bytes_per_launch"] = traffic
+                entry["hbm_GBps"] = traffic / (med[i] * 1e-3) / 1e9
             res["top_kernels"].append(entry)
     res["host_np"], res["n_distinct"] = host_np, n_distinct
     return res
@@ -481,6 +482,13 @@ def workload_entry(wl, r, world, K, peaks, precision):
         "l2": f"{r['n_distinct']} distinct input frames per rank ({r['n_distinct'] * px * 3 / 1e6:.0f} MB) cycled and a per-frame "
               "activation working set >= 1 GB: both exceed the 126 MB L2; no explicit flush",
     }
+    for t in e["roofline"]["top_kernels"]:      # each launch against both ceilings: the larger fraction names its bound
+        if "achieved_tflops" in t:
+            t["tensor_frac_of_burst_peak"] = t["achieved_tflops"] / peaks["tflops_burst"]
+        if "hbm_GBps" in t:
+            t["hbm_frac_of_copy_peak"] = t["hbm_GBps"] / peaks["hbm_gbs"]
+        if "tensor_frac_of_burst_peak" in t and "hbm_frac_of_copy_peak" in t:
+            t["nearer_bound"] = "hbm" if t["hbm_frac_of_copy_peak"] >= t["tensor_frac_of_burst_peak"] else "tensor"
     if e["elementwise"]["K1_preprocess"]:
         for k in ("K1_preprocess", "K8_pack_rgb48"):
             e["elementwise"][k]["frac_of_hbm_peak"] = e["elementwise"][k]["achieved_GBps"] / peaks["hbm_gbs"]
