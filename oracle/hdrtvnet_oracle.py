@@ -549,3 +549,100 @@ def random_state_dict(seed: int = 0) -> dict:
                 w *= F32(0.3)
             sd[k] = w
     return sd
+
+
+# --------------------------------------------------------------------------
+# HG stage: Hallucination_Generator + HG_Composite
+# (src/models/hdrtvnet_modules/Hallucination_arch.py:53-137,
+#  src/models/hdrtvnet_modules/HG_Composite_arch.py:77-107)
+# --------------------------------------------------------------------------
+
+HG_BN_BLOCKS = ("conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2", "conv5_1", "conv5_2", "conv_code1",
+                "conv_code2")
+
+
+def max_pool2(x: np.ndarray) -> np.ndarray:
+    """nn.MaxPool2d(2) on (C,H,W) with even H, W (Hallucination_arch.py:57)."""
+    c, h, w = x.shape
+    return x[:, :h // 2 * 2, :w // 2 * 2].reshape(c, h // 2, 2, w // 2, 2).max(axis=(2, 4))
+
+
+def batch_norm_eval(x: np.ndarray, sd: dict, prefix: str, eps: float = 1e-5) -> np.ndarray:
+    """nn.BatchNorm2d in eval mode: (x - running_mean) / sqrt(running_var + eps) * weight + bias
+    (conv_block, Hallucination_arch.py:24-29)."""
+    mean = sd[prefix + ".running_mean"].astype(F32)[:, None, None]
+    var = sd[prefix + ".running_var"].astype(F32)[:, None, None]
+    g = sd[prefix + ".weight"].astype(F32)[:, None, None]
+    b = sd[prefix + ".bias"].astype(F32)[:, None, None]
+    return ((x - mean) / np.sqrt(var + F32(eps)) * g + b).astype(F32)
+
+
+def hg_fold_bn(sd: dict, eps: float = 1e-5) -> dict:
+    """Eval-time BatchNorm folded into the preceding conv, the arithmetic of
+    Hallucination_Generator_FusedBN._fold_bn_into_conv (Hallucination_arch.py:240-275):
+    scale = bn_w * rsqrt(var + eps); w' = w * scale; b' = (b - mean) * scale + bn_b."""
+    out = {k: np.asarray(v) for k, v in sd.items()}
+    for blk in HG_BN_BLOCKS:
+        if f"{blk}.1.running_var" not in out:
+            continue
+        scale = out[f"{blk}.1.weight"].astype(F32) / np.sqrt(out[f"{blk}.1.running_var"].astype(F32) + F32(eps))
+        out[f"{blk}.0.weight"] = (out[f"{blk}.0.weight"].astype(F32) * scale[:, None, None, None]).astype(F32)
+        out[f"{blk}.0.bias"] = ((out[f"{blk}.0.bias"].astype(F32) - out[f"{blk}.1.running_mean"].astype(F32)) * scale
+                                + out[f"{blk}.1.bias"].astype(F32)).astype(F32)
+        for s in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            out.pop(f"{blk}.1.{s}", None)
+    return out
+
+
+def hg_mask(img_chw: np.ndarray, r: float = 0.75, thresh: float = 0.1) -> np.ndarray:
+    """HG_Composite._make_mask (HG_Composite_arch.py:77-84): 1 where (max_c(img) - r) / (1 - r), clamped to
+    [0, 1], exceeds thresh.  fp32 arithmetic with the python-double constants rounded to fp32 as torch does."""
+    m = img_chw.astype(F32).max(axis=0, keepdims=True)
+    m = (m - F32(r)) / F32(1.0 - r)
+    m = np.clip(m, F32(0.0), F32(1.0))
+    return (m > F32(thresh)).astype(F32)
+
+
+def hg_unet(sd: dict, img: np.ndarray, return_intermediates: bool = False):
+    """Hallucination_Generator.forward without the final mask blend (Hallucination_arch.py:101-135):
+    (3,H,W) with H, W multiples of 32 -> conv_last(cat(conv10_out, img)) (3,H,W)."""
+    def block(name, x):
+        y = conv2d(x, sd[name + ".0.weight"], sd[name + ".0.bias"])
+        if name + ".1.running_var" in sd:
+            y = batch_norm_eval(y, sd, name + ".1")
+        return relu(y)
+
+    def up(name, x):
+        return relu(pixel_shuffle2(conv2d(x, sd[name + ".0.weight"], sd[name + ".0.bias"])))
+
+    def c1x1(name, x):
+        return conv2d(x, sd[name + ".weight"], sd[name + ".bias"])
+
+    t = {}
+    t["conv1"] = block("conv1", img)
+    t["conv2"] = block("conv2", max_pool2(t["conv1"]))
+    t["conv3"] = block("conv3_2", max_pool2(block("conv3_1", t["conv2"])))
+    t["conv4"] = block("conv4_2", max_pool2(block("conv4_1", t["conv3"])))
+    t["conv5"] = block("conv5_2", max_pool2(block("conv5_1", t["conv4"])))
+    t["code"] = block("conv_code2", max_pool2(block("conv_code1", t["conv5"])))
+    t["conv6"] = c1x1("conv6", np.concatenate((up("Up_conv1", t["code"]), t["conv5"]), axis=0))
+    t["conv7"] = c1x1("conv7", np.concatenate((up("Up_conv2", t["conv6"]), t["conv4"]), axis=0))
+    t["conv8"] = c1x1("conv8", np.concatenate((up("Up_conv3", t["conv7"]), t["conv3"]), axis=0))
+    t["conv9"] = c1x1("conv9", np.concatenate((up("Up_conv4", t["conv8"]), t["conv2"]), axis=0))
+    t["conv10"] = c1x1("conv10", np.concatenate((up("Up_conv5", t["conv9"]), t["conv1"]), axis=0))
+    out = c1x1("conv_last", np.concatenate((t["conv10"], img.astype(F32)), axis=0))
+    return (out, t) if return_intermediates else out
+
+
+def hg_stage(hg_sd: dict, base_out_1chw: np.ndarray, mask_r: float = 0.75):
+    """HG_Composite.forward after the base model (HG_Composite_arch.py:88-107): mask from the base output,
+    reflect-pad right / bottom to the next multiple of 32, HG, crop.  (1,3,H,W) fp32 -> (1,3,H,W) fp32."""
+    sd = {k: np.asarray(v) for k, v in hg_sd.items()}
+    base = base_out_1chw[0].astype(F32)
+    _, h, w = base.shape
+    mask = hg_mask(base, r=mask_r)
+    ph, pw = (32 - h % 32) % 32, (32 - w % 32) % 32
+    img = np.pad(base, ((0, 0), (0, ph), (0, pw)), mode="reflect") if (ph or pw) else base
+    mpad = np.pad(mask, ((0, 0), (0, ph), (0, pw)), mode="reflect") if (ph or pw) else mask
+    out = mpad * hg_unet(sd, img) + img            # Hallucination_arch.py:136
+    return out[None, :, :h, :w].astype(F32)

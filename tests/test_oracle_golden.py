@@ -213,3 +213,47 @@ def test_int8_mixed_layer_accumulators_fixture_is_self_consistent():
         wsum = O.conv2d(ones.astype(np.float32), w8.astype(np.float32), None, stride=stride).astype(np.float64)   # sum of w over VALID taps
         deq = acc * (s * ws) + raw[layer + ".bias"].astype(np.float64).reshape(-1, 1, 1) + z * ws * wsum
         assert np.abs(deq - out).max() <= 2e-4 * max(1.0, float(np.abs(out).max())), layer
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HG stage: fixtures = the reference's own HG_Composite run on CPU with the seeded stand-in for the
+# absent HG.pt (scripts/make_golden_hg.py)
+# ---------------------------------------------------------------------------------------------------------------------
+HG_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "hg_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def hg_weights():
+    from hdr_realtime_video_pipeline_b200.synth import hg_random_state_dict
+    return hg_random_state_dict(0)
+
+
+def test_hg_seeded_weights_have_the_reference_key_set(hg_weights):
+    from hdr_realtime_video_pipeline_b200.synth import hg_state_dict_spec
+    spec = hg_state_dict_spec()
+    assert len(spec) == 92 and set(spec) == set(hg_weights)          # Hallucination_Generator().state_dict(): 92 entries
+    assert spec["Up_conv1.0.weight"] == (2048, 512, 3, 3) and spec["conv6.weight"] == (512, 1024, 1, 1)
+    again = __import__("hdr_realtime_video_pipeline_b200.synth", fromlist=["x"]).hg_random_state_dict(0)
+    assert all(np.array_equal(again[k], hg_weights[k]) for k in spec)  # seed -> identical tensors
+
+
+@pytest.mark.parametrize("name", HG_CASES)
+def test_hg_stage_matches_reference(name, hg_weights):
+    g = load_golden(name)
+    assert np.array_equal(O.hg_mask(g["base_out"][0]).astype(np.uint8), g["mask"][0])     # threshold mask is exact
+    out = O.hg_stage(hg_weights, g["base_out"])
+    assert out.shape == g["hg_out"].shape
+    assert np.abs(out - g["hg_out"]).max() <= 2e-6                   # fp32 summation order only
+    folded = O.hg_stage(O.hg_fold_bn(hg_weights), g["base_out"])     # eval BatchNorm folded into the convs (FusedBN arithmetic)
+    assert np.abs(folded - g["hg_out"]).max() <= 2e-6
+
+
+def test_hg_reflect_pad_and_pool_primitives():
+    x = np.arange(2 * 6 * 10, dtype=np.float32).reshape(2, 6, 10)
+    p = O.max_pool2(x)
+    assert p.shape == (2, 3, 5) and p[1, 2, 4] == x[1, 5, 9] and p[0, 0, 0] == x[0, 1, 1]
+    # F.pad(mode="reflect") on the right / bottom: index W + i reads W - 2 - i (HG_Composite_arch.py:94-101)
+    base = np.random.default_rng(0).random((1, 3, 40, 50)).astype(np.float32)
+    img = np.pad(base[0], ((0, 0), (0, 24), (0, 14)), mode="reflect")
+    assert img.shape == (3, 64, 64) and np.array_equal(img[:, 40 + 3, :50], base[0, :, 40 - 2 - 3, :])
+    assert np.array_equal(img[:, :40, 50 + 5], base[0, :, :, 50 - 2 - 5])
