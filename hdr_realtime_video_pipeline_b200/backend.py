@@ -187,6 +187,7 @@ class HDRTVNetB200:
         self._buf_hw = None
         self._gpu_input = self._gpu_cond = self._gpu_raw = None
         self._gpu_out = self._gpu_agcm = self._gpu_u8 = None
+        self._gpu_hg_out = None
         self._pin_input = self._pin_output = None
         print(f"GPU: {torch.cuda.get_device_name(self.device)} (CUDA, sm_100a kernels)")
         print(f"B200 device : {self.device}")
@@ -235,17 +236,28 @@ class HDRTVNetB200:
             raise RuntimeError(
                 f"unsupported architecture (classifier={classifier!r}, le_arch={le_arch!r}, post_correction={post!r}); "
                 "this backend implements classifier='color_condition', le_arch='sft' (HDRUNet3T1) only")
+        self._hg_state = None
         if self._use_hg:
             hg = self._resolve_hg_weights(model_path)
-            if hg is not None:
-                print("WARNING: HG weights found but the HG stage is out of scope for the B200 backend; "
-                      "continuing with the no-HG (AGCM+LE) model.")
+            if hg is not None and self._int8:
+                print("WARNING: the INT8 layouts of the B200 backend cover AGCM+LE only (the reference's HG INT8 checkpoints "
+                      "are absent from its tree); continuing with the no-HG model.")
+                self._use_hg = False
+            elif hg is not None:
+                # HG_Composite (hdrtvnet_torch.py:2121-2143): base model + Hallucination_Generator, strict key check in the engine
+                hg_state, hg_ckpt_arch = load_state_dict_any(hg)
+                hg_arch = str(arch.get("hg_arch", hg_ckpt_arch.get("hg_arch", os.environ.get("HDRTVNET_HG_ARCH", ""))) or "").strip().lower()
+                if hg_arch.replace("-", "").replace("_", "") not in ("", "none", "pixelshuffle", "fusedbn"):
+                    raise RuntimeError(f"unsupported hg_arch {hg_arch!r}; this backend implements the PixelShuffle "
+                                       "Hallucination_Generator (with or without the FusedBN fold)")
+                self._hg_state = {k: v for k, v in hg_state.items() if not k.endswith("num_batches_tracked")}
+                self._hg_weights = hg if not isinstance(hg, dict) else "<state-dict>"
             elif self._hg_weights_explicit:
                 raise FileNotFoundError(f"HG weights not found: {self._hg_weights}\n"
                                         "  Check --hg-weights or disable HG with --use-hg 0.")
             else:
                 print("WARNING: HG weights not found; continuing with no-HG model.")
-            self._use_hg = False
+                self._use_hg = False
         if quant:          # before the weights: on the tensor-core path the weight pack builds the kind::i8 operands from them
             names = sorted(quant)
             arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
@@ -267,17 +279,42 @@ class HDRTVNetB200:
             for d in range(v.ndim):
                 descs[i].shape[d] = v.shape[d]
         self._check(self._lib.hdrtv_set_weights(self._handle, descs, len(tensors)), "hdrtv_set_weights")
+        if self._hg_state is not None:
+            self.set_hg_weights(self._hg_state)
+            self._hg_state = None
         self._n_params = int(sum(v.size for v in state.values()))
         self._layer_shapes = {k[: -len(".weight")]: tuple(v.shape) for k, v in state.items() if k.endswith(".weight")}
 
     def _check(self, rc, what):
         _native.check(rc, self._handle, what, self._lib)
 
+    def set_hg_weights(self, hg_state):
+        """Install (dict of arrays) or remove (None) the HG stage: model.hg.load_state_dict(strict=True),
+        hdrtvnet_torch.py:2141-2143.  The engine folds eval-mode BatchNorm and repacks the weights."""
+        if hg_state is None:
+            self._check(self._lib.hdrtv_set_hg_weights(self._handle, None, 0), "hdrtv_set_hg_weights")
+            self._use_hg = False
+            return
+        items = [(k, np.ascontiguousarray(v, dtype=np.float32)) for k, v in hg_state.items() if not k.endswith("num_batches_tracked")]
+        descs = (_native.TensorDesc * len(items))()
+        for i, (k, v) in enumerate(items):
+            if v.ndim > 4:
+                raise ValueError(f"HG tensor {k} has {v.ndim} dimensions")
+            descs[i].name = k.encode()
+            descs[i].data = v.ctypes.data_as(C.POINTER(C.c_float))
+            descs[i].ndim = v.ndim
+            for d in range(v.ndim):
+                descs[i].shape[d] = v.shape[d]
+        self._check(self._lib.hdrtv_set_hg_weights(self._handle, descs, len(items)), "hdrtv_set_hg_weights")
+        self._use_hg = True
+
     def _need_debug_library(self):
         if not self._debug_library:
             raise RuntimeError("this call needs the test build of the engine: HDRTVNetB200(..., debug_library=True)")
 
     def _resolve_hg_weights(self, model_path):
+        if isinstance(self._hg_weights, dict):        # extension: an in-memory state-dict (tests, benchmarks with seeded weights)
+            return self._hg_weights
         cands = [self._hg_weights]
         if not isinstance(model_path, dict):
             cands.append(os.path.join(os.path.dirname(os.path.abspath(str(model_path))), "HG.pt"))
@@ -310,6 +347,8 @@ class HDRTVNetB200:
         self._gpu_cond = torch.empty((1, 3, ch, cw), dtype=dt, device=dev)
         self._gpu_out = torch.empty((1, 3, h, w), dtype=dt, device=dev)
         self._gpu_agcm = torch.empty((1, 3, h, w), dtype=dt, device=dev)
+        # HG_Composite returns a float32 tensor in both precisions (mask.float() * out + img promotes)
+        self._gpu_hg_out = torch.empty((1, 3, h, w), dtype=torch.float32, device=dev) if self._use_hg else None
         self._gpu_raw = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
         self._gpu_u8 = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
         self._pin_inputs = [torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
@@ -429,7 +468,40 @@ class HDRTVNetB200:
                                           C.c_void_p(self._ev_inputs_free.cuda_event), self._stream())
             if rc != 0:
                 raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle, self._lib))
+            if self._use_hg:        # HG_Composite.forward: the base output goes through the highlight generator
+                if self._gpu_hg_out is None:
+                    self._gpu_hg_out = torch.empty((1, 3, h, w), dtype=torch.float32, device=self.device)
+                rc = self._lib.hdrtv_hg(self._handle, self._gpu_out.data_ptr(), h, w, self._gpu_hg_out.data_ptr(), self._stream())
+                if rc != 0:
+                    raise RuntimeError("B200 execution failed: " + _native.last_error(self._handle, self._lib))
+                return self._gpu_hg_out, self._gpu_agcm
         return self._gpu_out, self._gpu_agcm
+
+    @torch.inference_mode()
+    def hg_stage(self, base_out: torch.Tensor) -> torch.Tensor:
+        """Extension: the HG stage alone on a (1,3,H,W) base-model output (HG_Composite_arch.py:88-107) -> new float32 tensor."""
+        if not self._use_hg:
+            raise RuntimeError("HG weights are not installed")
+        h, w = int(base_out.shape[2]), int(base_out.shape[3])
+        with torch.cuda.device(self.device):
+            src = base_out.to(device=self.device, dtype=self._dtype).contiguous()
+            out = torch.empty((1, 3, h, w), dtype=torch.float32, device=self.device)
+            self._check(self._lib.hdrtv_hg(self._handle, src.data_ptr(), h, w, out.data_ptr(), self._stream()), "hdrtv_hg")
+            src.record_stream(torch.cuda.current_stream(self.device))
+        return out
+
+    def hg_time_plan(self, base_out: torch.Tensor):
+        """[(launch name, ms)] of one HG pass (FP16 contexts), CUDA events between launches."""
+        h, w = int(base_out.shape[2]), int(base_out.shape[3])
+        with torch.cuda.device(self.device):
+            src = base_out.to(device=self.device, dtype=self._dtype).contiguous()
+            out = torch.empty((1, 3, h, w), dtype=torch.float32, device=self.device)
+            ms = (C.c_float * 64)()
+            names = C.create_string_buffer(8192)
+            n = self._lib.hdrtv_hg_time_plan(self._handle, src.data_ptr(), h, w, out.data_ptr(), ms, 64, names, 8192, self._stream())
+            if n < 0:
+                raise RuntimeError("hdrtv_hg_time_plan failed: " + _native.last_error(self._handle, self._lib))
+        return list(zip(names.value.decode().strip().split("\n"), [float(ms[i]) for i in range(n)]))
 
     # ------------------------------------------------------------------ postprocess (hdrtvnet_torch.py:2352-2368)
     @torch.inference_mode()

@@ -19,6 +19,7 @@
 #include "chain_p8.cuh"
 #include "conv2x_p8.cuh"
 #include "conv3z_pair.cuh"
+#include "hg.cuh"
 #ifdef HDRTV_TEST_EXPORTS
 #include "../../include/hdrtv_b200_test.h"
 #include "probes.cuh"
@@ -202,6 +203,30 @@ struct ConvLaunch {
   bool join = false;                    // main-stream launch that needs everything queued on the side stream so far
 };
 
+struct HgLaunch {                       // one gconv_kernel launch of the HG stage (hg.cuh)
+  GConvParams p;
+  int kind = 0, NT = 0, epi = 0;
+  int grid = 0;
+  size_t smem = 0;
+  std::string name;
+};
+struct HgState {
+  bool has = false;
+  std::map<std::string, HostTensor> w;          // BatchNorm folded: "<layer>.weight" / "<layer>.bias"
+  std::map<std::string, float*> wd;             // FP32 path: device copies
+  std::map<std::string, __half*> wpk;           // FP16 path: packed B operands
+  HgTail* d_tail = nullptr;
+  std::vector<void*> wallocs;
+  int H = 0, W = 0, Hp = 0, Wp = 0, sms = 148;
+  std::vector<void*> ws;
+  size_t ws_bytes = 0;
+  std::vector<HgLaunch> plan;
+  std::map<std::string, P8> t;
+  std::map<std::string, float*> f32;
+  float* proc_out = nullptr;                    // hdrtv_process: fp32 HG output of the current resolution
+  int proc_H = 0, proc_W = 0;
+};
+
 struct DebugTensor {
   std::string name;
   int C, H, W;
@@ -272,6 +297,7 @@ struct Ctx {
   cudaEvent_t ev_in_free = nullptr, ev_pre_done = nullptr, ev_packed = nullptr, ev_user = nullptr;
   cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
   unsigned long long* d_cksum = nullptr;      // [2] frame checksums of the two RGB48 staging slots (hdrtv_process_ex)
+  HgState hg;                                 // HG stage (hg.cuh / hg_engine.cuh)
 };
 
 static int fail(Ctx* c, const std::string& m) {
@@ -2094,6 +2120,8 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
 }
 
 
+#include "hg_engine.cuh"
+
 #ifdef HDRTV_TEST_EXPORTS
 // ------------------------------------------------------------------------------------------------
 // tcgen05 issue-rate probe: `iters` back-to-back accumulating M=128 x N x K=16 MMAs from one thread, timed with
@@ -2206,6 +2234,8 @@ void hdrtv_destroy(hdrtv_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   release_workspace(c);
+  hg_release_ws(c);
+  hg_release_weights(c);
   for (void* p : c->weight_allocs) cudaFree(p);
   if (c->d_err) cudaFree(c->d_err);
   if (c->d_lut) cudaFree(c->d_lut);
@@ -2595,6 +2625,66 @@ int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint
   return pack_rgb48_impl(c, src, dtype, H, Wd, dst, transfer, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int hdrtv_set_hg_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {
+  if (!c || (n > 0 && !t)) return fail(c, "hdrtv_set_hg_weights: null argument");
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (n <= 0) {
+    hg_release_ws(c);
+    hg_release_weights(c);
+    return 0;
+  }
+  try {
+    return hg_set_weights(c, t, n);
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_set_hg_weights: ") + e.what());
+  }
+}
+
+int hdrtv_hg(hdrtv_t* c, const void* base_out, int H, int Wd, float* out, void* stream) {
+  if (!c || !base_out || !out) return fail(c, "hdrtv_hg: null argument");
+  cudaSetDevice(c->device);
+  try {
+    return hg_run(c, base_out, H, Wd, out, static_cast<cudaStream_t>(stream));
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_hg: ") + e.what());
+  }
+}
+
+int hdrtv_hg_time_plan(hdrtv_t* c, const void* base_out, int H, int Wd, float* out, float* ms, int cap, char* names, int names_cap,
+                       void* stream) {
+  if (!c || !base_out || !out || !ms) return fail(c, "hdrtv_hg_time_plan: null argument");
+  if (c->precision != HDRTV_FP16) return fail(c, "hdrtv_hg_time_plan: FP16 context required");
+  cudaSetDevice(c->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  try {
+    if (hg_prepare(c, H, Wd)) return -1;
+    if (hg_run(c, base_out, H, Wd, out, s)) return -1;            // warm
+    std::vector<cudaEvent_t> ev(c->hg.plan.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], s);
+    for (size_t i = 0; i < c->hg.plan.size(); ++i) {
+      CK(c, hg_launch(c->hg.plan[i], s));
+      cudaEventRecord(ev[i + 1], s);
+    }
+    CK(c, cudaStreamSynchronize(s));
+    std::string nm;
+    int n = 0;
+    for (size_t i = 0; i < c->hg.plan.size(); ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      if (n < cap) ms[n] = t;
+      ++n;
+      nm += "HG." + c->hg.plan[i].name + " tiles" + std::to_string(c->hg.plan[i].p.tiles) + " kg" + std::to_string(c->hg.plan[i].p.kgroups) + "\n";
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (names && names_cap > 0) snprintf(names, names_cap, "%s", nm.c_str());
+    return n;
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_hg_time_plan: ") + e.what());
+  }
+}
+
 int hdrtv_pack_bgr24(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint8_t* dst, void* stream) {
   if (!c || !src || !dst) return fail(c, "hdrtv_pack_bgr24: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -2691,7 +2781,20 @@ int hdrtv_process_ex(hdrtv_t* c, const uint8_t* bgr, int H, int Wd, uint16_t* rg
     if (!c->d_lut || c->precision != HDRTV_FP16) return fail(c, "hdrtv_process: LUT transfer needs fp16 precision and a table");
     lut = c->d_lut;
   }
-  if (plan_can_fuse_pack(c)) {
+  if (c->hg.has) {
+    // HG stage between the LE network and the pack (HG_Composite.forward): its output is fp32 in both precisions
+    if (lut) return fail(c, "hdrtv_process: the LUT transfer is indexed by half bit patterns; the HG output is float32");
+    if (c->hg.proc_H != H || c->hg.proc_W != Wd) {
+      if (hg_prepare(c, H, Wd)) return -1;
+      c->hg.proc_out = hg_ws_alloc<float>(c, npix * 3, false);
+      if (!c->hg.proc_out) return fail(c, "hdrtv_process: HG output allocation failed");
+      c->hg.proc_H = H;
+      c->hg.proc_W = Wd;
+    }
+    if (hdrtv_infer_ex(c, P.x, P.cond, H, Wd, P.out, P.agcm, 1, serial ? nullptr : c->ev_in_free, s)) return -1;
+    if (hdrtv_hg(c, P.out, H, Wd, c->hg.proc_out, s)) return -1;
+    if (pack_rgb48_impl(c, c->hg.proc_out, HDRTV_FP32, H, Wd, dst, transfer, cks, s)) return -1;
+  } else if (plan_can_fuse_pack(c)) {
     if (cks) CK(c, cudaMemsetAsync(cks, 0, sizeof(unsigned long long), s));
     FusedPack fp;
     fp.rgb48 = dst; fp.lut = lut; fp.cksum = cks;
@@ -2740,6 +2843,7 @@ int hdrtv_process_flush(hdrtv_t* c, void* stream) {
 
 const void* hdrtv_process_output(const hdrtv_t* c, int which) {
   if (!c || !c->proc.H) return nullptr;
+  if (which == 2) return c->hg.proc_out;      // fp32 HG output (when HG weights are installed)
   return which == 0 ? c->proc.out : (which == 1 ? c->proc.agcm : nullptr);
 }
 

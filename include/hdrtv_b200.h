@@ -106,7 +106,23 @@ int hdrtv_process(hdrtv_t* h, const uint8_t* bgr, int height, int width, uint16_
 int hdrtv_process_ex(hdrtv_t* h, const uint8_t* bgr, int height, int width, uint16_t* rgb48, int cond_mode, int transfer,
                      int flags, uint64_t* checksum_out, void* done_event, void* stream);
 int hdrtv_process_flush(hdrtv_t* h, void* stream);          /* `stream` waits for the copy-out stream's pending copies */
-const void* hdrtv_process_output(const hdrtv_t* h, int which); /* device (1,3,H,W) out (0) / agcm_out (1) of the last frame */
+const void* hdrtv_process_output(const hdrtv_t* h, int which); /* device (1,3,H,W) out (0) / agcm_out (1) / fp32 HG out (2) of the last frame */
+
+/* HG stage (third HDRTVNet++ stage).  hdrtv_set_hg_weights replaces                                 */
+/* model.hg.load_state_dict(hg_state, strict=True) (hdrtvnet_torch.py:2141-2143): the Hallucination_Generator state-dict */
+/* (Hallucination_arch.py:53-98, nf = 64; 92 tensors with BatchNorm, or 42 with the FusedBN fold already applied,         */
+/* :201-275); eval-mode BatchNorm is folded into the convs here.  n = 0 removes the stage.                                */
+/* hdrtv_hg replaces HG_Composite.forward after the base model (HG_Composite_arch.py:86-107) and                          */
+/* Hallucination_Generator.forward (Hallucination_arch.py:101-137): highlight mask from base_out, reflect pad to a        */
+/* multiple of 32, the 64..512-channel U-Net (K-streamed tcgen05 implicit GEMMs on HDRTV_FP16 contexts), mask blend,      */
+/* crop.  base_out = (1,3,H,W) planar of the context's precision (the `out` of hdrtv_infer); out = (1,3,H,W) planar       */
+/* FLOAT32 in both precisions, as in the reference (mask.float() * out + img promotes a half model's output).            */
+/* Once HG weights are installed, hdrtv_process / hdrtv_process_ex run the stage between the LE network and the pack.     */
+int hdrtv_set_hg_weights(hdrtv_t* h, const hdrtv_tensor_desc* tensors, int n);
+int hdrtv_hg(hdrtv_t* h, const void* base_out, int height, int width, float* out, void* stream);
+/* Per-launch device times (ms) of one hdrtv_hg (FP16 contexts), like hdrtv_time_plan; returns the count.                */
+int hdrtv_hg_time_plan(hdrtv_t* h, const void* base_out, int height, int width, float* out, float* ms, int cap, char* names,
+                       int names_cap, void* stream);
 
 /* HDRTVNetTorch.postprocess (hdrtvnet_torch.py:2352-2368): planar -> uint8 HxWx3 BGR, arithmetic in `dtype`.       */
 int hdrtv_pack_bgr24(hdrtv_t* h, const void* src, int dtype, int height, int width, uint8_t* dst, void* stream);

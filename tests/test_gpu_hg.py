@@ -1,0 +1,192 @@
+"""GPU parity tests of the HG stage, through the C ABI (hdrtv_set_hg_weights / hdrtv_hg / hdrtv_process).
+
+Checkers: fixtures made by running the reference's own HG_Composite on CPU (tests/golden/hg_*.npz,
+scripts/make_golden_hg.py), the numpy oracle (oracle/hdrtvnet_oracle.py hg_*), and - when baseline/_ref travelled with the
+snapshot - the reference's CUDA path on the same box.  HG.pt is absent from the reference tree, so the highlight generator
+carries the seeded stand-in weights of synth.hg_random_state_dict (same key set / shapes, non-trivial BatchNorm statistics).
+
+Tolerances (BASELINE.json): FP32 <= 1e-4, FP16 <= 2e-3 max-abs.  The highlight mask is a hard threshold on the base
+model's output (max_c > 0.775), so end-to-end comparisons exclude the pixels whose base value sits within the base
+model's own tolerance of the threshold (there `ours` and the reference may legitimately pick different sides); the stage
+itself is also compared on IDENTICAL base outputs, where the masks must agree exactly.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
+from hdr_realtime_video_pipeline_b200.synth import hg_random_state_dict  # noqa: E402
+from oracle import hdrtvnet_oracle as O  # noqa: E402
+from oracle import reference_loader as RL  # noqa: E402
+
+W_HR = os.path.join(GOLDEN, "weights_hr.npz")
+HG_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "hg_*.npz")))
+FP32_TOL, FP16_TOL = 1e-4, 2e-3
+REF = RL.load()
+needs_ref = pytest.mark.skipif(REF is None, reason="baseline/_ref not installed (scripts/install_reference.py)")
+
+
+@pytest.fixture(scope="module")
+def hg_sd():
+    return hg_random_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def nets(hg_sd):
+    made = {}
+
+    def get(precision):
+        if precision not in made:
+            made[precision] = hb.HDRTVNetB200(W_HR, device="cuda", precision=precision, warmup_passes=0, use_hg=True, hg_weights=hg_sd)
+        return made[precision]
+
+    yield get
+    for n in made.values():
+        n.close()
+
+
+def _stage(net, base):
+    out = net.hg_stage(torch.from_numpy(np.ascontiguousarray(base)).cuda())
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _near_threshold(base_1chw, margin):
+    return np.abs(base_1chw[0].max(axis=0) - 0.775) < margin
+
+
+@pytest.mark.parametrize("name", HG_CASES)
+def test_hg_fp32_matches_reference_fixture(nets, parity_log, name):
+    g = load_golden(name)
+    net = nets("fp32")
+    out = _stage(net, g["base_out"])
+    assert out.dtype == np.float32 and out.shape == g["hg_out"].shape
+    d_stage = float(np.abs(out - g["hg_out"]).max())
+    # end to end (preprocess -> AGCM + LE -> HG) on the fixture's frame
+    res, agcm = net.infer(net.preprocess(g["frame"]))
+    assert res.dtype == torch.float32
+    e2e = res.cpu().numpy()
+    keep = ~_near_threshold(g["base_out"], 2e-4)
+    d_e2e = float(np.abs(e2e - g["hg_out"])[0][:, keep].max())
+    parity_log.add(test="hg_fp32", case=name, stage_vs_ref32=d_stage, e2e_vs_ref32=d_e2e, excluded_px=int((~keep).sum()))
+    assert d_stage <= FP32_TOL, f"{name}: HG stage fp32 differs from the reference by {d_stage:.3e}"
+    assert d_e2e <= FP32_TOL, f"{name}: AGCM+LE+HG fp32 differs from the reference by {d_e2e:.3e}"
+    assert np.abs(agcm.cpu().numpy() - g["agcm_out"]).max() <= FP32_TOL
+
+
+@pytest.mark.parametrize("name", HG_CASES)
+def test_hg_fp16_matches_reference_fixture(nets, parity_log, name):
+    """Stage on the reference's own half base output (identical mask), then end to end; triangle ours / ref16 / ref32."""
+    g = load_golden(name)
+    net = nets("fp16")
+    base16 = g["base_out_fp16"].astype(np.float16)
+    out = _stage(net, base16)
+    ref16, ref32 = g["hg_out_fp16"], g["hg_out"]
+    d16 = float(np.abs(out - ref16).max())
+    # where the stage's OWN input is identical, the mask must be: every pixel the reference blended is blended here
+    delta_ref = np.abs(ref16 - base16.astype(np.float32)).max(axis=1)[0] > 0
+    delta_our = np.abs(out - base16.astype(np.float32)).max(axis=1)[0] > 0
+    m16 = O.hg_mask(base16.astype(np.float32)[0])[0] > 0
+    assert not (delta_ref & ~m16).any()
+    assert not (delta_our & ~m16).any(), "HG changed pixels outside the highlight mask"
+    res, _ = net.infer(net.preprocess(g["frame"]))
+    assert res.dtype == torch.float32          # HG_Composite promotes (mask.float() * out + img), fixtures record it
+    assert str(g["hg_out_fp16_dtype"]) == "torch.float32"
+    e2e = res.cpu().numpy()
+    keep = ~(_near_threshold(g["base_out_fp16"], 4e-3) | _near_threshold(g["base_out"], 4e-3))
+    e16 = float(np.abs(e2e - ref16)[0][:, keep].max())
+    e32 = float(np.abs(e2e - ref32)[0][:, keep].max())
+    eref = float(np.abs(ref16 - ref32)[0][:, keep].max())
+    parity_log.add(test="hg_fp16", case=name, stage_vs_ref16=d16, e2e_vs_ref16=e16, e2e_vs_ref32=e32, ref16_vs_ref32=eref,
+                   excluded_px=int((~keep).sum()))
+    assert d16 <= FP16_TOL, f"{name}: HG stage fp16 differs from the reference's half model by {d16:.3e}"
+    # end to end the base model's own FP16 noise enters (see test_gpu_parity.fp16_gate): within 2e-3 of ref16, or at least as
+    # close to the reference's FP32 output as the reference's half model is
+    assert e16 <= FP16_TOL or e32 <= eref, f"{name}: e2e fp16 {e16:.3e} vs ref16, {e32:.3e} vs ref32 (reference: {eref:.3e})"
+
+
+@pytest.mark.parametrize("h,w", [(40, 200), (33, 70), (64, 260)])
+def test_hg_matches_oracle_on_ragged_sizes(nets, hg_sd, h, w):
+    """Sizes that are not multiples of 32 (reflect pad), narrower / wider than one 128-pixel strip, several row blocks."""
+    rng = np.random.default_rng(h * 1000 + w)
+    base = (0.55 + 0.45 * rng.random((1, 3, h, w))).astype(np.float32)        # about half of the pixels above the threshold
+    base16 = base.astype(np.float16)
+    want32 = O.hg_stage(hg_sd, base)
+    got32 = _stage(nets("fp32"), base)
+    assert np.abs(got32 - want32).max() <= FP32_TOL
+    want16 = O.hg_stage(hg_sd, base16.astype(np.float32))
+    got16 = _stage(nets("fp16"), base16)
+    keep = ~_near_threshold(base16.astype(np.float32), 1e-3)                   # half arithmetic of the mask near the threshold
+    assert np.abs(got16 - want16)[0][:, keep].max() <= FP16_TOL
+
+
+def test_hg_one_call_path_matches_the_three_calls(nets):
+    """hdrtv_process with HG installed = preprocess -> infer (AGCM + LE + HG) -> RGB48 pack, bit for bit."""
+    net = nets("fp16")
+    for idx, cls in ((0, "noise"), (3, "white_salt")):
+        frame = hb.synth_frame(idx, 136, 248, cls)
+        out, _ = net.infer(net.preprocess(frame))
+        fr = hb.tensor_to_rgb48_bytes(out, {})
+        want = fr.numpy().copy()
+        fr.release()
+        pf = net.process_rgb48(frame, serial=True)
+        pf.wait_ready()
+        got = pf.numpy().copy()
+        pf.release()
+        assert np.array_equal(got, want)
+        assert np.array_equal(want, O.pack_rgb48(out.cpu().numpy()))
+
+
+def test_hg_weights_are_checked_strictly(hg_sd):
+    bad = dict(hg_sd)
+    bad.pop("conv7.weight")
+    with pytest.raises(RuntimeError, match="missing key conv7.weight"):
+        hb.HDRTVNetB200(W_HR, device="cuda", precision="fp16", warmup_passes=0, use_hg=True, hg_weights=bad)
+    with pytest.raises(FileNotFoundError):
+        hb.HDRTVNetB200(W_HR, device="cuda", precision="fp16", warmup_passes=0, use_hg=True, hg_weights="/nonexistent/HG.pt")
+    # fused-BN checkpoints (Hallucination_Generator_FusedBN) load as well and give the same result
+    net = hb.HDRTVNetB200(W_HR, device="cuda", precision="fp32", warmup_passes=0, use_hg=True, hg_weights=O.hg_fold_bn(hg_sd))
+    g = load_golden(HG_CASES[0])
+    assert np.abs(_stage(net, g["base_out"]) - g["hg_out"]).max() <= FP32_TOL
+    net.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("h,w,cls", [(540, 960, "white_salt"), (1080, 1920, "mixed")])
+def test_hg_fp16_matches_live_cuda_reference(nets, hg_sd, parity_log, tmp_path, h, w, cls):
+    """The reference's own wrapper (HDRTVNetTorch with HG_Composite, CUDA FP16 eager) on the same box, full frame."""
+    path = tmp_path / "HG.pt"
+    torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in hg_sd.items()}, path)
+    ref = REF.HDRTVNetTorch(REF.weights("HR.pt"), device="cuda", precision="fp16", compile_model=False, use_hg=True,
+                            hg_weights=str(path), warmup_passes=0)
+    if cls == "mixed":
+        frame = hb.synth_frame(1, h, w, "ramps")
+        frame[:, w // 2:] = hb.synth_frame(1, h, w, "white_salt")[:, w // 2:]
+    else:
+        frame = hb.synth_frame(3, h, w, cls)
+    with torch.inference_mode():
+        t, c = ref.preprocess(frame)
+        model = getattr(ref.model, "_orig_mod", ref.model)
+        base_ref, _ = model.base((t.clone(), c.clone()))
+        res = ref.infer((t.clone(), c.clone()))
+        torch.cuda.synchronize()
+        ref_out = res[0].float().contiguous().cpu().numpy()
+        base_ref = base_ref.contiguous()
+    net = nets("fp16")
+    got = net.hg_stage(base_ref)               # the stage on the reference's own base output: masks agree exactly
+    torch.cuda.synchronize()
+    d16 = float(np.abs(got.cpu().numpy() - ref_out).max())
+    mask_on = float((O.hg_mask(base_ref.float().cpu().numpy()[0]) > 0).mean())
+    parity_log.add(test="hg_fp16_live", case=f"{cls}_{h}x{w}", stage_vs_ref16_cuda=d16, mask_fraction=mask_on)
+    assert res[0].dtype == torch.float32
+    assert mask_on > 0.2
+    assert d16 <= FP16_TOL, f"HG stage vs the reference's CUDA FP16 HG at {h}x{w}: {d16:.3e}"
+    del ref
+    torch.cuda.empty_cache()
