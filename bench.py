@@ -73,6 +73,15 @@ for _name in ("r2_traffic.json", "r1_ncu_top_kernels.json"):
         break
     except Exception:
         continue
+NCU_HG_TRAFFIC = {}        # DRAM bytes of one HG pass (ncu launch list of scripts/profile_hg.py, profiles/r2_hg_traffic.json)
+try:
+    with open(os.path.join(REPO, "profiles", "r2_hg_traffic.json")) as _f:
+        _j = json.load(_f)
+    for _wl in ("1080p", "4k"):
+        if _j.get(f"frame_dram_bytes_{_wl}", {}).get("total"):
+            NCU_HG_TRAFFIC[_wl] = int(_j[f"frame_dram_bytes_{_wl}"]["total"])
+except Exception:
+    pass
 WEIGHTS = os.path.join(REPO, "tests", "golden", "weights_hr.npz")
 # the reference's INT8 checkpoints (src/models/weights/original/pytorch_int8/hr/*_qat.pt) as raw-array fixtures
 W_INT8 = {"int8-full": os.path.join(REPO, "tests", "golden", "weights_int8_full_qat.npz"),
@@ -437,6 +446,157 @@ def measure_workload(net, packer, hb, torch, dev, barrier, wl, K, Wm, rank, loca
     return res
 
 
+# HG stage: conv shapes of Hallucination_Generator (nf = 64) -> FLOPs of one frame at the padded size
+HG_CONVS = [  # (name, cin, cout, ksize, level)
+    ("conv1.0", 3, 64, 3, 0), ("conv2.0", 64, 128, 3, 1), ("conv3_1.0", 128, 256, 3, 1), ("conv3_2.0", 256, 256, 3, 2),
+    ("conv4_1.0", 256, 512, 3, 2), ("conv4_2.0", 512, 512, 3, 3), ("conv5_1.0", 512, 512, 3, 3), ("conv5_2.0", 512, 512, 3, 4),
+    ("conv_code1.0", 512, 512, 3, 4), ("conv_code2.0", 512, 512, 3, 5), ("Up_conv1.0", 512, 2048, 3, 5), ("conv6", 1024, 512, 1, 4),
+    ("Up_conv2.0", 512, 2048, 3, 4), ("conv7", 1024, 256, 1, 3), ("Up_conv3.0", 256, 1024, 3, 3), ("conv8", 512, 128, 1, 2),
+    ("Up_conv4.0", 128, 512, 3, 2), ("conv9", 256, 64, 1, 1), ("Up_conv5.0", 64, 256, 3, 1), ("conv10", 128, 3, 1, 0),
+    ("conv_last", 6, 3, 1, 0)]
+
+
+def hg_flops(h, w):
+    hp, wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    per = {n: 2.0 * ci * co * k * k * (hp >> lv) * (wp >> lv) for n, ci, co, k, lv in HG_CONVS}
+    return per, float(sum(per.values()))
+
+
+def measure_hg(hb, torch, dev, wl, K, Wm, peaks, weights, with_reference):
+    """AGCM + LE + HG (HG_Composite, the full HDRTVNet++): device-resident and end-to-end frames/s, the HG stage's own
+    roofline (tensor-bound: 64..2048-channel convs on the K-streamed tcgen05 kernel) with per-launch TFLOP/s, and the
+    unmodified reference with the same seeded HG weights on the same GPU (CUDA FP16 eager)."""
+    from hdr_realtime_video_pipeline_b200.synth import hg_random_state_dict
+    h, w = WORKLOADS[wl]
+    px = h * w
+    hg_sd = hg_random_state_dict(0)
+    net = hb.HDRTVNetB200(weights, device=f"cuda:{dev.index}", precision="fp16", warmup_passes=0, use_hg=True, hg_weights=hg_sd)
+    packer = hb.RGB48Packer(dev, ring_frames=3)
+    n_distinct = 16 if px <= 1080 * 1920 else 8
+    host_frames = [torch.from_numpy(hb.synth_frame(i, h, w)).pin_memory() for i in range(n_distinct)]
+    dev_frames = [f.to(dev) for f in host_frames]
+    host_np = [f.numpy() for f in host_frames]
+    out_dev = torch.empty((h, w, 3), dtype=torch.uint16, device=dev)
+
+    def step(i):
+        out = net.infer(net.preprocess_device(dev_frames[i % n_distinct], assume_ready=True))
+        packer.pack_device(out, out_dev)
+
+    for i in range(Wm):
+        step(i)
+    torch.cuda.synchronize(dev)
+    l0 = net.launch_count() + packer.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    step_ms = e0.elapsed_time(e1) / K
+    launches = net.launch_count() + packer.launch_count() - l0
+    # end to end: host u8 frame in -> RGB48 in a pinned ring slot, one C-ABI call per frame, three frames in flight
+    pending = []
+    for i in range(Wm):
+        net.process_rgb48(host_np[i % n_distinct]).release()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(K):
+        pending.append(net.process_rgb48(host_np[i % n_distinct]))
+        if len(pending) >= 3:
+            fr = pending.pop(0)
+            fr.wait_ready()
+            fr.release()
+    for fr in pending:
+        fr.wait_ready()
+        fr.release()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    # the stage alone + per-launch times
+    out, _ = net.infer(net.preprocess_device(dev_frames[3 % n_distinct], assume_ready=True))
+    base = net._gpu_out.clone()
+    per, total = hg_flops(h, w)
+    runs = [net.hg_time_plan(base) for _ in range(3)]
+    names = [n for n, _ in runs[0]]
+    med = np.median(np.array([[t for _, t in r] for r in runs]), axis=0)
+    top = []
+    for i in np.argsort(-med)[:5]:
+        f = per[names[i].split()[0][3:]]
+        tf = f / (med[i] * 1e-3) / 1e12
+        top.append({"launch": names[i], "ms": float(med[i]), "achieved_tflops": tf, "tensor_frac_of_sustained_peak": tf / peaks["tflops"],
+                    "tensor_frac_of_burst_peak": tf / peaks["tflops_burst"]})
+    for _ in range(3):
+        net.hg_stage(base)
+    e0.record()
+    for _ in range(10):
+        net.hg_stage(base)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    stage_ms = e0.elapsed_time(e1) / 10
+    stage_tf = total / (stage_ms * 1e-3) / 1e12
+    res = {
+        "config": f"HDRTVNet++ with the HG stage (HG_Composite: AGCM + LE + Hallucination_Generator) FP16 {w}x{h}, seeded stand-in "
+                  "for the absent HG.pt (synth.hg_random_state_dict), HR.pt base",
+        "value": 1000.0 / step_ms, "unit": "frames/s", "ms_per_step": step_ms, "steps": K, "gpu_launches": int(launches),
+        "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 6,
+                "api": "HDRTVNetB200.process_rgb48 with HG weights installed (hdrtv_process_ex: LE -> hdrtv_hg -> fp32 RGB48 pack)"},
+        "roofline": {"bound": "tensor", "kernel": "gconv_kernel family of the HG stage (19 launches) + stage-in + tail, CUDA events "
+                                                  "around 10 passes of hdrtv_hg on the launching stream",
+                     "achieved": stage_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": stage_tf / peaks["tflops"],
+                     "frac_of_burst_peak": stage_tf / peaks["tflops_burst"], "ms_per_frame": stage_ms,
+                     "algorithmic": f"{total / px:.0f} FLOP per output pixel x {px} px ({total / 1e12:.3f} TFLOP per frame at the "
+                                    "padded size)", "peak_source": peaks["source"],
+                     "traffic": NCU_HG_TRAFFIC.get(wl), "top_kernels": top},
+    }
+    packer.close()
+    net.close()
+    del net, packer
+    torch.cuda.empty_cache()
+    if with_reference:
+        res["gpu_eager_baseline"] = gpu_eager_baseline_hg(dev, host_np, hg_sd, torch)
+    return res
+
+
+def gpu_eager_baseline_hg(dev, host_np, hg_sd, torch):
+    """The unmodified reference with HG (HG_Composite through HDRTVNetTorch, CUDA FP16 eager, cudnn.benchmark) on this GPU."""
+    from oracle import reference_loader as RL
+    ref = RL.load()
+    if ref is None:
+        return {"unavailable": "baseline/_ref not installed (scripts/install_reference.py)"}
+    try:
+        import tempfile
+        path = os.path.join(tempfile.mkdtemp(), "HG.pt")
+        torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in hg_sd.items()}, path)
+        with contextlib.redirect_stdout(sys.stderr):
+            net = ref.HDRTVNetTorch(ref.weights("HR.pt"), device="cuda", precision="fp16", compile_model=False, use_hg=True,
+                                    hg_weights=path, warmup_passes=0)
+        state = {}
+
+        def one(i):
+            with torch.inference_mode():
+                out = net.infer(net.preprocess(host_np[i % len(host_np)]))
+            payload = ref.feeders._tensor_to_rgb48_bytes(out, state)
+            if hasattr(payload, "release"):
+                payload.wait_ready()
+                payload.release()
+
+        for i in range(3):
+            one(i)
+        torch.cuda.synchronize(dev)
+        n = 12 if host_np[0].shape[0] > 1080 else 24
+        t0 = time.perf_counter()
+        for i in range(n):
+            one(i)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        del net
+        torch.cuda.empty_cache()
+        return {"value": n / dt, "unit": "frames/s", "ms_per_frame": dt / n * 1000.0, "frames": n, "kind": "reference",
+                "what": "unmodified reference (baseline/_ref): HDRTVNetTorch(device='cuda', precision='fp16', use_hg=True) -> "
+                        "HG_Composite eager cuDNN, preprocess -> infer -> _tensor_to_rgb48_bytes, same seeded HG weights"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+
+
 def workload_entry(wl, r, world, K, peaks, precision):
     h, w = WORKLOADS[wl]
     px = h * w
@@ -601,6 +761,15 @@ def run_b200_arm(args):
                 frames = [hb.synth_frame(i, hh, ww) for i in range(8)]
                 line["gpu_eager_baseline"][wl] = gpu_eager_baseline(dev, hh, ww, 24 if wl == "4k" else 48, frames)
                 entries[wl]["gpu_eager_baseline"] = line["gpu_eager_baseline"][wl]
+        if world == 1 and precision == "fp16" and not args.no_hg:
+            line["hg"] = {}
+            with contextlib.redirect_stdout(sys.stderr):
+                for wl in wls:
+                    try:
+                        line["hg"][wl] = measure_hg(hb, torch, dev, wl, min(K, 40 if wl != "4k" else 20), Wm, peaks, weights,
+                                                    not args.no_gpu_baseline)
+                    except Exception as exc:                    # the extra workload must never take the headline line down
+                        line["hg"][wl] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             times, ncores, cpu = cpu_reference_sample(540, 960)
             cpu_px_s = 540 * 960 / float(np.mean(times))
@@ -681,6 +850,7 @@ def main():
     ap.add_argument("--no-export", action="store_true", help="skip the export_clip leg (config 4 / the e2e figure of the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-hg", action="store_true", help="skip the AGCM + LE + HG workloads (line['hg'])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -22,3 +22,14 @@ if d.get("export"):
     print("export:", d["export"]["frames"], "frames", f"{d['export']['frames_per_s']:.1f} frames/s", d["export"]["descriptors"]["match_serial_single_gpu_checksums"])
 if d.get("cpu_baseline"):
     print("cpu:", d["cpu_baseline"]["value"], d["cpu_baseline"]["kind"], d["cpu_baseline"]["cores"])
+for wl, e in (d.get("hg") or {}).items():
+    if "error" in e:
+        print(f"hg {wl}: ERROR {e['error']}")
+        continue
+    rf = e["roofline"]
+    print(f"hg {wl}: value {e['value']:.1f} e2e {e['e2e']['value']:.1f} frames/s ms/step {e['ms_per_step']:.3f}; HG stage {rf['ms_per_frame']:.3f} ms "
+          f"{rf['achieved']:.0f} TFLOP/s frac {rf['frac']:.3f} (burst {rf['frac_of_burst_peak']:.3f})")
+    for t in rf["top_kernels"]:
+        print(f"   {t['launch'][:44]:44s} {t['ms']:.4f} ms {t['achieved_tflops']:.0f} TF")
+    if e.get("gpu_eager_baseline"):
+        print("   gpu eager reference (with HG):", {k: v for k, v in e["gpu_eager_baseline"].items() if k != "what"})
