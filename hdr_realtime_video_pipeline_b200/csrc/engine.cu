@@ -216,6 +216,9 @@ struct HgState {
   std::map<std::string, float*> wd;             // FP32 path: device copies
   std::map<std::string, __half*> wpk;           // FP16 path: packed B operands
   HgTail* d_tail = nullptr;
+  float *d_dot_up = nullptr, *d_dot_skip = nullptr;   // conv10's weights split by producer, [3][64] each
+  float* d_part = nullptr;                      // conv10 partial sums written by the *_DOT epilogues, [6][3][Hp][Wp]
+  bool fuse_conv10 = true;
   std::vector<void*> wallocs;
   int H = 0, W = 0, Hp = 0, Wp = 0, sms = 148;
   std::vector<void*> ws;

@@ -29,7 +29,10 @@
 namespace hdrtv {
 
 enum GKind : int { G_3x3 = 0, G_3x3_C8 = 1, G_1x1 = 2 };
-enum GEpi : int { GE_P8 = 0, GE_POOL = 1, GE_PS = 2 };
+// GE_POOL_DOT / GE_PS_DOT: the layer's full-resolution output feeds only conv10 (1x1, 128 -> 3): instead of storing it
+// (128 B/px written and read back), the epilogue multiplies the half-rounded activations with conv10's weights and stores
+// the per-warp partial sums (3 floats per pixel and slice); hg_tail_dot_kernel adds the slices in a fixed order.
+enum GEpi : int { GE_P8 = 0, GE_POOL = 1, GE_PS = 2, GE_POOL_DOT = 3, GE_PS_DOT = 4 };
 constexpr int kGRows = 4;                       // output rows per tile (accumulators in TMEM)
 constexpr int kGThreads = 320;
 
@@ -69,13 +72,29 @@ struct GConvParams {
   P8 out;                    // GE_P8: H x W; GE_POOL: H/2 x W/2; GE_PS: 2H x 2W
   P8 out_full;               // GE_POOL: optional store of the un-pooled rows (skip connection)
   int has_full;
+  const float* dot_w;        // *_DOT: conv10 weights of this layer's channels, [3][channels] (half-rounded values)
+  float* dot_out;            // *_DOT: partial sums, [slices][3][dot_H][dot_W] planar fp32; slice = ntile * 2 + half
+  int dot_H, dot_W;
   int* err;
 };
+
+// 8 half-rounded channel values of one pixel x conv10 weights of channels [ch0, ch0 + 8) -> 3 partial sums
+__device__ __forceinline__ void dot3_acc(const float* val, const float* __restrict__ w, int channels, int ch0, float* acc) {
+  float f[8];
+  unpack8(pack8(val), f);                     // the tensor conv10 reads is a half tensor
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + k * channels + ch0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + k * channels + ch0 + 4));
+    acc[k] = fmaf(f[0], w0.x, acc[k]); acc[k] = fmaf(f[1], w0.y, acc[k]); acc[k] = fmaf(f[2], w0.z, acc[k]); acc[k] = fmaf(f[3], w0.w, acc[k]);
+    acc[k] = fmaf(f[4], w1.x, acc[k]); acc[k] = fmaf(f[5], w1.y, acc[k]); acc[k] = fmaf(f[6], w1.z, acc[k]); acc[k] = fmaf(f[7], w1.w, acc[k]);
+  }
+}
 
 template <int KIND, int NT, int EPI>
 __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_constant__ GConvParams p) {
   static_assert(NT == 64 || NT == 128, "N tile");
-  static_assert(EPI != GE_PS || NT == 128, "PixelShuffle epilogue: 128 conv channels = 32 output channels per tile");
+  static_assert((EPI != GE_PS && EPI != GE_PS_DOT) || NT == 128, "PixelShuffle epilogue: 128 conv channels = 32 output channels per tile");
   constexpr int PL = g_planes(KIND), ROWS = g_rows(KIND), NSTEPS = g_steps(KIND), S = g_stages(KIND);
   constexpr uint32_t A_BYTES = g_a_bytes(KIND), STAGE = g_stage_bytes(KIND, NT), BLK = NT * 32u;
   constexpr uint32_t kTmemCols = kGRows * NT;
@@ -225,10 +244,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
             }
           }
         }
-      } else if constexpr (EPI == GE_POOL) {
+      } else if constexpr (EPI == GE_POOL || EPI == GE_POOL_DOT) {
         ColRef out, full;
         out.init(p.out, x >> 1);
-        if (p.has_full) full.init(p.out_full, x);
+        if (EPI == GE_POOL && p.has_full) full.init(p.out_full, x);
         const int j0 = nt * (NT / 8) + half * CH;
 #pragma unroll 1
         for (int rp = 0; rp < kGRows / 2; ++rp) {
@@ -251,7 +270,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
           for (int k = 0; k < COLS; ++k) {
             if (relu) { a[k] = fmaxf(a[k], 0.f); b[k] = fmaxf(b[k], 0.f); }
           }
-          if (p.has_full && in) {
+          if constexpr (EPI == GE_POOL_DOT) {
+            if (in) {
+              float da[3] = {0.f, 0.f, 0.f}, db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+              for (int c = 0; c < CH; ++c) {
+                dot3_acc(a + 8 * c, p.dot_w, p.ntiles * NT, (j0 + c) * 8, da);
+                dot3_acc(b + 8 * c, p.dot_w, p.ntiles * NT, (j0 + c) * 8, db);
+              }
+              const long plane = static_cast<long>(p.dot_H) * p.dot_W;
+              float* o = p.dot_out + static_cast<long>(nt * 2 + half) * 3 * plane + static_cast<long>(y) * p.dot_W + x;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) { o[k * plane] = da[k]; o[k * plane + p.dot_W] = db[k]; }
+            }
+          } else if (p.has_full && in) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               *full.at(y, j0 + c) = pack8(a + 8 * c);
@@ -273,8 +305,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         // PixelShuffle(2) + ReLU: conv channel n = 4*c + 2*i + j -> output channel c at (2y + i, 2x + j).
         // This warp: conv channels [nt*128 + 64*half, +64) = output chunks nt*4 + 2*half, +1 of all four sub-pixels.
         ColRef out[2];
-        out[0].init(p.out, 2 * x);
-        out[1].init(p.out, 2 * x + 1);
+        if constexpr (EPI == GE_PS) {
+          out[0].init(p.out, 2 * x);
+          out[1].init(p.out, 2 * x + 1);
+        }
         const int j0 = nt * 4 + half * 2;
 #pragma unroll 1
         for (int r = 0; r < kGRows; ++r) {
@@ -289,6 +323,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
           if (x < p.W && y < p.H) {
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
+              float d[3] = {0.f, 0.f, 0.f};
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 float val[8];
@@ -297,7 +332,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
                   const float u = v[32 * c + 4 * cc + sub];
                   val[cc] = relu ? fmaxf(u, 0.f) : u;
                 }
-                *out[sub & 1].at(2 * y + (sub >> 1), j0 + c) = pack8(val);
+                if constexpr (EPI == GE_PS) *out[sub & 1].at(2 * y + (sub >> 1), j0 + c) = pack8(val);
+                else dot3_acc(val, p.dot_w, p.ntiles * 32, (j0 + c) * 8, d);
+              }
+              if constexpr (EPI == GE_PS_DOT) {
+                const long plane = static_cast<long>(p.dot_H) * p.dot_W;
+                float* o = p.dot_out + static_cast<long>(nt * 2 + half) * 3 * plane + static_cast<long>(2 * y + (sub >> 1)) * p.dot_W + 2 * x + (sub & 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o[k * plane] = d[k];
               }
             }
           }
@@ -388,6 +430,37 @@ __global__ void __launch_bounds__(128) hg_tail_kernel(P8 up, P8 skip, P8 img, co
     for (int i = 0; i < 3; ++i) v = fmaf(c10[i], s.wl[k][i], v);
 #pragma unroll
     for (int i = 0; i < 3; ++i) v = fmaf(im[i], s.wl[k][3 + i], v);
+    v = __half2float(__float2half_rn(v));
+    out[k * plane + o] = __fadd_rn(__fmul_rn(mask, v), im[k]);
+  }
+}
+
+// The same tail when conv10's two halves were reduced by the producers' epilogues (GE_POOL_DOT / GE_PS_DOT): `part` holds
+// `slices` partial sums per pixel and output channel, [slices][3][Hp][Wp]; they are added in slice order (bit-reproducible).
+__global__ void __launch_bounds__(128) hg_tail_dot_kernel(const float* __restrict__ part, int slices, int Hp, int Wp, P8 img,
+                                                          const HgTail* __restrict__ tw, float* __restrict__ out, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  const long pp = static_cast<long>(Hp) * Wp, po = static_cast<long>(y) * Wp + x;
+  float acc[3] = {__ldg(&tw->b10[0]), __ldg(&tw->b10[1]), __ldg(&tw->b10[2])};
+  for (int s = 0; s < slices; ++s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] += __ldcg(part + (static_cast<long>(s) * 3 + k) * pp + po);
+  }
+  float im[8];
+  unpack8(__ldcg(reinterpret_cast<const uint4*>(img.base) + img.entry(y, 0, x)), im);
+  float c10[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c10[k] = __half2float(__float2half_rn(acc[k]));
+  const float mask = hg_mask_half(fmaxf(im[0], fmaxf(im[1], im[2])));
+  const long plane = static_cast<long>(H) * W, o = static_cast<long>(y) * W + x;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = __ldg(&tw->bl[k]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v = fmaf(c10[i], __ldg(&tw->wl[k][i]), v);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v = fmaf(im[i], __ldg(&tw->wl[k][3 + i]), v);
     v = __half2float(__float2half_rn(v));
     out[k * plane + o] = __fadd_rn(__fmul_rn(mask, v), im[k]);
   }

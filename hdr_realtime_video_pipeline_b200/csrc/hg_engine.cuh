@@ -23,6 +23,7 @@ static void hg_release_ws(Ctx* c) {
   c->hg.H = c->hg.W = 0;
   c->hg.proc_out = nullptr;
   c->hg.proc_H = c->hg.proc_W = 0;
+  c->hg.d_part = nullptr;
 }
 static void hg_release_weights(Ctx* c) {
   for (void* p : c->hg.wallocs) cudaFree(p);
@@ -31,6 +32,7 @@ static void hg_release_weights(Ctx* c) {
   c->hg.wd.clear();
   c->hg.w.clear();
   c->hg.d_tail = nullptr;
+  c->hg.d_dot_up = c->hg.d_dot_skip = nullptr;
   c->hg.has = false;
 }
 template <typename T>
@@ -178,6 +180,13 @@ static int hg_set_weights(Ctx* c, const hdrtv_tensor_desc* t, int n) {
     }
     c->hg.d_tail = hg_w_upload(c, tw.get(), 1);
     if (!c->hg.d_tail) return fail(c, "hdrtv_set_hg_weights: upload failed for the tail");
+    // conv10's weights split by producer (cat((Up_conv5 output, conv1_out), 1)): [3][64] each, for the *_DOT epilogues
+    std::vector<float> dup(3 * 64), dsk(3 * 64);
+    for (int k = 0; k < 3; ++k)
+      for (int i = 0; i < 64; ++i) { dup[k * 64 + i] = tw->w10[k][i]; dsk[k * 64 + i] = tw->w10[k][64 + i]; }
+    c->hg.d_dot_up = hg_w_upload(c, dup.data(), dup.size());
+    c->hg.d_dot_skip = hg_w_upload(c, dsk.data(), dsk.size());
+    if (!c->hg.d_dot_up || !c->hg.d_dot_skip) return fail(c, "hdrtv_set_hg_weights: upload failed for the conv10 split");
   } else {
     for (auto& kv : c->hg.w) {
       float* d = hg_w_upload(c, kv.second.v.data(), kv.second.v.size());
@@ -225,10 +234,21 @@ static int hg_add(Ctx* c, const char* layer, int epi, const P8& in0, const P8* i
   p.out = out;
   if (out_full) { p.out_full = *out_full; p.has_full = 1; }
   p.err = c->d_err;
+  const bool pool = epi == GE_POOL || epi == GE_POOL_DOT;
   const int expect_c = epi == GE_PS ? spec->cout / 4 : spec->cout;
-  const int eh = epi == GE_POOL ? p.H / 2 : (epi == GE_PS ? 2 * p.H : p.H), ew = epi == GE_POOL ? p.W / 2 : (epi == GE_PS ? 2 * p.W : p.W);
-  if (out.chunks * 8 != expect_c || out.H != eh || out.W != ew) return fail(c, std::string("hg plan: output tensor mismatch for ") + layer);
-  if (epi == GE_POOL && ((p.H | p.W) & 1)) return fail(c, std::string("hg plan: pooled layer needs even dimensions: ") + layer);
+  const int eh = pool ? p.H / 2 : (epi == GE_PS ? 2 * p.H : p.H), ew = pool ? p.W / 2 : (epi == GE_PS ? 2 * p.W : p.W);
+  if (epi != GE_PS_DOT && (out.chunks * 8 != expect_c || out.H != eh || out.W != ew)) return fail(c, std::string("hg plan: output tensor mismatch for ") + layer);
+  if (pool && ((p.H | p.W) & 1)) return fail(c, std::string("hg plan: pooled layer needs even dimensions: ") + layer);
+  if (epi == GE_POOL_DOT || epi == GE_PS_DOT) {
+    // conv10 folded into this producer: partial sums into slices [first, first + 2 * ntiles) of the context's buffer
+    const bool skip = epi == GE_POOL_DOT;
+    const int Hd = skip ? p.H : 2 * p.H, Wd2 = skip ? p.W : 2 * p.W;
+    if (!c->hg.d_part || (skip ? spec->cout : spec->cout / 4) != 64) return fail(c, std::string("hg plan: conv10 fold needs a 64-channel producer: ") + layer);
+    p.dot_w = skip ? c->hg.d_dot_skip : c->hg.d_dot_up;
+    p.dot_out = c->hg.d_part + static_cast<long>(skip ? 0 : 2) * 3 * Hd * Wd2;
+    p.dot_H = Hd;
+    p.dot_W = Wd2;
+  }
   L.kind = sh.kind;
   L.NT = sh.NT;
   L.epi = epi;
@@ -252,6 +272,8 @@ static cudaError_t hg_launch_t(const HgLaunch& L, cudaStream_t s) {
 }
 static cudaError_t hg_launch(const HgLaunch& L, cudaStream_t s) {
   if (L.kind == G_3x3_C8 && L.NT == 64 && L.epi == GE_POOL) return hg_launch_t<G_3x3_C8, 64, GE_POOL>(L, s);
+  if (L.kind == G_3x3_C8 && L.NT == 64 && L.epi == GE_POOL_DOT) return hg_launch_t<G_3x3_C8, 64, GE_POOL_DOT>(L, s);
+  if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_PS_DOT) return hg_launch_t<G_3x3, 128, GE_PS_DOT>(L, s);
   if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_P8) return hg_launch_t<G_3x3, 128, GE_P8>(L, s);
   if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_POOL) return hg_launch_t<G_3x3, 128, GE_POOL>(L, s);
   if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_PS) return hg_launch_t<G_3x3, 128, GE_PS>(L, s);
@@ -278,13 +300,20 @@ static int hg_prepare(Ctx* c, int H, int Wd) {
   if (c->precision == HDRTV_FP16) {
     auto& T = c->hg.t;
     auto mk = [&](const char* n, int C, int l) { T[n] = hg_make_p8(c, C, h[l], w[l]); return T[n].base != nullptr; };
-    bool ok = mk("img", 8, 0) && mk("c1", 64, 0) && mk("p1", 64, 1) && mk("c2", 128, 1) && mk("p31", 256, 2) && mk("c3", 256, 2) &&
+    // conv10 (1x1 on cat(Up_conv5 output, conv1_out)) folded into its two producers' epilogues: neither 64-channel
+    // full-resolution tensor reaches HBM (2 x 128 B/px written + read), only 6 slices of 3 partial sums (72 B/px)
+    const bool fuse = env_int("HDRTV_HG_FUSE_CONV10", 1) != 0;
+    c->hg.fuse_conv10 = fuse;
+    c->hg.d_part = fuse ? hg_ws_alloc<float>(c, static_cast<size_t>(6) * 3 * Hp * Wp, false) : nullptr;
+    if (fuse && !c->hg.d_part) return fail(c, "hdrtv_hg: workspace allocation failed");
+    bool ok = mk("img", 8, 0) && (fuse || mk("c1", 64, 0)) && mk("p1", 64, 1) && mk("c2", 128, 1) && mk("p31", 256, 2) && mk("c3", 256, 2) &&
               mk("p41", 512, 3) && mk("c4", 512, 3) && mk("p51", 512, 4) && mk("c5", 512, 4) && mk("pc1", 512, 5) && mk("code", 512, 5) &&
               mk("u1", 512, 4) && mk("c6", 512, 4) && mk("u2", 512, 3) && mk("c7", 256, 3) && mk("u3", 256, 2) && mk("c8", 128, 2) &&
-              mk("u4", 128, 1) && mk("c9", 64, 1) && mk("u5", 64, 0);
+              mk("u4", 128, 1) && mk("c9", 64, 1) && (fuse || mk("u5", 64, 0));
     if (!ok) return fail(c, "hdrtv_hg: workspace allocation failed");
     int r = 0;
-    r |= hg_add(c, "conv1.0", GE_POOL, T["img"], nullptr, T["p1"], &T["c1"], true);
+    if (fuse) r |= hg_add(c, "conv1.0", GE_POOL_DOT, T["img"], nullptr, T["p1"], nullptr, true);
+    else r |= hg_add(c, "conv1.0", GE_POOL, T["img"], nullptr, T["p1"], &T["c1"], true);
     r |= hg_add(c, "conv2.0", GE_P8, T["p1"], nullptr, T["c2"], nullptr, true);
     r |= hg_add(c, "conv3_1.0", GE_POOL, T["c2"], nullptr, T["p31"], nullptr, true);
     r |= hg_add(c, "conv3_2.0", GE_P8, T["p31"], nullptr, T["c3"], nullptr, true);
@@ -302,7 +331,8 @@ static int hg_prepare(Ctx* c, int H, int Wd) {
     r |= hg_add(c, "conv8", GE_P8, T["u3"], &T["c3"], T["c8"], nullptr, false);
     r |= hg_add(c, "Up_conv4.0", GE_PS, T["c8"], nullptr, T["u4"], nullptr, true);
     r |= hg_add(c, "conv9", GE_P8, T["u4"], &T["c2"], T["c9"], nullptr, false);
-    r |= hg_add(c, "Up_conv5.0", GE_PS, T["c9"], nullptr, T["u5"], nullptr, true);
+    if (fuse) r |= hg_add(c, "Up_conv5.0", GE_PS_DOT, T["c9"], nullptr, T["c9"], nullptr, true);
+    else r |= hg_add(c, "Up_conv5.0", GE_PS, T["c9"], nullptr, T["u5"], nullptr, true);
     if (r) return -1;
   } else {
     auto& B = c->hg.f32;
@@ -361,7 +391,10 @@ static int hg_run(Ctx* c, const void* base_out, int H, int Wd, float* out, cudaS
       CK(c, hg_launch(L, s));
       ++c->launches;
     }
-    hg_tail_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(T.at("u5"), T.at("c1"), T.at("img"), c->hg.d_tail, out, H, Wd);
+    if (c->hg.fuse_conv10)
+      hg_tail_dot_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(c->hg.d_part, 6, Hp, Wp, T.at("img"), c->hg.d_tail, out, H, Wd);
+    else
+      hg_tail_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(T.at("u5"), T.at("c1"), T.at("img"), c->hg.d_tail, out, H, Wd);
     CK(c, cudaGetLastError());
     ++c->launches;
     return 0;
