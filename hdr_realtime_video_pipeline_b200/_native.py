@@ -47,6 +47,7 @@ _SIGNATURES = {
     "hdrtv_process_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hdrtv_process_output": (C.c_void_p, [C.c_void_p, C.c_int]),
     "hdrtv_set_transfer_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hdrtv_letterbox_bgr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "hdrtv_set_hg_weights": (C.c_int, [C.c_void_p, C.POINTER(TensorDesc), C.c_int]),
     "hdrtv_hg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hdrtv_hg_time_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int,

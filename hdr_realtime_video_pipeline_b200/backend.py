@@ -503,6 +503,34 @@ class HDRTVNetB200:
                 raise RuntimeError("hdrtv_hg_time_plan failed: " + _native.last_error(self._handle, self._lib))
         return list(zip(names.value.decode().strip().split("\n"), [float(ms[i]) for i in range(n)]))
 
+    # ------------------------------------------------------------------ letterbox (gui_scaling.py:228-244)
+    @torch.inference_mode()
+    def letterbox_bgr(self, frame, out_w: int, out_h: int):
+        """`_letterbox_bgr(frame, out_w, out_h)` on the GPU: aspect-preserving resize (INTER_AREA when shrinking,
+        INTER_CUBIC when enlarging) centred on a black canvas.  uint8 HxWx3 numpy array in -> numpy array out (like the
+        reference's host function), or CUDA uint8 tensor in -> CUDA tensor out (feed it to preprocess_device /
+        process_rgb48 without leaving the device).  A frame that already has the requested size is returned as is."""
+        is_np = isinstance(frame, np.ndarray)
+        if is_np:
+            if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+                raise ValueError("frame must be a uint8 HxWx3 BGR array")
+        elif not (isinstance(frame, torch.Tensor) and frame.device.type == "cuda" and frame.dtype == torch.uint8
+                  and frame.dim() == 3 and frame.shape[2] == 3):
+            raise ValueError("frame must be a uint8 HxWx3 numpy array or CUDA tensor")
+        h, w = int(frame.shape[0]), int(frame.shape[1])
+        out_w, out_h = int(out_w), int(out_h)
+        if w == out_w and h == out_h:
+            return frame
+        with torch.cuda.device(self.device):
+            src = torch.from_numpy(np.ascontiguousarray(frame)).to(self.device, non_blocking=False) if is_np else frame.contiguous()
+            dst = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device=self.device)
+            self._check(self._lib.hdrtv_letterbox_bgr(self._handle, src.data_ptr(), h, w, dst.data_ptr(), out_h, out_w, self._stream()),
+                        "hdrtv_letterbox_bgr")
+            if not is_np:
+                src.record_stream(torch.cuda.current_stream(self.device))
+                return dst
+            return dst.cpu().numpy()
+
     # ------------------------------------------------------------------ postprocess (hdrtvnet_torch.py:2352-2368)
     @torch.inference_mode()
     def postprocess(self, output):

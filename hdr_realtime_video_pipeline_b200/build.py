@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libhdrtv_b200.so")
 OUT_TEST = os.path.join(_HERE, "libhdrtv_b200_test.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", "conv_p8.cuh", "chain_p8.cuh", "conv2x_p8.cuh", "conv3z_pair.cuh", "hg.cuh", "hg_engine.cuh", "probes.cuh", "kernels_f32.cuh", "kernels_io.cuh",
+HEADERS = ["common.cuh", "ptx.cuh", "conv_p8.cuh", "chain_p8.cuh", "conv2x_p8.cuh", "conv3z_pair.cuh", "hg.cuh", "hg_engine.cuh", "letterbox_engine.cuh", "probes.cuh", "kernels_f32.cuh", "kernels_io.cuh",
            os.path.join("..", "..", "include", "hdrtv_b200.h"), os.path.join("..", "..", "include", "hdrtv_b200_test.h")]
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17"]

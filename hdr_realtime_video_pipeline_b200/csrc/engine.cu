@@ -230,6 +230,12 @@ struct HgState {
   int proc_H = 0, proc_W = 0;
 };
 
+struct LetterboxState {                 // GPU letterbox (kernels_io.cuh letterbox_kernel): tables of the current geometry
+  Letterbox p;
+  int key[4] = {0, 0, 0, 0};            // src H, W, canvas H, W
+  std::vector<void*> allocs;
+};
+
 struct DebugTensor {
   std::string name;
   int C, H, W;
@@ -301,6 +307,7 @@ struct Ctx {
   cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
   unsigned long long* d_cksum = nullptr;      // [2] frame checksums of the two RGB48 staging slots (hdrtv_process_ex)
   HgState hg;                                 // HG stage (hg.cuh / hg_engine.cuh)
+  LetterboxState lb;
 };
 
 static int fail(Ctx* c, const std::string& m) {
@@ -2124,6 +2131,7 @@ static int run_fp16(Ctx* c, const __half* x, const __half* cond, __half* out, __
 
 
 #include "hg_engine.cuh"
+#include "letterbox_engine.cuh"
 
 #ifdef HDRTV_TEST_EXPORTS
 // ------------------------------------------------------------------------------------------------
@@ -2239,6 +2247,7 @@ void hdrtv_destroy(hdrtv_t* c) {
   release_workspace(c);
   hg_release_ws(c);
   hg_release_weights(c);
+  lb_release(c);
   for (void* p : c->weight_allocs) cudaFree(p);
   if (c->d_err) cudaFree(c->d_err);
   if (c->d_lut) cudaFree(c->d_lut);
@@ -2626,6 +2635,24 @@ static int pack_rgb48_impl(hdrtv_t* c, const void* src, int dtype, int H, int Wd
 
 int hdrtv_pack_rgb48(hdrtv_t* c, const void* src, int dtype, int H, int Wd, uint16_t* dst, int transfer, void* stream) {
   return pack_rgb48_impl(c, src, dtype, H, Wd, dst, transfer, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int hdrtv_letterbox_bgr(hdrtv_t* c, const uint8_t* src, int H, int Wd, uint8_t* dst, int out_H, int out_W, void* stream) {
+  if (!c || !src || !dst) return fail(c, "hdrtv_letterbox_bgr: null argument");
+  if (H < 1 || Wd < 1 || out_H < 1 || out_W < 1) return fail(c, "hdrtv_letterbox_bgr: bad size");
+  cudaSetDevice(c->device);
+  try {
+    if (lb_prepare(c, H, Wd, out_H, out_W)) return -1;
+  } catch (const std::exception& e) {
+    return fail(c, std::string("hdrtv_letterbox_bgr: ") + e.what());
+  }
+  Letterbox p = c->lb.p;
+  p.src = src;
+  p.dst = dst;
+  letterbox_kernel<<<dim3((out_W + 255) / 256, out_H), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CK(c, cudaGetLastError());
+  ++c->launches;
+  return 0;
 }
 
 int hdrtv_set_hg_weights(hdrtv_t* c, const hdrtv_tensor_desc* t, int n) {

@@ -374,6 +374,107 @@ __global__ void planar_to_p8_kernel(const __half* __restrict__ src, P8 dst, int 
   reinterpret_cast<uint4*>(dst.base)[dst.entry(y, 0, x)] = *reinterpret_cast<const uint4*>(v);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Letterbox (gui_scaling.py:228-244 `_letterbox_bgr`): aspect-preserving cv2.resize (INTER_AREA when shrinking,
+// INTER_CUBIC when enlarging) centred on a black canvas, uint8 HxWx3 in and out, one thread per canvas pixel.
+// The arithmetic is OpenCV's own (modules/imgproc/src/resize.cpp, restated in oracle/hdrtvnet_oracle.py and pinned
+// against cv2 there), operation by operation so that the bytes are identical:
+//   LB_AREA_INT  integer factors: block sum; 2x2 -> (s + 2) >> 2, else rint(float(s) * float(1 / area))
+//   LB_AREA      general: fp32 table weights, horizontal then vertical accumulation in table order, every product
+//                rounded before it is added (__fmul_rn / __fadd_rn: no FMA contraction)
+//   LB_CUBIC     a = -0.75 weights as shorts (x 2048); horizontal pass exact in int32 over replicate-clamped taps;
+//                vertical pass in fp32 (S3*b3, S2*b2 + ., S1*b1 + ., S0*b0 + .) with b = short * 2^-22, rint; the last
+//                (new_w * 3) mod 8 bytes of a row use the fixed-point form (the scalar tail of OpenCV's vector loop)
+// ---------------------------------------------------------------------------------------------------------------------
+enum { LB_COPY = 0, LB_AREA_INT = 1, LB_AREA = 2, LB_CUBIC = 3 };
+struct Letterbox {
+  const uint8_t* src;
+  uint8_t* dst;
+  int H, W, out_H, out_W, new_H, new_W, y0, x0, mode;
+  int fy, fx;                       // LB_AREA_INT: integer factors
+  const int* xofs; const int* yofs; // LB_AREA: first source index per destination index; LB_CUBIC: 4 clamped tap indices
+  const int* xcnt; const int* ycnt; // LB_AREA: taps per destination index
+  const float* xw; const float* yw; // LB_AREA: [dst][K] weights; LB_CUBIC: yw = [dst][4] short weights * 2^-22
+  const int* xi; const int* yi;     // LB_CUBIC: [dst][4] short weights (as int)
+  int KX, KY;
+};
+__device__ __forceinline__ uint8_t lb_sat(float v) { return static_cast<uint8_t>(min(max(__float2int_rn(v), 0), 255)); }
+__global__ void __launch_bounds__(256) letterbox_kernel(const Letterbox p) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  if (X >= p.out_W) return;
+  uint8_t* o = p.dst + (static_cast<long>(Y) * p.out_W + X) * 3;
+  const int dx = X - p.x0, dy = Y - p.y0;
+  if (dx < 0 || dx >= p.new_W || dy < 0 || dy >= p.new_H) { o[0] = 0; o[1] = 0; o[2] = 0; return; }
+  const long rs = static_cast<long>(p.W) * 3;
+  if (p.mode == LB_COPY) {
+    const uint8_t* s = p.src + dy * rs + dx * 3;
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+  } else if (p.mode == LB_AREA_INT) {
+    int s0 = 0, s1 = 0, s2 = 0;
+    for (int ky = 0; ky < p.fy; ++ky) {
+      const uint8_t* s = p.src + (static_cast<long>(dy) * p.fy + ky) * rs + static_cast<long>(dx) * p.fx * 3;
+      for (int kx = 0; kx < p.fx; ++kx) { s0 += s[3 * kx]; s1 += s[3 * kx + 1]; s2 += s[3 * kx + 2]; }
+    }
+    if (p.fx == 2 && p.fy == 2) { o[0] = (s0 + 2) >> 2; o[1] = (s1 + 2) >> 2; o[2] = (s2 + 2) >> 2; }
+    else {
+      const float sc = 1.f / static_cast<float>(p.fx * p.fy);
+      o[0] = lb_sat(__fmul_rn(static_cast<float>(s0), sc));
+      o[1] = lb_sat(__fmul_rn(static_cast<float>(s1), sc));
+      o[2] = lb_sat(__fmul_rn(static_cast<float>(s2), sc));
+    }
+  } else if (p.mode == LB_AREA) {
+    const int sx0 = p.xofs[dx], nx = p.xcnt[dx], sy0 = p.yofs[dy], ny = p.ycnt[dy];
+    const float* xw = p.xw + static_cast<long>(dx) * p.KX;
+    const float* yw = p.yw + static_cast<long>(dy) * p.KY;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int ky = 0; ky < ny; ++ky) {
+      const uint8_t* s = p.src + (sy0 + ky) * rs + static_cast<long>(sx0) * 3;
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+      for (int kx = 0; kx < nx; ++kx) {
+        const float w = xw[kx];
+        b0 = __fadd_rn(b0, __fmul_rn(static_cast<float>(s[3 * kx]), w));
+        b1 = __fadd_rn(b1, __fmul_rn(static_cast<float>(s[3 * kx + 1]), w));
+        b2 = __fadd_rn(b2, __fmul_rn(static_cast<float>(s[3 * kx + 2]), w));
+      }
+      const float b = yw[ky];
+      a0 = ky ? __fadd_rn(a0, __fmul_rn(b0, b)) : __fmul_rn(b0, b);
+      a1 = ky ? __fadd_rn(a1, __fmul_rn(b1, b)) : __fmul_rn(b1, b);
+      a2 = ky ? __fadd_rn(a2, __fmul_rn(b2, b)) : __fmul_rn(b2, b);
+    }
+    o[0] = lb_sat(a0); o[1] = lb_sat(a1); o[2] = lb_sat(a2);
+  } else {
+    int hr[4][3];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const uint8_t* s = p.src + p.yofs[dy * 4 + ky] * rs;
+      int h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const uint8_t* q = s + static_cast<long>(p.xofs[dx * 4 + kx]) * 3;
+        const int a = p.xi[dx * 4 + kx];
+        h0 += q[0] * a; h1 += q[1] * a; h2 += q[2] * a;
+      }
+      hr[ky][0] = h0; hr[ky][1] = h1; hr[ky][2] = h2;
+    }
+    const int flat = p.new_W * 3, tail0 = flat - (flat & 7);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (dx * 3 + c >= tail0) {        // scalar tail of the vector loop: fixed point
+        long f = 0;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) f += static_cast<long>(hr[ky][c]) * p.yi[dy * 4 + ky];
+        o[c] = static_cast<uint8_t>(min(max(static_cast<int>((f + (1 << 21)) >> 22), 0), 255));
+      } else {
+        float acc = __fmul_rn(static_cast<float>(hr[3][c]), p.yw[dy * 4 + 3]);
+        acc = __fadd_rn(__fmul_rn(static_cast<float>(hr[2][c]), p.yw[dy * 4 + 2]), acc);
+        acc = __fadd_rn(__fmul_rn(static_cast<float>(hr[1][c]), p.yw[dy * 4 + 1]), acc);
+        acc = __fadd_rn(__fmul_rn(static_cast<float>(hr[0][c]), p.yw[dy * 4 + 0]), acc);
+        o[c] = lb_sat(acc);
+      }
+    }
+  }
+}
+
 // debug: P8 -> planar fp32 (C,H,W)
 __global__ void p8_to_planar_f32_kernel(P8 src, int j0, int C, float* dst) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;

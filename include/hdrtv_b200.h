@@ -108,6 +108,14 @@ int hdrtv_process_ex(hdrtv_t* h, const uint8_t* bgr, int height, int width, uint
 int hdrtv_process_flush(hdrtv_t* h, void* stream);          /* `stream` waits for the copy-out stream's pending copies */
 const void* hdrtv_process_output(const hdrtv_t* h, int which); /* device (1,3,H,W) out (0) / agcm_out (1) / fp32 HG out (2) of the last frame */
 
+/* _letterbox_bgr (src/gui_scaling.py:228-244), the resize the frame loop applies before preprocess                          */
+/* (gui_pipeline_worker_frame_processing.py): aspect-preserving cv2.resize - INTER_AREA when shrinking, INTER_CUBIC when    */
+/* enlarging, size = round(src * min(out_w / w, out_h / h)) - centred on a black canvas.  src = uint8 HxWx3 and             */
+/* dst = uint8 out_height x out_width x 3, both device memory.  Bytes equal OpenCV's own resize (resize.cpp) operation by  */
+/* operation; with the Intel-IPP dispatch of the pip wheel the cubic case differs from cv2 by at most one code.            */
+int hdrtv_letterbox_bgr(hdrtv_t* h, const uint8_t* src, int height, int width, uint8_t* dst, int out_height, int out_width,
+                        void* stream);
+
 /* HG stage (third HDRTVNet++ stage).  hdrtv_set_hg_weights replaces                                 */
 /* model.hg.load_state_dict(hg_state, strict=True) (hdrtvnet_torch.py:2141-2143): the Hallucination_Generator state-dict */
 /* (Hallucination_arch.py:53-98, nf = 64; 92 tensors with BatchNorm, or 42 with the FusedBN fold already applied,         */

@@ -646,3 +646,130 @@ def hg_stage(hg_sd: dict, base_out_1chw: np.ndarray, mask_r: float = 0.75):
     mpad = np.pad(mask, ((0, 0), (0, ph), (0, pw)), mode="reflect") if (ph or pw) else mask
     out = mpad * hg_unet(sd, img) + img            # Hallucination_arch.py:136
     return out[None, :, :h, :w].astype(F32)
+
+
+# --------------------------------------------------------------------------
+# Letterbox (second half): src/gui_scaling.py:228-244 `_letterbox_bgr`
+#   scale = min(out_w / w, out_h / h); new = round(size * scale); cv2.resize with INTER_AREA when shrinking, INTER_CUBIC
+#   when enlarging; centred on a black canvas.
+# cv2.resize is third-party (opencv-python 4.13 here); its published algorithm (modules/imgproc/src/resize.cpp) restated:
+#   INTER_AREA, integer factors : block sums; 2x2 -> (s + 2) >> 2, else saturate(rint(float(s) * float(1 / area)))
+#   INTER_AREA, general         : computeResizeAreaTab weights (fp32), horizontal then vertical accumulation in fp32, in
+#                                 table order, products rounded before they are added (no FMA), saturate(rint(.))
+#   INTER_CUBIC (8-bit)         : a = -0.75 cubic weights in fp32 -> short fixed point (x 2048, round-half-even);
+#                                 horizontal pass exact in int32 on replicate-clamped taps; vertical pass in fp32
+#                                 (weights x 2^-22): S3*b3, then S2*b2 + ., S1*b1 + ., S0*b0 + . (no FMA), rint, saturate
+# Pinned in tests/test_oracle_golden.py against cv2 itself: INTER_AREA bit-exact with and without IPP; INTER_CUBIC
+# bit-exact against OpenCV's own code path (cv2.ipp.setUseIPP(False)) and within 1 code of the closed-source Intel IPP
+# routine the pip wheel dispatches to by default.
+# --------------------------------------------------------------------------
+
+def letterbox_geometry(h: int, w: int, out_h: int, out_w: int):
+    """(new_h, new_w, y0, x0, shrink) of gui_scaling.py:234-243; python round() = round-half-even on the double."""
+    scale = min(out_w / max(w, 1), out_h / max(h, 1))
+    new_w = max(1, int(round(w * scale)))
+    new_h = max(1, int(round(h * scale)))
+    return new_h, new_w, (out_h - new_h) // 2, (out_w - new_w) // 2, scale < 1.0
+
+
+def _area_table(ssize: int, dsize: int):
+    """computeResizeAreaTab: list of (dst index, src index, fp32 weight)."""
+    import math
+    scale = 1.0 / (np.float64(dsize) / np.float64(ssize))
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, F32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, F32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, F32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area(img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
+    h, w, cn = img.shape
+    if h % new_h == 0 and w % new_w == 0:                                   # resizeAreaFast_
+        sy, sx = h // new_h, w // new_w
+        s = img.astype(np.int64).reshape(new_h, sy, new_w, sx, cn).sum((1, 3))
+        if sx == 2 and sy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        return np.clip(np.rint(s.astype(F32) * F32(1.0 / (sx * sy))), 0, 255).astype(np.uint8)
+    xt, yt = _area_table(w, new_w), _area_table(h, new_h)
+    src = img.astype(F32)
+    buf = np.zeros((h, new_w, cn), F32)
+    for dx, sx, a in xt:
+        buf[:, dx, :] = buf[:, dx, :] + (src[:, sx, :] * a).astype(F32)
+    out = np.zeros((new_h, new_w, cn), np.uint8)
+    prev, acc = -1, None
+    for dy, sy, b in yt:
+        if dy != prev:
+            if prev >= 0:
+                out[prev] = np.clip(np.rint(acc), 0, 255)
+            acc, prev = (buf[sy] * b).astype(F32), dy
+        else:
+            acc = acc + (buf[sy] * b).astype(F32)
+    out[prev] = np.clip(np.rint(acc), 0, 255)
+    return out
+
+
+def _cubic_table(n_src: int, n_dst: int):
+    """Tap indices (replicate-clamped) and short fixed-point weights of the 8-bit INTER_CUBIC path."""
+    scale = 1.0 / (np.float64(n_dst) / np.float64(n_src))
+    f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(F32)
+    s = np.floor(f).astype(np.int32)
+    x = (f - s.astype(F32)).astype(F32)
+    a = F32(-0.75)
+    one, two, three = F32(1), F32(2), F32(3)
+    c0 = ((a * (x + one) - F32(5) * a) * (x + one) + F32(8) * a) * (x + one) - F32(4) * a
+    c1 = ((a + two) * x - (a + three)) * x * x + one
+    y = one - x
+    c2 = ((a + two) * y - (a + three)) * y * y + one
+    c3 = one - c0 - c1 - c2
+    ic = np.rint(np.stack([c0, c1, c2, c3], -1).astype(F32) * F32(2048)).astype(np.int32)
+    idx = np.clip(s[:, None] + np.arange(-1, 3)[None, :], 0, n_src - 1)
+    return idx, ic
+
+
+def resize_cubic(img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
+    xi, xa = _cubic_table(img.shape[1], new_w)
+    yi, ya = _cubic_table(img.shape[0], new_h)
+    hor = (img.astype(np.int64)[:, xi, :] * xa[None, :, :, None]).sum(2)              # exact integers < 2^24
+    b = (ya.astype(F32) * F32(1.0 / (2048 * 2048))).astype(F32)
+    rows = hor[yi, :, :]                                                              # (new_h, 4, new_w, cn)
+    fl = rows.astype(F32)
+    acc = (fl[:, 3] * b[:, 3, None, None]).astype(F32)
+    for k in (2, 1, 0):
+        acc = ((fl[:, k] * b[:, k, None, None]).astype(F32) + acc).astype(F32)
+    out = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+    # scalar tail of OpenCV's vector loop (8 int16 lanes per step over width * channels): fixed point
+    flat = new_w * img.shape[2]
+    tail = flat - flat // 8 * 8
+    if tail:
+        fx = (rows * ya[:, :, None, None]).sum(1)
+        fixed = np.clip((fx + (1 << 21)) >> 22, 0, 255).astype(np.uint8).reshape(new_h, flat)
+        out = out.reshape(new_h, flat)
+        out[:, flat - tail:] = fixed[:, flat - tail:]
+        out = out.reshape(new_h, new_w, img.shape[2])
+    return out
+
+
+def letterbox_bgr(frame: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
+    """gui_scaling.py:228-244."""
+    h, w = frame.shape[:2]
+    if w == out_w and h == out_h:
+        return frame
+    new_h, new_w, y0, x0, shrink = letterbox_geometry(h, w, out_h, out_w)
+    if new_h == h and new_w == w:
+        resized = frame                                                               # cv2.resize to the same size copies
+    else:
+        resized = resize_area(frame, new_w, new_h) if shrink else resize_cubic(frame, new_w, new_h)
+    canvas = np.zeros((out_h, out_w, 3), dtype=frame.dtype)
+    canvas[y0:y0 + new_h, x0:x0 + new_w] = resized
+    return canvas

@@ -257,3 +257,56 @@ def test_hg_reflect_pad_and_pool_primitives():
     img = np.pad(base[0], ((0, 0), (0, 24), (0, 14)), mode="reflect")
     assert img.shape == (3, 64, 64) and np.array_equal(img[:, 40 + 3, :50], base[0, :, 40 - 2 - 3, :])
     assert np.array_equal(img[:, :40, 50 + 5], base[0, :, :, 50 - 2 - 5])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Letterbox (gui_scaling.py:228-244): the oracle restates cv2.resize (third party, opencv-python 4.13 in this image);
+# pinned against cv2 itself.  INTER_AREA: bit-exact with and without the Intel-IPP dispatch.  INTER_CUBIC: bit-exact
+# against OpenCV's own code path (IPP off); the closed-source IPP routine the wheel uses by default differs by <= 1 code.
+# ---------------------------------------------------------------------------------------------------------------------
+LETTERBOX_CASES = [(216, 384, 192, 108), (270, 480, 192, 108), (200, 300, 192, 108), (108, 192, 384, 216), (100, 133, 217, 160),
+                   (90, 160, 192, 108), (120, 160, 192, 108), (54, 96, 217, 123), (108, 192, 192, 108), (300, 200, 192, 108),
+                   (324, 576, 192, 108)]
+
+
+def _reference_letterbox(cv2, frame, out_w, out_h):
+    """gui_scaling.py:228-244, restated around the real cv2.resize."""
+    h, w = frame.shape[:2]
+    if w == out_w and h == out_h:
+        return frame
+    scale = min(out_w / max(w, 1), out_h / max(h, 1))
+    new_w = max(1, int(round(w * scale)))
+    new_h = max(1, int(round(h * scale)))
+    interp = cv2.INTER_AREA if scale < 1.0 else cv2.INTER_CUBIC
+    resized = cv2.resize(frame, (new_w, new_h), interpolation=interp)
+    canvas = np.zeros((out_h, out_w, 3), dtype=frame.dtype)
+    x, y = (out_w - new_w) // 2, (out_h - new_h) // 2
+    canvas[y:y + new_h, x:x + new_w] = resized
+    return canvas
+
+
+@pytest.mark.parametrize("case", LETTERBOX_CASES, ids=lambda c: "%dx%d_to_%dx%d" % c)
+def test_letterbox_matches_cv2(case):
+    cv2 = pytest.importorskip("cv2")
+    h, w, out_w, out_h = case
+    frame = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    mine = O.letterbox_bgr(frame, out_w, out_h)
+    ipp = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        assert np.array_equal(mine, _reference_letterbox(cv2, frame, out_w, out_h))           # OpenCV's own arithmetic: bit-exact
+        cv2.ipp.setUseIPP(True)
+        ref = _reference_letterbox(cv2, frame, out_w, out_h)
+        shrink = O.letterbox_geometry(h, w, out_h, out_w)[4]
+        d = np.abs(mine.astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= (0 if shrink else 1)                                              # IPP cubic: within one code
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+
+
+def test_letterbox_geometry_rounds_like_python():
+    # int(round(x)) is round-half-even: 2.5 -> 2, 3.5 -> 4 (gui_scaling.py:235-236)
+    assert O.letterbox_geometry(5, 10, 2, 100)[:2] == (2, 4)
+    assert O.letterbox_geometry(1080, 1920, 1080, 1920)[:2] == (1080, 1920)
+    assert O.letterbox_geometry(2160, 3840, 1080, 1920) == (1080, 1920, 0, 0, True)
+    assert O.letterbox_geometry(1080, 1440, 1080, 1920) == (1080, 1440, 0, 240, False)
