@@ -173,36 +173,49 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
     constexpr uint32_t a_lbo = (g_step_lbo(KIND) >> 4) << 16;
     uint32_t st = 0, ph = 0;
     int it = 0;
+    const bool lead = elect_one();        // the issuing lane, elected once: the loop below stays warp-uniform around it
+    // one accumulator row of one stage: 9 (6, 4) MMAs, + the bias step and the hand-over to the epilogue on the last stage
+    auto issue_row = [&](int r, uint32_t a16, uint32_t b16, bool first, bool last) {
+      const uint32_t d_tmem = tmem_base + r * NT;
+      static_for<0, NSTEPS>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int dy = g_step_dy(KIND, i);
+        constexpr uint32_t off16 = g_step_off(KIND, i) >> 4;
+        const uint32_t arow = a16 + static_cast<uint32_t>((r + dy) * PL) * (kPlaneBytes >> 4);
+        tc_mma_f16(d_tmem, mkdesc((arow + off16) | a_lbo), mkdesc(b16 + i * b_step), idesc, (first && i == 0) ? 0u : 1u);
+      });
+      if (last) {
+        tc_mma_f16(d_tmem, ones_desc, mkdesc(b16 + NSTEPS * b_step), idesc, 1u);      // + bias
+        tc_commit(tfull_bar(r));
+      }
+    };
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
       for (int kg = 0; kg < KG; ++kg) {
-        mbar_wait(full_bar(st), ph, p.err, 22);
-        tc_fence_after();
         const uint32_t a16 = (smem_u32(stage0) + st * STAGE) >> 4;
         const uint32_t b16 = ((smem_u32(stage0) + st * STAGE + A_BYTES) >> 4) | b_lbo;
         const bool first = kg == 0, last = kg == KG - 1;
+        mbar_wait(full_bar(st), ph, p.err, 22);
+        tc_fence_after();
+        if (first) {
+          // the previous tile's epilogue must have drained accumulator r: row by row, so that the first rows of this tile
+          // already run while the last rows of the previous one are still being read
 #pragma unroll
-        for (int r = 0; r < kGRows; ++r) {
-          if (first) {                     // the previous tile's epilogue must have drained accumulator r
+          for (int r = 0; r < kGRows; ++r) {
             mbar_wait(tempty_bar(r), (it & 1) ^ 1, p.err, 23);
             tc_fence_after();
+            if (lead) issue_row(r, a16, b16, true, last);
+            __syncwarp();
           }
-          const uint32_t d_tmem = tmem_base + r * NT;
-          if (elect_one()) {
-            static_for<0, NSTEPS>([&](auto ic) {
-              constexpr int i = decltype(ic)::value;
-              constexpr int dy = g_step_dy(KIND, i);
-              constexpr uint32_t off16 = g_step_off(KIND, i) >> 4;
-              const uint32_t arow = a16 + static_cast<uint32_t>((r + dy) * PL) * (kPlaneBytes >> 4);
-              tc_mma_f16(d_tmem, mkdesc((arow + off16) | a_lbo), mkdesc(b16 + i * b_step), idesc, (first && i == 0) ? 0u : 1u);
-            });
-            if (last) {
-              tc_mma_f16(d_tmem, ones_desc, mkdesc(b16 + NSTEPS * b_step), idesc, 1u);      // + bias
-              tc_commit(tfull_bar(r));
-            }
+        } else {
+          // steady state: all 36 MMAs of the stage in one straight run of the issuing lane (nothing between them but
+          // descriptor arithmetic: the pipe's queue is shallow, every detour of the issuer is idle pipe time)
+          if (lead) {
+#pragma unroll
+            for (int r = 0; r < kGRows; ++r) issue_row(r, a16, b16, false, last);
           }
           __syncwarp();
         }
-        if (elect_one()) tc_commit(empty_bar(st));
+        if (lead) tc_commit(empty_bar(st));
         __syncwarp();
         if (++st == S) { st = 0; ph ^= 1; }
       }
