@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
     grid_dep_wait();            // the epilogue overwrites buffers the previous kernel may still read
     const int g = (warp - 1) >> 2;
     const bool issuer = ((warp - 1) & 3) == (g & 3);  // this warp also issues the slot's MMAs; spread over the 4 SMSPs
+    const bool lead = elect_one();                     // the issuing lane of an issuer warp, elected once
     const int lg = warp & 3;                          // TMEM lane quadrant this warp may read
     const int m = lg * 32 + lane;                     // pixel inside the strip = TMEM lane
     const uint32_t d_tmem = tmem_base + g * kSlotCols;          // accumulator: 64 columns
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
                 mbar_wait(full_bar(slot), ph, p.err, 14);
                 tc_fence_after();
                 const uint32_t a16 = ring16 + slot * slot16;
-                if (elect_one()) {
+                if (lead) {
                   static_for<0, SPD>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
                     constexpr uint32_t a_off16 = Prog::A0_OFF[i] >> 4, a_lbo16 = Prog::A0_LBO[i] >> 4;
@@ -308,12 +309,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_p8_kernel(const __grid
                 }
                 __syncwarp();
               }
-              if (elect_one()) {
+              if (lead) {
                 tc_mma_f16(d_tmem, ones_desc, mkdesc(b_lo0 + NSTEPS * b_step), idesc, 1u);      // + bias
                 tc_commit(tfull_bar(g));
               }
             } else {
-              if (elect_one()) {
+              if (lead) {
                 // A = the previous layer's activations, written to TMEM by the epilogue (8 columns per K = 16 step)
 #pragma unroll
                 for (int i = 0; i < NSTEPS; ++i)

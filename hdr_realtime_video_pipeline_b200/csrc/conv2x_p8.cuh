@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
+    const bool lead = elect_one();         // the issuing lane of this warp, elected once
     // ------------------------------------------------------------------ MMA issuer, conv A (valid mid rows only)
     mbar_wait(wfull_bar, 0, p.err, 23);
     constexpr uint32_t b_lbo = static_cast<uint32_t>(3 * NA) << 16, b_step = 3 * NA * 2;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         const uint32_t idesc2 = make_idesc_f16_m128(static_cast<uint32_t>(NA * max(n2, 1)));
         const uint32_t b_lo1 = b_lo0 + static_cast<uint32_t>(NA * (2 - (q - lo_r))), b_lo2 = b_lo1 + static_cast<uint32_t>(NA * n1);
         const uint32_t a16 = ring16 + slot * slot16;
-        if (elect_one()) {
+        if (lead) {
           if (q < nmv)                                   // bias step: initialises the accumulator of the newest row
             tc_mma_f16(tmem_base + colA + static_cast<uint32_t>(pos_new) * NA, ones_desc, bias_desc, make_idesc_f16_m128(NA), 0u);
           static_for<0, SPDA>([&](auto ic) {
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
       g0 += nmv;
     }
   } else if (warp == 12) {
+    const bool lead = elect_one();         // the issuing lane of this warp, elected once
     // ------------------------------------------------------------------ MMA issuer, SFT stage-1 GEMM (scale | shift)
     if constexpr (SFTGA) {
       mbar_wait(wfull_bar, 0, p.err, 23);
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
             mbar_wait(st_empty(g & 1), ((g >> 1) & 1) ^ 1, p.err, 33);
             mbar_wait(in_full(slot), ph, p.err, 26);
             tc_fence_after();
-            if (elect_one()) {
+            if (lead) {
               const uint32_t sa16 = (sring16 + slot * (IN_SLOT >> 4)) | ((kPlaneBytes >> 4) << 16);
               const uint32_t s_tmem = tmem_base + colS + (g & 1) * 64;
               tc_mma_f16(s_tmem, mkdesc(sa16), mkdesc(sb16), idesc64, 0u);
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
       }
     }
   } else if (warp == 2) {
+    const bool lead = elect_one();         // the issuing lane of this warp, elected once
     // ------------------------------------------------------------------ MMA issuer, conv B (reads the mid ring)
     mbar_wait(wfull_bar, 0, p.err, 27);
     constexpr uint32_t b_lbo = static_cast<uint32_t>(3 * NB) << 16, b_step = 3 * NB * 2;
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) conv2x_p8_kernel(const __grid_c
         const uint32_t idesc2 = make_idesc_f16_m128(static_cast<uint32_t>(NB * max(n2, 1)));
         const uint32_t b_lo1 = b_lo0 + static_cast<uint32_t>(NB * (2 - (j - lo_t))), b_lo2 = b_lo1 + static_cast<uint32_t>(NB * n1);
         const uint32_t a16 = mring16 + slot * (kC2MidSlot >> 4);
-        if (elect_one()) {
+        if (lead) {
           if (j < n_out)
             tc_mma_f16(tmem_base + colB + static_cast<uint32_t>(pos_new) * NB, ones_desc, bias_desc, make_idesc_f16_m128(NB), 0u);
           static_for<0, SPDB>([&](auto ic) {

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv3z_pair_kernel(const __gr
       }
     }
   } else if (warp == 1) {
+    const bool lead = elect_one();         // the issuing lane, elected once
     // ------------------------------------------------------------------ leader: MMA issuer for the pair
     mbar_wait(wfull_bar, 0, p.err, 43);      // the follower's half: implied by its first relayed row (see the relay warp)
     constexpr uint32_t idesc = make_idesc_f16_m256(kPairN);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv3z_pair_kernel(const __gr
         mbar_wait(peer_full_bar(slot), ph, p.err, 46);
         tc_fence_after();
         const uint32_t a16 = ring16 + slot * slot16;
-        if (elect_one()) {
+        if (lead) {
           if (fin) {
             const uint32_t d = tmem_base + static_cast<uint32_t>((row_cur - 1) & 1) * kPairN;
             static_for<0, SPD>([&](auto ic) {

@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
     // elected lane issues.  Tap-step offsets are compile-time constants: the issuing warp looks nothing up while
     // the tensor pipe waits (an M=128 x N<=64 x K=16 MMA costs the pipe only ~45 cycles).
     mbar_wait(wfull_bar, 0, p.err, 2);
+    const bool lead = elect_one();         // the issuing lane, elected once (an elect.sync per row is ~50 cycles of idle pipe)
     constexpr uint32_t idesc = make_idesc_f16_m128(N);
     constexpr uint32_t idesc_i8 = make_idesc_i8_m128(N);
     (void)idesc_i8;
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         const uint32_t b1 = even ? bE0 + static_cast<uint32_t>(lo == m ? N : 0) : bO0, b2 = b1 + static_cast<uint32_t>(N * n1);
         const uint32_t bstep = even ? bE_step : bO_step;
         const uint32_t a16 = ring16 + slot * slot16;
-        if (elect_one()) {
+        if (lead) {
           if (has_new)                                         // bias step: initialises the accumulator of the newest row
             tc_mma_f16(tmem_base + static_cast<uint32_t>(m % R) * N, ones_desc, bias_desc, idesc, 0u);
           static_for<0, SPD>([&](auto ic) {
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
           tc_fence_after();
         }
         const uint32_t a16 = ring16 + slot * slot16;
-        if (elect_one()) {
+        if (lead) {
           static_for<0, SPD>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr uint32_t a_off16 = kind_a_off(KIND, KCH, i) >> 4;
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kConvThreads, (MODE == STORE_PS) ? 1 : 2) conv
         mbar_wait(sfull_bar(sslot), sph, p.err, 7);
         if (PSG && t > 0) mbar_wait(tempty_bar((t - 1) & 1), ((t - 1) >> 1) & 1, p.err, 8);
         tc_fence_after();
-        if (elect_one()) {
+        if (lead) {
           constexpr uint32_t idesc64 = make_idesc_f16_m128(64);
           const uint32_t sb = (smem_u32(wsm2) >> 4) | (64u << 16);
 #pragma unroll
