@@ -39,7 +39,7 @@ constexpr int kGThreads = 320;
 __host__ __device__ constexpr int g_planes(int k) { return k == G_3x3 ? 2 : (k == G_3x3_C8 ? 1 : 8); }      // per K group
 __host__ __device__ constexpr int g_rows(int k) { return k == G_1x1 ? kGRows : kGRows + 2; }               // A rows per stage
 __host__ __device__ constexpr int g_steps(int k) { return k == G_3x3 ? 9 : (k == G_3x3_C8 ? 6 : 4); }       // MMAs per row and group
-__host__ __device__ constexpr int g_stages(int k) { return k == G_3x3 ? 3 : 2; }
+__host__ __device__ constexpr int g_stages(int k) { return k == G_3x3 ? 3 : (k == G_3x3_C8 ? 4 : 2); }     // C8: one K group per tile, 27 KB stages: prefetch 4 tiles deep
 __host__ __device__ constexpr int g_group_channels(int k) { return k == G_3x3 ? 16 : (k == G_3x3_C8 ? 8 : 64); }
 // A operand of step i for output row r: input-row slot and byte offset inside the stage's A block, K-half distance
 __host__ __device__ constexpr int g_step_dy(int k, int i) { return k == G_3x3 ? i / 3 : (k == G_3x3_C8 ? i / 2 : 0); }
