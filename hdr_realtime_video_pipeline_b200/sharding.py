@@ -59,6 +59,14 @@ def pin_rank_to_local_cores(local_rank: int, local_world: int, device_of_rank=No
         os.sched_setaffinity(0, set(mine))
     except OSError:
         return allowed
+    # torch sized its intra-op pool for the affinity mask the process STARTED with (all cores of the box): on this rank's
+    # share that pool oversubscribes the cores (8 ranks x 32 threads on 32 cores) and every host-side tensor copy of the
+    # frame loop (the staging copy into pinned memory of `preprocess`) fights for them
+    try:
+        import torch
+        torch.set_num_threads(max(1, len(mine)))
+    except Exception:
+        pass
     return sorted(mine)
 
 
