@@ -462,7 +462,7 @@ def hg_flops(h, w):
     return per, float(sum(per.values()))
 
 
-def measure_hg(hb, torch, dev, wl, K, Wm, peaks, weights, with_reference):
+def measure_hg(hb, torch, dev, wl, K, Wm, peaks, weights, with_reference, with_cpu=False):
     """AGCM + LE + HG (HG_Composite, the full HDRTVNet++): device-resident and end-to-end frames/s, the HG stage's own
     roofline (tensor-bound: 64..2048-channel convs on the K-streamed tcgen05 kernel) with per-launch TFLOP/s, and the
     unmodified reference with the same seeded HG weights on the same GPU (CUDA FP16 eager)."""
@@ -553,7 +553,47 @@ def measure_hg(hb, torch, dev, wl, K, Wm, peaks, weights, with_reference):
     torch.cuda.empty_cache()
     if with_reference:
         res["gpu_eager_baseline"] = gpu_eager_baseline_hg(dev, host_np, hg_sd, torch)
+    if with_cpu:
+        res["cpu_baseline"] = cpu_baseline_hg(hg_sd, h, w, torch)
     return res
+
+
+def cpu_baseline_hg(hg_sd, h, w, torch):
+    """The reference's CPU eager path WITH the HG stage (setup_cpu + HG_Composite) on a bounded sample: 960x540 frames, all
+    host threads, first frame discarded; frames/s scaled by pixel count to the workload."""
+    from oracle import reference_loader as RL
+    from hdr_realtime_video_pipeline_b200.synth import synth_frame
+    ref = RL.load()
+    if ref is None:
+        return {"unavailable": "baseline/_ref not installed (scripts/install_reference.py)"}
+    try:
+        import tempfile
+        _use_all_host_threads()
+        path = os.path.join(tempfile.mkdtemp(), "HG.pt")
+        torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in hg_sd.items()}, path)
+        with contextlib.redirect_stdout(sys.stderr):
+            net = ref.HDRTVNetTorch(ref.weights("HR.pt"), device="cpu", precision="fp32", compile_model=False, use_hg=True,
+                                    hg_weights=path, warmup_passes=0)
+        sh, sw = 540, 960
+        times = []
+        t_start = time.perf_counter()
+        for i in range(6):
+            f = synth_frame(i, sh, sw)
+            t0 = time.perf_counter()
+            with torch.inference_mode():
+                net.postprocess(net.infer(net.preprocess(f)))
+            if i:
+                times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > 20.0 and len(times) >= 2:
+                break
+        px_s = sh * sw / float(np.mean(times))
+        return {"value": px_s / (h * w), "unit": "frames/s", "cores": torch.get_num_threads(), "host_cpu_count": os.cpu_count(),
+                "kind": "reference", "pixels_per_s": px_s,
+                "sample": f"{len(times)} synthetic {sw}x{sh} frames through the unmodified reference (HDRTVNetTorch device='cpu', "
+                          f"fp32, use_hg=True -> HG_Composite), first frame discarded, {float(np.mean(times)) * 1000:.0f} ms/frame; "
+                          f"frames/s scaled by pixel count to {w}x{h}"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 def gpu_eager_baseline_hg(dev, host_np, hg_sd, torch):
@@ -767,7 +807,7 @@ def run_b200_arm(args):
                 for wl in wls:
                     try:
                         line["hg"][wl] = measure_hg(hb, torch, dev, wl, min(K, 40 if wl != "4k" else 20), Wm, peaks, weights,
-                                                    not args.no_gpu_baseline)
+                                                    not args.no_gpu_baseline, with_cpu=(not args.no_cpu_baseline and wl == wls[-1]))
                     except Exception as exc:                    # the extra workload must never take the headline line down
                         line["hg"][wl] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
