@@ -237,23 +237,38 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         ColRef out;
         out.init(p.out, x);
         const int j0 = nt * (NT / 8) + half * CH;
+        // rows are drained in pairs before anything is stored: an accumulator row goes back to the MMA warp as soon as it
+        // is in registers, not after the previous row's convert / address / store chain
 #pragma unroll 1
-        for (int r = 0; r < kGRows; ++r) {
-          mbar_wait(tfull_bar(r), tpar, p.err, 24);
+        for (int rp = 0; rp < kGRows / 2; ++rp) {
+          float va[COLS], vb[COLS];
+          mbar_wait(tfull_bar(2 * rp), tpar, p.err, 24);
           tc_fence_after();
-          float v[COLS];
-          tmem_ld_cols<COLS>(tlane + r * NT, v);
+          tmem_ld_cols<COLS>(tlane + (2 * rp) * NT, va);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(r));
-          const int y = y0 + r;
-          if (x < p.W && y < p.H) {
+          if (lane == 0) mbar_arrive(tempty_bar(2 * rp));
+          mbar_wait(tfull_bar(2 * rp + 1), tpar, p.err, 24);
+          tc_fence_after();
+          tmem_ld_cols<COLS>(tlane + (2 * rp + 1) * NT, vb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(2 * rp + 1));
+          const int y = y0 + 2 * rp;
+          if (x < p.W) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               float val[8];
+              if (y < p.H) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) val[k] = relu ? fmaxf(v[c * 8 + k], 0.f) : v[c * 8 + k];
-              *out.at(y, j0 + c) = pack8(val);
+                for (int k = 0; k < 8; ++k) val[k] = relu ? fmaxf(va[c * 8 + k], 0.f) : va[c * 8 + k];
+                *out.at(y, j0 + c) = pack8(val);
+              }
+              if (y + 1 < p.H) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) val[k] = relu ? fmaxf(vb[c * 8 + k], 0.f) : vb[c * 8 + k];
+                *out.at(y + 1, j0 + c) = pack8(val);
+              }
             }
           }
         }
@@ -324,35 +339,45 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         }
         const int j0 = nt * 4 + half * 2;
 #pragma unroll 1
-        for (int r = 0; r < kGRows; ++r) {
-          mbar_wait(tfull_bar(r), tpar, p.err, 24);
+        for (int rp = 0; rp < kGRows / 2; ++rp) {
+          float vv[2][64];                             // two rows drained before either is shuffled out (see GE_P8)
+          mbar_wait(tfull_bar(2 * rp), tpar, p.err, 24);
           tc_fence_after();
-          float v[64];
-          tmem_ld_cols<64>(tlane + r * NT, v);
+          tmem_ld_cols<64>(tlane + (2 * rp) * NT, vv[0]);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(r));
-          const int y = y0 + r;
-          if (x < p.W && y < p.H) {
+          if (lane == 0) mbar_arrive(tempty_bar(2 * rp));
+          mbar_wait(tfull_bar(2 * rp + 1), tpar, p.err, 24);
+          tc_fence_after();
+          tmem_ld_cols<64>(tlane + (2 * rp + 1) * NT, vv[1]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(2 * rp + 1));
 #pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-              float d[3] = {0.f, 0.f, 0.f};
+          for (int rr = 0; rr < 2; ++rr) {
+            const float* v = vv[rr];
+            const int y = y0 + 2 * rp + rr;
+            if (x < p.W && y < p.H) {
 #pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                float val[8];
+              for (int sub = 0; sub < 4; ++sub) {
+                float d[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                  const float u = v[32 * c + 4 * cc + sub];
-                  val[cc] = relu ? fmaxf(u, 0.f) : u;
+                for (int c = 0; c < 2; ++c) {
+                  float val[8];
+#pragma unroll
+                  for (int cc = 0; cc < 8; ++cc) {
+                    const float u = v[32 * c + 4 * cc + sub];
+                    val[cc] = relu ? fmaxf(u, 0.f) : u;
+                  }
+                  if constexpr (EPI == GE_PS) *out[sub & 1].at(2 * y + (sub >> 1), j0 + c) = pack8(val);
+                  else dot3_acc(val, p.dot_w, p.ntiles * 32, (j0 + c) * 8, d);
                 }
-                if constexpr (EPI == GE_PS) *out[sub & 1].at(2 * y + (sub >> 1), j0 + c) = pack8(val);
-                else dot3_acc(val, p.dot_w, p.ntiles * 32, (j0 + c) * 8, d);
-              }
-              if constexpr (EPI == GE_PS_DOT) {
-                const long plane = static_cast<long>(p.dot_H) * p.dot_W;
-                float* o = p.dot_out + static_cast<long>(nt * 2 + half) * 3 * plane + static_cast<long>(2 * y + (sub >> 1)) * p.dot_W + 2 * x + (sub & 1);
+                if constexpr (EPI == GE_PS_DOT) {
+                  const long plane = static_cast<long>(p.dot_H) * p.dot_W;
+                  float* o = p.dot_out + static_cast<long>(nt * 2 + half) * 3 * plane + static_cast<long>(2 * y + (sub >> 1)) * p.dot_W + 2 * x + (sub & 1);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) o[k * plane] = d[k];
+                  for (int k = 0; k < 3; ++k) o[k * plane] = d[k];
+                }
               }
             }
           }
