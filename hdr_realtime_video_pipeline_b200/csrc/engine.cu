@@ -205,7 +205,7 @@ struct ConvLaunch {
 
 struct HgLaunch {                       // one gconv_kernel launch of the HG stage (hg.cuh)
   GConvParams p;
-  int kind = 0, NT = 0, epi = 0;
+  int kind = 0, NT = 0, epi = 0, rb = 4;
   int grid = 0;
   size_t smem = 0;
   std::string name;
@@ -2705,7 +2705,7 @@ int hdrtv_hg_time_plan(hdrtv_t* c, const void* base_out, int H, int Wd, float* o
       cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
       if (n < cap) ms[n] = t;
       ++n;
-      nm += "HG." + c->hg.plan[i].name + " tiles" + std::to_string(c->hg.plan[i].p.tiles) + " kg" + std::to_string(c->hg.plan[i].p.kgroups) + "\n";
+      nm += "HG." + c->hg.plan[i].name + " tiles" + std::to_string(c->hg.plan[i].p.tiles) + " kg" + std::to_string(c->hg.plan[i].p.kgroups) + " rb" + std::to_string(c->hg.plan[i].rb) + "\n";
     }
     for (auto& e : ev) cudaEventDestroy(e);
     if (names && names_cap > 0) snprintf(names, names_cap, "%s", nm.c_str());

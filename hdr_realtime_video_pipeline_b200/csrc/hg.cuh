@@ -37,9 +37,10 @@ constexpr int kGRows = 4;                       // output rows per tile (accumul
 constexpr int kGThreads = 320;
 
 __host__ __device__ constexpr int g_planes(int k) { return k == G_3x3 ? 2 : (k == G_3x3_C8 ? 1 : 8); }      // per K group
-__host__ __device__ constexpr int g_rows(int k) { return k == G_1x1 ? kGRows : kGRows + 2; }               // A rows per stage
+__host__ __device__ constexpr int g_rows(int k, int rb = kGRows) { return k == G_1x1 ? rb : rb + 2; }               // A rows per stage
 __host__ __device__ constexpr int g_steps(int k) { return k == G_3x3 ? 9 : (k == G_3x3_C8 ? 6 : 4); }       // MMAs per row and group
-__host__ __device__ constexpr int g_stages(int k) { return k == G_3x3 ? 3 : (k == G_3x3_C8 ? 4 : 2); }     // C8: one K group per tile, 27 KB stages: prefetch 4 tiles deep
+// C8: one K group per tile, 14-27 KB stages: prefetch 4 tiles deep.  (3x3 with two-row tiles: 57 KB stages, four would not fit)
+__host__ __device__ constexpr int g_stages(int k, int rb = kGRows) { return k == G_3x3 ? 3 : (k == G_3x3_C8 ? 4 : 2); }
 __host__ __device__ constexpr int g_group_channels(int k) { return k == G_3x3 ? 16 : (k == G_3x3_C8 ? 8 : 64); }
 // A operand of step i for output row r: input-row slot and byte offset inside the stage's A block, K-half distance
 __host__ __device__ constexpr int g_step_dy(int k, int i) { return k == G_3x3 ? i / 3 : (k == G_3x3_C8 ? i / 2 : 0); }
@@ -49,11 +50,13 @@ __host__ __device__ constexpr uint32_t g_step_off(int k, int i) {
   return static_cast<uint32_t>(2 * i) * kPlaneBytes + 16u;                // 1x1: planes 2i, 2i+1; +16 skips the halo entry
 }
 __host__ __device__ constexpr uint32_t g_step_lbo(int k) { return k == G_3x3_C8 ? 16u : static_cast<uint32_t>(kPlaneBytes); }
-__host__ __device__ constexpr uint32_t g_a_bytes(int k) { return static_cast<uint32_t>(g_rows(k) * g_planes(k)) * kPlaneBytes; }
+__host__ __device__ constexpr uint32_t g_a_bytes(int k, int rb = kGRows) { return static_cast<uint32_t>(g_rows(k, rb) * g_planes(k)) * kPlaneBytes; }
 __host__ __device__ constexpr uint32_t g_b_bytes(int k, int nt) { return static_cast<uint32_t>(g_steps(k) + 1) * nt * 32u; }
-__host__ __device__ constexpr uint32_t g_stage_bytes(int k, int nt) { return g_a_bytes(k) + g_b_bytes(k, nt); }
+__host__ __device__ constexpr uint32_t g_stage_bytes(int k, int nt, int rb = kGRows) { return g_a_bytes(k, rb) + g_b_bytes(k, nt); }
 constexpr int kGHeader = 256 + kPlaneBytes + 128;                          // barriers, TMEM slot, constant "ones" operand
-__host__ __device__ constexpr size_t g_smem_bytes(int k, int nt) { return kGHeader + static_cast<size_t>(g_stages(k)) * g_stage_bytes(k, nt) + 128; }
+__host__ __device__ constexpr size_t g_smem_bytes(int k, int nt, int rb = kGRows) { return kGHeader + static_cast<size_t>(g_stages(k, rb)) * g_stage_bytes(k, nt, rb) + 128; }
+static_assert(g_smem_bytes(G_3x3, 128, 4) <= 227 * 1024 && g_smem_bytes(G_3x3, 128, 2) <= 227 * 1024 && g_smem_bytes(G_1x1, 128, 4) <= 227 * 1024,
+              "pipeline stages exceed shared memory");
 
 struct GConvParams {
   const uint4* in0;          // source 0 (P8, natural layout)
@@ -91,13 +94,21 @@ __device__ __forceinline__ void dot3_acc(const float* val, const float* __restri
   }
 }
 
-template <int KIND, int NT, int EPI>
+// RB = output rows per tile.  4: the accumulators fill TMEM (4 x NT columns) and roll row by row between consecutive tiles -
+// least L2 traffic per MMA, right for deep K.  2: two tiles' accumulators alternate in TMEM (2 x 2 x NT columns), so a tile's
+// epilogue overlaps the whole next tile and no stage is a row-by-row hand-over - right for the layers with 1-4 K groups per
+// tile, where that hand-over stage is a quarter (or all) of the tile.
+template <int KIND, int NT, int EPI, int RB = kGRows>
 __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_constant__ GConvParams p) {
   static_assert(NT == 64 || NT == 128, "N tile");
+  static_assert(RB == 4 || (RB == 2 && KIND != G_1x1), "rows per tile");
   static_assert((EPI != GE_PS && EPI != GE_PS_DOT) || NT == 128, "PixelShuffle epilogue: 128 conv channels = 32 output channels per tile");
-  constexpr int PL = g_planes(KIND), ROWS = g_rows(KIND), NSTEPS = g_steps(KIND), S = g_stages(KIND);
-  constexpr uint32_t A_BYTES = g_a_bytes(KIND), STAGE = g_stage_bytes(KIND, NT), BLK = NT * 32u;
-  constexpr uint32_t kTmemCols = kGRows * NT;
+  constexpr int PL = g_planes(KIND), ROWS = g_rows(KIND, RB), NSTEPS = g_steps(KIND), S = g_stages(KIND, RB);
+  constexpr uint32_t A_BYTES = g_a_bytes(KIND, RB), STAGE = g_stage_bytes(KIND, NT, RB), BLK = NT * 32u;
+  constexpr uint32_t kTmemCols = 4 * NT;                 // RB = 4: one tile of four rows; RB = 2: two tiles of two rows
+  // accumulator block / barrier index of row r of this CTA's `it`-th tile, and the parity its barriers are in
+  auto acc_idx = [](int it, int r) { return RB == 4 ? r : ((it & 1) * 2 + r); };
+  auto acc_par = [](int it) { return static_cast<uint32_t>(RB == 4 ? (it & 1) : ((it >> 1) & 1)); };
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   const uint32_t bar0 = smem_u32(smem);
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
-    for (int i = 0; i < kGRows; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
     mbar_fence_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kPlaneEntries) {
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
       uint32_t st = 0, ph = 1;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         const int nt = t % p.ntiles, rest = t / p.ntiles;
-        const int x0 = (rest % p.strips) * kTileM, y0 = (rest / p.strips) * kGRows;
+        const int x0 = (rest % p.strips) * kTileM, y0 = (rest / p.strips) * RB;
         const uint4* wt = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wpk) + static_cast<long>(nt) * p.w_tile_bytes);
         for (int kg = 0; kg < KG; ++kg) {
           mbar_wait(empty_bar(st), ph, p.err, 21);
@@ -175,8 +186,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
     int it = 0;
     const bool lead = elect_one();        // the issuing lane, elected once: the loop below stays warp-uniform around it
     // one accumulator row of one stage: 9 (6, 4) MMAs, + the bias step and the hand-over to the epilogue on the last stage
-    auto issue_row = [&](int r, uint32_t a16, uint32_t b16, bool first, bool last) {
-      const uint32_t d_tmem = tmem_base + r * NT;
+    auto issue_row = [&](int it_, int r, uint32_t a16, uint32_t b16, bool first, bool last) {
+      const uint32_t d_tmem = tmem_base + acc_idx(it_, r) * NT;
       static_for<0, NSTEPS>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         constexpr int dy = g_step_dy(KIND, i);
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
       });
       if (last) {
         tc_mma_f16(d_tmem, ones_desc, mkdesc(b16 + NSTEPS * b_step), idesc, 1u);      // + bias
-        tc_commit(tfull_bar(r));
+        tc_commit(tfull_bar(acc_idx(it_, r)));
       }
     };
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
@@ -200,10 +211,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
           // the previous tile's epilogue must have drained accumulator r: row by row, so that the first rows of this tile
           // already run while the last rows of the previous one are still being read
 #pragma unroll
-          for (int r = 0; r < kGRows; ++r) {
-            mbar_wait(tempty_bar(r), (it & 1) ^ 1, p.err, 23);
+          for (int r = 0; r < RB; ++r) {
+            mbar_wait(tempty_bar(acc_idx(it, r)), acc_par(it) ^ 1, p.err, 23);
             tc_fence_after();
-            if (lead) issue_row(r, a16, b16, true, last);
+            if (lead) issue_row(it, r, a16, b16, true, last);
             __syncwarp();
           }
         } else {
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
           // descriptor arithmetic: the pipe's queue is shallow, every detour of the issuer is idle pipe time)
           if (lead) {
 #pragma unroll
-            for (int r = 0; r < kGRows; ++r) issue_row(r, a16, b16, false, last);
+            for (int r = 0; r < RB; ++r) issue_row(it, r, a16, b16, false, last);
           }
           __syncwarp();
         }
@@ -231,8 +242,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
     int it = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
       const int nt = t % p.ntiles, rest = t / p.ntiles;
-      const int x = (rest % p.strips) * kTileM + lg * 32 + lane, y0 = (rest / p.strips) * kGRows;
-      const uint32_t tpar = it & 1;
+      const int x = (rest % p.strips) * kTileM + lg * 32 + lane, y0 = (rest / p.strips) * RB;
+      const uint32_t tpar = acc_par(it);
+      const int ab = acc_idx(it, 0);                   // first accumulator block / barrier of this tile
       if constexpr (EPI == GE_P8) {
         ColRef out;
         out.init(p.out, x);
@@ -240,20 +252,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         // rows are drained in pairs before anything is stored: an accumulator row goes back to the MMA warp as soon as it
         // is in registers, not after the previous row's convert / address / store chain
 #pragma unroll 1
-        for (int rp = 0; rp < kGRows / 2; ++rp) {
+        for (int rp = 0; rp < RB / 2; ++rp) {
           float va[COLS], vb[COLS];
-          mbar_wait(tfull_bar(2 * rp), tpar, p.err, 24);
+          mbar_wait(tfull_bar(ab + 2 * rp), tpar, p.err, 24);
           tc_fence_after();
-          tmem_ld_cols<COLS>(tlane + (2 * rp) * NT, va);
+          tmem_ld_cols<COLS>(tlane + (ab + 2 * rp) * NT, va);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(2 * rp));
-          mbar_wait(tfull_bar(2 * rp + 1), tpar, p.err, 24);
+          if (lane == 0) mbar_arrive(tempty_bar(ab + 2 * rp));
+          mbar_wait(tfull_bar(ab + 2 * rp + 1), tpar, p.err, 24);
           tc_fence_after();
-          tmem_ld_cols<COLS>(tlane + (2 * rp + 1) * NT, vb);
+          tmem_ld_cols<COLS>(tlane + (ab + 2 * rp + 1) * NT, vb);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(2 * rp + 1));
+          if (lane == 0) mbar_arrive(tempty_bar(ab + 2 * rp + 1));
           const int y = y0 + 2 * rp;
           if (x < p.W) {
 #pragma unroll
@@ -278,20 +290,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         if (EPI == GE_POOL && p.has_full) full.init(p.out_full, x);
         const int j0 = nt * (NT / 8) + half * CH;
 #pragma unroll 1
-        for (int rp = 0; rp < kGRows / 2; ++rp) {
+        for (int rp = 0; rp < RB / 2; ++rp) {
           float a[COLS], b[COLS];
-          mbar_wait(tfull_bar(2 * rp), tpar, p.err, 24);
+          mbar_wait(tfull_bar(ab + 2 * rp), tpar, p.err, 24);
           tc_fence_after();
-          tmem_ld_cols<COLS>(tlane + (2 * rp) * NT, a);
+          tmem_ld_cols<COLS>(tlane + (ab + 2 * rp) * NT, a);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(2 * rp));
-          mbar_wait(tfull_bar(2 * rp + 1), tpar, p.err, 24);
+          if (lane == 0) mbar_arrive(tempty_bar(ab + 2 * rp));
+          mbar_wait(tfull_bar(ab + 2 * rp + 1), tpar, p.err, 24);
           tc_fence_after();
-          tmem_ld_cols<COLS>(tlane + (2 * rp + 1) * NT, b);
+          tmem_ld_cols<COLS>(tlane + (ab + 2 * rp + 1) * NT, b);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(2 * rp + 1));
+          if (lane == 0) mbar_arrive(tempty_bar(ab + 2 * rp + 1));
           const int y = y0 + 2 * rp;
           const bool in = x < p.W && y < p.H;        // H, W even: row y + 1 and column x ^ 1 are inside with (y, x)
 #pragma unroll
@@ -339,20 +351,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         }
         const int j0 = nt * 4 + half * 2;
 #pragma unroll 1
-        for (int rp = 0; rp < kGRows / 2; ++rp) {
+        for (int rp = 0; rp < RB / 2; ++rp) {
           float vv[2][64];                             // two rows drained before either is shuffled out (see GE_P8)
-          mbar_wait(tfull_bar(2 * rp), tpar, p.err, 24);
+          mbar_wait(tfull_bar(ab + 2 * rp), tpar, p.err, 24);
           tc_fence_after();
-          tmem_ld_cols<64>(tlane + (2 * rp) * NT, vv[0]);
+          tmem_ld_cols<64>(tlane + (ab + 2 * rp) * NT, vv[0]);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(2 * rp));
-          mbar_wait(tfull_bar(2 * rp + 1), tpar, p.err, 24);
+          if (lane == 0) mbar_arrive(tempty_bar(ab + 2 * rp));
+          mbar_wait(tfull_bar(ab + 2 * rp + 1), tpar, p.err, 24);
           tc_fence_after();
-          tmem_ld_cols<64>(tlane + (2 * rp + 1) * NT, vv[1]);
+          tmem_ld_cols<64>(tlane + (ab + 2 * rp + 1) * NT, vv[1]);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(2 * rp + 1));
+          if (lane == 0) mbar_arrive(tempty_bar(ab + 2 * rp + 1));
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
             const float* v = vv[rr];

@@ -227,8 +227,13 @@ static int hg_add(Ctx* c, const char* layer, int epi, const P8& in0, const P8* i
   p.ntiles = (spec->cout + sh.NT - 1) / sh.NT;
   p.H = in0.H;
   p.W = in0.W;
+  // two-row tiles with alternating accumulators (hg.cuh, RB): measured on every 3x3 layer with <= 8 K groups per tile - only the
+  // PixelShuffle layer with 4 K groups gains (Up_conv5 135 -> 125 us at 1080p, 498 -> 479 us at 4K); conv1 / conv2 / conv3_1 lose
+  // 4-15 % to the extra L2 traffic of the shorter tiles
+  const bool ps = epi == GE_PS || epi == GE_PS_DOT;
+  const int rb = (sh.kind == G_3x3 && ps && p.kgroups <= env_int("HDRTV_HG_RB2_MAXKG", 4)) ? 2 : kGRows;
   p.strips = (p.W + kTileM - 1) / kTileM;
-  p.rowblocks = (p.H + kGRows - 1) / kGRows;
+  p.rowblocks = (p.H + rb - 1) / rb;
   p.tiles = p.ntiles * p.strips * p.rowblocks;
   p.relu = relu ? 1 : 0;
   p.out = out;
@@ -252,25 +257,32 @@ static int hg_add(Ctx* c, const char* layer, int epi, const P8& in0, const P8* i
   L.kind = sh.kind;
   L.NT = sh.NT;
   L.epi = epi;
+  L.rb = rb;
   L.grid = std::min(p.tiles, c->hg.sms);
-  L.smem = g_smem_bytes(sh.kind, sh.NT);
+  L.smem = g_smem_bytes(sh.kind, sh.NT, rb);
   L.name = layer;
   c->hg.plan.push_back(L);
   return 0;
 }
 
-template <int KIND, int NT, int EPI>
+template <int KIND, int NT, int EPI, int RB = kGRows>
 static cudaError_t hg_launch_t(const HgLaunch& L, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gconv_kernel<KIND, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g_smem_bytes(KIND, NT)));
+    cudaError_t e = cudaFuncSetAttribute(gconv_kernel<KIND, NT, EPI, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(g_smem_bytes(KIND, NT, RB)));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gconv_kernel<KIND, NT, EPI><<<L.grid, kGThreads, L.smem, s>>>(L.p);
+  gconv_kernel<KIND, NT, EPI, RB><<<L.grid, kGThreads, L.smem, s>>>(L.p);
   return cudaGetLastError();
 }
 static cudaError_t hg_launch(const HgLaunch& L, cudaStream_t s) {
+  if (L.rb == 2) {
+    if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_PS) return hg_launch_t<G_3x3, 128, GE_PS, 2>(L, s);
+    if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_PS_DOT) return hg_launch_t<G_3x3, 128, GE_PS_DOT, 2>(L, s);
+    return cudaErrorInvalidValue;
+  }
   if (L.kind == G_3x3_C8 && L.NT == 64 && L.epi == GE_POOL) return hg_launch_t<G_3x3_C8, 64, GE_POOL>(L, s);
   if (L.kind == G_3x3_C8 && L.NT == 64 && L.epi == GE_POOL_DOT) return hg_launch_t<G_3x3_C8, 64, GE_POOL_DOT>(L, s);
   if (L.kind == G_3x3 && L.NT == 128 && L.epi == GE_PS_DOT) return hg_launch_t<G_3x3, 128, GE_PS_DOT>(L, s);
