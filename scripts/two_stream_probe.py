@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput of N independent contexts on N streams of one GPU (frames are independent: SURVEY §8e) against one context.
-    python scripts/two_stream_probe.py [1080p|4k] [n_contexts] [frames]"""
+    python scripts/two_stream_probe.py [1080p|4k] [n_contexts] [frames] [--hg]"""
 import os
 import sys
 
@@ -12,13 +12,19 @@ import hdr_realtime_video_pipeline_b200 as hb  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "1080p"
 nctx = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 120
+HG = "--hg" in sys.argv
 h, w = {"540p": (540, 960), "1080p": (1080, 1920), "4k": (2160, 3840)}[wl]
 W = os.path.join(REPO, "tests/golden/weights_hr.npz")
 frames = [torch.from_numpy(hb.synth_frame(i, h, w)).cuda() for i in range(8)]
 
 
 def run(n):
-    nets = [hb.HDRTVNetB200(W, precision="fp16", warmup_passes=0, use_hg=False) for _ in range(n)]
+    if HG:
+        from hdr_realtime_video_pipeline_b200.synth import hg_random_state_dict
+        sd = hg_random_state_dict(0)
+        nets = [hb.HDRTVNetB200(W, precision="fp16", warmup_passes=0, use_hg=True, hg_weights=sd) for _ in range(n)]
+    else:
+        nets = [hb.HDRTVNetB200(W, precision="fp16", warmup_passes=0, use_hg=False) for _ in range(n)]
     packers = [hb.RGB48Packer("cuda", ring_frames=3) for _ in range(n)]
     streams = [torch.cuda.Stream() for _ in range(n)]
     outs = [torch.empty((h, w, 3), dtype=torch.uint16, device="cuda") for _ in range(n)]
