@@ -219,6 +219,7 @@ struct HgState {
   float *d_dot_up = nullptr, *d_dot_skip = nullptr;   // conv10's weights split by producer, [3][64] each
   float* d_part = nullptr;                      // conv10 partial sums written by the *_DOT epilogues, [6][3][Hp][Wp]
   bool fuse_conv10 = true;
+  int* d_gate = nullptr;                        // 1 when the current frame has a pixel inside the highlight mask (early-out gate)
   std::vector<void*> wallocs;
   int H = 0, W = 0, Hp = 0, Wp = 0, sms = 148;
   std::vector<void*> ws;
@@ -2694,6 +2695,7 @@ int hdrtv_hg_time_plan(hdrtv_t* c, const void* base_out, int H, int Wd, float* o
     for (auto& e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], s);
     for (size_t i = 0; i < c->hg.plan.size(); ++i) {
+      c->hg.plan[i].p.gate = nullptr;                             // per-launch times of the dense evaluation
       CK(c, hg_launch(c->hg.plan[i], s));
       cudaEventRecord(ev[i + 1], s);
     }

@@ -78,6 +78,8 @@ struct GConvParams {
   const float* dot_w;        // *_DOT: conv10 weights of this layer's channels, [3][channels] (half-rounded values)
   float* dot_out;            // *_DOT: partial sums, [slices][3][dot_H][dot_W] planar fp32; slice = ntile * 2 + half
   int dot_H, dot_W;
+  const int* gate;           // optional: *gate == 0 -> no pixel of this frame is inside the highlight mask, the stage's output
+                             // is the base image itself (mask * hg + img with mask = 0) and the launch returns at once
   int* err;
 };
 
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
   static_assert((EPI != GE_PS && EPI != GE_PS_DOT) || NT == 128, "PixelShuffle epilogue: 128 conv channels = 32 output channels per tile");
   constexpr int PL = g_planes(KIND), ROWS = g_rows(KIND, RB), NSTEPS = g_steps(KIND), S = g_stages(KIND, RB);
   constexpr uint32_t A_BYTES = g_a_bytes(KIND, RB), STAGE = g_stage_bytes(KIND, NT, RB), BLK = NT * 32u;
+  if (p.gate != nullptr && *reinterpret_cast<const volatile int*>(p.gate) == 0) return;      // uniform: before any barrier / TMEM
   constexpr uint32_t kTmemCols = 4 * NT;                 // RB = 4: one tile of four rows; RB = 2: two tiles of two rows
   // accumulator block / barrier index of row r of this CTA's `it`-th tile, and the parity its barriers are in
   auto acc_idx = [](int it, int r) { return RB == 4 ? r : ((it & 1) * 2 + r); };
@@ -408,14 +411,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
 // of 32), reflect padding on the right / bottom (F.pad(mode="reflect"), HG_Composite_arch.py:94-101: index n + i reads
 // n - 2 - i).  Channels 3..7 of an entry are zero.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float hg_mask_half(float m);
 template <typename T>
-__global__ void hg_stage_in_kernel(const T* __restrict__ src, P8 dst, int H, int W, int Hp, int Wp) {
+__global__ void hg_stage_in_kernel(const T* __restrict__ src, P8 dst, int H, int W, int Hp, int Wp, int* any_mask) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= Wp || y >= Hp) return;
   const int sx = x < W ? x : 2 * W - 2 - x, sy = y < H ? y : 2 * H - 2 - y;
   const long plane = static_cast<long>(H) * W, o = static_cast<long>(sy) * W + sx;
   float v[8] = {static_cast<float>(src[o]), static_cast<float>(src[plane + o]), static_cast<float>(src[2 * plane + o]), 0.f, 0.f, 0.f, 0.f, 0.f};
   reinterpret_cast<uint4*>(dst.base)[dst.entry(y, 0, x)] = pack8(v);
+  // does any pixel of the (un-padded) frame lie inside the highlight mask?  (the gate of the gconv launches)
+  if (any_mask != nullptr && x < W && y < H && hg_mask_half(fmaxf(v[0], fmaxf(v[1], v[2]))) != 0.f) *any_mask = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -488,9 +494,17 @@ __global__ void __launch_bounds__(128) hg_tail_kernel(P8 up, P8 skip, P8 img, co
 // The same tail when conv10's two halves were reduced by the producers' epilogues (GE_POOL_DOT / GE_PS_DOT): `part` holds
 // `slices` partial sums per pixel and output channel, [slices][3][Hp][Wp]; they are added in slice order (bit-reproducible).
 __global__ void __launch_bounds__(128) hg_tail_dot_kernel(const float* __restrict__ part, int slices, int Hp, int Wp, P8 img,
-                                                          const HgTail* __restrict__ tw, float* __restrict__ out, int H, int W) {
+                                                          const HgTail* __restrict__ tw, float* __restrict__ out, int H, int W,
+                                                          const int* gate) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= W || y >= H) return;
+  if (gate != nullptr && *gate == 0) {         // no highlight anywhere: mask * hg + img = img (the U-Net did not run)
+    float im0[8];
+    unpack8(__ldcg(reinterpret_cast<const uint4*>(img.base) + img.entry(y, 0, x)), im0);
+    const long pl = static_cast<long>(H) * W, oo = static_cast<long>(y) * W + x;
+    out[oo] = im0[0]; out[pl + oo] = im0[1]; out[2 * pl + oo] = im0[2];
+    return;
+  }
   const long pp = static_cast<long>(Hp) * Wp, po = static_cast<long>(y) * Wp + x;
   float acc[3] = {__ldg(&tw->b10[0]), __ldg(&tw->b10[1]), __ldg(&tw->b10[2])};
   for (int s = 0; s < slices; ++s) {

@@ -24,6 +24,7 @@ static void hg_release_ws(Ctx* c) {
   c->hg.proc_out = nullptr;
   c->hg.proc_H = c->hg.proc_W = 0;
   c->hg.d_part = nullptr;
+  c->hg.d_gate = nullptr;
 }
 static void hg_release_weights(Ctx* c) {
   for (void* p : c->hg.wallocs) cudaFree(p);
@@ -317,7 +318,8 @@ static int hg_prepare(Ctx* c, int H, int Wd) {
     const bool fuse = env_int("HDRTV_HG_FUSE_CONV10", 1) != 0;
     c->hg.fuse_conv10 = fuse;
     c->hg.d_part = fuse ? hg_ws_alloc<float>(c, static_cast<size_t>(6) * 3 * Hp * Wp, false) : nullptr;
-    if (fuse && !c->hg.d_part) return fail(c, "hdrtv_hg: workspace allocation failed");
+    c->hg.d_gate = hg_ws_alloc<int>(c, 1, true);
+    if ((fuse && !c->hg.d_part) || !c->hg.d_gate) return fail(c, "hdrtv_hg: workspace allocation failed");
     bool ok = mk("img", 8, 0) && (fuse || mk("c1", 64, 0)) && mk("p1", 64, 1) && mk("c2", 128, 1) && mk("p31", 256, 2) && mk("c3", 256, 2) &&
               mk("p41", 512, 3) && mk("c4", 512, 3) && mk("p51", 512, 4) && mk("c5", 512, 4) && mk("pc1", 512, 5) && mk("code", 512, 5) &&
               mk("u1", 512, 4) && mk("c6", 512, 4) && mk("u2", 512, 3) && mk("c7", 256, 3) && mk("u3", 256, 2) && mk("c8", 128, 2) &&
@@ -396,15 +398,25 @@ static int hg_run(Ctx* c, const void* base_out, int H, int Wd, float* out, cudaS
   const int Hp = c->hg.Hp, Wp = c->hg.Wp;
   if (c->precision == HDRTV_FP16) {
     auto& T = c->hg.t;
-    hg_stage_in_kernel<__half><<<dim3((Wp + 127) / 128, Hp), 128, 0, s>>>(static_cast<const __half*>(base_out), T.at("img"), H, Wd, Hp, Wp);
+    // Frames without a single pixel inside the highlight mask (max_c(base) <= 0.775: no speculars, lamps or white areas)
+    // leave the stage as they entered it (mask * hg + img with mask = 0 everywhere): the stage-in pass raises a device
+    // flag when it sees a masked pixel and the 19 U-Net launches return at once while it is down.  Bit-identical to the
+    // dense evaluation; HDRTV_HG_EARLY_OUT=0 always runs the U-Net (benchmarks quote that figure).  Needs the conv10 fold's
+    // tail kernel.
+    const char* eo_env = getenv("HDRTV_HG_EARLY_OUT");
+    const bool early = c->hg.fuse_conv10 && c->hg.d_gate && !(eo_env && eo_env[0] == '0');
+    int* gate = early ? c->hg.d_gate : nullptr;
+    if (gate) CK(c, cudaMemsetAsync(gate, 0, sizeof(int), s));
+    hg_stage_in_kernel<__half><<<dim3((Wp + 127) / 128, Hp), 128, 0, s>>>(static_cast<const __half*>(base_out), T.at("img"), H, Wd, Hp, Wp, gate);
     CK(c, cudaGetLastError());
     ++c->launches;
-    for (const HgLaunch& L : c->hg.plan) {
+    for (HgLaunch& L : c->hg.plan) {
+      L.p.gate = gate;
       CK(c, hg_launch(L, s));
       ++c->launches;
     }
     if (c->hg.fuse_conv10)
-      hg_tail_dot_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(c->hg.d_part, 6, Hp, Wp, T.at("img"), c->hg.d_tail, out, H, Wd);
+      hg_tail_dot_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(c->hg.d_part, 6, Hp, Wp, T.at("img"), c->hg.d_tail, out, H, Wd, gate);
     else
       hg_tail_kernel<<<dim3((Wd + 127) / 128, H), 128, 0, s>>>(T.at("u5"), T.at("c1"), T.at("img"), c->hg.d_tail, out, H, Wd);
     CK(c, cudaGetLastError());

@@ -31,6 +31,8 @@ for wl, e in (d.get("hg") or {}).items():
           f"{rf['achieved']:.0f} TFLOP/s frac {rf['frac']:.3f} (burst {rf['frac_of_burst_peak']:.3f})")
     for t in rf["top_kernels"]:
         print(f"   {t['launch'][:44]:44s} {t['ms']:.4f} ms {t['achieved_tflops']:.0f} TF")
+    if e.get("mask_early_out"):
+        print(f"   with the highlight-mask early-out (product default, not the headline): {e['mask_early_out']['value']:.1f} frames/s")
     if e.get("cpu_baseline"):
         print("   cpu reference (with HG):", {k: v for k, v in e["cpu_baseline"].items() if k not in ("sample",)})
     if e.get("gpu_eager_baseline"):

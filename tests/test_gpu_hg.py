@@ -167,6 +167,41 @@ def test_hg_is_bit_reproducible_and_follows_resolution_changes(nets):
             assert sig == first[hw], f"HG output changed between passes at {hw}, pass {rep}"
 
 
+def test_hg_mask_early_out_is_bit_identical_to_the_dense_stage(nets, monkeypatch):
+    """Frames without a pixel inside the highlight mask skip the U-Net (device-side gate raised by the stage-in pass); the
+    result must equal the dense evaluation bit for bit, and a masked frame right after an unmasked one must not see stale
+    partial sums."""
+    net = nets("fp16")
+    rng = np.random.default_rng(3)
+    dark = (0.70 * rng.random((1, 3, 136, 248))).astype(np.float16)                  # max 0.70 < 0.775: mask empty
+    one = dark.copy()
+    one[0, :, 70, 123] = np.float16(0.9)                                             # a single highlight pixel
+    bright = (0.55 + 0.45 * rng.random((1, 3, 136, 248))).astype(np.float16)
+    seq = [bright, dark, one, dark, bright, dark]
+    monkeypatch.setenv("HDRTV_HG_EARLY_OUT", "0")
+    dense = [_stage(net, b) for b in seq]
+    monkeypatch.setenv("HDRTV_HG_EARLY_OUT", "1")
+    gated = [_stage(net, b) for b in seq]
+    for i, (d, g, b) in enumerate(zip(dense, gated, seq)):
+        assert np.array_equal(d, g), f"early-out changed frame {i}"
+    assert np.array_equal(gated[1], dark.astype(np.float32))                          # no highlight: the base image itself
+    assert (gated[2] != one.astype(np.float32)).any(axis=1).sum() == 1               # exactly the one masked pixel moved
+    # the gate really skips the work: an unmasked frame costs a fraction of a masked one
+    base_d, base_b = torch.from_numpy(dark).cuda(), torch.from_numpy(bright).cuda()
+
+    def ms(base):
+        for _ in range(3):
+            net.hg_stage(base)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            net.hg_stage(base)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10
+    assert ms(base_d) < 0.6 * ms(base_b)
+
+
 def test_hg_weights_are_checked_strictly(hg_sd):
     bad = dict(hg_sd)
     bad.pop("conv7.weight")
