@@ -202,6 +202,33 @@ def test_hg_mask_early_out_is_bit_identical_to_the_dense_stage(nets, monkeypatch
     assert ms(base_d) < 0.6 * ms(base_b)
 
 
+@needs_ref
+def test_p7_reference_playback_loop_runs_unchanged_with_the_hg_stage(nets):
+    """The reference's own _process_frame + _hdr_feeder_fn thread (imported, not edited) on this backend WITH HG: the float32
+    HG output goes through its 4-deep empty_like / copy_(non_blocking) staging pool and both RGB48 packs; every frame must be
+    byte-equal to serial execution of the three calls and to the one-call path."""
+    from test_gpu_reference_live import _play
+    net = nets("fp16")
+    h, w = 136, 248
+    frames = [hb.synth_frame(i, h, w) for i in range(60)]
+    want = []
+    for f in frames:
+        out, _ = net.infer(net.preprocess(f))
+        assert out.dtype == torch.float32
+        torch.cuda.synchronize()
+        want.append(O.pack_rgb48(out.cpu().numpy()).tobytes())
+    got_ref_pack, _ = _play(net, frames)
+    got_our_pack, _ = _play(net, frames, pack_fn=hb.tensor_to_rgb48_bytes)
+    assert [i for i, (a, b) in enumerate(zip(got_ref_pack, want)) if a != b] == []
+    assert [i for i, (a, b) in enumerate(zip(got_our_pack, want)) if a != b] == []
+    one = []
+    for f in frames[:16]:
+        fr = net.process_rgb48(f)
+        one.append(bytes(fr.buffer_view()))
+        fr.release()
+    assert one == want[:16]
+
+
 def test_hg_weights_are_checked_strictly(hg_sd):
     bad = dict(hg_sd)
     bad.pop("conv7.weight")
