@@ -34,6 +34,8 @@ enum GKind : int { G_3x3 = 0, G_3x3_C8 = 1, G_1x1 = 2 };
 // the per-warp partial sums (3 floats per pixel and slice); hg_tail_dot_kernel adds the slices in a fixed order.
 enum GEpi : int { GE_P8 = 0, GE_POOL = 1, GE_PS = 2, GE_POOL_DOT = 3, GE_PS_DOT = 4 };
 constexpr int kGRows = 4;                       // output rows per tile (accumulators in TMEM)
+constexpr int kHgNoMask = 0x7f7f7f7f;           // gate words after cudaMemset(0x7f): no masked pixel seen
+constexpr int kHgCone = 192;                    // >= 186: reach of the U-Net's dependency cone in full-resolution pixels
 constexpr int kGThreads = 320;
 
 __host__ __device__ constexpr int g_planes(int k) { return k == G_3x3 ? 2 : (k == G_3x3_C8 ? 1 : 8); }      // per K group
@@ -78,8 +80,13 @@ struct GConvParams {
   const float* dot_w;        // *_DOT: conv10 weights of this layer's channels, [3][channels] (half-rounded values)
   float* dot_out;            // *_DOT: partial sums, [slices][3][dot_H][dot_W] planar fp32; slice = ntile * 2 + half
   int dot_H, dot_W;
-  const int* gate;           // optional: *gate == 0 -> no pixel of this frame is inside the highlight mask, the stage's output
-                             // is the base image itself (mask * hg + img with mask = 0) and the launch returns at once
+  // Highlight gate (optional).  gate[0..3] = {x_min, y_min, -x_max, -y_max} of the frame's masked pixels (kHgNoMask when
+  // there is none).  No masked pixel: the stage's output is the base image itself (mask * hg + img with mask = 0) and the
+  // launch returns at once.  Otherwise only the tiles that intersect the bounding box grown by kHgCone full-resolution
+  // pixels are computed: no element further than 186 pixels from a masked pixel can reach a masked output (the U-Net's
+  // dependency cone, five 2x poolings and their 3x3 convs), and unmasked outputs do not use the U-Net at all.
+  const int* gate;
+  int lvl;                   // resolution level of this conv's pixels (0 = full resolution, 5 = 1/32)
   int* err;
 };
 
@@ -107,7 +114,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
   static_assert((EPI != GE_PS && EPI != GE_PS_DOT) || NT == 128, "PixelShuffle epilogue: 128 conv channels = 32 output channels per tile");
   constexpr int PL = g_planes(KIND), ROWS = g_rows(KIND, RB), NSTEPS = g_steps(KIND), S = g_stages(KIND, RB);
   constexpr uint32_t A_BYTES = g_a_bytes(KIND, RB), STAGE = g_stage_bytes(KIND, NT, RB), BLK = NT * 32u;
-  if (p.gate != nullptr && *reinterpret_cast<const volatile int*>(p.gate) == 0) return;      // uniform: before any barrier / TMEM
+  int ax0 = 0, ax1 = 0x7fffffff, ay0 = 0, ay1 = 0x7fffffff;      // active pixel range of this level (gate)
+  if (p.gate != nullptr) {
+    const volatile int* g = reinterpret_cast<const volatile int*>(p.gate);
+    const int gx0 = g[0], gy0 = g[1], gx1 = -g[2], gy1 = -g[3];
+    if (gx0 == kHgNoMask) return;                                  // uniform: before any barrier / TMEM
+    ax0 = max(gx0 - kHgCone, 0) >> p.lvl;
+    ay0 = max(gy0 - kHgCone, 0) >> p.lvl;
+    ax1 = (gx1 + kHgCone) >> p.lvl;
+    ay1 = (gy1 + kHgCone) >> p.lvl;
+  }
+  auto tile_on = [&](int x0, int y0) { return x0 <= ax1 && x0 + kTileM - 1 >= ax0 && y0 <= ay1 && y0 + RB - 1 >= ay0; };
   constexpr uint32_t kTmemCols = 4 * NT;                 // RB = 4: one tile of four rows; RB = 2: two tiles of two rows
   // accumulator block / barrier index of row r of this CTA's `it`-th tile, and the parity its barriers are in
   auto acc_idx = [](int it, int r) { return RB == 4 ? r : ((it & 1) * 2 + r); };
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         const int nt = t % p.ntiles, rest = t / p.ntiles;
         const int x0 = (rest % p.strips) * kTileM, y0 = (rest / p.strips) * RB;
+        if (!tile_on(x0, y0)) continue;
         const uint4* wt = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wpk) + static_cast<long>(nt) * p.w_tile_bytes);
         for (int kg = 0; kg < KG; ++kg) {
           mbar_wait(empty_bar(st), ph, p.err, 21);
@@ -203,7 +221,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         tc_commit(tfull_bar(acc_idx(it_, r)));
       }
     };
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      {
+        const int rest = t / p.ntiles;
+        if (!tile_on((rest % p.strips) * kTileM, (rest / p.strips) * RB)) continue;      // same decision in all three roles
+      }
       for (int kg = 0; kg < KG; ++kg) {
         const uint32_t a16 = (smem_u32(stage0) + st * STAGE) >> 4;
         const uint32_t b16 = ((smem_u32(stage0) + st * STAGE + A_BYTES) >> 4) | b_lbo;
@@ -233,6 +255,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
         __syncwarp();
         if (++st == S) { st = 0; ph ^= 1; }
       }
+      ++it;                                   // tiles this CTA has processed (barrier phases), not tiles it has looked at
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quadrant
@@ -243,9 +266,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + half * COLS;
     const bool relu = p.relu != 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       const int nt = t % p.ntiles, rest = t / p.ntiles;
       const int x = (rest % p.strips) * kTileM + lg * 32 + lane, y0 = (rest / p.strips) * RB;
+      if (!tile_on((rest % p.strips) * kTileM, y0)) continue;
       const uint32_t tpar = acc_par(it);
       const int ab = acc_idx(it, 0);                   // first accumulator block / barrier of this tile
       if constexpr (EPI == GE_P8) {
@@ -398,6 +422,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
           }
         }
       }
+      ++it;
     }
   }
 
@@ -413,15 +438,27 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float hg_mask_half(float m);
 template <typename T>
-__global__ void hg_stage_in_kernel(const T* __restrict__ src, P8 dst, int H, int W, int Hp, int Wp, int* any_mask) {
+__global__ void __launch_bounds__(128) hg_stage_in_kernel(const T* __restrict__ src, P8 dst, int H, int W, int Hp, int Wp, int* gate) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= Wp || y >= Hp) return;
-  const int sx = x < W ? x : 2 * W - 2 - x, sy = y < H ? y : 2 * H - 2 - y;
-  const long plane = static_cast<long>(H) * W, o = static_cast<long>(sy) * W + sx;
-  float v[8] = {static_cast<float>(src[o]), static_cast<float>(src[plane + o]), static_cast<float>(src[2 * plane + o]), 0.f, 0.f, 0.f, 0.f, 0.f};
-  reinterpret_cast<uint4*>(dst.base)[dst.entry(y, 0, x)] = pack8(v);
-  // does any pixel of the (un-padded) frame lie inside the highlight mask?  (the gate of the gconv launches)
-  if (any_mask != nullptr && x < W && y < H && hg_mask_half(fmaxf(v[0], fmaxf(v[1], v[2]))) != 0.f) *any_mask = 1;
+  bool masked = false;
+  if (x < Wp && y < Hp) {
+    const int sx = x < W ? x : 2 * W - 2 - x, sy = y < H ? y : 2 * H - 2 - y;
+    const long plane = static_cast<long>(H) * W, o = static_cast<long>(sy) * W + sx;
+    float v[8] = {static_cast<float>(src[o]), static_cast<float>(src[plane + o]), static_cast<float>(src[2 * plane + o]), 0.f, 0.f, 0.f, 0.f, 0.f};
+    reinterpret_cast<uint4*>(dst.base)[dst.entry(y, 0, x)] = pack8(v);
+    masked = x < W && y < H && hg_mask_half(fmaxf(v[0], fmaxf(v[1], v[2]))) != 0.f;
+  }
+  // bounding box of the frame's masked pixels (un-padded area: only those outputs exist), one atomic set per warp that saw one
+  if (gate != nullptr) {
+    const int lo = __reduce_min_sync(0xffffffffu, masked ? x : kHgNoMask);
+    const int nhi = __reduce_min_sync(0xffffffffu, masked ? -x : kHgNoMask);
+    if ((threadIdx.x & 31) == 0 && lo != kHgNoMask) {
+      atomicMin(gate + 0, lo);
+      atomicMin(gate + 1, y);
+      atomicMin(gate + 2, nhi);
+      atomicMin(gate + 3, -y);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -498,7 +535,7 @@ __global__ void __launch_bounds__(128) hg_tail_dot_kernel(const float* __restric
                                                           const int* gate) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= W || y >= H) return;
-  if (gate != nullptr && *gate == 0) {         // no highlight anywhere: mask * hg + img = img (the U-Net did not run)
+  if (gate != nullptr && *gate == kHgNoMask) { // no highlight anywhere: mask * hg + img = img (the U-Net did not run)
     float im0[8];
     unpack8(__ldcg(reinterpret_cast<const uint4*>(img.base) + img.entry(y, 0, x)), im0);
     const long pl = static_cast<long>(H) * W, oo = static_cast<long>(y) * W + x;
@@ -526,7 +563,8 @@ __global__ void __launch_bounds__(128) hg_tail_dot_kernel(const float* __restric
 #pragma unroll
     for (int i = 0; i < 3; ++i) v = fmaf(im[i], __ldg(&tw->wl[k][3 + i]), v);
     v = __half2float(__float2half_rn(v));
-    out[k * plane + o] = __fadd_rn(__fmul_rn(mask, v), im[k]);
+    // outside the mask the partial sums may come from tiles the gate skipped (stale, possibly not even finite): not used
+    out[k * plane + o] = __fadd_rn(__fmul_rn(mask, mask != 0.f ? v : 0.f), im[k]);
   }
 }
 

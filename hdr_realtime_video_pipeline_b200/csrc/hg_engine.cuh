@@ -237,6 +237,9 @@ static int hg_add(Ctx* c, const char* layer, int epi, const P8& in0, const P8* i
   p.rowblocks = (p.H + rb - 1) / rb;
   p.tiles = p.ntiles * p.strips * p.rowblocks;
   p.relu = relu ? 1 : 0;
+  p.lvl = 0;
+  while ((c->hg.Hp >> p.lvl) > p.H) ++p.lvl;            // resolution level of this conv's pixels
+  if ((c->hg.Hp >> p.lvl) != p.H || (c->hg.Wp >> p.lvl) != p.W) return fail(c, std::string("hg plan: level mismatch for ") + layer);
   p.out = out;
   if (out_full) { p.out_full = *out_full; p.has_full = 1; }
   p.err = c->d_err;
@@ -306,6 +309,10 @@ static int hg_prepare(Ctx* c, int H, int Wd) {
   c->hg.sms = prop.multiProcessorCount;
   // HG_Composite_arch.py:91-93: five 2x poolings -> pad to the next multiple of 32
   const int Hp = rup(H, 32), Wp = rup(Wd, 32);
+  // F.pad(mode="reflect") needs pad < size (torch raises otherwise): a 16-row frame cannot be reflected up to 32 rows
+  if (Hp - H >= H || Wp - Wd >= Wd)
+    return fail(c, "hdrtv_hg: reflect padding to a multiple of 32 needs more rows / columns than the padding (" + std::to_string(H) + "x" +
+                       std::to_string(Wd) + "), as torch.nn.functional.pad(mode='reflect') does");
   c->hg.Hp = Hp;
   c->hg.Wp = Wp;
   int h[6], w[6];
@@ -317,8 +324,8 @@ static int hg_prepare(Ctx* c, int H, int Wd) {
     // full-resolution tensor reaches HBM (2 x 128 B/px written + read), only 6 slices of 3 partial sums (72 B/px)
     const bool fuse = env_int("HDRTV_HG_FUSE_CONV10", 1) != 0;
     c->hg.fuse_conv10 = fuse;
-    c->hg.d_part = fuse ? hg_ws_alloc<float>(c, static_cast<size_t>(6) * 3 * Hp * Wp, false) : nullptr;
-    c->hg.d_gate = hg_ws_alloc<int>(c, 1, true);
+    c->hg.d_part = fuse ? hg_ws_alloc<float>(c, static_cast<size_t>(6) * 3 * Hp * Wp, true) : nullptr;
+    c->hg.d_gate = hg_ws_alloc<int>(c, 4, true);
     if ((fuse && !c->hg.d_part) || !c->hg.d_gate) return fail(c, "hdrtv_hg: workspace allocation failed");
     bool ok = mk("img", 8, 0) && (fuse || mk("c1", 64, 0)) && mk("p1", 64, 1) && mk("c2", 128, 1) && mk("p31", 256, 2) && mk("c3", 256, 2) &&
               mk("p41", 512, 3) && mk("c4", 512, 3) && mk("p51", 512, 4) && mk("c5", 512, 4) && mk("pc1", 512, 5) && mk("code", 512, 5) &&
@@ -398,15 +405,16 @@ static int hg_run(Ctx* c, const void* base_out, int H, int Wd, float* out, cudaS
   const int Hp = c->hg.Hp, Wp = c->hg.Wp;
   if (c->precision == HDRTV_FP16) {
     auto& T = c->hg.t;
-    // Frames without a single pixel inside the highlight mask (max_c(base) <= 0.775: no speculars, lamps or white areas)
-    // leave the stage as they entered it (mask * hg + img with mask = 0 everywhere): the stage-in pass raises a device
-    // flag when it sees a masked pixel and the 19 U-Net launches return at once while it is down.  Bit-identical to the
-    // dense evaluation; HDRTV_HG_EARLY_OUT=0 always runs the U-Net (benchmarks quote that figure).  Needs the conv10 fold's
-    // tail kernel.
+    // Highlight gate.  The stage's output differs from its input only inside the mask (max_c(base) > 0.775: speculars,
+    // lamps, white areas), and a masked output depends on nothing further than 186 pixels away.  The stage-in pass leaves
+    // the bounding box of the frame's masked pixels in device memory; the 19 U-Net launches read it, return at once when
+    // there is none and otherwise compute only the tiles within kHgCone pixels of the box.  No host synchronisation, the
+    // launch sequence is the same for every frame.  Bit-identical to the dense evaluation; HDRTV_HG_EARLY_OUT=0 always runs
+    // the whole U-Net (benchmarks quote that figure).  Needs the conv10 fold's tail kernel.
     const char* eo_env = getenv("HDRTV_HG_EARLY_OUT");
     const bool early = c->hg.fuse_conv10 && c->hg.d_gate && !(eo_env && eo_env[0] == '0');
     int* gate = early ? c->hg.d_gate : nullptr;
-    if (gate) CK(c, cudaMemsetAsync(gate, 0, sizeof(int), s));
+    if (gate) CK(c, cudaMemsetAsync(gate, 0x7f, 4 * sizeof(int), s));      // kHgNoMask in all four words
     hg_stage_in_kernel<__half><<<dim3((Wp + 127) / 128, Hp), 128, 0, s>>>(static_cast<const __half*>(base_out), T.at("img"), H, Wd, Hp, Wp, gate);
     CK(c, cudaGetLastError());
     ++c->launches;

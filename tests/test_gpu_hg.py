@@ -168,38 +168,45 @@ def test_hg_is_bit_reproducible_and_follows_resolution_changes(nets):
 
 
 def test_hg_mask_early_out_is_bit_identical_to_the_dense_stage(nets, monkeypatch):
-    """Frames without a pixel inside the highlight mask skip the U-Net (device-side gate raised by the stage-in pass); the
-    result must equal the dense evaluation bit for bit, and a masked frame right after an unmasked one must not see stale
-    partial sums."""
+    """Highlight gate: frames without a masked pixel skip the U-Net, frames with highlights compute only the tiles within the
+    dependency cone (186 px) of the masked pixels' bounding box.  The result must equal the dense evaluation bit for bit -
+    also for highlights in corners / on edges, right after frames with other (or no) highlights (stale tiles), and at a
+    size where most tiles really are skipped."""
     net = nets("fp16")
     rng = np.random.default_rng(3)
-    dark = (0.70 * rng.random((1, 3, 136, 248))).astype(np.float16)                  # max 0.70 < 0.775: mask empty
-    one = dark.copy()
-    one[0, :, 70, 123] = np.float16(0.9)                                             # a single highlight pixel
-    bright = (0.55 + 0.45 * rng.random((1, 3, 136, 248))).astype(np.float16)
-    seq = [bright, dark, one, dark, bright, dark]
+    h, w = 540, 960
+    dark = (0.70 * rng.random((1, 3, h, w))).astype(np.float16)                      # max 0.70 < 0.775: mask empty
+    bright = (0.55 + 0.45 * rng.random((1, 3, h, w))).astype(np.float16)
+
+    def spot(y0, y1, x0, x1):
+        f = dark.copy()
+        f[0, :, y0:y1, x0:x1] = np.float16(0.9)
+        return f
+    seq = [bright, dark, spot(270, 271, 480, 481), spot(0, 1, 0, 1), dark, spot(539, 540, 959, 960), spot(100, 110, 700, 712),
+           spot(530, 540, 0, 5), bright, spot(0, 3, 955, 960), dark]
     monkeypatch.setenv("HDRTV_HG_EARLY_OUT", "0")
     dense = [_stage(net, b) for b in seq]
     monkeypatch.setenv("HDRTV_HG_EARLY_OUT", "1")
     gated = [_stage(net, b) for b in seq]
-    for i, (d, g, b) in enumerate(zip(dense, gated, seq)):
-        assert np.array_equal(d, g), f"early-out changed frame {i}"
+    for i, (d, g) in enumerate(zip(dense, gated)):
+        assert np.array_equal(d, g), f"the highlight gate changed frame {i}: {int((d != g).sum())} values differ"
     assert np.array_equal(gated[1], dark.astype(np.float32))                          # no highlight: the base image itself
-    assert (gated[2] != one.astype(np.float32)).any(axis=1).sum() == 1               # exactly the one masked pixel moved
-    # the gate really skips the work: an unmasked frame costs a fraction of a masked one
-    base_d, base_b = torch.from_numpy(dark).cuda(), torch.from_numpy(bright).cuda()
-
+    assert (gated[2] != seq[2].astype(np.float32)).any(axis=1).sum() == 1            # exactly the one masked pixel moved
+    # the gate really skips the work: no highlight ~ free, one small highlight a fraction of a frame full of them
     def ms(base):
+        t = torch.from_numpy(base).cuda()
         for _ in range(3):
-            net.hg_stage(base)
+            net.hg_stage(t)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            net.hg_stage(base)
+            net.hg_stage(t)
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / 10
-    assert ms(base_d) < 0.6 * ms(base_b)
+    t_full, t_none, t_spot = ms(bright), ms(dark), ms(seq[6])
+    print(f"HG stage 540p: all highlights {t_full:.3f} ms, none {t_none:.3f} ms, one 10x12 highlight {t_spot:.3f} ms")
+    assert t_none < 0.5 * t_full and t_spot < t_full          # (at 540p the deep levels' K chains bound the stage: see 4K in DESIGN)
 
 
 @needs_ref
@@ -236,6 +243,12 @@ def test_hg_weights_are_checked_strictly(hg_sd):
         hb.HDRTVNetB200(W_HR, device="cuda", precision="fp16", warmup_passes=0, use_hg=True, hg_weights=bad)
     with pytest.raises(FileNotFoundError):
         hb.HDRTVNetB200(W_HR, device="cuda", precision="fp16", warmup_passes=0, use_hg=True, hg_weights="/nonexistent/HG.pt")
+    # reflect padding needs pad < size (torch raises too): 16 rows cannot be reflected up to 32
+    small = hb.HDRTVNetB200(W_HR, device="cuda", precision="fp16", warmup_passes=0, use_hg=True, hg_weights=hg_sd)
+    with pytest.raises(RuntimeError, match="reflect padding"):
+        small.hg_stage(torch.zeros((1, 3, 16, 40), dtype=torch.float16, device="cuda"))
+    assert small.hg_stage(torch.zeros((1, 3, 17, 40), dtype=torch.float16, device="cuda")).shape == (1, 3, 17, 40)
+    small.close()
     # fused-BN checkpoints (Hallucination_Generator_FusedBN) load as well and give the same result
     net = hb.HDRTVNetB200(W_HR, device="cuda", precision="fp32", warmup_passes=0, use_hg=True, hg_weights=O.hg_fold_bn(hg_sd))
     g = load_golden(HG_CASES[0])
