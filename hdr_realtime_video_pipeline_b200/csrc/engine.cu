@@ -219,7 +219,8 @@ struct HgState {
   float *d_dot_up = nullptr, *d_dot_skip = nullptr;   // conv10's weights split by producer, [3][64] each
   float* d_part = nullptr;                      // conv10 partial sums written by the *_DOT epilogues, [6][3][Hp][Wp]
   bool fuse_conv10 = true;
-  int* d_gate = nullptr;                        // 1 when the current frame has a pixel inside the highlight mask (early-out gate)
+  int* d_gate = nullptr;                        // highlight gate: flag word + cell maps (hg.cuh, GConvParams::gate)
+  int gate_cw = 0, gate_ch = 0;
   std::vector<void*> wallocs;
   int H = 0, W = 0, Hp = 0, Wp = 0, sms = 148;
   std::vector<void*> ws;

@@ -35,7 +35,9 @@ enum GKind : int { G_3x3 = 0, G_3x3_C8 = 1, G_1x1 = 2 };
 enum GEpi : int { GE_P8 = 0, GE_POOL = 1, GE_PS = 2, GE_POOL_DOT = 3, GE_PS_DOT = 4 };
 constexpr int kGRows = 4;                       // output rows per tile (accumulators in TMEM)
 constexpr int kHgNoMask = 0x7f7f7f7f;           // gate words after cudaMemset(0x7f): no masked pixel seen
-constexpr int kHgCone = 192;                    // >= 186: reach of the U-Net's dependency cone in full-resolution pixels
+constexpr int kHgCell = 64;                     // gate cell (full-resolution pixels)
+constexpr int kHgCellShift = 6;
+constexpr int kHgCellReach = 3;                 // floor(186 / 64) + 1: cells a dependency cone of 186 px can reach
 constexpr int kGThreads = 320;
 
 __host__ __device__ constexpr int g_planes(int k) { return k == G_3x3 ? 2 : (k == G_3x3_C8 ? 1 : 8); }      // per K group
@@ -80,12 +82,14 @@ struct GConvParams {
   const float* dot_w;        // *_DOT: conv10 weights of this layer's channels, [3][channels] (half-rounded values)
   float* dot_out;            // *_DOT: partial sums, [slices][3][dot_H][dot_W] planar fp32; slice = ntile * 2 + half
   int dot_H, dot_W;
-  // Highlight gate (optional).  gate[0..3] = {x_min, y_min, -x_max, -y_max} of the frame's masked pixels (kHgNoMask when
-  // there is none).  No masked pixel: the stage's output is the base image itself (mask * hg + img with mask = 0) and the
-  // launch returns at once.  Otherwise only the tiles that intersect the bounding box grown by kHgCone full-resolution
-  // pixels are computed: no element further than 186 pixels from a masked pixel can reach a masked output (the U-Net's
-  // dependency cone, five 2x poolings and their 3x3 convs), and unmasked outputs do not use the U-Net at all.
+  // Highlight gate (optional).  gate[0] = kHgNoMask while no pixel of the frame is inside the highlight mask: the stage's
+  // output is then the base image itself (mask * hg + img with mask = 0) and the launch returns at once.  Otherwise
+  // `gate_active` is a map of kHgCell x kHgCell full-resolution cells: 1 = within kHgCellReach cells (186 pixels: the reach of the
+  // U-Net's dependency cone: five 2x poolings and their 3x3 convs) of a cell with a masked pixel.  Only tiles that touch
+  // an active cell are computed: nothing else can reach a masked output, and unmasked outputs do not use the U-Net.
   const int* gate;
+  const uint8_t* gate_active;
+  int gate_cw, gate_ch;      // cells per row / column
   int lvl;                   // resolution level of this conv's pixels (0 = full resolution, 5 = 1/32)
   int* err;
 };
@@ -114,17 +118,17 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
   static_assert((EPI != GE_PS && EPI != GE_PS_DOT) || NT == 128, "PixelShuffle epilogue: 128 conv channels = 32 output channels per tile");
   constexpr int PL = g_planes(KIND), ROWS = g_rows(KIND, RB), NSTEPS = g_steps(KIND), S = g_stages(KIND, RB);
   constexpr uint32_t A_BYTES = g_a_bytes(KIND, RB), STAGE = g_stage_bytes(KIND, NT, RB), BLK = NT * 32u;
-  int ax0 = 0, ax1 = 0x7fffffff, ay0 = 0, ay1 = 0x7fffffff;      // active pixel range of this level (gate)
-  if (p.gate != nullptr) {
-    const volatile int* g = reinterpret_cast<const volatile int*>(p.gate);
-    const int gx0 = g[0], gy0 = g[1], gx1 = -g[2], gy1 = -g[3];
-    if (gx0 == kHgNoMask) return;                                  // uniform: before any barrier / TMEM
-    ax0 = max(gx0 - kHgCone, 0) >> p.lvl;
-    ay0 = max(gy0 - kHgCone, 0) >> p.lvl;
-    ax1 = (gx1 + kHgCone) >> p.lvl;
-    ay1 = (gy1 + kHgCone) >> p.lvl;
-  }
-  auto tile_on = [&](int x0, int y0) { return x0 <= ax1 && x0 + kTileM - 1 >= ax0 && y0 <= ay1 && y0 + RB - 1 >= ay0; };
+  if (p.gate != nullptr && *reinterpret_cast<const volatile int*>(p.gate) == kHgNoMask) return;      // uniform: before any barrier / TMEM
+  // does the tile (x0 .. x0+127, y0 .. y0+RB-1 at this conv's level) touch an active gate cell?
+  auto tile_on = [&](int x0, int y0) -> bool {
+    if (p.gate == nullptr) return true;
+    const int cx0 = (x0 << p.lvl) >> kHgCellShift, cx1 = min((((x0 + kTileM) << p.lvl) - 1) >> kHgCellShift, p.gate_cw - 1);
+    const int cy0 = (y0 << p.lvl) >> kHgCellShift, cy1 = min((((y0 + RB) << p.lvl) - 1) >> kHgCellShift, p.gate_ch - 1);
+    for (int cy = cy0; cy <= cy1; ++cy)
+      for (int cx = cx0; cx <= cx1; ++cx)
+        if (__ldg(p.gate_active + cy * p.gate_cw + cx)) return true;      // <= 2 KB map, written before this launch: L1-resident
+    return false;
+  };
   constexpr uint32_t kTmemCols = 4 * NT;                 // RB = 4: one tile of four rows; RB = 2: two tiles of two rows
   // accumulator block / barrier index of row r of this CTA's `it`-th tile, and the parity its barriers are in
   auto acc_idx = [](int it, int r) { return RB == 4 ? r : ((it & 1) * 2 + r); };
@@ -438,7 +442,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gconv_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float hg_mask_half(float m);
 template <typename T>
-__global__ void __launch_bounds__(128) hg_stage_in_kernel(const T* __restrict__ src, P8 dst, int H, int W, int Hp, int Wp, int* gate) {
+__global__ void __launch_bounds__(128) hg_stage_in_kernel(const T* __restrict__ src, P8 dst, int H, int W, int Hp, int Wp, int* gate,
+                                                          uint8_t* seen, int cw) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   bool masked = false;
   if (x < Wp && y < Hp) {
@@ -448,16 +453,23 @@ __global__ void __launch_bounds__(128) hg_stage_in_kernel(const T* __restrict__ 
     reinterpret_cast<uint4*>(dst.base)[dst.entry(y, 0, x)] = pack8(v);
     masked = x < W && y < H && hg_mask_half(fmaxf(v[0], fmaxf(v[1], v[2]))) != 0.f;
   }
-  // bounding box of the frame's masked pixels (un-padded area: only those outputs exist), one atomic set per warp that saw one
-  if (gate != nullptr) {
-    const int lo = __reduce_min_sync(0xffffffffu, masked ? x : kHgNoMask);
-    const int nhi = __reduce_min_sync(0xffffffffu, masked ? -x : kHgNoMask);
-    if ((threadIdx.x & 31) == 0 && lo != kHgNoMask) {
-      atomicMin(gate + 0, lo);
-      atomicMin(gate + 1, y);
-      atomicMin(gate + 2, nhi);
-      atomicMin(gate + 3, -y);
-    }
+  // gate: which cells hold a masked pixel (un-padded area: only those outputs exist); gate[0] leaves kHgNoMask with the first one
+  if (gate != nullptr && masked) {
+    seen[(y >> kHgCellShift) * cw + (x >> kHgCellShift)] = 1;
+    *gate = 0;
+  }
+}
+// active cell = within kHgCellReach cells of a cell that holds a masked pixel (one small block per frame)
+__global__ void hg_gate_dilate_kernel(const uint8_t* __restrict__ seen, uint8_t* __restrict__ active, int cw, int ch) {
+  for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
+    const int cx = i % cw, cy = i / cw;
+    uint8_t a = 0;
+    for (int dy = -kHgCellReach; dy <= kHgCellReach; ++dy)
+      for (int dx = -kHgCellReach; dx <= kHgCellReach; ++dx) {
+        const int yy = cy + dy, xx = cx + dx;
+        if (yy >= 0 && yy < ch && xx >= 0 && xx < cw && seen[yy * cw + xx]) a = 1;
+      }
+    active[i] = a;
   }
 }
 

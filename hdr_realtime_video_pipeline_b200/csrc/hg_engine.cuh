@@ -325,7 +325,10 @@ static int hg_prepare(Ctx* c, int H, int Wd) {
     const bool fuse = env_int("HDRTV_HG_FUSE_CONV10", 1) != 0;
     c->hg.fuse_conv10 = fuse;
     c->hg.d_part = fuse ? hg_ws_alloc<float>(c, static_cast<size_t>(6) * 3 * Hp * Wp, true) : nullptr;
-    c->hg.d_gate = hg_ws_alloc<int>(c, 4, true);
+    c->hg.gate_cw = (Wp + kHgCell - 1) / kHgCell;
+    c->hg.gate_ch = (Hp + kHgCell - 1) / kHgCell;
+    // gate: one flag word (+ 3 spare), then the `seen` and `active` cell maps (one byte per cell each)
+    c->hg.d_gate = reinterpret_cast<int*>(hg_ws_alloc<uint8_t>(c, 16 + 2 * static_cast<size_t>(c->hg.gate_cw) * c->hg.gate_ch, true));
     if ((fuse && !c->hg.d_part) || !c->hg.d_gate) return fail(c, "hdrtv_hg: workspace allocation failed");
     bool ok = mk("img", 8, 0) && (fuse || mk("c1", 64, 0)) && mk("p1", 64, 1) && mk("c2", 128, 1) && mk("p31", 256, 2) && mk("c3", 256, 2) &&
               mk("p41", 512, 3) && mk("c4", 512, 3) && mk("p51", 512, 4) && mk("c5", 512, 4) && mk("pc1", 512, 5) && mk("code", 512, 5) &&
@@ -406,20 +409,35 @@ static int hg_run(Ctx* c, const void* base_out, int H, int Wd, float* out, cudaS
   if (c->precision == HDRTV_FP16) {
     auto& T = c->hg.t;
     // Highlight gate.  The stage's output differs from its input only inside the mask (max_c(base) > 0.775: speculars,
-    // lamps, white areas), and a masked output depends on nothing further than 186 pixels away.  The stage-in pass leaves
-    // the bounding box of the frame's masked pixels in device memory; the 19 U-Net launches read it, return at once when
-    // there is none and otherwise compute only the tiles within kHgCone pixels of the box.  No host synchronisation, the
-    // launch sequence is the same for every frame.  Bit-identical to the dense evaluation; HDRTV_HG_EARLY_OUT=0 always runs
+    // lamps, white areas), and a masked output depends on nothing further than 186 pixels away.  The stage-in pass marks
+    // the 64 x 64 cells that hold a masked pixel, a one-block kernel grows that map by three cells, and the 19 U-Net
+    // launches compute only the tiles that touch an active cell (none at all: they return at once).  No host
+    // synchronisation, the launch sequence is the same for every frame.  Bit-identical to the dense evaluation; HDRTV_HG_EARLY_OUT=0 always runs
     // the whole U-Net (benchmarks quote that figure).  Needs the conv10 fold's tail kernel.
     const char* eo_env = getenv("HDRTV_HG_EARLY_OUT");
     const bool early = c->hg.fuse_conv10 && c->hg.d_gate && !(eo_env && eo_env[0] == '0');
     int* gate = early ? c->hg.d_gate : nullptr;
-    if (gate) CK(c, cudaMemsetAsync(gate, 0x7f, 4 * sizeof(int), s));      // kHgNoMask in all four words
-    hg_stage_in_kernel<__half><<<dim3((Wp + 127) / 128, Hp), 128, 0, s>>>(static_cast<const __half*>(base_out), T.at("img"), H, Wd, Hp, Wp, gate);
+    const int cells = c->hg.gate_cw * c->hg.gate_ch;
+    uint8_t* seen = gate ? reinterpret_cast<uint8_t*>(gate) + 16 : nullptr;
+    uint8_t* active = gate ? seen + cells : nullptr;
+    if (gate) {
+      CK(c, cudaMemsetAsync(gate, 0x7f, 16, s));                           // kHgNoMask
+      CK(c, cudaMemsetAsync(seen, 0, cells, s));
+    }
+    hg_stage_in_kernel<__half><<<dim3((Wp + 127) / 128, Hp), 128, 0, s>>>(static_cast<const __half*>(base_out), T.at("img"), H, Wd, Hp, Wp, gate,
+                                                                          seen, c->hg.gate_cw);
     CK(c, cudaGetLastError());
     ++c->launches;
+    if (gate) {
+      hg_gate_dilate_kernel<<<1, 256, 0, s>>>(seen, active, c->hg.gate_cw, c->hg.gate_ch);
+      CK(c, cudaGetLastError());
+      ++c->launches;
+    }
     for (HgLaunch& L : c->hg.plan) {
       L.p.gate = gate;
+      L.p.gate_active = active;
+      L.p.gate_cw = c->hg.gate_cw;
+      L.p.gate_ch = c->hg.gate_ch;
       CK(c, hg_launch(L, s));
       ++c->launches;
     }

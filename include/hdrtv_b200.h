@@ -127,8 +127,8 @@ int hdrtv_letterbox_bgr(hdrtv_t* h, const uint8_t* src, int height, int width, u
 /* FLOAT32 in both precisions, as in the reference (mask.float() * out + img promotes a half model's output).            */
 /* Once HG weights are installed, hdrtv_process / hdrtv_process_ex run the stage between the LE network and the pack.     */
 /* Outside the mask the stage leaves the frame unchanged (mask * hg + img, mask = 0) and a masked pixel depends on nothing   */
-/* further than 186 pixels away: on HDRTV_FP16 contexts the stage-in pass leaves the bounding box of the masked pixels in    */
-/* device memory and the U-Net launches compute only the tiles within that reach of it (none: they return at once) - no host */
+/* further than 186 pixels away: on HDRTV_FP16 contexts the stage-in pass leaves a map of the cells holding masked pixels in */
+/* device memory and the U-Net launches compute only the tiles within that reach of them (none: they return at once) - no host */
 /* synchronisation, bit-identical output (environment HDRTV_HG_EARLY_OUT=0 forces the dense evaluation).                    */
 int hdrtv_set_hg_weights(hdrtv_t* h, const hdrtv_tensor_desc* tensors, int n);
 int hdrtv_hg(hdrtv_t* h, const void* base_out, int height, int width, float* out, void* stream);
